@@ -1,0 +1,195 @@
+/*
+ * ta_b200.h — C-ABI of libta_b200.so: the sm_100a kernels behind the TransferAttack
+ * `Attack` hook API (reference: transferattack/attack.py and its gradient/,
+ * input_transformation/, ensemble/ plugins).
+ *
+ * Conventions (every entry point):
+ *   - plain C symbols, no torch / C++ types in any signature;
+ *   - all tensor pointers are BORROWED device pointers to contiguous fp32 NCHW data
+ *     (what `tensor.data_ptr()` returns); the caller keeps them alive until `stream`
+ *     has been synchronised; nothing is allocated, freed or synchronised inside;
+ *   - `stream` is a `cudaStream_t` passed as void* (0 = legacy default stream);
+ *   - the return value is TA_OK (0) or a negative TA_E* code; the message for the last
+ *     failure on the calling thread is returned by ta_last_error();
+ *   - B = number of samples, n = elements per sample (C*H*W), N = total elements;
+ *   - arithmetic is IEEE fp32, round-to-nearest, one rounding per reference op, never
+ *     contracted into FMA unless the reference's own expression is an FMA (the
+ *     bilinear source index, see ta_dim_fwd). This is what makes the results
+ *     bit-comparable with the reference's eager PyTorch ops.
+ *
+ * Each declaration cites the reference code (file:line under the reference repo's
+ * transferattack/ directory) that it replaces.
+ */
+#ifndef TA_B200_H
+#define TA_B200_H
+
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define TA_ABI_VERSION 1
+
+enum {
+  TA_OK = 0,
+  TA_EINVAL = -1,       /* bad shape / null pointer / misaligned pointer */
+  TA_ECUDA = -2,        /* CUDA runtime reported an error (launch, attribute, driver entry point) */
+  TA_EUNSUPPORTED = -3  /* valid request this build cannot serve (e.g. kernel size too large) */
+};
+
+/* how ta_abs_mean_per_sample / ta_fused_update_linf form mean|g| */
+enum {
+  TA_MEAN_EXACT = 0,    /* fp64 accumulation, mean = (float)(sum / n): order-independent up to the final rounding */
+  TA_MEAN_ATEN = 1      /* replays ATen's CUDA reduction order for sum(|g|) over a contiguous row of n floats
+                           followed by `* (float)(1/n)` (torch.mean on sm_100, 148 SMs) */
+};
+
+/* direction modes of ta_update_linf */
+enum {
+  TA_DIR_SIGN = 0,      /* step = alpha * sign(dir)  (attack.py:147) */
+  TA_DIR_RAW = 1        /* step = alpha * dir        (caller already holds a direction) */
+};
+
+typedef void* ta_stream_t;
+
+/* ---- library ---------------------------------------------------------------------- */
+
+int ta_version(void);                   /* TA_ABI_VERSION of the loaded library */
+const char* ta_last_error(void);        /* thread-local message of the last non-OK return */
+/* SM count / compute capability of the current device; TA_ECUDA when no device is usable. */
+int ta_device_info(int* sm_count, int* cc_major, int* cc_minor);
+/* number of kernels this library has launched in this process since load (bench.py's gpu_launches) */
+int64_t ta_launch_count(void);
+
+/* ---- get_momentum  (attack.py:124-128) ----------------------------------------------
+ *   momentum * decay + grad / mean_{C,H,W}(|grad|)                                       */
+
+/* mean_out[b] = mean over the sample of |g|.  mode: TA_MEAN_EXACT or TA_MEAN_ATEN.
+ * ws: caller-provided scratch of ta_abs_mean_ws_bytes(B, n) bytes (may be NULL when that is 0). */
+int64_t ta_abs_mean_ws_bytes(int B, int64_t n);
+int ta_abs_mean_per_sample(const float* g, float* mean_out, int B, int64_t n, int mode,
+                           void* ws, ta_stream_t stream);
+
+/* m_out = m * decay + g / scale[b]      (m == NULL means the reference's `momentum = 0` first call)
+ * scale: [B] per-sample mean|g| (from torch or from ta_abs_mean_per_sample). m_out may alias m. */
+int ta_momentum(const float* g, const float* m, const float* scale, float decay, float* m_out,
+                int B, int64_t n, ta_stream_t stream);
+
+/* ---- update_delta (attack.py:145-153), clamp (utils.py:68-69) --------------------------
+ *   L-inf: delta' = clamp(clamp(delta + alpha * sign(dir), -eps, eps), lo - x, hi - x)
+ *   alpha_t (nullable): full-shape [B,n] tensor step (gradient/gra.py:149, fgsra.py:213);
+ *   when alpha_t != NULL the scalar `alpha` is ignored.  NaN propagates exactly as in
+ *   torch.clamp / torch.min / torch.max.  delta_out may alias delta.                      */
+int ta_update_linf(const float* delta, const float* data, const float* dir, const float* alpha_t,
+                   float alpha, float eps, float lo, float hi, int dir_mode, float* delta_out,
+                   int64_t N, ta_stream_t stream);
+
+/* L2 (attack.py:148-152): ghat = g / (||g||_2 + 1e-20); y = delta + ghat * alpha;
+ * rows with ||y||_2 > eps are scaled by eps / (||y||_2 + 1e-7) (torch.renorm); then box clamp.
+ * ws: scratch of ta_update_l2_ws_bytes(B) bytes. */
+int64_t ta_update_l2_ws_bytes(int B);
+int ta_update_l2(const float* delta, const float* data, const float* g, float alpha, float eps,
+                 float lo, float hi, float* delta_out, int B, int64_t n, void* ws, ta_stream_t stream);
+
+/* init_delta's final projection (attack.py:141): out = min(max(delta, lo - x), hi - x). */
+int ta_clamp_box(const float* delta, const float* data, float lo, float hi, float* out,
+                 int64_t N, ta_stream_t stream);
+
+/* L2 random start (attack.py:136-140): delta *= r / ||delta_row||_2 * eps, then box clamp.
+ * delta holds the normal_ draw, r the uniform_(0,1) draw (both from torch's device generator). */
+int ta_init_l2_scale(const float* delta, const float* r, const float* data, float eps, float lo, float hi,
+                     float* out, int B, int64_t n, void* ws, ta_stream_t stream);
+
+/* ---- the fused iteration tail (attack.py:97-100 + next iteration's attack.py:88) --------
+ *   mu_b   = scale[b]                  if scale != NULL   (strict: torch computed it)
+ *          = mean|g_b| (mean_mode)     otherwise          (fused in-kernel reduction)
+ *   m'     = m * decay + g / mu_b      (m may be NULL on the first iteration: m' = 0 + g/mu_b)
+ *   delta' = L-inf update_delta(delta, data, m', alpha)
+ *   xadv   = data + delta'             (only when xadv_out != NULL; the next model input)
+ * m_out / delta_out may alias m / delta (in place). scale_out (nullable, [B]) receives mu_b.
+ * One launch; with the in-kernel reduction g is read from HBM once (cluster-resident).      */
+int ta_fused_update_linf(const float* g, const float* m, float* m_out,
+                         const float* delta, float* delta_out, const float* data,
+                         float* xadv_out, const float* scale, float* scale_out, int mean_mode,
+                         float decay, float alpha, float eps, float lo, float hi,
+                         int B, int64_t n, ta_stream_t stream);
+
+/* ---- model-input staging (attack.py:88, gradient/nifgsm.py:35-39) -------------------------
+ *   out = data + delta                         (look == NULL)
+ *   out = (data + delta) + coef * look         (NI / VNI look-ahead; coef = alpha*decay as fp32) */
+int ta_stage_add(const float* data, const float* delta, const float* look, float coef, float* out,
+                 int64_t N, ta_stream_t stream);
+
+/* PreprocessingModel's Normalize (utils.py:72-79): out = (x - mean[c]) / std[c]; adjoint gin = gout / std[c].
+ * mean/std: [C] fp32 DEVICE arrays. plane = H*W. */
+int ta_normalize_fwd(const float* x, const float* mean, const float* std, float* out,
+                     int B, int C, int64_t plane, ta_stream_t stream);
+int ta_normalize_bwd(const float* gout, const float* std, float* gin,
+                     int B, int C, int64_t plane, ta_stream_t stream);
+
+/* ---- SIM (input_transformation/sim.py:36-46) ----------------------------------------------
+ *   out[s*N + i] = x[i] / 2^s, s = 0..S-1 (scale-major concat along the batch axis)
+ *   adjoint: gin[i] = ((((g_{S-1}/2^{S-1}) + g_{S-2}/2^{S-2}) + ...) + g_0)  (autograd's accumulation order) */
+int ta_sim_fwd(const float* x, float* out, int S, int64_t N, ta_stream_t stream);
+int ta_sim_bwd(const float* gout, float* gin, int S, int64_t N, ta_stream_t stream);
+
+/* ---- Admix (input_transformation/admix.py:40-51) --------------------------------------------
+ *   out[((s*A + a)*B + b)] = (x[b] + strength * x[perm[a*B + b]]) / 2^s ; perm: int32 DEVICE array [A*B]
+ *   (torch.randperm draws, made on the host generator by the caller).
+ *   adjoint wrt the first x only (the mixed-in image is .detach()ed in the reference).           */
+int ta_admix_fwd(const float* x, const int32_t* perm, float strength, float* out,
+                 int S, int A, int B, int64_t n, ta_stream_t stream);
+int ta_admix_bwd(const float* gout, float* gin, int S, int A, int B, int64_t n, ta_stream_t stream);
+
+/* ---- DIM (input_transformation/dim.py:42-68) ---------------------------------------------------
+ *   y1 = bilinear(x -> rnd x rnd); y2 = zero-pad y1 to R x R at (pad_top, pad_left);
+ *   out = bilinear(y2 -> H x W); align_corners=False, no antialias; one (rnd, pad) for the batch.
+ *   Source index = max(0, fmaf(scale, dst + 0.5f, -0.5f)), scale = (float)in / (float)out (ATen).
+ *   planes = B*C; H == W required (the reference uses x.shape[-1] for both).
+ *   ta_dim_bwd is the exact adjoint in deterministic gather form (ATen's uses atomicAdd).        */
+int ta_dim_fwd(const float* x, float* out, int planes, int S, int rnd, int R, int pad_top, int pad_left,
+               ta_stream_t stream);
+int ta_dim_bwd(const float* gout, float* gin, int planes, int S, int rnd, int R, int pad_top, int pad_left,
+               ta_stream_t stream);
+
+/* ---- TIM (input_transformation/tim.py:68-73) ------------------------------------------------------
+ *   out = conv2d(g, K[C,1,ks,ks], stride 1, zero padding 'same', groups=C)  (cross-correlation)
+ *   k: [C, ks, ks] DEVICE array, ks odd, ks <= 31.
+ *   ta_dwconv2d_sep: K[c] = outer(kcol[c], krow[c]) (rank-1 kernels: gaussian / uniform / linear of
+ *   tim.py:42-66): out = sum_i kcol[i] * (sum_j krow[j] * g[y+i-r, x+j-r]).                          */
+int ta_dwconv2d(const float* g, const float* k, int ks, float* out, int B, int C, int H, int W,
+                ta_stream_t stream);
+int ta_dwconv2d_sep(const float* g, const float* kcol, const float* krow, int ks, float* out,
+                    int B, int C, int H, int W, ta_stream_t stream);
+
+/* ---- EMI (gradient/emifgsm.py:53-58, 86-103) ---------------------------------------------------------
+ *   out[k*N + i] = x[i] + coef[k] * gbar[i]  (coef[k] = (float)(factor_k * alpha), host array, K <= 32)
+ *   gbar == NULL is the first iteration (`bar_grad = 0`): out[k*N+i] = x[i] + 0.
+ *   adjoint: gin[i] = (((g_{K-1}) + g_{K-2}) + ... ) + g_0                                              */
+int ta_lin_sample_fwd(const float* x, const float* gbar, const float* coef_host, int K, float* out,
+                      int64_t N, ta_stream_t stream);
+int ta_lin_sample_bwd(const float* gout, float* gin, int K, int64_t N, ta_stream_t stream);
+
+/* ---- VMI / VNI (gradient/vmifgsm.py:42-58) ---------------------------------------------------------------
+ *   neighbour input: out = ((data + delta) + noise) [+ coef * look]   (noise = torch uniform_(-r, r) draw)
+ *   accumulate:      acc = (first ? g : acc + g)        (`grad = 0; grad += ...`)
+ *   finalize:        v = acc / num_neighbor - cur_grad                                                  */
+int ta_neighbor_stage(const float* data, const float* delta, const float* noise, const float* look,
+                      float coef, float* out, int64_t N, ta_stream_t stream);
+int ta_accumulate(float* acc, const float* g, int first, int64_t N, ta_stream_t stream);
+int ta_variance_finalize(const float* acc, const float* cur, int num_neighbor, float* out,
+                         int64_t N, ta_stream_t stream);
+/* out = a + b (vmifgsm.py:87 `grad + variance`) */
+int ta_add(const float* a, const float* b, float* out, int64_t N, ta_stream_t stream);
+
+/* ---- output path (utils.py:63-66 save_images) ---------------------------------------------------------------
+ *   u8 = (uint8) trunc((data + delta) * 255)   as numpy's float32 -> uint8 cast of in-range values;
+ *   layout NCHW -> NHWC (the permute((0,2,3,1)) of save_images) when to_nhwc != 0.                 */
+int ta_quantize_u8(const float* data, const float* delta, uint8_t* out, int B, int C, int64_t plane,
+                   int to_nhwc, ta_stream_t stream);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* TA_B200_H */
