@@ -61,6 +61,9 @@ const char* ta_last_error(void);        /* thread-local message of the last non-
 int ta_device_info(int* sm_count, int* cc_major, int* cc_minor);
 /* number of kernels this library has launched in this process since load (bench.py's gpu_launches) */
 int64_t ta_launch_count(void);
+/* runtime tuning knobs for the benchmark sweep ("fused.cluster", "fused.threads", "fused.unroll",
+ * "fused.variant", "reduce.cluster", "dim.tma"); not part of the reference-facing surface. */
+int ta_tune_set(const char* key, int value);
 
 /* ---- get_momentum  (attack.py:124-128) ----------------------------------------------
  *   momentum * decay + grad / mean_{C,H,W}(|grad|)                                       */
@@ -117,7 +120,8 @@ int ta_fused_update_linf(const float* g, const float* m, float* m_out,
 
 /* ---- model-input staging (attack.py:88, gradient/nifgsm.py:35-39) -------------------------
  *   out = data + delta                         (look == NULL)
- *   out = (data + delta) + coef * look         (NI / VNI look-ahead; coef = alpha*decay as fp32) */
+ *   out = (data + delta) + coef * look         (NI / VNI look-ahead; coef = alpha*decay as fp32)
+ *   delta == NULL: `data` already holds the sum (out = data + coef * look).                     */
 int ta_stage_add(const float* data, const float* delta, const float* look, float coef, float* out,
                  int64_t N, ta_stream_t stream);
 

@@ -1,0 +1,134 @@
+"""TESTS ONLY: a stand-in for ``transferattack_b200.ops.CudaBackend`` that serves the same method surface from the
+C oracle on CPU tensors. It lets the host-side logic of the package (loop control flow, hook argument tolerance, RNG
+consumption order, plugin classes, multi-process sharding) run on a box without a GPU and be compared bit for bit
+with the reference. The product never installs it (``ops._install_backend_for_tests`` is only called from tests/)."""
+import numpy as np
+import torch
+
+import oracle
+
+
+def _np(t):
+    return None if t is None else t.detach().cpu().contiguous().numpy()
+
+
+def _t(a, like=None):
+    return torch.from_numpy(np.ascontiguousarray(a))
+
+
+class OracleBackend:
+    calls = None
+
+    def __init__(self):
+        self.calls = []
+
+    def _log(self, name):
+        self.calls.append(name)
+
+    def abs_mean(self, g, mode=0):
+        self._log("abs_mean")
+        return _t(oracle.abs_mean_per_sample(_np(g)))
+
+    def momentum(self, g, m, scale, decay, out=None):
+        self._log("momentum")
+        r = _t(oracle.momentum(_np(g), _np(m), _np(scale).reshape(-1), float(decay)))
+        if out is not None:
+            out.copy_(r); return out
+        return r
+
+    def update_linf(self, delta, data, direction, alpha, eps, lo, hi, alpha_t=None, dir_mode=0, out=None):
+        self._log("update_linf")
+        r = _t(oracle.update_linf(_np(delta), _np(data), _np(direction), float(alpha), float(eps), float(lo), float(hi),
+                                  alpha_t=_np(alpha_t), dir_mode=dir_mode))
+        if out is not None:
+            out.copy_(r); return out
+        return r
+
+    def update_l2(self, delta, data, g, alpha, eps, lo, hi):
+        self._log("update_l2")
+        return _t(oracle.update_l2(_np(delta), _np(data), _np(g), float(alpha), float(eps), float(lo), float(hi)))
+
+    def clamp_box(self, delta, data, lo, hi):
+        self._log("clamp_box")
+        return _t(oracle.clamp_box(_np(delta), _np(data), float(lo), float(hi)))
+
+    def init_l2_scale(self, delta, r, data, eps, lo, hi):
+        self._log("init_l2_scale")
+        return _t(oracle.init_l2_scale(_np(delta), _np(r), _np(data), float(eps), float(lo), float(hi)))
+
+    def fused_update_linf(self, g, m, m_out, delta, delta_out, data, xadv_out, scale, scale_out, decay, alpha, eps, lo, hi,
+                          mean_mode=0):
+        self._log("fused_update_linf")
+        gn = _np(g)
+        sc = _np(scale).reshape(-1) if scale is not None else oracle.abs_mean_per_sample(gn)
+        mo, do, xo = oracle.fused_update_linf(gn, _np(m), _np(delta), _np(data), sc, float(decay), float(alpha), float(eps),
+                                              float(lo), float(hi), want_xadv=xadv_out is not None)
+        with torch.no_grad():
+            m_out.copy_(_t(mo)); delta_out.copy_(_t(do))
+            if xadv_out is not None:
+                xadv_out.copy_(_t(xo))
+            if scale_out is not None:
+                scale_out.copy_(_t(sc))
+
+    def stage_add(self, data, delta, look=None, coef=0.0, out=None):
+        self._log("stage_add")
+        d = _np(data)
+        if delta is None:   # x + coef*look on an already formed x
+            r = d if look is None else (d + (np.float32(coef) * _np(look)).astype(np.float32)).astype(np.float32)
+            return _t(r)
+        return _t(oracle.stage_add(d, _np(delta), _np(look), float(coef)))
+
+    def neighbor_stage(self, data, delta, noise, look=None, coef=0.0, out=None):
+        self._log("neighbor_stage")
+        return _t(oracle.neighbor_stage(_np(data), _np(delta), _np(noise), _np(look), float(coef)))
+
+    def normalize(self, x, mean, std, forward=True):
+        self._log("normalize")
+        if forward:
+            return _t(oracle.normalize_fwd(_np(x), _np(mean), _np(std)))
+        return _t(oracle.normalize_bwd(_np(x), _np(std)))
+
+    def sim(self, x, S, forward=True):
+        self._log("sim")
+        return _t(oracle.sim_fwd(_np(x), S) if forward else oracle.sim_bwd(_np(x), S))
+
+    def admix(self, x, perm, strength, S, A, forward=True):
+        self._log("admix")
+        if forward:
+            return _t(oracle.admix_fwd(_np(x), _np(perm), float(strength), S))
+        return _t(oracle.admix_bwd(_np(x), S, A))
+
+    def dim(self, x, rnd, R, top, left, forward=True):
+        self._log("dim")
+        fn = oracle.dim_fwd if forward else oracle.dim_bwd
+        return _t(fn(_np(x), int(rnd), int(R), int(top), int(left)))
+
+    def dwconv2d(self, g, k):
+        self._log("dwconv2d")
+        return _t(oracle.dwconv2d(_np(g), _np(k)))
+
+    def dwconv2d_sep(self, g, kcol, krow):
+        self._log("dwconv2d_sep")
+        return _t(oracle.dwconv2d_sep(_np(g), _np(kcol), _np(krow)))
+
+    def lin_sample(self, x, gbar, coefs, forward=True):
+        self._log("lin_sample")
+        if forward:
+            return _t(oracle.lin_sample_fwd(_np(x), _np(gbar), np.asarray(coefs, np.float32)))
+        return _t(oracle.lin_sample_bwd(_np(x), len(coefs)))
+
+    def accumulate(self, acc, g, first):
+        self._log("accumulate")
+        return _t(oracle.accumulate(_np(acc), _np(g), first))
+
+    def variance_finalize(self, acc, cur, num_neighbor):
+        self._log("variance_finalize")
+        return _t(oracle.variance_finalize(_np(acc), _np(cur), num_neighbor))
+
+    def add(self, a, b):
+        self._log("add")
+        return _t(oracle.add(_np(a), _np(b)))
+
+    def quantize_u8(self, data, delta, to_nhwc=True):
+        self._log("quantize_u8")
+        return torch.from_numpy(oracle.quantize_u8(_np(data), _np(delta), to_nhwc))

@@ -1,0 +1,223 @@
+"""The ``Attack`` plugin base: the iterative loop and its eight overridable hooks.
+
+Same class name, constructor, hook names/signatures, return types and error behaviour as the reference's
+``transferattack/attack.py`` (lines cited per method), so existing attack subclasses run unchanged on top
+of it. What is different is underneath: every per-iteration op around the surrogate's forward/backward is
+a hand-written sm_100a kernel reached through ``ops`` (C-ABI ``libta_b200.so``):
+
+  reference eager op chain                       here
+  ---------------------------------------------  ------------------------------------------------------------
+  data + delta                    (attack.py:88)  ``ta_stage_add`` inside an identity-backward autograd node,
+                                                  or the ``xadv`` output of the previous fused update
+  get_momentum: 5 ATen kernels   (attack.py:128)  ``ta_momentum`` (+ ``ta_abs_mean_per_sample`` / torch's mean)
+  update_delta: 8 ATen kernels   (attack.py:147)  ``ta_update_linf`` / ``ta_update_l2``
+  momentum+update+next data+delta                 ONE ``ta_fused_update_linf`` launch when neither hook is
+                                                  overridden (the base loop owns delta/momentum, so in-place)
+  init_delta clamp               (attack.py:141)  ``ta_clamp_box`` / ``ta_init_l2_scale``
+
+The surrogate forward and ``torch.autograd.grad`` backward stay PyTorch. There is no CPU path: the hooks
+raise on CPU tensors (``ops``), exactly like a missing ``libta_b200.so`` does.
+
+``mean_mode`` selects how ``mean(|grad|)`` per sample is formed:
+  'torch' (default) — the reference's own ``grad.abs().mean(dim=(1,2,3))`` ATen reduction, so that momentum
+                      and perturbation are bit-identical to the reference given the same gradient;
+  'exact'           — reduced inside the kernels in fp64 (``TA_MEAN_EXACT``): one launch for the whole tail,
+                      correctly rounded mean, may differ from torch's fp32 tree sum in the last bit.
+"""
+import os
+
+import torch
+import torch.nn as nn
+
+from . import _lib, ops
+from .utils import *  # noqa: F401,F403  (plugins expect the reference's star-exports through this module too)
+from .utils import EnsembleModel, clamp, img_max, img_min, models, timm, wrap_model
+
+_ZERO_TYPES = (int, float)
+
+
+def _is_zero_scalar(v):
+    return isinstance(v, _ZERO_TYPES) and not isinstance(v, bool) and v == 0
+
+
+class Attack(object):
+    """Base class of every attack plugin (reference attack.py:8-169)."""
+
+    #: 'torch' | 'exact' — see module docstring. Env override: TA_B200_MEAN.
+    mean_mode = os.environ.get("TA_B200_MEAN", "torch")
+    #: use the single-launch fused tail in the base loop when the hooks are not overridden
+    fuse_update = os.environ.get("TA_B200_FUSE", "1") != "0"
+
+    def __init__(self, attack, model_name, epsilon, targeted, random_start, norm, loss, device=None):
+        """attack.py:12-38 — same arguments, same attributes, same ``Unsupported norm`` exception."""
+        if norm not in ['l2', 'linfty']:
+            raise Exception("Unsupported norm {}".format(norm))
+        self.attack = attack
+        self.model = self.load_model(model_name)
+        self.epsilon = epsilon
+        self.targeted = targeted
+        self.random_start = random_start
+        self.norm = norm
+        if isinstance(self.model, EnsembleModel):
+            self.device = self.model.device
+        else:
+            self.device = next(self.model.parameters()).device if device is None else device
+        self.loss = self.loss_function(loss)
+
+    # ------------------------------------------------------------------------------------------------
+    def load_model(self, model_name):
+        """attack.py:40-65 — torchvision first, then timm; ``.eval().cuda()``; list → EnsembleModel.
+        Subclasses with customised surrogates override this (documented override point)."""
+        def load_single_model(name):
+            if name in models.__dict__.keys():
+                print('=> Loading model {} from torchvision.models'.format(name))
+                model = models.__dict__[name](weights="DEFAULT")
+            elif name in timm.list_models():
+                print('=> Loading model {} from timm.models'.format(name))
+                model = timm.create_model(name, pretrained=True)
+            else:
+                raise ValueError('Model {} not supported'.format(name))
+            return wrap_model(model.eval().cuda())
+
+        if isinstance(model_name, list):
+            return EnsembleModel([load_single_model(name) for name in model_name])
+        return load_single_model(model_name)
+
+    # ------------------------------------------------------------------------------------------------
+    def _to_device(self, t):
+        """attack.py:79-80 clones then moves. The kernels never write into ``data``/``label``, so a tensor that
+        is already on the device is used as is, and host tensors go up with one (async if pinned) copy."""
+        t = t.detach()
+        if t.device == torch.device(self.device) or (t.is_cuda and torch.device(self.device).index is None):
+            return t
+        return t.to(self.device, non_blocking=t.is_pinned() if not t.is_cuda else False)
+
+    def _fusable(self):
+        cls = type(self)
+        return (self.fuse_update and self.norm == 'linfty'
+                and cls.get_momentum is Attack.get_momentum and cls.update_delta is Attack.update_delta
+                and cls.init_delta is Attack.init_delta
+                and isinstance(self.alpha, (int, float)) and isinstance(self.decay, (int, float)))
+
+    def forward(self, data, label, **kwargs):
+        """The general attack procedure (attack.py:67-102).
+
+        data (N, C, H, W); label (N,) or (2, N) = [ground truth, target] when targeted. Returns delta.detach().
+        """
+        if self.targeted:
+            assert len(label) == 2
+            label = label[1]
+        data = self._to_device(data)
+        label = self._to_device(label)
+
+        delta = self.init_delta(data)
+        if self._fusable():
+            return self._loop_fused(data, label, delta)
+
+        momentum = 0
+        for _ in range(self.epoch):
+            logits = self.get_logits(self.transform(ops.stage_add(data, delta), momentum=momentum))
+            loss = self.get_loss(logits, label)
+            grad = self.get_grad(loss, delta)
+            momentum = self.get_momentum(grad, momentum)
+            delta = self.update_delta(delta, data, momentum, self.alpha)
+        return delta.detach()
+
+    def _loop_fused(self, data, label, delta):
+        """attack.py:86-100 with get_momentum + update_delta + the next `data + delta` in one launch per
+        iteration. delta / momentum / x_adv live in buffers this loop owns and are updated in place."""
+        be = ops.backend()
+        m_buf = torch.empty_like(data)
+        xadv = torch.empty_like(data)
+        scale_out = torch.empty(data.shape[0], device=data.device, dtype=torch.float32)
+        momentum, pre = None, None
+        for _ in range(self.epoch):
+            x = ops.stage_add(data, delta, precomputed=pre)
+            logits = self.get_logits(self.transform(x, momentum=0 if momentum is None else momentum))
+            loss = self.get_loss(logits, label)
+            grad = self.get_grad(loss, delta)
+            scale = self._torch_abs_mean(grad) if self.mean_mode == 'torch' else None
+            with torch.no_grad():
+                be.fused_update_linf(grad, momentum, m_buf, delta, delta, data, xadv, scale, scale_out,
+                                     self.decay, self.alpha, self.epsilon, img_min, img_max, _lib.TA_MEAN_EXACT)
+            momentum, pre = m_buf, xadv
+        return delta.detach()
+
+    # ------------------------------------------------------------------------------------------------
+    def get_logits(self, x, **kwargs):
+        """attack.py:104-108"""
+        return self.model(x)
+
+    def get_loss(self, logits, label):
+        """attack.py:110-115"""
+        return -self.loss(logits, label) if self.targeted else self.loss(logits, label)
+
+    def get_grad(self, loss, delta, **kwargs):
+        """attack.py:118-122 — the surrogate's backward (torch autograd; the staging kernels' adjoints are
+        autograd nodes inside that graph)."""
+        return torch.autograd.grad(loss, delta, retain_graph=False, create_graph=False)[0]
+
+    @staticmethod
+    def _torch_abs_mean(grad):
+        return grad.abs().mean(dim=(1, 2, 3))
+
+    def _abs_mean(self, grad):
+        if self.mean_mode == 'torch':
+            return self._torch_abs_mean(grad)
+        return ops.backend().abs_mean(grad, _lib.TA_MEAN_EXACT)
+
+    def get_momentum(self, grad, momentum, **kwargs):
+        """attack.py:124-128: momentum * decay + grad / mean(|grad|) per sample. ``momentum`` may be the
+        Python 0 of the first iteration; unknown kwargs (e.g. ``decay=``) are ignored like in the reference."""
+        m = None if _is_zero_scalar(momentum) else momentum
+        if m is not None and not torch.is_tensor(m):
+            raise TypeError("momentum must be a tensor or 0, got {}".format(type(momentum)))
+        return ops.backend().momentum(grad, m, self._abs_mean(grad), self.decay)
+
+    def init_delta(self, data, **kwargs):
+        """attack.py:130-143. Random draws come from torch's device generator (same stream of numbers as the
+        reference); the projection runs in ``ta_clamp_box`` / ``ta_init_l2_scale``."""
+        delta = torch.zeros_like(data).to(self.device)
+        if self.random_start:
+            be = ops.backend()
+            if self.norm == 'linfty':
+                delta.uniform_(-self.epsilon, self.epsilon)
+                delta = be.clamp_box(delta, data, img_min, img_max)
+            else:
+                delta.normal_(-self.epsilon, self.epsilon)
+                r = torch.zeros_like(data).uniform_(0, 1).to(self.device)
+                delta = be.init_l2_scale(delta, r, data, self.epsilon, img_min, img_max)
+        delta.requires_grad = True
+        return delta
+
+    def update_delta(self, delta, data, grad, alpha, **kwargs):
+        """attack.py:145-153. ``alpha`` may be a float (also negative) or a tensor broadcastable to delta.
+        Returns a fresh leaf with requires_grad=True; the inputs are not modified."""
+        be = ops.backend()
+        if self.norm == 'linfty':
+            if torch.is_tensor(alpha):
+                if alpha.numel() == 1:
+                    out = be.update_linf(delta, data, grad, float(alpha), self.epsilon, img_min, img_max)
+                else:
+                    a = alpha.to(device=delta.device, dtype=torch.float32).expand_as(delta)
+                    out = be.update_linf(delta, data, grad, 0.0, self.epsilon, img_min, img_max, alpha_t=a)
+            else:
+                out = be.update_linf(delta, data, grad, alpha, self.epsilon, img_min, img_max)
+        else:
+            out = be.update_l2(delta, data, grad, alpha, self.epsilon, img_min, img_max)
+        return out.detach().requires_grad_(True)
+
+    def loss_function(self, loss):
+        """attack.py:155-162"""
+        if loss == 'crossentropy':
+            return nn.CrossEntropyLoss()
+        raise Exception("Unsupported loss {}".format(loss))
+
+    def transform(self, data, **kwargs):
+        """attack.py:164-165"""
+        return data
+
+    def __call__(self, *input, **kwargs):
+        """attack.py:167-169"""
+        self.model.eval()
+        return self.forward(*input, **kwargs)

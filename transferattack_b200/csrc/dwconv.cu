@@ -1,0 +1,228 @@
+// dwconv.cu — TIM's depthwise convolution of the input gradient (input_transformation/tim.py:68-73):
+//   out = conv2d(g, K[C,1,ks,ks], stride 1, zero 'same' padding, groups=C)   (cross-correlation)
+//
+// ta_dwconv2d_sep: the kernels tim.py:42-66 generates (gaussian / uniform / linear) are rank-1, K = outer(kcol, krow);
+//   the convolution is done as a row pass then a column pass inside one CTA (intermediate in shared memory), 2*ks
+//   FMAs per output instead of ks*ks, which moves the op from FFMA-bound (225 MAC/elem at ks=15) back to HBM-bound
+//   (8 B/elem). Accumulation: fp32 FMA chains from 0 in tap order j = 0..ks-1 then i = 0..ks-1 — the order the
+//   oracle (orc_dwconv2d_sep) replays, so kernel and oracle agree bit for bit.
+// ta_dwconv2d: any [C,ks,ks] kernel, fp32 FMA chain in (ky,kx) raster order (orc_dwconv2d order).
+//
+// Tiling: 32x32 outputs per CTA, 256 threads, halo tile (32+ks-1)^2 in shared memory with an odd row stride
+// (bank-conflict-free 4-wide register blocking); zero padding comes from the guarded tile load.
+#include "common.cuh"
+
+using namespace ta;
+
+namespace {
+
+constexpr int TH = 32, TW = 32, kThreads = 256, kMaxKs = 31;
+
+__device__ __forceinline__ int odd_up(int v) { return v | 1; }
+
+// cooperative guarded load of the halo tile: s_in[(TH+ks-1)][IS], zero outside the image
+__device__ __forceinline__ void load_tile(const float* __restrict__ gp, float* s_in, int IS, int ks, int H, int W, int y0, int x0) {
+  const int r = ks >> 1, th = TH + ks - 1, tw = TW + ks - 1;
+  for (int e = threadIdx.x; e < th * tw; e += kThreads) {
+    const int ty = e / tw, tx = e % tw;
+    const int yy = y0 + ty - r, xx = x0 + tx - r;
+    s_in[ty * IS + tx] = (yy >= 0 && yy < H && xx >= 0 && xx < W) ? __ldg(gp + (int64_t)yy * W + xx) : 0.0f;
+  }
+}
+
+// KS > 0: compile-time size, weights in registers, 4-wide register blocking. KS == 0: runtime size, generic loops.
+template <int KS>
+__global__ void __launch_bounds__(kThreads) dwconv_sep_kernel(const float* __restrict__ g, const float* __restrict__ kcol,
+                                                              const float* __restrict__ krow, int ks_rt, float* __restrict__ out,
+                                                              int C, int H, int W) {
+  extern __shared__ __align__(16) float smem[];
+  const int ks = KS > 0 ? KS : ks_rt;
+  const int th = TH + ks - 1;
+  const int IS = odd_up(TW + ks - 1);
+  float* s_in = smem;                 // [th][IS]
+  float* s_tmp = s_in + th * IS;      // [th][TW]
+  float* s_kr = s_tmp + th * TW;      // [ks]
+  float* s_kc = s_kr + kMaxKs;        // [ks]
+
+  const int plane = blockIdx.z, c = plane % C;
+  const int y0 = blockIdx.y * TH, x0 = blockIdx.x * TW;
+  const float* gp = g + (int64_t)plane * H * W;
+  float* op = out + (int64_t)plane * H * W;
+  const int tid = threadIdx.x;
+  if (tid < ks) { s_kr[tid] = __ldg(krow + c * ks + tid); s_kc[tid] = __ldg(kcol + c * ks + tid); }
+  load_tile(gp, s_in, IS, ks, H, W, y0, x0);
+  __syncthreads();
+
+  if (KS > 0) {
+    float wr[KS > 0 ? KS : 1];
+#pragma unroll
+    for (int j = 0; j < KS; ++j) wr[j] = s_kr[j];
+    // row pass: th rows x 8 groups of 4 outputs
+    for (int e = tid; e < th * (TW / 4); e += kThreads) {
+      const int y = e / (TW / 4), xg = e % (TW / 4);
+      const float* row = s_in + y * IS + 4 * xg;
+      float v[(KS > 0 ? KS : 1) + 3];
+#pragma unroll
+      for (int t = 0; t < KS + 3; ++t) v[t] = row[t];
+      float a0 = 0.f, a1 = 0.f, a2 = 0.f, a3 = 0.f;
+#pragma unroll
+      for (int j = 0; j < KS; ++j) {
+        a0 = fmaf(wr[j], v[j], a0); a1 = fmaf(wr[j], v[j + 1], a1);
+        a2 = fmaf(wr[j], v[j + 2], a2); a3 = fmaf(wr[j], v[j + 3], a3);
+      }
+      float* t4 = s_tmp + y * TW + 4 * xg;
+      t4[0] = a0; t4[1] = a1; t4[2] = a2; t4[3] = a3;
+    }
+    __syncthreads();
+    float wc[KS > 0 ? KS : 1];
+#pragma unroll
+    for (int i = 0; i < KS; ++i) wc[i] = s_kc[i];
+    // column pass: 8 groups of 4 rows x 32 columns = 256 items, one per thread
+    {
+      const int x = tid % TW, yg = tid / TW;
+      float v[(KS > 0 ? KS : 1) + 3];
+#pragma unroll
+      for (int t = 0; t < KS + 3; ++t) v[t] = s_tmp[(4 * yg + t) * TW + x];
+      float a[4] = {0.f, 0.f, 0.f, 0.f};
+#pragma unroll
+      for (int i = 0; i < KS; ++i) {
+        a[0] = fmaf(wc[i], v[i], a[0]); a[1] = fmaf(wc[i], v[i + 1], a[1]);
+        a[2] = fmaf(wc[i], v[i + 2], a[2]); a[3] = fmaf(wc[i], v[i + 3], a[3]);
+      }
+#pragma unroll
+      for (int o = 0; o < 4; ++o) {
+        const int yy = y0 + 4 * yg + o, xx = x0 + x;
+        if (yy < H && xx < W) op[(int64_t)yy * W + xx] = a[o];
+      }
+    }
+  } else {
+    for (int e = tid; e < th * TW; e += kThreads) {
+      const int y = e / TW, x = e % TW;
+      float acc = 0.f;
+      for (int j = 0; j < ks; ++j) acc = fmaf(s_kr[j], s_in[y * IS + x + j], acc);
+      s_tmp[e] = acc;
+    }
+    __syncthreads();
+    for (int e = tid; e < TH * TW; e += kThreads) {
+      const int y = e / TW, x = e % TW;
+      float acc = 0.f;
+      for (int i = 0; i < ks; ++i) acc = fmaf(s_kc[i], s_tmp[(y + i) * TW + x], acc);
+      const int yy = y0 + y, xx = x0 + x;
+      if (yy < H && xx < W) op[(int64_t)yy * W + xx] = acc;
+    }
+  }
+}
+
+template <int KS>
+__global__ void __launch_bounds__(kThreads) dwconv2d_kernel(const float* __restrict__ g, const float* __restrict__ k, int ks_rt,
+                                                            float* __restrict__ out, int C, int H, int W) {
+  extern __shared__ __align__(16) float smem[];
+  const int ks = KS > 0 ? KS : ks_rt;
+  const int th = TH + ks - 1;
+  const int IS = odd_up(TW + ks - 1);
+  float* s_in = smem;                 // [th][IS]
+  float* s_k = s_in + th * IS;        // [ks*ks]
+
+  const int plane = blockIdx.z, c = plane % C;
+  const int y0 = blockIdx.y * TH, x0 = blockIdx.x * TW;
+  const float* gp = g + (int64_t)plane * H * W;
+  float* op = out + (int64_t)plane * H * W;
+  const int tid = threadIdx.x;
+  for (int e = tid; e < ks * ks; e += kThreads) s_k[e] = __ldg(k + (int64_t)c * ks * ks + e);
+  load_tile(gp, s_in, IS, ks, H, W, y0, x0);
+  __syncthreads();
+
+  // each thread: 4 consecutive outputs of one row; 32 rows x 8 groups = 256 items
+  const int y = tid / (TW / 4), xg = tid % (TW / 4);
+  float a0 = 0.f, a1 = 0.f, a2 = 0.f, a3 = 0.f;
+  if (KS > 0) {
+#pragma unroll 1
+    for (int i = 0; i < KS; ++i) {
+      const float* row = s_in + (y + i) * IS + 4 * xg;
+      float v[(KS > 0 ? KS : 1) + 3];
+#pragma unroll
+      for (int t = 0; t < KS + 3; ++t) v[t] = row[t];
+#pragma unroll
+      for (int j = 0; j < KS; ++j) {
+        const float w = s_k[i * KS + j];
+        a0 = fmaf(w, v[j], a0); a1 = fmaf(w, v[j + 1], a1); a2 = fmaf(w, v[j + 2], a2); a3 = fmaf(w, v[j + 3], a3);
+      }
+    }
+  } else {
+    for (int i = 0; i < ks; ++i) {
+      const float* row = s_in + (y + i) * IS + 4 * xg;
+      for (int j = 0; j < ks; ++j) {
+        const float w = s_k[i * ks + j];
+        a0 = fmaf(w, row[j], a0); a1 = fmaf(w, row[j + 1], a1); a2 = fmaf(w, row[j + 2], a2); a3 = fmaf(w, row[j + 3], a3);
+      }
+    }
+  }
+  const int yy = y0 + y;
+  if (yy < H) {
+    const int xx = x0 + 4 * xg;
+    float* o = op + (int64_t)yy * W + xx;
+    if (xx < W) o[0] = a0;
+    if (xx + 1 < W) o[1] = a1;
+    if (xx + 2 < W) o[2] = a2;
+    if (xx + 3 < W) o[3] = a3;
+  }
+}
+
+int check_conv(const char* who, const void* g, const void* k, const void* out, int ks, int B, int C, int H, int W) {
+  TA_REQUIRE(g && k && out, "%s: null pointer", who);
+  TA_REQUIRE(B > 0 && C > 0 && H > 0 && W > 0, "%s: empty shape", who);
+  TA_REQUIRE(ks >= 1 && (ks & 1) == 1, "%s: kernel size %d must be odd ('same' padding)", who, ks);
+  if (ks > kMaxKs) { set_error("%s: kernel size %d > %d not supported", who, ks, kMaxKs); return TA_EUNSUPPORTED; }
+  TA_REQUIRE((int64_t)B * C <= 65535, "%s: B*C=%lld exceeds 65535 planes", who, (long long)B * C);
+  return TA_OK;
+}
+
+}  // namespace
+
+extern "C" {
+
+int ta_dwconv2d_sep(const float* g, const float* kcol, const float* krow, int ks, float* out, int B, int C, int H, int W,
+                    ta_stream_t stream) {
+  int rc = check_conv("ta_dwconv2d_sep", g, kcol, out, ks, B, C, H, W);
+  if (rc != TA_OK) return rc;
+  TA_REQUIRE(krow, "ta_dwconv2d_sep: null krow");
+  const int th = TH + ks - 1, IS = (TW + ks - 1) | 1;
+  const size_t smem = sizeof(float) * ((size_t)th * IS + (size_t)th * TW + 2 * kMaxKs);
+  dim3 grid((unsigned)((W + TW - 1) / TW), (unsigned)((H + TH - 1) / TH), (unsigned)(B * C));
+  cudaStream_t s = (cudaStream_t)stream;
+#define TA_SEP_CASE(K)                                                                          \
+  case K:                                                                                       \
+    dwconv_sep_kernel<K><<<grid, kThreads, smem, s>>>(g, kcol, krow, ks, out, C, H, W);         \
+    break;
+  switch (ks) {
+    TA_SEP_CASE(3) TA_SEP_CASE(5) TA_SEP_CASE(7) TA_SEP_CASE(9) TA_SEP_CASE(11) TA_SEP_CASE(15)
+    default:
+      dwconv_sep_kernel<0><<<grid, kThreads, smem, s>>>(g, kcol, krow, ks, out, C, H, W);
+  }
+#undef TA_SEP_CASE
+  count_launch();
+  return check_launch("ta_dwconv2d_sep");
+}
+
+int ta_dwconv2d(const float* g, const float* k, int ks, float* out, int B, int C, int H, int W, ta_stream_t stream) {
+  int rc = check_conv("ta_dwconv2d", g, k, out, ks, B, C, H, W);
+  if (rc != TA_OK) return rc;
+  const int th = TH + ks - 1, IS = (TW + ks - 1) | 1;
+  const size_t smem = sizeof(float) * ((size_t)th * IS + (size_t)ks * ks);
+  dim3 grid((unsigned)((W + TW - 1) / TW), (unsigned)((H + TH - 1) / TH), (unsigned)(B * C));
+  cudaStream_t s = (cudaStream_t)stream;
+#define TA_2D_CASE(K)                                                                  \
+  case K:                                                                              \
+    dwconv2d_kernel<K><<<grid, kThreads, smem, s>>>(g, k, ks, out, C, H, W);           \
+    break;
+  switch (ks) {
+    TA_2D_CASE(3) TA_2D_CASE(5) TA_2D_CASE(7) TA_2D_CASE(15)
+    default:
+      dwconv2d_kernel<0><<<grid, kThreads, smem, s>>>(g, k, ks, out, C, H, W);
+  }
+#undef TA_2D_CASE
+  count_launch();
+  return check_launch("ta_dwconv2d");
+}
+
+}  // extern "C"

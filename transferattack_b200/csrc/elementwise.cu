@@ -1,0 +1,398 @@
+// elementwise.cu — the HBM-bound streaming kernels behind the Attack hooks: momentum, L-inf update,
+// box clamp, model-input staging, Normalize, SIM / Admix / EMI replication + adjoints, VMI neighbour ops,
+// uint8 quantisation. All are 128-bit vectorised grid-stride kernels (scalar fallback when a pointer or the
+// per-sample length is not 16-byte friendly); one rounding per reference op (see common.cuh).
+#include "common.cuh"
+
+using namespace ta;
+
+namespace {
+
+template <class... P>
+bool all_aligned(P... p) {
+  bool ok = true;
+  const void* a[] = {static_cast<const void*>(p)...};
+  for (const void* q : a) ok = ok && (q == nullptr || aligned16(q));
+  return ok;
+}
+
+// ---- attack.py:128 ---------------------------------------------------------------------------------------
+struct MomentumOp {
+  const float* g; const float* m; const float* scale; float* out; float decay; int64_t n;
+  template <int V> __device__ void run(int64_t i) const {
+    const float mu = __ldg(scale + (i * V) / n);
+    const Vec<V> gv = ldv<V>(g, i);
+    Vec<V> o;
+    if (m) {
+      const Vec<V> mv = ldv_rw<V>(m, i);
+#pragma unroll
+      for (int k = 0; k < V; ++k) o.v[k] = add_rn(mul_rn(mv.v[k], decay), div_rn(gv.v[k], mu));
+    } else {
+#pragma unroll
+      for (int k = 0; k < V; ++k) o.v[k] = add_rn(0.0f, div_rn(gv.v[k], mu));
+    }
+    stv<V>(out, i, o);
+  }
+};
+
+// ---- attack.py:147,152 -------------------------------------------------------------------------------------
+struct UpdateLinfOp {
+  const float* delta; const float* data; const float* dir; const float* alpha_t; float* out;
+  float alpha, eps, lo, hi; int dir_mode;
+  template <int V> __device__ void run(int64_t i) const {
+    const Vec<V> dv = ldv_rw<V>(delta, i), xv = ldv<V>(data, i), gv = ldv<V>(dir, i);
+    Vec<V> av;
+    if (alpha_t) av = ldv<V>(alpha_t, i);
+    Vec<V> o;
+#pragma unroll
+    for (int k = 0; k < V; ++k) {
+      const float d = (dir_mode == TA_DIR_SIGN) ? sign_t(gv.v[k]) : gv.v[k];
+      const float a = alpha_t ? av.v[k] : alpha;
+      o.v[k] = project_linf(dv.v[k], mul_rn(a, d), xv.v[k], eps, lo, hi);
+    }
+    stv<V>(out, i, o);
+  }
+};
+
+// ---- attack.py:141 -------------------------------------------------------------------------------------------
+struct ClampBoxOp {
+  const float* delta; const float* data; float* out; float lo, hi;
+  template <int V> __device__ void run(int64_t i) const {
+    const Vec<V> dv = ldv_rw<V>(delta, i), xv = ldv<V>(data, i);
+    Vec<V> o;
+#pragma unroll
+    for (int k = 0; k < V; ++k) o.v[k] = min_nan(max_nan(dv.v[k], sub_rn(lo, xv.v[k])), sub_rn(hi, xv.v[k]));
+    stv<V>(out, i, o);
+  }
+};
+
+// ---- attack.py:88 / nifgsm.py:39 / vmifgsm.py:50 ------------------------------------------------------------------
+struct StageOp {
+  const float* data; const float* delta; const float* noise; const float* look; float* out; float coef;
+  template <int V> __device__ void run(int64_t i) const {
+    const Vec<V> xv = ldv<V>(data, i);
+    Vec<V> dv, nv, lv;
+    if (delta) dv = ldv<V>(delta, i);
+    if (noise) nv = ldv<V>(noise, i);
+    if (look) lv = ldv<V>(look, i);
+    Vec<V> o;
+#pragma unroll
+    for (int k = 0; k < V; ++k) {
+      float x = delta ? add_rn(xv.v[k], dv.v[k]) : xv.v[k];
+      if (noise) x = add_rn(x, nv.v[k]);
+      if (look) x = add_rn(x, mul_rn(coef, lv.v[k]));
+      o.v[k] = x;
+    }
+    stv<V>(out, i, o);
+  }
+};
+
+// ---- utils.py:72-79 Normalize ---------------------------------------------------------------------------------------
+struct NormalizeOp {
+  const float* x; const float* mean; const float* std; float* out; int C; int64_t plane; bool fwd;
+  template <int V> __device__ void run(int64_t i) const {
+    const int c = (int)(((i * V) / plane) % C);
+    const float sd = __ldg(std + c);
+    const Vec<V> xv = ldv_rw<V>(x, i);
+    Vec<V> o;
+    if (fwd) {
+      const float mu = __ldg(mean + c);
+#pragma unroll
+      for (int k = 0; k < V; ++k) o.v[k] = div_rn(sub_rn(xv.v[k], mu), sd);
+    } else {
+#pragma unroll
+      for (int k = 0; k < V; ++k) o.v[k] = div_rn(xv.v[k], sd);
+    }
+    stv<V>(out, i, o);
+  }
+};
+
+// ---- sim.py:40 ----------------------------------------------------------------------------------------------------------
+struct SimFwdOp {
+  const float* x; float* out; int S; int64_t nvec_per_copy;
+  template <int V> __device__ void run(int64_t i) const {
+    const Vec<V> xv = ldv<V>(x, i);
+    for (int s = 0; s < S; ++s) {
+      const float d = (float)(1u << s);
+      Vec<V> o;
+#pragma unroll
+      for (int k = 0; k < V; ++k) o.v[k] = div_rn(xv.v[k], d);
+      stv<V>(out, (int64_t)s * nvec_per_copy + i, o);
+    }
+  }
+};
+struct SimBwdOp {
+  const float* gout; float* gin; int S; int64_t nvec_per_copy;
+  template <int V> __device__ void run(int64_t i) const {
+    Vec<V> acc = ldv<V>(gout, (int64_t)(S - 1) * nvec_per_copy + i);
+    {
+      const float d = (float)(1u << (S - 1));
+#pragma unroll
+      for (int k = 0; k < V; ++k) acc.v[k] = div_rn(acc.v[k], d);
+    }
+    for (int s = S - 2; s >= 0; --s) {
+      const Vec<V> gv = ldv<V>(gout, (int64_t)s * nvec_per_copy + i);
+      const float d = (float)(1u << s);
+#pragma unroll
+      for (int k = 0; k < V; ++k) acc.v[k] = add_rn(acc.v[k], div_rn(gv.v[k], d));
+    }
+    stv<V>(gin, i, acc);
+  }
+};
+
+// ---- admix.py:44-45 ------------------------------------------------------------------------------------------------------
+struct AdmixFwdOp {
+  const float* x; const int32_t* perm; float* out; float strength; int S, A, B; int64_t nv;   // nv = vectors per sample
+  template <int V> __device__ void run(int64_t i) const {   // i over A*B*nv
+    const int64_t e = i % nv;
+    const int64_t ab = i / nv;
+    const int b = (int)(ab % B);
+    const int src = __ldg(perm + ab);
+    const Vec<V> xs = ldv<V>(x, (int64_t)b * nv + e), xp = ldv<V>(x, (int64_t)src * nv + e);
+    Vec<V> u;
+#pragma unroll
+    for (int k = 0; k < V; ++k) u.v[k] = add_rn(xs.v[k], mul_rn(strength, xp.v[k]));
+    for (int s = 0; s < S; ++s) {
+      const float d = (float)(1u << s);
+      Vec<V> o;
+#pragma unroll
+      for (int k = 0; k < V; ++k) o.v[k] = div_rn(u.v[k], d);
+      stv<V>(out, ((int64_t)s * A * B + ab) * nv + e, o);
+    }
+  }
+};
+struct AdmixBwdOp {
+  const float* gout; float* gin; int S, A, B; int64_t nv;
+  template <int V> __device__ void run(int64_t i) const {   // i over B*nv
+    const int64_t e = i % nv;
+    const int b = (int)(i / nv);
+    Vec<V> outer;
+    for (int a = A - 1; a >= 0; --a) {
+      Vec<V> acc = ldv<V>(gout, (((int64_t)(S - 1) * A + a) * B + b) * nv + e);
+      {
+        const float d = (float)(1u << (S - 1));
+#pragma unroll
+        for (int k = 0; k < V; ++k) acc.v[k] = div_rn(acc.v[k], d);
+      }
+      for (int s = S - 2; s >= 0; --s) {
+        const Vec<V> gv = ldv<V>(gout, (((int64_t)s * A + a) * B + b) * nv + e);
+        const float d = (float)(1u << s);
+#pragma unroll
+        for (int k = 0; k < V; ++k) acc.v[k] = add_rn(acc.v[k], div_rn(gv.v[k], d));
+      }
+      if (a == A - 1) outer = acc;
+      else {
+#pragma unroll
+        for (int k = 0; k < V; ++k) outer.v[k] = add_rn(outer.v[k], acc.v[k]);
+      }
+    }
+    stv<V>(gin, i, outer);
+  }
+};
+
+// ---- emifgsm.py:57-58 ----------------------------------------------------------------------------------------------------------
+struct CoefTable { float c[32]; };
+struct LinSampleFwdOp {
+  const float* x; const float* gbar; float* out; CoefTable coef; int K; int64_t nvec_per_copy;
+  template <int V> __device__ void run(int64_t i) const {
+    const Vec<V> xv = ldv<V>(x, i);
+    Vec<V> gv;
+    if (gbar) gv = ldv<V>(gbar, i);
+    for (int k = 0; k < K; ++k) {
+      Vec<V> o;
+#pragma unroll
+      for (int j = 0; j < V; ++j) o.v[j] = add_rn(xv.v[j], gbar ? mul_rn(coef.c[k], gv.v[j]) : 0.0f);
+      stv<V>(out, (int64_t)k * nvec_per_copy + i, o);
+    }
+  }
+};
+struct LinSampleBwdOp {
+  const float* gout; float* gin; int K; int64_t nvec_per_copy;
+  template <int V> __device__ void run(int64_t i) const {
+    Vec<V> acc = ldv<V>(gout, (int64_t)(K - 1) * nvec_per_copy + i);
+    for (int k = K - 2; k >= 0; --k) {
+      const Vec<V> gv = ldv<V>(gout, (int64_t)k * nvec_per_copy + i);
+#pragma unroll
+      for (int j = 0; j < V; ++j) acc.v[j] = add_rn(acc.v[j], gv.v[j]);
+    }
+    stv<V>(gin, i, acc);
+  }
+};
+
+// ---- vmifgsm.py:56,58,87 ----------------------------------------------------------------------------------------------------------
+struct AccumulateOp {
+  float* acc; const float* g; int first;
+  template <int V> __device__ void run(int64_t i) const {
+    Vec<V> gv = ldv<V>(g, i);
+    if (!first) {
+      const Vec<V> av = ldv_rw<V>(acc, i);
+#pragma unroll
+      for (int k = 0; k < V; ++k) gv.v[k] = add_rn(av.v[k], gv.v[k]);
+    }
+    stv<V>(acc, i, gv);
+  }
+};
+struct VarianceOp {
+  const float* acc; const float* cur; float* out; float nn;
+  template <int V> __device__ void run(int64_t i) const {
+    const Vec<V> av = ldv_rw<V>(acc, i), cv = ldv_rw<V>(cur, i);
+    Vec<V> o;
+#pragma unroll
+    for (int k = 0; k < V; ++k) o.v[k] = sub_rn(div_rn(av.v[k], nn), cv.v[k]);
+    stv<V>(out, i, o);
+  }
+};
+struct AddOp {
+  const float* a; const float* b; float* out;
+  template <int V> __device__ void run(int64_t i) const {
+    const Vec<V> av = ldv_rw<V>(a, i), bv = ldv_rw<V>(b, i);
+    Vec<V> o;
+#pragma unroll
+    for (int k = 0; k < V; ++k) o.v[k] = add_rn(av.v[k], bv.v[k]);
+    stv<V>(out, i, o);
+  }
+};
+
+// ---- utils.py:64 save_images quantisation ---------------------------------------------------------------------------------------------
+// One thread per (b, pixel): reads C planes coalesced across the warp, writes C consecutive bytes.
+__global__ void __launch_bounds__(256) quantize_kernel(const float* __restrict__ data, const float* __restrict__ delta,
+                                                       uint8_t* __restrict__ out, int B, int C, int64_t plane, int to_nhwc) {
+  const int64_t total = (int64_t)B * plane;
+  const int64_t stride = (int64_t)gridDim.x * blockDim.x;
+  for (int64_t t = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; t < total; t += stride) {
+    const int64_t b = t / plane, i = t % plane;
+    for (int c = 0; c < C; ++c) {
+      const int64_t j = (b * C + c) * plane + i;
+      const float v = mul_rn(add_rn(__ldg(data + j), __ldg(delta + j)), 255.0f);
+      const int q = __float2int_rz(v);                       // numpy astype(uint8): truncation toward zero
+      out[to_nhwc ? (b * plane + i) * C + c : j] = (uint8_t)q;
+    }
+  }
+}
+
+}  // namespace
+
+extern "C" {
+
+int ta_momentum(const float* g, const float* m, const float* scale, float decay, float* m_out, int B, int64_t n,
+                ta_stream_t stream) {
+  TA_REQUIRE(g && scale && m_out && B > 0 && n > 0, "ta_momentum: null pointer or empty shape (B=%d n=%lld)", B, (long long)n);
+  const bool v4 = (n % 4 == 0) && all_aligned(g, m, m_out);
+  return launch_ew("ta_momentum", (int64_t)B * n, v4, MomentumOp{g, m, scale, m_out, decay, n}, (cudaStream_t)stream);
+}
+
+int ta_update_linf(const float* delta, const float* data, const float* dir, const float* alpha_t, float alpha, float eps,
+                   float lo, float hi, int dir_mode, float* delta_out, int64_t N, ta_stream_t stream) {
+  TA_REQUIRE(delta && data && dir && delta_out && N > 0, "ta_update_linf: null pointer or N=%lld", (long long)N);
+  TA_REQUIRE(dir_mode == TA_DIR_SIGN || dir_mode == TA_DIR_RAW, "ta_update_linf: dir_mode %d", dir_mode);
+  const bool v4 = (N % 4 == 0) && all_aligned(delta, data, dir, alpha_t, delta_out);
+  return launch_ew("ta_update_linf", N, v4, UpdateLinfOp{delta, data, dir, alpha_t, delta_out, alpha, eps, lo, hi, dir_mode},
+                   (cudaStream_t)stream);
+}
+
+int ta_clamp_box(const float* delta, const float* data, float lo, float hi, float* out, int64_t N, ta_stream_t stream) {
+  TA_REQUIRE(delta && data && out && N > 0, "ta_clamp_box: null pointer or N=%lld", (long long)N);
+  const bool v4 = (N % 4 == 0) && all_aligned(delta, data, out);
+  return launch_ew("ta_clamp_box", N, v4, ClampBoxOp{delta, data, out, lo, hi}, (cudaStream_t)stream);
+}
+
+int ta_stage_add(const float* data, const float* delta, const float* look, float coef, float* out, int64_t N,
+                 ta_stream_t stream) {
+  TA_REQUIRE(data && out && N > 0, "ta_stage_add: null pointer or N=%lld", (long long)N);
+  const bool v4 = (N % 4 == 0) && all_aligned(data, delta, look, out);
+  return launch_ew("ta_stage_add", N, v4, StageOp{data, delta, nullptr, look, out, coef}, (cudaStream_t)stream);
+}
+
+int ta_neighbor_stage(const float* data, const float* delta, const float* noise, const float* look, float coef, float* out,
+                      int64_t N, ta_stream_t stream) {
+  TA_REQUIRE(data && delta && noise && out && N > 0, "ta_neighbor_stage: null pointer or N=%lld", (long long)N);
+  const bool v4 = (N % 4 == 0) && all_aligned(data, delta, noise, look, out);
+  return launch_ew("ta_neighbor_stage", N, v4, StageOp{data, delta, noise, look, out, coef}, (cudaStream_t)stream);
+}
+
+int ta_normalize_fwd(const float* x, const float* mean, const float* std, float* out, int B, int C, int64_t plane,
+                     ta_stream_t stream) {
+  TA_REQUIRE(x && mean && std && out && B > 0 && C > 0 && plane > 0, "ta_normalize_fwd: bad arguments");
+  const bool v4 = (plane % 4 == 0) && all_aligned(x, out);
+  return launch_ew("ta_normalize_fwd", (int64_t)B * C * plane, v4, NormalizeOp{x, mean, std, out, C, plane, true},
+                   (cudaStream_t)stream);
+}
+
+int ta_normalize_bwd(const float* gout, const float* std, float* gin, int B, int C, int64_t plane, ta_stream_t stream) {
+  TA_REQUIRE(gout && std && gin && B > 0 && C > 0 && plane > 0, "ta_normalize_bwd: bad arguments");
+  const bool v4 = (plane % 4 == 0) && all_aligned(gout, gin);
+  return launch_ew("ta_normalize_bwd", (int64_t)B * C * plane, v4, NormalizeOp{gout, nullptr, std, gin, C, plane, false},
+                   (cudaStream_t)stream);
+}
+
+int ta_sim_fwd(const float* x, float* out, int S, int64_t N, ta_stream_t stream) {
+  TA_REQUIRE(x && out && S >= 1 && S <= 31 && N > 0, "ta_sim_fwd: bad arguments (S=%d N=%lld)", S, (long long)N);
+  const bool v4 = (N % 4 == 0) && all_aligned(x, out);
+  return launch_ew("ta_sim_fwd", N, v4, SimFwdOp{x, out, S, v4 ? N / 4 : N}, (cudaStream_t)stream);
+}
+
+int ta_sim_bwd(const float* gout, float* gin, int S, int64_t N, ta_stream_t stream) {
+  TA_REQUIRE(gout && gin && S >= 1 && S <= 31 && N > 0, "ta_sim_bwd: bad arguments (S=%d N=%lld)", S, (long long)N);
+  const bool v4 = (N % 4 == 0) && all_aligned(gout, gin);
+  return launch_ew("ta_sim_bwd", N, v4, SimBwdOp{gout, gin, S, v4 ? N / 4 : N}, (cudaStream_t)stream);
+}
+
+int ta_admix_fwd(const float* x, const int32_t* perm, float strength, float* out, int S, int A, int B, int64_t n,
+                 ta_stream_t stream) {
+  TA_REQUIRE(x && perm && out && S >= 1 && S <= 31 && A >= 1 && B >= 1 && n > 0, "ta_admix_fwd: bad arguments");
+  const bool v4 = (n % 4 == 0) && all_aligned(x, out);
+  const int64_t nv = v4 ? n / 4 : n;
+  return launch_ew("ta_admix_fwd", (int64_t)A * B * n, v4, AdmixFwdOp{x, perm, out, strength, S, A, B, nv}, (cudaStream_t)stream);
+}
+
+int ta_admix_bwd(const float* gout, float* gin, int S, int A, int B, int64_t n, ta_stream_t stream) {
+  TA_REQUIRE(gout && gin && S >= 1 && S <= 31 && A >= 1 && B >= 1 && n > 0, "ta_admix_bwd: bad arguments");
+  const bool v4 = (n % 4 == 0) && all_aligned(gout, gin);
+  const int64_t nv = v4 ? n / 4 : n;
+  return launch_ew("ta_admix_bwd", (int64_t)B * n, v4, AdmixBwdOp{gout, gin, S, A, B, nv}, (cudaStream_t)stream);
+}
+
+int ta_lin_sample_fwd(const float* x, const float* gbar, const float* coef_host, int K, float* out, int64_t N,
+                      ta_stream_t stream) {
+  TA_REQUIRE(x && coef_host && out && K >= 1 && K <= 32 && N > 0, "ta_lin_sample_fwd: bad arguments (K=%d)", K);
+  CoefTable t;
+  for (int k = 0; k < 32; ++k) t.c[k] = k < K ? coef_host[k] : 0.0f;
+  const bool v4 = (N % 4 == 0) && all_aligned(x, gbar, out);
+  return launch_ew("ta_lin_sample_fwd", N, v4, LinSampleFwdOp{x, gbar, out, t, K, v4 ? N / 4 : N}, (cudaStream_t)stream);
+}
+
+int ta_lin_sample_bwd(const float* gout, float* gin, int K, int64_t N, ta_stream_t stream) {
+  TA_REQUIRE(gout && gin && K >= 1 && N > 0, "ta_lin_sample_bwd: bad arguments (K=%d)", K);
+  const bool v4 = (N % 4 == 0) && all_aligned(gout, gin);
+  return launch_ew("ta_lin_sample_bwd", N, v4, LinSampleBwdOp{gout, gin, K, v4 ? N / 4 : N}, (cudaStream_t)stream);
+}
+
+int ta_accumulate(float* acc, const float* g, int first, int64_t N, ta_stream_t stream) {
+  TA_REQUIRE(acc && g && N > 0, "ta_accumulate: bad arguments");
+  const bool v4 = (N % 4 == 0) && all_aligned(acc, g);
+  return launch_ew("ta_accumulate", N, v4, AccumulateOp{acc, g, first}, (cudaStream_t)stream);
+}
+
+int ta_variance_finalize(const float* acc, const float* cur, int num_neighbor, float* out, int64_t N, ta_stream_t stream) {
+  TA_REQUIRE(acc && cur && out && num_neighbor > 0 && N > 0, "ta_variance_finalize: bad arguments");
+  const bool v4 = (N % 4 == 0) && all_aligned(acc, cur, out);
+  return launch_ew("ta_variance_finalize", N, v4, VarianceOp{acc, cur, out, (float)num_neighbor}, (cudaStream_t)stream);
+}
+
+int ta_add(const float* a, const float* b, float* out, int64_t N, ta_stream_t stream) {
+  TA_REQUIRE(a && b && out && N > 0, "ta_add: bad arguments");
+  const bool v4 = (N % 4 == 0) && all_aligned(a, b, out);
+  return launch_ew("ta_add", N, v4, AddOp{a, b, out}, (cudaStream_t)stream);
+}
+
+int ta_quantize_u8(const float* data, const float* delta, uint8_t* out, int B, int C, int64_t plane, int to_nhwc,
+                   ta_stream_t stream) {
+  TA_REQUIRE(data && delta && out && B > 0 && C > 0 && plane > 0, "ta_quantize_u8: bad arguments");
+  const int64_t total = (int64_t)B * plane;
+  const int64_t want = (total + 255) / 256, cap = (int64_t)sm_count() * 8;
+  quantize_kernel<<<(unsigned)(want < cap ? want : cap), 256, 0, (cudaStream_t)stream>>>(data, delta, out, B, C, plane, to_nhwc);
+  count_launch();
+  return check_launch("ta_quantize_u8");
+}
+
+}  // extern "C"

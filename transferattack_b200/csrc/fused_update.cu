@@ -1,0 +1,257 @@
+// fused_update.cu — ta_fused_update_linf: the whole tail of one attack iteration in ONE launch
+//   (attack.py:124-128 get_momentum, :145-153 update_delta, and the next iteration's :88 `data + delta`).
+//
+//   mu_b   = mean|g_b|                               per sample b
+//   m'     = m * decay + g / mu_b
+//   delta' = clamp(clamp(delta + alpha*sign(m'), -eps, eps), lo - x, hi - x)
+//   xadv   = x + delta'
+//
+// HBM roofline: 16 B/elem read (g, m, delta, x) + 12 B/elem written (m', delta', xadv) = 28 B/elem
+// (24 without xadv). The per-sample mean needs all of g_b before the first output can be formed, so the
+// kernel runs one thread-block CLUSTER per sample:
+//   phase A: every CTA pulls its slice of g_b into shared memory with bulk-TMA (cp.async.bulk, chunked on
+//            mbarriers so the |g| reduction of chunk c overlaps the transfer of chunk c+1), reduces it in
+//            fp64, and the cluster combines the partials through DSMEM in rank order;
+//   phase B: streams m, delta, x with 128-bit loads, takes g from shared memory (so g crosses HBM once),
+//            and writes m', delta', xadv with 128-bit stores.
+// Variant 1 keeps nothing in shared memory and re-reads g in phase B (an L2 hit: the cluster touched it
+// microseconds earlier); it trades L2 bandwidth for occupancy. Both are exposed through ta_tune_set for the
+// sweep in bench/; the default is chosen from measurements.
+//
+// With `scale` given (strict mode: torch computed mean|g| with the reference's own op) there is no phase A
+// and the work is a flat 128-bit streaming kernel.
+#include "common.cuh"
+
+using namespace ta;
+
+namespace {
+
+struct FusedParams {
+  const float* g; const float* m; float* m_out; const float* delta; float* delta_out; const float* data;
+  float* xadv; const float* scale; float* scale_out;
+  float decay, alpha, eps, lo, hi;
+  int64_t n;
+};
+
+// one element of the fused tail; all roundings as in the reference's eager ops
+__device__ __forceinline__ void fused_elem(float g, float m, bool has_m, float d, float x, float mu, const FusedParams& p,
+                                           float& m_new, float& d_new, float& xa) {
+  const float t1 = has_m ? mul_rn(m, p.decay) : 0.0f;
+  m_new = add_rn(t1, div_rn(g, mu));
+  d_new = project_linf(d, mul_rn(p.alpha, sign_t(m_new)), x, p.eps, p.lo, p.hi);
+  xa = add_rn(x, d_new);
+}
+
+// ---- strict / fallback path: scale[b] given, flat streaming ---------------------------------------------------
+struct FusedStreamOp {
+  FusedParams p;
+  template <int V> __device__ void run(int64_t i) const {
+    const float mu = __ldg(p.scale + (i * V) / p.n);
+    const Vec<V> gv = ldv<V>(p.g, i), xv = ldv<V>(p.data, i);
+    const Vec<V> dv = ldv_rw<V>(p.delta, i);
+    Vec<V> mv;
+    if (p.m) mv = ldv_rw<V>(p.m, i);
+    Vec<V> mo, dn, xa;
+#pragma unroll
+    for (int k = 0; k < V; ++k) fused_elem(gv.v[k], p.m ? mv.v[k] : 0.0f, p.m != nullptr, dv.v[k], xv.v[k], mu, p, mo.v[k], dn.v[k], xa.v[k]);
+    stv<V>(p.m_out, i, mo);
+    stv<V>(p.delta_out, i, dn);
+    if (p.xadv) stv<V>(p.xadv, i, xa);
+  }
+};
+
+// ---- cluster kernel ----------------------------------------------------------------------------------------------
+constexpr int kChunks = 4;
+
+// STAGE = true : g slice resident in shared memory (bulk-TMA), read from HBM once
+// STAGE = false: g re-read through L2 in phase B
+template <int THREADS, int U, bool STAGE>
+__global__ void __launch_bounds__(THREADS) fused_cluster_kernel(FusedParams p) {
+  extern __shared__ __align__(128) unsigned char smem_raw[];
+  __shared__ double s_scratch[32];
+  __shared__ double s_part;
+  __shared__ __align__(8) uint64_t s_bar[kChunks];
+
+  const int tid = threadIdx.x;
+  const int64_t nvec = p.n >> 2;
+  const int64_t nr = cluster_nctarank(), rank = cluster_ctarank();
+  const int64_t per = (nvec + nr - 1) / nr;
+  const int64_t begin = rank * per < nvec ? rank * per : nvec;
+  const int64_t end = (rank + 1) * per < nvec ? (rank + 1) * per : nvec;
+  const int64_t cnt = end - begin;                                   // 128-bit vectors in this CTA's slice
+  const int64_t off = (int64_t)blockIdx.y * nvec + begin;            // slice start, in vectors, in the batch
+  const float4* g4 = reinterpret_cast<const float4*>(p.g) + off;
+  float4* sg4 = reinterpret_cast<float4*>(smem_raw);
+  const int64_t per_chunk = (cnt + kChunks - 1) / kChunks;
+
+  // ---------------- phase A: sum |g| over the slice ----------------
+  double acc = 0.0;
+  if (STAGE) {
+    if (tid == 0) {
+#pragma unroll
+      for (int c = 0; c < kChunks; ++c) mbar_init(&s_bar[c], 1);
+      mbar_fence_init();
+    }
+    __syncthreads();
+    if (tid == 0) {
+#pragma unroll
+      for (int c = 0; c < kChunks; ++c) {
+        const int64_t c0 = c * per_chunk, c1 = (c0 + per_chunk < cnt) ? c0 + per_chunk : cnt;
+        if (c1 > c0) {
+          const uint32_t bytes = (uint32_t)((c1 - c0) * 16);
+          mbar_expect_tx(&s_bar[c], bytes);
+          tma_bulk_g2s(sg4 + c0, g4 + c0, bytes, &s_bar[c]);
+        }
+      }
+    }
+#pragma unroll
+    for (int c = 0; c < kChunks; ++c) {
+      const int64_t c0 = c * per_chunk, c1 = (c0 + per_chunk < cnt) ? c0 + per_chunk : cnt;
+      if (c1 > c0) {
+        mbar_wait(&s_bar[c], 0);
+        for (int64_t i = c0 + tid; i < c1; i += THREADS) {
+          const float4 v = sg4[i];
+          acc += (double)fabsf(v.x); acc += (double)fabsf(v.y); acc += (double)fabsf(v.z); acc += (double)fabsf(v.w);
+        }
+      }
+    }
+  } else {
+    for (int64_t i = tid; i < cnt; i += THREADS) {
+      const float4 v = __ldg(g4 + i);
+      acc += (double)fabsf(v.x); acc += (double)fabsf(v.y); acc += (double)fabsf(v.z); acc += (double)fabsf(v.w);
+    }
+  }
+  const double part = block_sum(acc, s_scratch);
+  if (tid == 0) s_part = part;
+  cluster_sync_all();
+  double tot = 0.0;
+  for (uint32_t r = 0; r < (uint32_t)nr; ++r) tot += dsmem_ld_f64(&s_part, r);
+  cluster_arrive();                       // "done reading remote shared memory"; matched by cluster_wait() at exit
+  const float mu = (float)(tot / (double)p.n);
+  if (rank == 0 && tid == 0 && p.scale_out) p.scale_out[blockIdx.y] = mu;
+
+  // ---------------- phase B: stream the update ----------------
+  const bool has_m = p.m != nullptr;
+  const float4* m4 = reinterpret_cast<const float4*>(p.m) + off;
+  const float4* d4 = reinterpret_cast<const float4*>(p.delta) + off;
+  const float4* x4 = reinterpret_cast<const float4*>(p.data) + off;
+  float4* mo4 = reinterpret_cast<float4*>(p.m_out) + off;
+  float4* do4 = reinterpret_cast<float4*>(p.delta_out) + off;
+  float4* xa4 = reinterpret_cast<float4*>(p.xadv) + off;
+  for (int64_t i0 = tid; i0 < cnt; i0 += (int64_t)THREADS * U) {
+    float4 gv[U], mv[U], dv[U], xv[U];
+#pragma unroll
+    for (int u = 0; u < U; ++u) {
+      const int64_t i = i0 + (int64_t)u * THREADS;
+      if (i < cnt) {
+        gv[u] = STAGE ? sg4[i] : __ldg(g4 + i);
+        xv[u] = __ldg(x4 + i);
+        dv[u] = d4[i];
+        mv[u] = has_m ? m4[i] : make_float4(0.f, 0.f, 0.f, 0.f);
+      }
+    }
+#pragma unroll
+    for (int u = 0; u < U; ++u) {
+      const int64_t i = i0 + (int64_t)u * THREADS;
+      if (i < cnt) {
+        float4 mo, dn, xa;
+        fused_elem(gv[u].x, mv[u].x, has_m, dv[u].x, xv[u].x, mu, p, mo.x, dn.x, xa.x);
+        fused_elem(gv[u].y, mv[u].y, has_m, dv[u].y, xv[u].y, mu, p, mo.y, dn.y, xa.y);
+        fused_elem(gv[u].z, mv[u].z, has_m, dv[u].z, xv[u].z, mu, p, mo.z, dn.z, xa.z);
+        fused_elem(gv[u].w, mv[u].w, has_m, dv[u].w, xv[u].w, mu, p, mo.w, dn.w, xa.w);
+        mo4[i] = mo;
+        do4[i] = dn;
+        if (p.xadv) xa4[i] = xa;
+      }
+    }
+  }
+  cluster_wait();                         // keep s_part alive until every rank has read it
+}
+
+template <int THREADS, int U, bool STAGE>
+int launch_fused(const FusedParams& p, int B, int cl, size_t smem, cudaStream_t s) {
+  auto k = fused_cluster_kernel<THREADS, U, STAGE>;
+  if (smem > 48 * 1024) {
+    const cudaError_t e = cudaFuncSetAttribute(k, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+    if (e != cudaSuccess) {
+      set_error("ta_fused_update_linf: cannot reserve %zu B of shared memory: %s", smem, cudaGetErrorString(e));
+      cudaGetLastError();
+      return TA_ECUDA;
+    }
+  }
+  if (cl > 8) {
+    const cudaError_t e = cudaFuncSetAttribute(k, cudaFuncAttributeNonPortableClusterSizeAllowed, 1);
+    if (e != cudaSuccess) {
+      set_error("ta_fused_update_linf: cluster size %d not allowed: %s", cl, cudaGetErrorString(e));
+      cudaGetLastError();
+      return TA_ECUDA;
+    }
+  }
+  return launch_cluster("ta_fused_update_linf", k, cl, B, THREADS, smem, s, p);
+}
+
+constexpr size_t kMaxStageBytes = 200 * 1024;   // per-CTA g slice bound (227 KB/SM minus static + system use)
+
+}  // namespace
+
+extern "C" int ta_fused_update_linf(const float* g, const float* m, float* m_out, const float* delta, float* delta_out,
+                                    const float* data, float* xadv_out, const float* scale, float* scale_out, int mean_mode,
+                                    float decay, float alpha, float eps, float lo, float hi, int B, int64_t n,
+                                    ta_stream_t stream) {
+  TA_REQUIRE(g && m_out && delta && delta_out && data && B > 0 && n > 0,
+             "ta_fused_update_linf: null pointer or empty shape (B=%d n=%lld)", B, (long long)n);
+  TA_REQUIRE(B <= 65535, "ta_fused_update_linf: B=%d exceeds 65535", B);
+  cudaStream_t s = (cudaStream_t)stream;
+  FusedParams p{g, m, m_out, delta, delta_out, data, xadv_out, scale, scale_out, decay, alpha, eps, lo, hi, n};
+  const bool v4 = (n % 4 == 0) && aligned16(g) && aligned16(m) && aligned16(m_out) && aligned16(delta) &&
+                  aligned16(delta_out) && aligned16(data) && aligned16(xadv_out);
+
+  if (scale) {   // strict: no reduction, flat streaming
+    if (scale_out && scale_out != scale) {
+      const cudaError_t e = cudaMemcpyAsync(scale_out, scale, sizeof(float) * (size_t)B, cudaMemcpyDeviceToDevice, s);
+      if (e != cudaSuccess) { set_error("ta_fused_update_linf: scale copy failed: %s", cudaGetErrorString(e)); return TA_ECUDA; }
+    }
+    return launch_ew("ta_fused_update_linf[stream]", (int64_t)B * n, v4, FusedStreamOp{p}, s);
+  }
+
+  if (mean_mode != TA_MEAN_EXACT) {
+    set_error("ta_fused_update_linf: mean_mode %d not available in this build", mean_mode);
+    return TA_EUNSUPPORTED;
+  }
+
+  // cluster geometry
+  int cl = tune_get("fused.cluster", 0);
+  if (cl <= 0) {
+    cl = 1;
+    while (cl < 8 && n / (cl * 2) >= 2048) cl *= 2;          // >= 2K elements per CTA before splitting further
+  }
+  const int variant = tune_get("fused.variant", 0);          // 0 = g staged in smem by bulk-TMA, 1 = re-read via L2
+  const int threads = tune_get("fused.threads", 512);
+  const int unroll = tune_get("fused.unroll", 2);
+  const int64_t nvec = n / 4;
+  const size_t slice_bytes = (size_t)((nvec + cl - 1) / cl) * 16;
+
+  if (!v4) {
+    // generic fallback: exact mean into scale_out, then the streaming kernel (two launches)
+    TA_REQUIRE(scale_out, "ta_fused_update_linf: n %% 4 != 0 or misaligned pointers need scale_out as scratch");
+    const int rc = ta_abs_mean_per_sample(g, scale_out, B, n, TA_MEAN_EXACT, nullptr, stream);
+    if (rc != TA_OK) return rc;
+    p.scale = scale_out;
+    return launch_ew("ta_fused_update_linf[stream]", (int64_t)B * n, false, FusedStreamOp{p}, s);
+  }
+
+  const bool stage = (variant == 0) && slice_bytes <= kMaxStageBytes;
+  const size_t smem = stage ? slice_bytes : 0;
+#define TA_FUSED_CASE(T, U_)                                                        \
+  if (threads == T && unroll == U_)                                                 \
+    return stage ? launch_fused<T, U_, true>(p, B, cl, smem, s) : launch_fused<T, U_, false>(p, B, cl, 0, s);
+  TA_FUSED_CASE(256, 2)
+  TA_FUSED_CASE(256, 4)
+  TA_FUSED_CASE(512, 2)
+  TA_FUSED_CASE(512, 4)
+  TA_FUSED_CASE(1024, 1)
+  TA_FUSED_CASE(1024, 2)
+#undef TA_FUSED_CASE
+  set_error("ta_fused_update_linf: unsupported tuning threads=%d unroll=%d", threads, unroll);
+  return TA_EUNSUPPORTED;
+}

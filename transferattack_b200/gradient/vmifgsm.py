@@ -1,0 +1,46 @@
+"""VMI-FGSM (Wang & He, CVPR 2021): momentum of (gradient + variance), where the variance is the mean gradient over
+``num_neighbor`` uniformly perturbed copies minus the current gradient.
+Reference: transferattack/gradient/vmifgsm.py:33-97 (same constructor, ``get_variance`` and loop order; the
+neighbour noise is drawn with the same torch call so the device generator is consumed identically).
+
+Kernels per neighbour: ``ta_neighbor_stage`` ((data+delta)+noise, identity backward) and ``ta_accumulate``;
+once per iteration ``ta_variance_finalize`` (acc/N - g), ``ta_add`` (g + v), then the base hooks."""
+from ..utils import *
+from .. import ops
+from ..attack import Attack
+
+
+class VMIFGSM(Attack):
+    def __init__(self, model_name, epsilon=16/255, alpha=1.6/255, beta=1.5, num_neighbor=20, epoch=10, decay=1., targeted=False,
+                 random_start=False, norm='linfty', loss='crossentropy', device=None, attack='VMI-FGSM', **kwargs):
+        super().__init__(attack, model_name, epsilon, targeted, random_start, norm, loss, device)
+        self.alpha, self.epoch, self.decay = alpha, epoch, decay
+        self.radius = beta * epsilon
+        self.num_neighbor = num_neighbor
+
+    def get_variance(self, data, delta, label, cur_grad, momentum, **kwargs):
+        be = ops.backend()
+        acc = None
+        for k in range(self.num_neighbor):
+            noise = torch.zeros_like(delta).uniform_(-self.radius, self.radius).to(self.device)
+            x_near = ops.neighbor_stage(data, delta, noise)
+            loss = self.get_loss(self.get_logits(self.transform(x_near, momentum=momentum)), label)
+            acc = be.accumulate(acc, self.get_grad(loss, delta), first=(k == 0))
+        return be.variance_finalize(acc, cur_grad, self.num_neighbor)
+
+    def forward(self, data, label, **kwargs):
+        if self.targeted:
+            assert len(label) == 2
+            label = label[1]
+        data = self._to_device(data)
+        label = self._to_device(label)
+        be = ops.backend()
+        delta = self.init_delta(data)
+        momentum, variance = 0, None
+        for _ in range(self.epoch):
+            loss = self.get_loss(self.get_logits(self.transform(ops.stage_add(data, delta), momentum=momentum)), label)
+            grad = self.get_grad(loss, delta)
+            momentum = self.get_momentum(grad if variance is None else be.add(grad, variance), momentum)
+            variance = self.get_variance(data, delta, label, grad, momentum)
+            delta = self.update_delta(delta, data, momentum, self.alpha)
+        return delta.detach()

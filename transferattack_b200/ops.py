@@ -1,0 +1,390 @@
+"""Tensor-level entry points of the sm_100a kernels (libta_b200.so through ctypes) and the
+``torch.autograd.Function`` wrappers that put the staging kernels inside the autograd graph.
+
+Every function takes/returns ``torch.Tensor``s on a CUDA device (fp32, made contiguous), launches on the
+current torch stream and never synchronises. There is NO CPU or eager-PyTorch fallback: a CPU tensor, a
+missing library or a non-CUDA build raises. (``_install_backend_for_tests`` exists so that the host-side
+control flow can be unit-tested on a box without a GPU; nothing in this package ever calls it.)
+"""
+import ctypes
+
+import torch
+
+from . import _lib
+
+_test_backend = None
+
+
+def _install_backend_for_tests(backend):
+    """TESTS ONLY: route the raw compute calls to `backend` (tests/oracle_backend.py) instead of CUDA."""
+    global _test_backend
+    _test_backend = backend
+
+
+# =====================================================================================================
+# CUDA backend: raw pointers into the C-ABI
+# =====================================================================================================
+def _ptr(t):
+    return None if t is None else ctypes.c_void_p(t.data_ptr())
+
+
+def _stream():
+    return ctypes.c_void_p(torch.cuda.current_stream().cuda_stream)
+
+
+def _f32c(t, name="tensor"):
+    if t is None:
+        return None
+    if not t.is_cuda:
+        raise RuntimeError("transferattack_b200 kernels need CUDA tensors; %s is on %s (no CPU fallback)" % (name, t.device))
+    if t.dtype != torch.float32:
+        raise TypeError("transferattack_b200 kernels are fp32; %s is %s" % (name, t.dtype))
+    t = t.detach()
+    return t if t.is_contiguous() else t.contiguous()
+
+
+class _DeviceOf:
+    """Make the tensor's device current for the launch (no-op when it already is)."""
+
+    def __init__(self, t):
+        self.idx = t.device.index
+        self.prev = None
+
+    def __enter__(self):
+        cur = torch.cuda.current_device()
+        if self.idx is not None and self.idx != cur:
+            self.prev = cur
+            torch.cuda.set_device(self.idx)
+
+    def __exit__(self, *a):
+        if self.prev is not None:
+            torch.cuda.set_device(self.prev)
+
+
+class CudaBackend:
+    def __init__(self):
+        self.lib = _lib.load()
+        if not torch.cuda.is_available():
+            raise RuntimeError("transferattack_b200: no CUDA device; the attack hooks have no CPU path")
+
+    # ---- reductions -------------------------------------------------------------------------------
+    def abs_mean(self, g, mode=_lib.TA_MEAN_EXACT):
+        g = _f32c(g, "grad"); B = g.shape[0]; n = g.numel() // B
+        out = torch.empty(B, device=g.device, dtype=torch.float32)
+        with _DeviceOf(g):
+            _lib.check(self.lib.ta_abs_mean_per_sample(_ptr(g), _ptr(out), B, n, mode, None, _stream()), "ta_abs_mean_per_sample")
+        return out
+
+    # ---- hooks ------------------------------------------------------------------------------------
+    def momentum(self, g, m, scale, decay, out=None):
+        g = _f32c(g, "grad"); m = _f32c(m, "momentum"); scale = _f32c(scale, "scale")
+        B = g.shape[0]; n = g.numel() // B
+        out = torch.empty_like(g) if out is None else out
+        with _DeviceOf(g):
+            _lib.check(self.lib.ta_momentum(_ptr(g), _ptr(m), _ptr(scale), float(decay), _ptr(out), B, n, _stream()), "ta_momentum")
+        return out
+
+    def update_linf(self, delta, data, direction, alpha, eps, lo, hi, alpha_t=None, dir_mode=_lib.TA_DIR_SIGN, out=None):
+        delta = _f32c(delta, "delta"); data = _f32c(data, "data"); direction = _f32c(direction, "grad"); alpha_t = _f32c(alpha_t, "alpha")
+        out = torch.empty_like(delta) if out is None else out
+        with _DeviceOf(delta):
+            _lib.check(self.lib.ta_update_linf(_ptr(delta), _ptr(data), _ptr(direction), _ptr(alpha_t), float(alpha), float(eps),
+                                               float(lo), float(hi), dir_mode, _ptr(out), delta.numel(), _stream()), "ta_update_linf")
+        return out
+
+    def update_l2(self, delta, data, g, alpha, eps, lo, hi):
+        delta = _f32c(delta, "delta"); data = _f32c(data, "data"); g = _f32c(g, "grad")
+        B = g.shape[0]; n = g.numel() // B
+        out = torch.empty_like(delta)
+        with _DeviceOf(delta):
+            _lib.check(self.lib.ta_update_l2(_ptr(delta), _ptr(data), _ptr(g), float(alpha), float(eps), float(lo), float(hi),
+                                             _ptr(out), B, n, None, _stream()), "ta_update_l2")
+        return out
+
+    def clamp_box(self, delta, data, lo, hi):
+        delta = _f32c(delta, "delta"); data = _f32c(data, "data")
+        out = torch.empty_like(delta)
+        with _DeviceOf(delta):
+            _lib.check(self.lib.ta_clamp_box(_ptr(delta), _ptr(data), float(lo), float(hi), _ptr(out), delta.numel(), _stream()), "ta_clamp_box")
+        return out
+
+    def init_l2_scale(self, delta, r, data, eps, lo, hi):
+        delta = _f32c(delta, "delta"); r = _f32c(r, "r"); data = _f32c(data, "data")
+        B = delta.shape[0]; n = delta.numel() // B
+        out = torch.empty_like(delta)
+        with _DeviceOf(delta):
+            _lib.check(self.lib.ta_init_l2_scale(_ptr(delta), _ptr(r), _ptr(data), float(eps), float(lo), float(hi), _ptr(out), B, n,
+                                                 None, _stream()), "ta_init_l2_scale")
+        return out
+
+    def fused_update_linf(self, g, m, m_out, delta, delta_out, data, xadv_out, scale, scale_out, decay, alpha, eps, lo, hi,
+                          mean_mode=_lib.TA_MEAN_EXACT):
+        g = _f32c(g, "grad"); B = g.shape[0]; n = g.numel() // B
+        with _DeviceOf(g):
+            _lib.check(self.lib.ta_fused_update_linf(_ptr(g), _ptr(m), _ptr(m_out), _ptr(delta), _ptr(delta_out), _ptr(data),
+                                                     _ptr(xadv_out), _ptr(scale), _ptr(scale_out), mean_mode, float(decay),
+                                                     float(alpha), float(eps), float(lo), float(hi), B, n, _stream()),
+                       "ta_fused_update_linf")
+
+    # ---- staging ----------------------------------------------------------------------------------
+    def stage_add(self, data, delta, look=None, coef=0.0, out=None):
+        data = _f32c(data, "data"); delta = _f32c(delta, "delta"); look = _f32c(look, "momentum")
+        out = torch.empty_like(data) if out is None else out
+        with _DeviceOf(data):
+            _lib.check(self.lib.ta_stage_add(_ptr(data), _ptr(delta), _ptr(look), float(coef), _ptr(out), data.numel(), _stream()), "ta_stage_add")
+        return out
+
+    def neighbor_stage(self, data, delta, noise, look=None, coef=0.0, out=None):
+        data = _f32c(data, "data"); delta = _f32c(delta, "delta"); noise = _f32c(noise, "noise"); look = _f32c(look, "momentum")
+        out = torch.empty_like(data) if out is None else out
+        with _DeviceOf(data):
+            _lib.check(self.lib.ta_neighbor_stage(_ptr(data), _ptr(delta), _ptr(noise), _ptr(look), float(coef), _ptr(out),
+                                                  data.numel(), _stream()), "ta_neighbor_stage")
+        return out
+
+    def normalize(self, x, mean, std, forward=True):
+        x = _f32c(x, "x"); B, C = x.shape[0], x.shape[1]; plane = x.numel() // (B * C)
+        out = torch.empty_like(x)
+        with _DeviceOf(x):
+            if forward:
+                _lib.check(self.lib.ta_normalize_fwd(_ptr(x), _ptr(mean), _ptr(std), _ptr(out), B, C, plane, _stream()), "ta_normalize_fwd")
+            else:
+                _lib.check(self.lib.ta_normalize_bwd(_ptr(x), _ptr(std), _ptr(out), B, C, plane, _stream()), "ta_normalize_bwd")
+        return out
+
+    def sim(self, x, S, forward=True):
+        x = _f32c(x, "x")
+        with _DeviceOf(x):
+            if forward:
+                out = torch.empty((S * x.shape[0],) + tuple(x.shape[1:]), device=x.device, dtype=torch.float32)
+                _lib.check(self.lib.ta_sim_fwd(_ptr(x), _ptr(out), S, x.numel(), _stream()), "ta_sim_fwd")
+            else:
+                out = torch.empty((x.shape[0] // S,) + tuple(x.shape[1:]), device=x.device, dtype=torch.float32)
+                _lib.check(self.lib.ta_sim_bwd(_ptr(x), _ptr(out), S, out.numel(), _stream()), "ta_sim_bwd")
+        return out
+
+    def admix(self, x, perm, strength, S, A, forward=True):
+        x = _f32c(x, "x")
+        with _DeviceOf(x):
+            if forward:
+                B = x.shape[0]; n = x.numel() // B
+                out = torch.empty((S * A * B,) + tuple(x.shape[1:]), device=x.device, dtype=torch.float32)
+                _lib.check(self.lib.ta_admix_fwd(_ptr(x), _ptr(perm), float(strength), _ptr(out), S, A, B, n, _stream()), "ta_admix_fwd")
+            else:
+                B = x.shape[0] // (S * A); n = x.numel() // x.shape[0]
+                out = torch.empty((B,) + tuple(x.shape[1:]), device=x.device, dtype=torch.float32)
+                _lib.check(self.lib.ta_admix_bwd(_ptr(x), _ptr(out), S, A, B, n, _stream()), "ta_admix_bwd")
+        return out
+
+    def dim(self, x, rnd, R, top, left, forward=True):
+        x = _f32c(x, "x"); S = x.shape[-1]
+        if x.shape[-2] != S:
+            raise ValueError("DIM kernels need square images (the reference resizes with x.shape[-1] only)")
+        planes = x.numel() // (S * S)
+        out = torch.empty_like(x)
+        fn = self.lib.ta_dim_fwd if forward else self.lib.ta_dim_bwd
+        with _DeviceOf(x):
+            _lib.check(fn(_ptr(x), _ptr(out), planes, S, int(rnd), int(R), int(top), int(left), _stream()), "ta_dim")
+        return out
+
+    def dwconv2d(self, g, k):
+        g = _f32c(g, "grad"); k = _f32c(k, "kernel"); B, C, H, W = g.shape; ks = k.shape[-1]
+        out = torch.empty_like(g)
+        with _DeviceOf(g):
+            _lib.check(self.lib.ta_dwconv2d(_ptr(g), _ptr(k), ks, _ptr(out), B, C, H, W, _stream()), "ta_dwconv2d")
+        return out
+
+    def dwconv2d_sep(self, g, kcol, krow):
+        g = _f32c(g, "grad"); kcol = _f32c(kcol, "kcol"); krow = _f32c(krow, "krow"); B, C, H, W = g.shape; ks = kcol.shape[-1]
+        out = torch.empty_like(g)
+        with _DeviceOf(g):
+            _lib.check(self.lib.ta_dwconv2d_sep(_ptr(g), _ptr(kcol), _ptr(krow), ks, _ptr(out), B, C, H, W, _stream()), "ta_dwconv2d_sep")
+        return out
+
+    def lin_sample(self, x, gbar, coefs, forward=True):
+        x = _f32c(x, "x"); K = len(coefs)
+        with _DeviceOf(x):
+            if forward:
+                gbar = _f32c(gbar, "bar_grad")
+                arr = (ctypes.c_float * K)(*[float(c) for c in coefs])
+                out = torch.empty((K * x.shape[0],) + tuple(x.shape[1:]), device=x.device, dtype=torch.float32)
+                _lib.check(self.lib.ta_lin_sample_fwd(_ptr(x), _ptr(gbar), arr, K, _ptr(out), x.numel(), _stream()), "ta_lin_sample_fwd")
+            else:
+                out = torch.empty((x.shape[0] // K,) + tuple(x.shape[1:]), device=x.device, dtype=torch.float32)
+                _lib.check(self.lib.ta_lin_sample_bwd(_ptr(x), _ptr(out), K, out.numel(), _stream()), "ta_lin_sample_bwd")
+        return out
+
+    def accumulate(self, acc, g, first):
+        g = _f32c(g, "grad")
+        acc = torch.empty_like(g) if acc is None else acc
+        with _DeviceOf(g):
+            _lib.check(self.lib.ta_accumulate(_ptr(acc), _ptr(g), 1 if first else 0, g.numel(), _stream()), "ta_accumulate")
+        return acc
+
+    def variance_finalize(self, acc, cur, num_neighbor):
+        acc = _f32c(acc, "acc"); cur = _f32c(cur, "cur_grad")
+        out = torch.empty_like(acc)
+        with _DeviceOf(acc):
+            _lib.check(self.lib.ta_variance_finalize(_ptr(acc), _ptr(cur), int(num_neighbor), _ptr(out), acc.numel(), _stream()), "ta_variance_finalize")
+        return out
+
+    def add(self, a, b):
+        a = _f32c(a, "a"); b = _f32c(b, "b")
+        out = torch.empty_like(a)
+        with _DeviceOf(a):
+            _lib.check(self.lib.ta_add(_ptr(a), _ptr(b), _ptr(out), a.numel(), _stream()), "ta_add")
+        return out
+
+    def quantize_u8(self, data, delta, to_nhwc=True):
+        data = _f32c(data, "data"); delta = _f32c(delta, "delta"); B, C = data.shape[0], data.shape[1]
+        plane = data.numel() // (B * C)
+        shape = (B,) + tuple(data.shape[2:]) + (C,) if to_nhwc else tuple(data.shape)
+        out = torch.empty(shape, device=data.device, dtype=torch.uint8)
+        with _DeviceOf(data):
+            _lib.check(self.lib.ta_quantize_u8(_ptr(data), _ptr(delta), _ptr(out), B, C, plane, 1 if to_nhwc else 0, _stream()), "ta_quantize_u8")
+        return out
+
+
+_cuda_backend = None
+
+
+def backend():
+    """The compute backend: CUDA kernels, always (tests may have installed a stand-in)."""
+    global _cuda_backend
+    if _test_backend is not None:
+        return _test_backend
+    if _cuda_backend is None:
+        _cuda_backend = CudaBackend()
+    return _cuda_backend
+
+
+# =====================================================================================================
+# autograd wrappers for the ops that sit between delta and the surrogate
+# =====================================================================================================
+class StageAdd(torch.autograd.Function):
+    """x = data + delta (+ coef * look).  d x / d delta = I, so backward hands the incoming gradient through
+    untouched (no copy). `precomputed` lets the fused update kernel's xadv output stand in for the sum."""
+
+    @staticmethod
+    def forward(ctx, data, delta, look, coef, precomputed):
+        if precomputed is not None:
+            return precomputed.view_as(delta)
+        return backend().stage_add(data, delta, look, coef)
+
+    @staticmethod
+    def backward(ctx, gout):
+        return None, gout, None, None, None
+
+
+class LookAhead(torch.autograd.Function):
+    """NI-FGSM's x + (alpha*decay) * momentum on an already formed x (nifgsm.py:39); identity backward."""
+
+    @staticmethod
+    def forward(ctx, x, look, coef):
+        return backend().stage_add(x, None, look, coef)
+
+    @staticmethod
+    def backward(ctx, gout):
+        return gout, None, None
+
+
+class NeighborStage(torch.autograd.Function):
+    """VMI neighbour input ((data + delta) + noise) [+ coef*look]; gradient wrt delta is the identity."""
+
+    @staticmethod
+    def forward(ctx, data, delta, noise, look, coef):
+        return backend().neighbor_stage(data, delta, noise, look, coef)
+
+    @staticmethod
+    def backward(ctx, gout):
+        return None, gout, None, None, None
+
+
+class Normalize(torch.autograd.Function):
+    @staticmethod
+    def forward(ctx, x, mean, std):
+        ctx.save_for_backward(std)
+        return backend().normalize(x, mean, std, True)
+
+    @staticmethod
+    def backward(ctx, gout):
+        (std,) = ctx.saved_tensors
+        return backend().normalize(gout, None, std, False), None, None
+
+
+class SimScale(torch.autograd.Function):
+    @staticmethod
+    def forward(ctx, x, S):
+        ctx.S = S
+        return backend().sim(x, S, True)
+
+    @staticmethod
+    def backward(ctx, gout):
+        return backend().sim(gout, ctx.S, False), None
+
+
+class AdmixMix(torch.autograd.Function):
+    @staticmethod
+    def forward(ctx, x, perm, strength, S, A):
+        ctx.cfg = (S, A)
+        return backend().admix(x, perm, strength, S, A, True)
+
+    @staticmethod
+    def backward(ctx, gout):
+        S, A = ctx.cfg
+        return backend().admix(gout, None, 0.0, S, A, False), None, None, None, None
+
+
+class DimResizePad(torch.autograd.Function):
+    @staticmethod
+    def forward(ctx, x, rnd, R, top, left):
+        ctx.cfg = (rnd, R, top, left)
+        return backend().dim(x, rnd, R, top, left, True)
+
+    @staticmethod
+    def backward(ctx, gout):
+        rnd, R, top, left = ctx.cfg
+        return backend().dim(gout, rnd, R, top, left, False), None, None, None, None
+
+
+class LinSample(torch.autograd.Function):
+    @staticmethod
+    def forward(ctx, x, gbar, coefs):
+        ctx.K = len(coefs)
+        return backend().lin_sample(x, gbar, coefs, True)
+
+    @staticmethod
+    def backward(ctx, gout):
+        return backend().lin_sample(gout, None, [0.0] * ctx.K, False), None, None
+
+
+def stage_add(data, delta, look=None, coef=0.0, precomputed=None):
+    return StageAdd.apply(data, delta, look, coef, precomputed)
+
+
+def look_ahead(x, momentum, coef):
+    return LookAhead.apply(x, momentum, coef)
+
+
+def neighbor_stage(data, delta, noise, look=None, coef=0.0):
+    return NeighborStage.apply(data, delta, noise, look, coef)
+
+
+def normalize(x, mean, std):
+    return Normalize.apply(x, mean, std)
+
+
+def sim_scale(x, S):
+    return SimScale.apply(x, S)
+
+
+def admix_mix(x, perm, strength, S, A):
+    return AdmixMix.apply(x, perm, strength, S, A)
+
+
+def dim_resize_pad(x, rnd, R, top, left):
+    return DimResizePad.apply(x, rnd, R, top, left)
+
+
+def lin_sample(x, gbar, coefs):
+    return LinSample.apply(x, gbar, coefs)
