@@ -1,0 +1,363 @@
+"""-m gpu: every entry point of libta_b200.so (called through the C-ABI, ctypes → raw device pointers) against
+  (1) the golden vectors produced by the unmodified reference (tests/golden/*.npz),
+  (2) the C oracle on seeded inputs (bit-exact wherever kernel and oracle share the op order),
+  (3) size-independent properties at BASELINE sizes (B=64 x 3x224x224): adjoint identities, fused == unfused, bounds.
+Tolerances are stated where used; everything else is bit-exact (NaN == NaN)."""
+import json
+import os
+
+import numpy as np
+import pytest
+import torch
+
+import oracle
+from conftest import bits_equal, load_golden, n_diff_bits, ulp_diff, ROOT
+
+pytestmark = pytest.mark.gpu
+
+EPS = 16 / 255
+ALPHA = 1.6 / 255
+
+
+@pytest.fixture(scope="module")
+def be():
+    from transferattack_b200 import ops
+    ops._install_backend_for_tests(None)
+    return ops.backend()
+
+
+def cu(a):
+    return None if a is None else torch.from_numpy(np.ascontiguousarray(a)).cuda()
+
+
+def npy(t):
+    return t.detach().cpu().numpy()
+
+
+def test_library_and_device(be):
+    from transferattack_b200 import _lib
+    import ctypes
+    lib = _lib.load()
+    sm, ma, mi = ctypes.c_int(), ctypes.c_int(), ctypes.c_int()
+    assert lib.ta_device_info(ctypes.byref(sm), ctypes.byref(ma), ctypes.byref(mi)) == 0
+    assert (ma.value, mi.value) == (10, 0), "these kernels are built for sm_100a only"
+    assert sm.value >= 100
+    before = _lib.launch_count()
+    be.add(torch.zeros(8, device="cuda"), torch.zeros(8, device="cuda"))
+    assert _lib.launch_count() == before + 1
+
+
+def test_cpu_tensor_is_rejected_loudly(be):
+    with pytest.raises(RuntimeError, match="no CPU fallback"):
+        be.add(torch.zeros(4), torch.zeros(4))
+
+
+# ---------------------------------------------------------------------------------------------- golden: hooks
+@pytest.fixture(scope="module")
+def H():
+    return load_golden("hooks")
+
+
+@pytest.mark.parametrize("key,decay,first", [("mom_first", 1.0, True), ("mom_d1", 1.0, False), ("mom_d07", 0.7, False),
+                                             ("mom_d0", 0.0, False)])
+def test_momentum_golden(be, H, key, decay, first):
+    out = be.momentum(cu(H["g"]), None if first else cu(H["m"]), cu(H["scale"]), decay)
+    assert bits_equal(npy(out), H[key]), n_diff_bits(npy(out), H[key])
+
+
+def test_momentum_nan_sample(be, H):
+    scale = np.array(H["scale"]); scale[1] = 0.0
+    out = npy(be.momentum(cu(H["gz"]), cu(H["m"]), cu(scale), 1.0))
+    assert bits_equal(out, H["mom_nan"]) and np.isnan(out[1]).all()
+
+
+def test_update_linf_golden(be, H):
+    eps, alpha = float(H["eps"]), float(H["alpha"])
+    d, x, m = cu(H["delta"]), cu(H["data"]), cu(H["mom_d1"])
+    assert bits_equal(npy(be.update_linf(d, x, m, alpha, eps, 0, 1.0)), H["upd_linf"])
+    assert bits_equal(npy(be.update_linf(d, x, m, -alpha, eps, 0, 1.0)), H["upd_linf_neg"])
+    assert bits_equal(npy(be.update_linf(d, x, m, 0.0, eps, 0, 1.0, alpha_t=cu(H["alpha_t"]))), H["upd_linf_tensor"])
+    assert bits_equal(npy(be.update_linf(d, x, cu(H["mom_nan"]), alpha, eps, 0, 1.0)), H["upd_nan"])
+
+
+def test_fused_update_golden_strict(be, H):
+    eps, alpha = float(H["eps"]), float(H["alpha"])
+    g, m, d, x = cu(H["g"]), cu(H["m"]), cu(H["delta"]), cu(H["data"])
+    m_out, d_out, xa = torch.empty_like(g), torch.empty_like(g), torch.empty_like(g)
+    so = torch.empty(g.shape[0], device="cuda")
+    be.fused_update_linf(g, m, m_out, d, d_out, x, xa, cu(H["scale"]), so, 1.0, alpha, eps, 0, 1.0)
+    assert bits_equal(npy(m_out), H["mom_d1"]) and bits_equal(npy(d_out), H["upd_linf"])
+    assert bits_equal(npy(xa), (H["data"] + H["upd_linf"]).astype(np.float32))
+    assert bits_equal(npy(so), H["scale"])
+    be.fused_update_linf(g, None, m_out, d, d_out, x, None, cu(H["scale"]), None, 1.0, alpha, eps, 0, 1.0)
+    assert bits_equal(npy(m_out), H["mom_first"])
+
+
+def test_l2_and_init_golden(be, H):
+    eps = float(H["eps"])
+    out = be.update_l2(cu(H["delta"] * np.float32(0.01)), cu(H["data"]), cu(H["g_l2"]), 0.01, eps, 0, 1.0)
+    np.testing.assert_allclose(npy(out), H["upd_l2_small"], rtol=0, atol=2e-7)   # fp64 vs torch fp32 norm
+    out = be.update_l2(cu(H["delta"]), cu(H["data"]), cu(H["g_l2"]), 2.0, eps, 0, 1.0)
+    np.testing.assert_allclose(npy(out), H["upd_l2_big"], rtol=0, atol=2e-7)
+    assert bits_equal(npy(out), oracle.update_l2(H["delta"], H["data"], H["g_l2"], 2.0, eps)) or \
+        np.abs(npy(out) - oracle.update_l2(H["delta"], H["data"], H["g_l2"], 2.0, eps)).max() < 1e-7
+    assert bits_equal(npy(be.clamp_box(cu(H["init_noise"]), cu(H["data"]), 0, 1.0)), H["init_linf"])
+    out = be.init_l2_scale(cu(H["init_l2_normal"]), cu(H["init_l2_r"]), cu(H["data"]), eps, 0, 1.0)
+    np.testing.assert_allclose(npy(out), H["init_l2"], rtol=0, atol=1e-8)
+
+
+def test_stage_golden(be, H):
+    assert bits_equal(npy(be.stage_add(cu(H["data"]), cu(H["delta"]))), H["x_adv"])
+    assert bits_equal(npy(be.stage_add(cu(H["data"]), cu(H["delta"]), cu(H["m"]), float(H["ni_coef"]))), H["ni_x"])
+    assert bits_equal(npy(be.stage_add(cu(H["x_adv"]), None, cu(H["m"]), float(H["ni_coef"]))), H["ni_x"])
+
+
+def test_misc_golden(be):
+    M = load_golden("misc")
+    mean, std = cu(M["norm_mean"]), cu(M["norm_std"])
+    assert bits_equal(npy(be.normalize(cu(M["norm_x"]), mean, std, True)), M["norm_y"])
+    assert bits_equal(npy(be.normalize(cu(M["norm_gout"]), None, std, False)), M["norm_gin"])
+    u8 = npy(be.quantize_u8(cu(M["q_data"]), cu(M["q_delta"]), True))
+    assert np.array_equal(u8, M["q_u8"])
+    u8c = npy(be.quantize_u8(cu(M["q_data"]), cu(M["q_delta"]), False))
+    assert np.array_equal(u8c.transpose(0, 2, 3, 1), M["q_u8"])
+
+
+def test_sim_admix_emi_golden(be):
+    G = load_golden("sim_admix_emi")
+    x = cu(G["sim_x"])
+    S = int(G["sim_S"])
+    assert bits_equal(npy(be.sim(x, S, True)), G["sim_y"])
+    assert bits_equal(npy(be.sim(cu(G["sim_gout"]), S, False)), G["sim_gin"])
+    S, A = int(G["admix_S"]), int(G["admix_A"])
+    perm = torch.from_numpy(G["admix_perm"]).cuda()
+    assert bits_equal(npy(be.admix(x, perm, float(G["admix_strength"]), S, A, True)), G["admix_y"])
+    assert bits_equal(npy(be.admix(cu(G["admix_gout"]), None, 0.0, S, A, False)), G["admix_gin"])
+    coef = [float(c) for c in G["emi_coef"]]
+    assert bits_equal(npy(be.lin_sample(x, cu(G["emi_gbar"]), coef, True)), G["emi_y"])
+    assert bits_equal(npy(be.lin_sample(x, None, coef, True)), G["emi_y0"])
+    assert bits_equal(npy(be.lin_sample(cu(G["emi_gout"]), None, coef, False)), G["emi_gin"])
+
+
+def test_vmi_golden(be):
+    V = load_golden("vmi")
+    N = int(V["N"])
+    acc = None
+    for k in range(N):
+        xn = be.neighbor_stage(cu(V["data"]), cu(V["delta"]), cu(V["noises"][k]))
+        assert bits_equal(npy(xn), V["x_near"][k])
+        acc = be.accumulate(acc, cu(V["grads"][k]), first=(k == 0))
+    var = be.variance_finalize(acc, cu(V["cur"]), N)
+    assert bits_equal(npy(var), V["variance"])
+    assert bits_equal(npy(be.add(cu(V["cur"]), var)), V["g_plus_v"])
+
+
+# ---------------------------------------------------------------------------------------------- DIM
+def _dim_cases():
+    D = load_golden("dim")
+    return D, sorted({k.rsplit("_", 1)[0] for k in D.files})
+
+
+@pytest.mark.parametrize("tma", [1, 0])
+def test_dim_forward(be, tma):
+    from transferattack_b200 import _lib
+    _lib.tune_set("dim.tma", tma)
+    try:
+        D, cases = _dim_cases()
+        for c in cases:
+            rnd, R, top, left, _ = [int(v) for v in D[c + "_params"]]
+            out = npy(be.dim(cu(D[c + "_x"]), rnd, R, top, left, True))
+            ref = oracle.dim_fwd(D[c + "_x"], rnd, R, top, left)
+            assert bits_equal(out, ref), (c, n_diff_bits(out, ref), np.abs(out - ref).max())       # same op order as the oracle
+            np.testing.assert_allclose(out, D[c + "_y"], rtol=0, atol=3e-7, err_msg=c)            # ATen: FMA-contraction level
+    finally:
+        _lib.tune_set("dim.tma", 1)
+
+
+def test_dim_backward(be):
+    D, cases = _dim_cases()
+    for c in cases:
+        rnd, R, top, left, _ = [int(v) for v in D[c + "_params"]]
+        gin = npy(be.dim(cu(D[c + "_gout"]), rnd, R, top, left, False))
+        np.testing.assert_allclose(gin, oracle.dim_bwd(D[c + "_gout"], rnd, R, top, left), rtol=0, atol=2e-6, err_msg=c)
+        np.testing.assert_allclose(gin, D[c + "_gin"], rtol=0, atol=3e-6, err_msg=c)
+
+
+def test_dim_edge_geometries(be):
+    rng = np.random.default_rng(3)
+    for S, rate in [(224, 1.1), (299, 1.1), (64, 1.5), (33, 1.2), (16, 2.0)]:
+        R = int(S * rate)
+        x = rng.random((2, 3, S, S), dtype=np.float32)
+        g = rng.standard_normal((2, 3, S, S)).astype(np.float32)
+        for rnd, top, left in [(S, 0, 0), (R - 1, 0, 0), (R - 1, 1, 1), (S, R - S, R - S), ((S + R) // 2, 1, (R - (S + R) // 2))]:
+            out = npy(be.dim(cu(x), rnd, R, top, left, True))
+            ref = oracle.dim_fwd(x, rnd, R, top, left)
+            assert bits_equal(out, ref), (S, rnd, top, left, n_diff_bits(out, ref))
+            gin = npy(be.dim(cu(g), rnd, R, top, left, False))
+            np.testing.assert_allclose(gin, oracle.dim_bwd(g, rnd, R, top, left), rtol=0, atol=3e-6)
+
+
+# ---------------------------------------------------------------------------------------------- TIM
+def test_tim_conv(be):
+    import transferattack_b200.input_transformation.tim as tim
+    T = load_golden("tim")
+    for key in sorted(k[:-7] for k in T.files if k.endswith("_kernel")):
+        kt, ks = key.rstrip("0123456789"), int(key[len(key.rstrip("0123456789")):])
+        k2d, kcol, krow = tim.make_kernel(kt, ks)
+        assert bits_equal(k2d, T[key + "_kernel"])
+        kc3, kr3 = np.stack([kcol] * 3), np.stack([krow] * 3)
+        for tag in "abc":
+            if key + "_" + tag + "_in" not in T.files:
+                continue
+            x = T[key + "_" + tag + "_in"]
+            out2d = npy(be.dwconv2d(cu(x), cu(k2d.reshape(3, ks, ks))))
+            assert bits_equal(out2d, oracle.dwconv2d(x, k2d)), (key, tag, "2d")
+            outs = npy(be.dwconv2d_sep(cu(x), cu(kc3), cu(kr3)))
+            assert bits_equal(outs, oracle.dwconv2d_sep(x, kc3, kr3)), (key, tag, "sep")
+            # vs the reference's F.conv2d: summation order differs on both sides (N(0,1) inputs, weights sum to 1)
+            np.testing.assert_allclose(out2d, T[key + "_" + tag + "_out"], rtol=0, atol=1e-6)
+            np.testing.assert_allclose(outs, T[key + "_" + tag + "_out"], rtol=0, atol=1e-6)
+
+
+def test_tim_generic_kernel_sizes(be):
+    rng = np.random.default_rng(5)
+    for ks in (1, 9, 11, 13, 21, 31):
+        x = rng.standard_normal((1, 2, 40, 70)).astype(np.float32)
+        k = rng.random((2, ks, ks), dtype=np.float32)
+        assert bits_equal(npy(be.dwconv2d(cu(x), cu(k))), oracle.dwconv2d(x, k.reshape(2, 1, ks, ks))), ks
+        kc, kr = rng.random((2, ks), dtype=np.float32), rng.random((2, ks), dtype=np.float32)
+        assert bits_equal(npy(be.dwconv2d_sep(cu(x), cu(kc), cu(kr))), oracle.dwconv2d_sep(x, kc, kr)), ks
+
+
+# ---------------------------------------------------------------------------------------------- reductions + fused
+@pytest.mark.parametrize("B,shape", [(5, (3, 224, 224)), (3, (3, 20, 20)), (2, (37,)), (2, (3, 299, 299)), (1, (3, 512, 512)), (4, (8,))])
+def test_abs_mean_exact(be, B, shape):
+    rng = np.random.default_rng(B)
+    g = (rng.standard_normal((B,) + shape) * 1e-3).astype(np.float32)
+    got = npy(be.abs_mean(cu(g)))
+    ref = oracle.abs_mean_per_sample(g)
+    assert ulp_diff(got, ref).max() <= 1, (got, ref)
+
+
+FUSED_SHAPES = [(5, (3, 224, 224)), (3, (3, 20, 20)), (2, (3, 299, 299)), (2, (37,)), (9, (3, 64, 64)), (1, (3, 512, 512))]
+FUSED_TUNES = [dict(), {"fused.variant": 1}, {"fused.threads": 256, "fused.unroll": 4}, {"fused.threads": 1024, "fused.unroll": 1},
+               {"fused.cluster": 4}, {"fused.cluster": 16, "fused.threads": 256, "fused.unroll": 2},
+               {"fused.cluster": 1, "fused.variant": 1}, {"fused.variant": 1, "fused.threads": 256, "fused.unroll": 2}]
+
+
+@pytest.mark.parametrize("tune", FUSED_TUNES, ids=lambda t: ",".join("%s=%s" % kv for kv in t.items()) or "default")
+def test_fused_update_exact_mean(be, tune):
+    from transferattack_b200 import _lib
+    keys = ["fused.variant", "fused.threads", "fused.unroll", "fused.cluster"]
+    defaults = {"fused.variant": 0, "fused.threads": 512, "fused.unroll": 2, "fused.cluster": 0}
+    for k in keys:
+        _lib.tune_set(k, tune.get(k, defaults[k]))
+    try:
+        for B, shape in FUSED_SHAPES:
+            rng = np.random.default_rng(B * 7 + len(shape))
+            full = (B,) + shape
+            g = (rng.standard_normal(full) * 1e-3).astype(np.float32)
+            g.reshape(-1)[:7] = 0.0
+            m = rng.standard_normal(full).astype(np.float32)
+            x = rng.random(full, dtype=np.float32)
+            d = ((rng.random(full, dtype=np.float32) * 2 - 1) * EPS).astype(np.float32)
+            for has_m in (True, False):
+                gm, dd = cu(m), cu(d)
+                m_out, xa = torch.empty_like(gm), torch.empty_like(gm)
+                so = torch.empty(B, device="cuda")
+                # in place on momentum and delta, as the base loop uses it
+                be.fused_update_linf(cu(g), gm if has_m else None, gm if has_m else m_out, dd, dd, cu(x), xa, None, so, 0.9, ALPHA, EPS, 0, 1.0)
+                scale = npy(so)
+                assert ulp_diff(scale, oracle.abs_mean_per_sample(g)).max() <= 1
+                mo, do, xo = oracle.fused_update_linf(g, m if has_m else None, d, x, scale, 0.9, ALPHA, EPS)
+                got_m = npy(gm if has_m else m_out)
+                assert bits_equal(got_m, mo), (B, shape, has_m, n_diff_bits(got_m, mo))
+                assert bits_equal(npy(dd), do), (B, shape, has_m, n_diff_bits(npy(dd), do))
+                assert bits_equal(npy(xa), xo), (B, shape, has_m)
+    finally:
+        for k in keys:
+            _lib.tune_set(k, defaults[k])
+
+
+def test_fused_all_zero_gradient_sample(be):
+    rng = np.random.default_rng(0)
+    full = (3, 3, 32, 32)
+    g = rng.standard_normal(full).astype(np.float32); g[1] = 0
+    m = rng.standard_normal(full).astype(np.float32)
+    x = rng.random(full, dtype=np.float32)
+    d = np.zeros(full, np.float32)
+    gm, dd = cu(m), cu(d)
+    so = torch.empty(3, device="cuda")
+    be.fused_update_linf(cu(g), gm, gm, dd, dd, cu(x), None, None, so, 1.0, ALPHA, EPS, 0, 1.0)
+    assert npy(so)[1] == 0.0 and np.isnan(npy(gm)[1]).all()      # 0/0 → NaN momentum, as in the reference
+    assert np.array_equal(npy(dd)[1], d[1])                      # sign(NaN) = 0 → delta does not move
+    mo, do, _ = oracle.fused_update_linf(g, m, d, x, npy(so), 1.0, ALPHA, EPS)
+    assert bits_equal(npy(gm), mo) and bits_equal(npy(dd), do)
+
+
+# ---------------------------------------------------------------------------------------------- BASELINE-size properties
+def test_full_size_fused_equals_unfused_and_bounds(be):
+    torch.manual_seed(0)
+    B = 64
+    g = torch.randn(B, 3, 224, 224, device="cuda") * 1e-4
+    m = torch.randn_like(g)
+    x = torch.rand_like(g)
+    d = (torch.rand_like(g) * 2 - 1) * EPS
+    m2, d2, x2, so = torch.empty_like(g), torch.empty_like(g), torch.empty_like(g), torch.empty(B, device="cuda")
+    be.fused_update_linf(g, m, m2, d, d2, x, x2, None, so, 1.0, ALPHA, EPS, 0, 1.0)
+    scale = be.abs_mean(g)
+    assert ulp_diff(npy(so), npy(scale)).max() <= 1          # two fp64 reduction trees, same value up to a final-rounding tie
+    scale = so
+    m1 = be.momentum(g, m, scale, 1.0)
+    d1 = be.update_linf(d, x, m1, ALPHA, EPS, 0, 1.0)
+    x1 = be.stage_add(x, d1)
+    assert torch.equal(m1, m2) and torch.equal(d1, d2) and torch.equal(x1, x2)
+    m3, d3, x3 = torch.empty_like(g), torch.empty_like(g), torch.empty_like(g)
+    be.fused_update_linf(g, m, m3, d, d3, x, x3, scale, None, 1.0, ALPHA, EPS, 0, 1.0)   # strict path
+    assert torch.equal(m1, m3) and torch.equal(d1, d3) and torch.equal(x1, x3)
+    assert float(d2.abs().max()) <= np.float32(EPS)
+    assert float(x2.min()) >= 0.0 and float(x2.max()) <= 1.0 + 1e-7
+    # projection is idempotent
+    assert torch.equal(be.clamp_box(d2, x, 0, 1.0), d2)
+    # a sample-wise check of the mean against the oracle (order-independent up to the last bit)
+    ref = oracle.abs_mean_per_sample(npy(g[:4]))
+    assert ulp_diff(npy(so[:4]), ref).max() <= 1
+
+
+def test_full_size_adjoint_identities(be):
+    """<A x, g> == <x, A^T g> for the staging kernels at B=64 (fp64 dot products, relative 1e-5)."""
+    torch.manual_seed(1)
+    B = 64
+    x = torch.rand(B, 3, 224, 224, device="cuda")
+
+    def dot(a, b):
+        return float((a.double() * b.double()).sum())
+
+    y = be.sim(x, 5, True); g = torch.randn_like(y)
+    assert abs(dot(y, g) - dot(x, be.sim(g, 5, False))) <= 1e-5 * abs(dot(y, g)) + 1e-3
+    y = be.dim(x, 235, 246, 5, 7, True); g = torch.randn_like(y)
+    assert abs(dot(y, g) - dot(x, be.dim(g, 235, 246, 5, 7, False))) <= 1e-5 * abs(dot(y, g)) + 1e-2
+    coef = [float(np.float32(c * ALPHA)) for c in np.linspace(-7, 7, 11)]
+    xs = x[:16]
+    y = be.lin_sample(xs, None, coef, True); g = torch.randn_like(y)
+    assert abs(dot(y, g) - dot(xs, be.lin_sample(g, None, coef, False))) <= 1e-5 * abs(dot(y, g)) + 1e-3
+
+
+def test_full_size_tim_properties(be):
+    import transferattack_b200.input_transformation.tim as tim
+    k2d, kcol, krow = tim.make_kernel("gaussian", 15)
+    kc3, kr3 = cu(np.stack([kcol] * 3)), cu(np.stack([krow] * 3))
+    g = torch.randn(64, 3, 224, 224, device="cuda")
+    a = be.dwconv2d_sep(g, kc3, kr3)
+    b = be.dwconv2d(g, cu(k2d.reshape(3, 15, 15)))
+    assert float((a - b).abs().max()) <= 2e-6            # separable vs direct: fp32 re-association only
+    ones = torch.ones(2, 3, 224, 224, device="cuda")
+    o = be.dwconv2d_sep(ones, kc3, kr3)
+    assert float((o[:, :, 7:-7, 7:-7] - 1).abs().max()) <= 1e-6      # weights sum to 1 away from the zero padding
+    # linearity
+    g2 = torch.randn_like(g)
+    lhs = be.dwconv2d_sep(be.add(g, g2), kc3, kr3)
+    rhs = be.add(a, be.dwconv2d_sep(g2, kc3, kr3))
+    assert float((lhs - rhs).abs().max()) <= 1e-5
+    # one sample against the oracle, bit-exact
+    assert bits_equal(npy(a[:1]), oracle.dwconv2d_sep(npy(g[:1]), npy(kc3), npy(kr3)))

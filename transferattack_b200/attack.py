@@ -107,7 +107,7 @@ class Attack(object):
         if self.targeted:
             assert len(label) == 2
             label = label[1]
-        data = self._to_device(data)
+        data = self._to_device(data).contiguous()
         label = self._to_device(label)
 
         delta = self.init_delta(data)
@@ -137,9 +137,16 @@ class Attack(object):
             loss = self.get_loss(logits, label)
             grad = self.get_grad(loss, delta)
             scale = self._torch_abs_mean(grad) if self.mean_mode == 'torch' else None
+            ev = getattr(self, "_kernel_events", None)      # bench.py: CUDA events around the launch, on its stream
+            if ev is not None:
+                e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+                e0.record()
             with torch.no_grad():
                 be.fused_update_linf(grad, momentum, m_buf, delta, delta, data, xadv, scale, scale_out,
                                      self.decay, self.alpha, self.epsilon, img_min, img_max, _lib.TA_MEAN_EXACT)
+            if ev is not None:
+                e1.record()
+                ev.append((e0, e1))
             momentum, pre = m_buf, xadv
         return delta.detach()
 
