@@ -44,6 +44,7 @@ def parse():
     p.add_argument("--kernels", action="store_true")
     p.add_argument("--sweep", action="store_true")
     p.add_argument("--no-cpu-baseline", action="store_true")
+    p.add_argument("--cpu-worker", default="", help="internal: 'budget_seconds,steps,warmup,max_b' → JSON on stdout")
     p.add_argument("--no-eager-gpu", action="store_true")
     return p.parse_args()
 
@@ -111,6 +112,21 @@ class ClockSampler:
         return out
 
 
+def host_cores():
+    """threads the CPU legs may really use: scheduler affinity, capped by the cgroup CPU quota"""
+    try:
+        n = len(os.sched_getaffinity(0))
+    except Exception:
+        n = os.cpu_count() or 1
+    try:
+        q, per = open("/sys/fs/cgroup/cpu.max").read().split()
+        if q != "max":
+            n = max(1, min(n, int(float(q) / float(per))))
+    except Exception:
+        pass
+    return n
+
+
 def build_attack(pkg, name, net, **kw):
     cls = pkg.load_attack_class(name)
     wrap = pkg.utils.wrap_model
@@ -156,7 +172,7 @@ def cpu_reference_run(args, sample_b, steps, warmup):
     """oracle/torch_ref.py (eager restatement of the reference; the Python reference cannot travel to this box) on the
     host cores, all threads."""
     from oracle import torch_ref
-    torch.set_num_threads(os.cpu_count() or 1)
+    torch.set_num_threads(host_cores())
     net = make_net(args.arch, "cpu")
     atk = torch_ref.REF_ZOO[args.attack](torch_ref.ref_wrap_model(net), epoch=args.epoch)
     x, y = synth(sample_b)
@@ -172,7 +188,7 @@ def cpu_reference_run(args, sample_b, steps, warmup):
 def cpu_probe(args):
     """seconds per image for one full attack on the host, from a short probe (epoch=2 on 2 images)."""
     from oracle import torch_ref
-    torch.set_num_threads(os.cpu_count() or 1)
+    torch.set_num_threads(host_cores())
     net = make_net(args.arch, "cpu")
     atk = torch_ref.REF_ZOO[args.attack](torch_ref.ref_wrap_model(net), epoch=2)
     x, y = synth(4)
@@ -181,14 +197,39 @@ def cpu_probe(args):
     return dt / 4 / 2 * args.epoch
 
 
+def cpu_worker(args):
+    """child process: size a bounded sample from a probe, time it, print JSON"""
+    budget, steps, warmup, max_b = [float(v) for v in args.cpu_worker.split(",")]
+    steps, warmup, max_b = int(steps), int(warmup), int(max_b)
+    per_img = cpu_probe(args)
+    sample_b = int(max(1, min(max_b, budget / max(per_img * (steps + warmup), 1e-9))))
+    val, per_step = cpu_reference_run(args, sample_b, steps, warmup)
+    print(json.dumps({"value": val, "per_step_s": per_step, "sample_b": sample_b, "cores": host_cores(), "probe_s_per_img": per_img}), flush=True)
+
+
+def cpu_leg(args, budget, steps, warmup, max_b, hard_timeout):
+    """run the CPU leg in a child with a hard wall-clock bound (killed by PID on overrun)"""
+    cmd = [sys.executable, os.path.abspath(__file__), "--cpu-worker", "%g,%d,%d,%d" % (budget, steps, warmup, max_b),
+           "--arch", args.arch, "--attack", args.attack, "--epoch", str(args.epoch)]
+    env = dict(os.environ, CUDA_VISIBLE_DEVICES="")
+    try:
+        out = subprocess.run(cmd, capture_output=True, text=True, timeout=hard_timeout, env=env)
+        for ln in reversed(out.stdout.strip().splitlines()):
+            if ln.startswith("{"):
+                return json.loads(ln)
+        return {"error": (out.stderr or "no output")[-300:]}
+    except subprocess.TimeoutExpired:
+        return {"error": "cpu leg exceeded %ds" % hard_timeout}
+
+
 def run_reference_arm(args, rank):
     if rank != 0:
         return
-    per_img = cpu_probe(args)
-    total_steps = args.steps + args.warmup
-    sample_b = int(max(1, min(args.batch, 120.0 / max(per_img * total_steps, 1e-9))))
-    val, per_step = cpu_reference_run(args, sample_b, args.steps, args.warmup)
-    cores = os.cpu_count() or 1
+    r = cpu_leg(args, 120.0, args.steps, args.warmup, args.batch, 420)
+    if "error" in r:   # the oracle always exists; report the failure loudly but keep the line parseable
+        r = {"value": float("nan"), "per_step_s": float("nan"), "sample_b": 0, "cores": host_cores(), "error": r["error"]}
+    val, per_step, sample_b = r["value"], r["per_step_s"], r["sample_b"]
+    cores = r["cores"]
     sample = "%d of %d images per step, %d iterations each" % (sample_b, args.batch, args.epoch)
     line = {
         "impl": "reference", "metric": METRIC, "value": val, "unit": "images/s", "n_gpus": args.gpus, "steps": args.steps,
@@ -318,11 +359,13 @@ def run_ours(args, rank, local_rank, world, dist):
 
     cpu_base = None
     if rank == 0 and world == 1 and not args.no_cpu_baseline:
-        per_img = cpu_probe(args)
-        sample_b = int(max(1, min(16, 20.0 / max(per_img, 1e-9))))
-        v, _ = cpu_reference_run(args, sample_b, 1, 0)
-        cpu_base = {"value": v, "unit": "images/s", "cores": os.cpu_count() or 1, "kind": "port",
-                    "sample": "1 step of %d images (of %d), %d iterations, oracle/torch_ref.py on all host threads" % (sample_b, B, args.epoch)}
+        r = cpu_leg(args, 20.0, 1, 0, 16, 240)
+        if "error" in r:
+            cpu_base = {"value": None, "unit": "images/s", "cores": host_cores(), "kind": "port", "sample": "failed: " + r["error"]}
+        else:
+            cpu_base = {"value": r["value"], "unit": "images/s", "cores": r["cores"], "kind": "port",
+                        "sample": "1 step of %d images (of %d), %d iterations, oracle/torch_ref.py on %d host threads"
+                                  % (r["sample_b"], B, args.epoch, r["cores"])}
 
     if rank == 0:
         line = {
@@ -470,6 +513,9 @@ def main():
     rank = int(os.environ.get("RANK", "0"))
     local_rank = int(os.environ.get("LOCAL_RANK", "0"))
     world = int(os.environ.get("WORLD_SIZE", "1"))
+    if args.cpu_worker:
+        cpu_worker(args)
+        return
     if args.impl == "reference":
         run_reference_arm(args, rank)
         return

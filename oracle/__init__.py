@@ -165,10 +165,12 @@ def admix_bwd(gout, S, A):
     return gin
 
 
-def dim_fwd(x, rnd, R, pad_top, pad_left):
+def dim_fwd(x, rnd, R, pad_top, pad_left, blend=0):
     x = _c(x); S = x.shape[-1]; planes = x.size // (S * S)
     out = np.empty_like(x)
+    lib().orc_set_dim_blend(int(blend))
     rc = lib().orc_dim_fwd(_fp(x), _fp(out), planes, S, rnd, R, pad_top, pad_left)
+    lib().orc_set_dim_blend(0)
     assert rc == 0
     return out
 

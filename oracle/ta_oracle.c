@@ -246,21 +246,31 @@ static void lin_taps(int in, int out, lin_tap* t) {
     t[d].l0 = 1.0f - t[d].l1;
   }
 }
+static int g_blend_mode = 0; /* 0: every op rounded; 1-4: FMA contractions of ATen's expression (see csrc/dim.cu) */
+ORC_API void orc_set_dim_blend(int mode) { g_blend_mode = mode; }
 static void bilinear_plane(const float* in, int ih, int iw, float* out, int oh, int ow, const lin_tap* th,
                            const lin_tap* tw) {
+  (void)ih;
+  const int mode = g_blend_mode;
   for (int y = 0; y < oh; ++y) {
     const float* r0 = in + (int64_t)th[y].i0 * iw;
     const float* r1 = in + (int64_t)th[y].i1 * iw;
     for (int x = 0; x < ow; ++x) {
-      const float a = tw[x].l0 * r0[tw[x].i0];
-      const float b = tw[x].l1 * r0[tw[x].i1];
-      const float top = a + b;
-      const float c = tw[x].l0 * r1[tw[x].i0];
-      const float d = tw[x].l1 * r1[tw[x].i1];
-      const float bot = c + d;
-      const float e = th[y].l0 * top;
-      const float f = th[y].l1 * bot;
-      out[(int64_t)y * ow + x] = e + f;
+      const float w0 = tw[x].l0, w1 = tw[x].l1, h0 = th[y].l0, h1 = th[y].l1;
+      const float p00 = r0[tw[x].i0], p01 = r0[tw[x].i1], p10 = r1[tw[x].i0], p11 = r1[tw[x].i1];
+      float top, bot, val;
+      if (mode == 0) {
+        const float a = w0 * p00, b = w1 * p01, c = w0 * p10, d = w1 * p11;
+        top = a + b; bot = c + d;
+        const float e = h0 * top, f = h1 * bot;
+        val = e + f;
+      } else {
+        if (mode == 1 || mode == 3) { const float b = w1 * p01, d = w1 * p11; top = fmaf(w0, p00, b); bot = fmaf(w0, p10, d); }
+        else { const float a = w0 * p00, c = w0 * p10; top = fmaf(w1, p01, a); bot = fmaf(w1, p11, c); }
+        if (mode == 1 || mode == 4) { const float f = h1 * bot; val = fmaf(h0, top, f); }
+        else { const float e = h0 * top; val = fmaf(h1, bot, e); }
+      }
+      out[(int64_t)y * ow + x] = val;
     }
   }
 }

@@ -100,8 +100,9 @@ class OracleBackend:
 
     def dim(self, x, rnd, R, top, left, forward=True):
         self._log("dim")
-        fn = oracle.dim_fwd if forward else oracle.dim_bwd
-        return _t(fn(_np(x), int(rnd), int(R), int(top), int(left)))
+        if forward:
+            return _t(oracle.dim_fwd(_np(x), int(rnd), int(R), int(top), int(left), blend=1))
+        return _t(oracle.dim_bwd(_np(x), int(rnd), int(R), int(top), int(left)))
 
     def dwconv2d(self, g, k):
         self._log("dwconv2d")

@@ -124,7 +124,9 @@ def test_dim_tim_single_iteration_tolerance(name):
     seed_all(5); d = atk(x, y)
     st = _stats(d, dr, x)
     REPORT["one_iter/" + name] = st
-    assert st["n_gt_1e-5"] <= 5e-3 * st["numel"], st      # only sign flips of near-zero momentum entries
+    # forward is bit-identical to torch's CUDA kernels; only the adjoint's summation order differs (ATen: atomicAdd) →
+    # sign flips of momentum entries that are zero to rounding
+    assert st["n_gt_1e-5"] <= 2e-4 * st["numel"], st
 
 
 @pytest.mark.parametrize("name", ["dim", "tim", "ditimi"])

@@ -166,12 +166,33 @@ def test_dim_forward(be, tma):
         D, cases = _dim_cases()
         for c in cases:
             rnd, R, top, left, _ = [int(v) for v in D[c + "_params"]]
-            out = npy(be.dim(cu(D[c + "_x"]), rnd, R, top, left, True))
-            ref = oracle.dim_fwd(D[c + "_x"], rnd, R, top, left)
-            assert bits_equal(out, ref), (c, n_diff_bits(out, ref), np.abs(out - ref).max())       # same op order as the oracle
-            np.testing.assert_allclose(out, D[c + "_y"], rtol=0, atol=3e-7, err_msg=c)            # ATen: FMA-contraction level
+            for blend in (0, 1):
+                _lib.tune_set("dim.blend", blend)
+                out = npy(be.dim(cu(D[c + "_x"]), rnd, R, top, left, True))
+                ref = oracle.dim_fwd(D[c + "_x"], rnd, R, top, left, blend=blend)
+                assert bits_equal(out, ref), (c, blend, n_diff_bits(out, ref), np.abs(out - ref).max())   # same op order as the oracle
+                np.testing.assert_allclose(out, D[c + "_y"], rtol=0, atol=3e-7, err_msg=c)               # ATen CPU golden: contraction level
     finally:
         _lib.tune_set("dim.tma", 1)
+        _lib.tune_set("dim.blend", 1)
+
+
+def test_dim_forward_bit_identical_to_torch_cuda(be):
+    """The reference runs F.interpolate / F.pad / F.interpolate on the GPU; with the default blend (the FMA contraction of
+    torch's own CUDA kernel) ta_dim_fwd reproduces that chain bit for bit. The adjoint is compared with autograd's
+    (atomicAdd scatter) result at rounding level."""
+    import torch.nn.functional as F
+    torch.manual_seed(0)
+    for S, rnd, R, top, left in [(224, 235, 246, 5, 6), (224, 224, 246, 0, 21), (224, 245, 246, 1, 0), (64, 67, 70, 1, 2), (299, 310, 328, 7, 9), (30, 31, 33, 1, 1)]:
+        x = torch.rand(3, 3, S, S, device="cuda", requires_grad=True)
+        y = F.interpolate(F.pad(F.interpolate(x, size=[rnd, rnd], mode="bilinear", align_corners=False),
+                                [left, R - rnd - left, top, R - rnd - top], value=0), size=[S, S], mode="bilinear", align_corners=False)
+        out = be.dim(x, rnd, R, top, left, True)
+        assert torch.equal(out, y.detach()), (S, rnd, int((out != y).sum()))
+        g = torch.randn_like(y)
+        (gin_ref,) = torch.autograd.grad(y, x, g)
+        gin = be.dim(g, rnd, R, top, left, False)
+        assert float((gin - gin_ref).abs().max()) <= 2e-6 * max(1.0, float(gin_ref.abs().max()))
 
 
 def test_dim_backward(be):
@@ -191,7 +212,7 @@ def test_dim_edge_geometries(be):
         g = rng.standard_normal((2, 3, S, S)).astype(np.float32)
         for rnd, top, left in [(S, 0, 0), (R - 1, 0, 0), (R - 1, 1, 1), (S, R - S, R - S), ((S + R) // 2, 1, (R - (S + R) // 2))]:
             out = npy(be.dim(cu(x), rnd, R, top, left, True))
-            ref = oracle.dim_fwd(x, rnd, R, top, left)
+            ref = oracle.dim_fwd(x, rnd, R, top, left, blend=1)
             assert bits_equal(out, ref), (S, rnd, top, left, n_diff_bits(out, ref))
             gin = npy(be.dim(cu(g), rnd, R, top, left, False))
             np.testing.assert_allclose(gin, oracle.dim_bwd(g, rnd, R, top, left), rtol=0, atol=3e-6)

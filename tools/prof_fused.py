@@ -1,0 +1,29 @@
+"""Launch the dominant kernels a few times at BASELINE size (B=64) for an `ncu --set full` capture."""
+import os, sys
+import torch
+sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
+from transferattack_b200 import ops
+
+which = sys.argv[1] if len(sys.argv) > 1 else "fused"
+be = ops.backend()
+B = 64
+g = torch.randn(B, 3, 224, 224, device="cuda") * 1e-4
+m = torch.randn_like(g); x = torch.rand_like(g); d = (torch.rand_like(g) * 2 - 1) * (16 / 255)
+m2, d2, xa = torch.empty_like(g), torch.empty_like(g), torch.empty_like(g)
+so = torch.empty(B, device="cuda")
+scale = be.abs_mean(g)
+flush = torch.empty(256 * 1024 * 1024 // 4, device="cuda")
+for it in range(6):
+    flush.zero_()
+    if which == "fused":
+        be.fused_update_linf(g, m, m2, d, d2, x, xa, None, so, 1.0, 1.6 / 255, 16 / 255, 0, 1.0)
+        flush.zero_()
+        be.fused_update_linf(g, m, m2, d, d2, x, xa, scale, None, 1.0, 1.6 / 255, 16 / 255, 0, 1.0)
+    elif which == "dim":
+        be.dim(x, 235, 246, 5, 6, True); be.dim(g, 235, 246, 5, 6, False)
+    elif which == "tim":
+        import numpy as np
+        import transferattack_b200.input_transformation.tim as tim
+        k2d, kcol, krow = tim.make_kernel("gaussian", 15)
+        be.dwconv2d_sep(g, torch.from_numpy(np.stack([kcol] * 3)).cuda(), torch.from_numpy(np.stack([krow] * 3)).cuda())
+torch.cuda.synchronize()

@@ -6,6 +6,8 @@ for the attacks on the accelerated path; every other reference plugin runs uncha
 """
 import importlib
 
+from . import utils, attack   # noqa: F401  (reference-style `pkg.utils.wrap_model` / `pkg.attack.Attack` access)
+
 attack_zoo = {
     # gradient
     'fgsm': ('.gradient.fgsm', 'FGSM'),

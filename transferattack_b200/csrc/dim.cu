@@ -35,13 +35,31 @@ __device__ __forceinline__ Tap make_tap(int in, float scale, int d) {
   return t;
 }
 
-__device__ __forceinline__ float blend(float hl0, float hl1, float wl0, float wl1, float p00, float p01, float p10, float p11) {
-  const float top = add_rn(mul_rn(wl0, p00), mul_rn(wl1, p01));
-  const float bot = add_rn(mul_rn(wl0, p10), mul_rn(wl1, p11));
-  return add_rn(mul_rn(hl0, top), mul_rn(hl1, bot));
+// ATen's expression is  hl0*(wl0*p00 + wl1*p01) + hl1*(wl0*p10 + wl1*p11).
+// mode 1 (default): top = fma(wl0,p00, wl1*p01), bot likewise, val = fma(hl0,top, hl1*bot) — the contraction nvcc applied
+//   to torch's own CUDA kernel; MEASURED on B200 (tools/diag_dim_aten.py, profiles/diag_dim_r1.json): 0 differing bits
+//   against F.interpolate -> F.pad -> F.interpolate for every geometry tried, so DIM's forward is bit-identical to the
+//   reference's GPU path. mode 0: every product and sum rounded separately (closest to ATen's CPU kernel, used with the
+//   CPU goldens). modes 2-4: the other contraction orders (kept for the diagnostic).
+__device__ __forceinline__ float blend(int mode, float hl0, float hl1, float wl0, float wl1, float p00, float p01, float p10, float p11) {
+  float top, bot;
+  if (mode == 0) {
+    top = add_rn(mul_rn(wl0, p00), mul_rn(wl1, p01));
+    bot = add_rn(mul_rn(wl0, p10), mul_rn(wl1, p11));
+    return add_rn(mul_rn(hl0, top), mul_rn(hl1, bot));
+  }
+  if (mode == 1 || mode == 3) {
+    top = fmaf(wl0, p00, mul_rn(wl1, p01));
+    bot = fmaf(wl0, p10, mul_rn(wl1, p11));
+  } else {
+    top = fmaf(wl1, p01, mul_rn(wl0, p00));
+    bot = fmaf(wl1, p11, mul_rn(wl0, p10));
+  }
+  if (mode == 1 || mode == 4) return fmaf(hl0, top, mul_rn(hl1, bot));
+  return fmaf(hl1, bot, mul_rn(hl0, top));
 }
 
-struct DimGeom { int S, rnd, R, top, left; int y1_rows_max, src_rows_max; };
+struct DimGeom { int S, rnd, R, top, left; int y1_rows_max, src_rows_max; int blend; };
 
 // shared-memory carve-up (dynamic): [taps2: S][taps1: rnd][y1 band: y1_rows_max*rnd floats][src band: src_rows_max*S floats]
 template <bool TMA_STAGE>
@@ -100,7 +118,7 @@ __global__ void __launch_bounds__(kThreads) dim_fwd_kernel(const float* __restri
         const float* r1 = xp + (int64_t)th.i1 * S;
         p00 = __ldg(r0 + tw.i0); p01 = __ldg(r0 + tw.i1); p10 = __ldg(r1 + tw.i0); p11 = __ldg(r1 + tw.i1);
       }
-      s_y1[e] = blend(th.l0, th.l1, tw.l0, tw.l1, p00, p01, p10, p11);
+      s_y1[e] = blend(gm.blend, th.l0, th.l1, tw.l0, tw.l1, p00, p01, p10, p11);
     }
   }
   __syncthreads();
@@ -117,7 +135,7 @@ __global__ void __launch_bounds__(kThreads) dim_fwd_kernel(const float* __restri
     const float v01 = (ya_in && xb_in) ? s_y1[(ya - q0) * rnd + xb] : 0.0f;
     const float v10 = (yb_in && xa_in) ? s_y1[(yb - q0) * rnd + xa] : 0.0f;
     const float v11 = (yb_in && xb_in) ? s_y1[(yb - q0) * rnd + xb] : 0.0f;
-    op[(int64_t)oy * S + ox] = blend(th.l0, th.l1, tw.l0, tw.l1, v00, v01, v10, v11);
+    op[(int64_t)oy * S + ox] = blend(gm.blend, th.l0, th.l1, tw.l0, tw.l1, v00, v01, v10, v11);
   }
 }
 
@@ -228,7 +246,7 @@ int ta_dim_fwd(const float* x, float* out, int planes, int S, int rnd, int R, in
   TA_REQUIRE(x && out, "ta_dim_fwd: null pointer");
   int rc = check_geom("ta_dim_fwd", planes, S, rnd, R, pad_top, pad_left);
   if (rc != TA_OK) return rc;
-  DimGeom gm{S, rnd, R, pad_top, pad_left, 0, 0};
+  DimGeom gm{S, rnd, R, pad_top, pad_left, 0, 0, tune_get("dim.blend", 1)};
   gm.y1_rows_max = band_rows(RB, R, S);
   if (gm.y1_rows_max > rnd) gm.y1_rows_max = rnd;
   gm.src_rows_max = band_rows(gm.y1_rows_max, S, rnd);
@@ -252,7 +270,7 @@ int ta_dim_bwd(const float* gout, float* gin, int planes, int S, int rnd, int R,
   TA_REQUIRE(gout && gin, "ta_dim_bwd: null pointer");
   int rc = check_geom("ta_dim_bwd", planes, S, rnd, R, pad_top, pad_left);
   if (rc != TA_OK) return rc;
-  DimGeom gm{S, rnd, R, pad_top, pad_left, 0, 0};
+  DimGeom gm{S, rnd, R, pad_top, pad_left, 0, 0, 0};
   // y1 rows reading RB consecutive source rows of the S -> rnd resize
   gm.y1_rows_max = (int)((double)(RB + 1) * (double)rnd / (double)S) + 3;
   if (gm.y1_rows_max > rnd) gm.y1_rows_max = rnd;

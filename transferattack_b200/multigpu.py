@@ -1,0 +1,149 @@
+"""Multi-GPU execution of the hot path: one process per GPU (``torch.distributed``, NCCL over NVLink on the box, gloo in
+the CPU tests). The reference is single-GPU (``main.py:31`` pins one device; ``EnsembleModel`` runs its members one
+after another on it, utils.py:94-97), so everything here is new functionality behind the same plugin API.
+
+1. Batch sharding — ``shard`` / ``run_sharded``.  Samples are independent on this path (eval-mode BN, per-sample
+   L1-normalisation / epsilon-ball / box clamp), so each rank attacks a contiguous slice of the batch and there is NO
+   collective on the data path. Two details keep a sharded run equal to the unsharded one shard by shard:
+   * ``CrossEntropyLoss`` is a batch MEAN (attack.py:160): a shard's gradient is the full-batch gradient times
+     B/B_shard, a factor that cancels exactly in ``g / mean|g|`` when it is a power of two and at rounding level otherwise;
+   * DIM draws ONE (coin, size, pad) per call from the CPU generator (dim.py:47-62): ``sync_host_rng`` seeds every
+     rank's generators identically so all shards see the transform an unsharded run would.
+   Admix mixes images ACROSS the batch (admix.py:44) and therefore runs as replicas, not shards (``run_sharded`` refuses).
+
+2. One surrogate per GPU — ``ShardedEnsembleModel``.  ENS's loss is CE(mean_k logits_k) (utils.py:98-100, attack.py:115).
+   With member k on rank k and every rank holding the same (data, delta):
+       forward : all_reduce(SUM) of the local logits [B, classes], divided by K
+       backward: d mean / d logits_k = gout / K locally, then all_reduce(SUM) of the input gradient [B,3,H,W]
+   after which every rank runs the same fused update on the same numbers (replicated, deterministic). A gradient-only
+   all-reduce would optimise mean_k CE(logits_k) — a different loss — hence the two collectives.
+   With K = 2 the result is bit-identical to the single-device ``EnsembleModel`` (two-term sums commute); for K > 2 the
+   collective's summation order differs from ``torch.mean(stack)``'s at rounding level.
+"""
+import numpy as np
+import torch
+import torch.distributed as dist
+import torch.nn as nn
+
+
+def _world(group=None):
+    if not (dist.is_available() and dist.is_initialized()):
+        return 0, 1
+    return dist.get_rank(group), dist.get_world_size(group)
+
+
+def sync_host_rng(seed, group=None):
+    """Give every rank the same torch-CPU / numpy / python generator state (rank 0's `seed` wins)."""
+    import random
+    rank, world = _world(group)
+    if world > 1:
+        box = [int(seed)]
+        dist.broadcast_object_list(box, src=0, group=group)
+        seed = box[0]
+    cpu_state = torch.random.default_generator.manual_seed(int(seed))   # CPU generator only: device generators stay per rank
+    np.random.seed(int(seed) % (2 ** 32))
+    random.seed(int(seed))
+    return cpu_state
+
+
+def shard_bounds(n, rank, world):
+    """Contiguous slice [lo, hi) of n samples for `rank`; the first n % world ranks get one extra sample."""
+    base, extra = divmod(n, world)
+    lo = rank * base + min(rank, extra)
+    return lo, lo + base + (1 if rank < extra else 0)
+
+
+def shard(data, label, group=None):
+    """This rank's slice of (data, label); label may be [N] or the targeted [2, N] layout (attack.py:76-78)."""
+    rank, world = _world(group)
+    lo, hi = shard_bounds(data.shape[0], rank, world)
+    lab = label[:, lo:hi] if (label.dim() == 2 and label.shape[0] == 2 and label.shape[1] == data.shape[0]) else label[lo:hi]
+    return data[lo:hi], lab
+
+
+def run_sharded(attacker, data, label, seed=None, gather=False, group=None, **kwargs):
+    """Attack `data` with the batch sharded over the ranks of `group`. Returns this rank's perturbation slice, or with
+    ``gather=True`` the full perturbation on every rank (an all_gather AFTER the attack; not on the data path)."""
+    from .input_transformation.admix import Admix
+    rank, world = _world(group)
+    if isinstance(attacker, Admix) and world > 1:
+        raise RuntimeError("Admix mixes images across the batch (admix.py:44): run it as replicas, not batch shards")
+    if seed is not None:
+        sync_host_rng(seed, group)
+    d_local, l_local = shard(data, label, group)
+    if d_local.shape[0] == 0:
+        delta = torch.empty((0,) + tuple(data.shape[1:]), dtype=torch.float32, device=attacker.device)
+    else:
+        delta = attacker(d_local, l_local, **kwargs)
+    if not gather or world == 1:
+        return delta
+    sizes = [hi - lo for lo, hi in (shard_bounds(data.shape[0], r, world) for r in range(world))]
+    widest = max(sizes)                         # all_gather wants equal shapes: pad the short shards, trim after
+    padded = torch.zeros((widest,) + tuple(data.shape[1:]), dtype=delta.dtype, device=delta.device)
+    padded[:delta.shape[0]] = delta
+    parts = [torch.empty_like(padded) for _ in range(world)]
+    dist.all_gather(parts, padded, group=group)
+    return torch.cat([p[:n] for p, n in zip(parts, sizes)], dim=0)
+
+
+class _SumGradAcrossRanks(torch.autograd.Function):
+    """identity forward; backward all_reduce(SUM)s the gradient wrt the (replicated) model input"""
+
+    @staticmethod
+    def forward(ctx, x, group):
+        ctx.group = group
+        return x.view_as(x)
+
+    @staticmethod
+    def backward(ctx, gout):
+        g = gout.contiguous()
+        if g.data_ptr() == gout.data_ptr():
+            g = g.clone()                      # never reduce in place into autograd's buffer
+        dist.all_reduce(g, op=dist.ReduceOp.SUM, group=ctx.group)
+        return g, None
+
+
+class _MeanLogitsAcrossRanks(torch.autograd.Function):
+    """forward: (sum_k logits_k) / K via all_reduce(SUM); backward: gout / K (the local member's share of the mean)"""
+
+    @staticmethod
+    def forward(ctx, logits, group, K):
+        ctx.K = K
+        out = logits.detach().clone()
+        dist.all_reduce(out, op=dist.ReduceOp.SUM, group=group)
+        return out / K
+
+    @staticmethod
+    def backward(ctx, gout):
+        return gout / ctx.K, None, None
+
+
+class ShardedEnsembleModel(nn.Module):
+    """Ensemble with ONE member per rank: the drop-in for ``EnsembleModel`` (utils.py:82-105, mode 'mean') when the
+    attack runs as one process per GPU. ``member`` is this rank's wrapped surrogate; all ranks must feed the same input."""
+
+    def __init__(self, member, group=None):
+        super().__init__()
+        self.member = member
+        self.group = group
+        self.device = next(member.parameters()).device
+        self.models = [member]                 # this rank's view (attacks that index all members need EnsembleModel)
+        self.num_models = _world(group)[1]
+        self.mode = 'mean'
+        self.type_name = 'ensemble'
+        self.softmax = torch.nn.Softmax(dim=1)
+
+    def forward(self, x):
+        if self.num_models == 1:
+            return self.member(x)
+        x = _SumGradAcrossRanks.apply(x, self.group)
+        return _MeanLogitsAcrossRanks.apply(self.member(x), self.group, self.num_models)
+
+
+def make_ens_attack(attack_cls, member, group=None, **kwargs):
+    """Instantiate an ENS-style attack class whose surrogate is the per-rank sharded ensemble (``load_model`` is the
+    reference's documented override point, attack.py:40-65). The base ``Attack`` treats ``ShardedEnsembleModel`` like any
+    module; ``device`` is taken from the member."""
+    model = ShardedEnsembleModel(member, group)
+    P = type("Sharded" + attack_cls.__name__, (attack_cls,), {"load_model": lambda self, _n: model})
+    return P(model_name="sharded-ensemble", device=model.device, **kwargs)
