@@ -184,6 +184,32 @@ int launch_ew(const char* name, int64_t N, bool can_vec4, F f, cudaStream_t s) {
   return check_launch(name);
 }
 
+// ---- per-row variant: blockIdx.y = row (a sample, or a (sample, channel) plane); the functor gets (row, i) with i the
+// V-wide vector index inside the row, so per-row constants (scale[b], mean[c]) cost no 64-bit division per vector -----
+// F provides:  template <int V> __device__ void run(int row, int64_t i) const;
+template <int V, class F>
+__global__ void __launch_bounds__(256) ew_rows_kernel(int64_t nvec_per_row, F f) {
+  const int row = blockIdx.y;
+  const int64_t stride = (int64_t)gridDim.x * blockDim.x;
+  for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < nvec_per_row; i += stride) f.template run<V>(row, i);
+}
+
+template <class F>
+int launch_ew_rows(const char* name, int rows, int64_t n_per_row, bool can_vec4, F f, cudaStream_t s) {
+  if (rows <= 0 || n_per_row <= 0) return TA_OK;
+  if (rows > 65535) { set_error("%s: %d rows exceed the grid limit 65535", name, rows); return TA_EINVAL; }
+  const int threads = 256;
+  const int64_t nvec = can_vec4 ? n_per_row / 4 : n_per_row;
+  const int64_t want = (nvec + threads - 1) / threads;
+  int64_t per_row = ((int64_t)sm_count() * 8 + rows - 1) / rows;      // ~8 resident CTAs per SM over all rows
+  if (per_row < 1) per_row = 1;
+  const dim3 grid((unsigned)(want < per_row ? want : per_row), (unsigned)rows);
+  if (can_vec4) ew_rows_kernel<4, F><<<grid, threads, 0, s>>>(nvec, f);
+  else ew_rows_kernel<1, F><<<grid, threads, 0, s>>>(nvec, f);
+  count_launch();
+  return check_launch(name);
+}
+
 // ---- cluster-wide sum + cluster launch --------------------------------------------------------------------------
 // Sum over the cluster of a per-thread double; every thread of every CTA receives the same total (combined in
 // rank order → deterministic). s_scratch: >= 32 doubles, s_part: 1 double (both CTA-local shared memory).

@@ -9,7 +9,7 @@
 // i0 = (int)src; i1 = i0 + (i0 < in-1); l1 = src - i0; l0 = 1 - l1;
 // val = hl0*(wl0*p00 + wl1*p01) + hl1*(wl0*p10 + wl1*p11), every product/sum rounded once (no FMA).
 //
-// Each CTA owns a band of RB output rows of one plane. The source rows that band depends on are contiguous in
+// Each CTA owns a band of RB (= 16) output rows of one plane. The source rows that band depends on are contiguous in
 // memory, so they are staged into shared memory with one bulk-TMA copy (cp.async.bulk + mbarrier); the y1 band is
 // formed once in shared memory (not 4x per output) and the outputs gather from it. HBM traffic: 4 B/elem in (+ halo
 // rows) and 4 B/elem out.
@@ -19,7 +19,7 @@ using namespace ta;
 
 namespace {
 
-constexpr int RB = 8;          // output rows per CTA
+constexpr int RB = 16;         // output rows per CTA
 constexpr int kThreads = 256;
 
 struct Tap { int i0, i1; float l0, l1; };

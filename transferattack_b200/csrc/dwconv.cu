@@ -113,6 +113,114 @@ __global__ void __launch_bounds__(kThreads) dwconv_sep_kernel(const float* __res
   }
 }
 
+
+// ---- band variant of the separable convolution (the TIM hot case: W % 4 == 0, W <= 512) ---------------------------------
+// One CTA = BH output rows x the full width of one plane. The (BH + ks - 1) input rows it needs are whole image rows, i.e.
+// contiguous in memory: each valid row is brought into shared memory by one bulk-TMA copy (cp.async.bulk, all rows on one
+// mbarrier) into a row-padded layout whose left/right margins and out-of-image rows are zero (that IS the 'same' zero
+// padding). Row pass: 4 outputs per item from 128-bit conflict-free LDS; column pass: 4 rows per item, stride-1 LDS.
+// Same FMA order as orc_dwconv2d_sep (taps ascending from 0) → bit-identical to the tile kernel and the oracle.
+constexpr int BH = 32, kBandThreads = 512;
+
+template <int KS>
+__global__ void __launch_bounds__(kBandThreads) dwconv_sep_band_kernel(const float* __restrict__ g, const float* __restrict__ kcol,
+                                                                       const float* __restrict__ krow, float* __restrict__ out,
+                                                                       int C, int H, int W) {
+  extern __shared__ __align__(128) unsigned char smem_raw[];
+  __shared__ __align__(8) uint64_t s_bar;
+  constexpr int R = KS / 2;
+  constexpr int PADX = (R + 3) & ~3;               // left/right zero margin, multiple of 4 floats (16-B aligned rows)
+  constexpr int NV = (KS + 3 + (PADX - R) + 3) / 4;       // aligned float4 loads covering the 4-output window
+  const int WP = W + 2 * PADX;
+  const int rows = BH + KS - 1;
+  float* s_in = reinterpret_cast<float*>(smem_raw);            // [rows][WP]
+  float* s_tmp = s_in + rows * WP;                               // [rows][W]
+  const int tid = threadIdx.x;
+  const int plane = blockIdx.y, c = plane % C;
+  const int y0 = blockIdx.x * BH;
+  const float* gp = g + (int64_t)plane * H * W;
+  float* op = out + (int64_t)plane * H * W;
+
+  float wr[KS], wc[KS];
+#pragma unroll
+  for (int j = 0; j < KS; ++j) { wr[j] = __ldg(krow + c * KS + j); wc[j] = __ldg(kcol + c * KS + j); }
+
+  // valid input rows of this band: image rows [ya, yb)
+  const int ya = max(y0 - R, 0), yb = min(y0 + BH + R, H);
+  if (tid == 0) { mbar_init(&s_bar, 1); mbar_fence_init(); }
+  // zero the margins of every row and the rows that fall outside the image (disjoint from the TMA destinations)
+  for (int e = tid; e < rows * 2 * PADX; e += kBandThreads) {
+    const int r = e / (2 * PADX), q = e % (2 * PADX);
+    s_in[r * WP + (q < PADX ? q : W + q)] = 0.0f;
+  }
+  for (int r = 0; r < rows; ++r) {
+    const int yy = y0 - R + r;
+    if (yy < 0 || yy >= H)
+      for (int x = tid; x < W; x += kBandThreads) s_in[r * WP + PADX + x] = 0.0f;
+  }
+  __syncthreads();
+  if (tid == 0) {
+    mbar_expect_tx(&s_bar, (uint32_t)((yb - ya) * W * 4));
+    for (int yy = ya; yy < yb; ++yy) tma_bulk_g2s(s_in + (yy - (y0 - R)) * WP + PADX, gp + (int64_t)yy * W, (uint32_t)(W * 4), &s_bar);
+  }
+  mbar_wait(&s_bar, 0);
+
+  // row pass: tmp[r][x] = sum_j krow[j] * in[r][x + j - R]
+  const int groups = W >> 2;
+  for (int e = tid; e < rows * groups; e += kBandThreads) {
+    const int r = e / groups, xg = e % groups;
+    // outputs x = 4xg..4xg+3 read padded columns 4xg + (PADX - R) + [0, KS + 3)
+    const float4* row4 = reinterpret_cast<const float4*>(s_in + r * WP + 4 * xg);
+    float v[4 * NV];
+#pragma unroll
+    for (int t = 0; t < NV; ++t) {
+      const float4 q = row4[t];
+      v[4 * t] = q.x; v[4 * t + 1] = q.y; v[4 * t + 2] = q.z; v[4 * t + 3] = q.w;
+    }
+    float a0 = 0.f, a1 = 0.f, a2 = 0.f, a3 = 0.f;
+#pragma unroll
+    for (int j = 0; j < KS; ++j) {
+      const int b = (PADX - R) + j;
+      a0 = fmaf(wr[j], v[b], a0); a1 = fmaf(wr[j], v[b + 1], a1); a2 = fmaf(wr[j], v[b + 2], a2); a3 = fmaf(wr[j], v[b + 3], a3);
+    }
+    *reinterpret_cast<float4*>(s_tmp + r * W + 4 * xg) = make_float4(a0, a1, a2, a3);
+  }
+  __syncthreads();
+
+  // column pass: out[y][x] = sum_i kcol[i] * tmp[y + i][x]; item = (4 rows, 1 column)
+  for (int e = tid; e < (BH / 4) * W; e += kBandThreads) {
+    const int yg = e / W, x = e % W;
+    float v[KS + 3];
+#pragma unroll
+    for (int t = 0; t < KS + 3; ++t) v[t] = s_tmp[(4 * yg + t) * W + x];
+    float a[4] = {0.f, 0.f, 0.f, 0.f};
+#pragma unroll
+    for (int i = 0; i < KS; ++i) {
+      a[0] = fmaf(wc[i], v[i], a[0]); a[1] = fmaf(wc[i], v[i + 1], a[1]); a[2] = fmaf(wc[i], v[i + 2], a[2]); a[3] = fmaf(wc[i], v[i + 3], a[3]);
+    }
+#pragma unroll
+    for (int o = 0; o < 4; ++o) {
+      const int yy = y0 + 4 * yg + o;
+      if (yy < H) op[(int64_t)yy * W + x] = a[o];
+    }
+  }
+}
+
+template <int KS>
+int launch_band(const float* g, const float* kcol, const float* krow, float* out, int B, int C, int H, int W, cudaStream_t s) {
+  constexpr int R = KS / 2, PADX = (R + 3) & ~3;
+  const size_t smem = sizeof(float) * ((size_t)(BH + KS - 1) * (W + 2 * PADX) + (size_t)(BH + KS - 1) * W);
+  auto k = dwconv_sep_band_kernel<KS>;
+  if (smem > 48 * 1024) {
+    const cudaError_t e = cudaFuncSetAttribute(k, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+    if (e != cudaSuccess) { set_error("ta_dwconv2d_sep: smem attribute: %s", cudaGetErrorString(e)); cudaGetLastError(); return TA_ECUDA; }
+  }
+  dim3 grid((unsigned)((H + BH - 1) / BH), (unsigned)(B * C));
+  k<<<grid, kBandThreads, smem, s>>>(g, kcol, krow, out, C, H, W);
+  count_launch();
+  return check_launch("ta_dwconv2d_sep[band]");
+}
+
 template <int KS>
 __global__ void __launch_bounds__(kThreads) dwconv2d_kernel(const float* __restrict__ g, const float* __restrict__ k, int ks_rt,
                                                             float* __restrict__ out, int C, int H, int W) {
@@ -186,6 +294,17 @@ int ta_dwconv2d_sep(const float* g, const float* kcol, const float* krow, int ks
   int rc = check_conv("ta_dwconv2d_sep", g, kcol, out, ks, B, C, H, W);
   if (rc != TA_OK) return rc;
   TA_REQUIRE(krow, "ta_dwconv2d_sep: null krow");
+  // hot case (TIM on 224 / 299-class images): full-width bands staged by bulk-TMA
+  if ((W % 4 == 0) && W >= 32 && W <= 512 && aligned16(g) && tune_get("tim.band", 1) != 0) {
+    cudaStream_t bs = (cudaStream_t)stream;
+    switch (ks) {
+      case 3: return launch_band<3>(g, kcol, krow, out, B, C, H, W, bs);
+      case 5: return launch_band<5>(g, kcol, krow, out, B, C, H, W, bs);
+      case 7: return launch_band<7>(g, kcol, krow, out, B, C, H, W, bs);
+      case 15: return launch_band<15>(g, kcol, krow, out, B, C, H, W, bs);
+      default: break;
+    }
+  }
   const int th = TH + ks - 1, IS = (TW + ks - 1) | 1;
   const size_t smem = sizeof(float) * ((size_t)th * IS + (size_t)th * TW + 2 * kMaxKs);
   dim3 grid((unsigned)((W + TW - 1) / TW), (unsigned)((H + TH - 1) / TH), (unsigned)(B * C));

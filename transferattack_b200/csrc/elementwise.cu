@@ -18,9 +18,10 @@ bool all_aligned(P... p) {
 
 // ---- attack.py:128 ---------------------------------------------------------------------------------------
 struct MomentumOp {
-  const float* g; const float* m; const float* scale; float* out; float decay; int64_t n;
-  template <int V> __device__ void run(int64_t i) const {
-    const float mu = __ldg(scale + (i * V) / n);
+  const float* g; const float* m; const float* scale; float* out; float decay; int64_t nvec;   // nvec: vectors per sample
+  template <int V> __device__ void run(int row, int64_t j) const {
+    const float mu = __ldg(scale + row);
+    const int64_t i = (int64_t)row * nvec + j;
     const Vec<V> gv = ldv<V>(g, i);
     Vec<V> o;
     if (m) {
@@ -89,9 +90,10 @@ struct StageOp {
 
 // ---- utils.py:72-79 Normalize ---------------------------------------------------------------------------------------
 struct NormalizeOp {
-  const float* x; const float* mean; const float* std; float* out; int C; int64_t plane; bool fwd;
-  template <int V> __device__ void run(int64_t i) const {
-    const int c = (int)(((i * V) / plane) % C);
+  const float* x; const float* mean; const float* std; float* out; int C; int64_t nvec; bool fwd;    // nvec: vectors per plane
+  template <int V> __device__ void run(int row, int64_t j) const {     // row = b * C + c
+    const int c = row % C;
+    const int64_t i = (int64_t)row * nvec + j;
     const float sd = __ldg(std + c);
     const Vec<V> xv = ldv_rw<V>(x, i);
     Vec<V> o;
@@ -270,6 +272,32 @@ __global__ void __launch_bounds__(256) quantize_kernel(const float* __restrict__
   }
 }
 
+// vectorised: each thread takes 4 consecutive pixels of one image (float4 per channel) and, for C == 3 NHWC, writes the
+// 12 output bytes as three 32-bit stores. grid = (x, B).
+__global__ void __launch_bounds__(256) quantize_nhwc3_kernel(const float* __restrict__ data, const float* __restrict__ delta,
+                                                             uint8_t* __restrict__ out, int64_t plane4) {
+  const int b = blockIdx.y;
+  const float4* x4 = reinterpret_cast<const float4*>(data) + (int64_t)b * 3 * plane4;
+  const float4* d4 = reinterpret_cast<const float4*>(delta) + (int64_t)b * 3 * plane4;
+  uint32_t* o = reinterpret_cast<uint32_t*>(out) + (int64_t)b * 3 * plane4;      // 12 bytes = 3 words per 4 pixels
+  const int64_t stride = (int64_t)gridDim.x * blockDim.x;
+  for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < plane4; i += stride) {
+    uint32_t q[3][4];
+#pragma unroll
+    for (int c = 0; c < 3; ++c) {
+      const float4 xv = __ldg(x4 + c * plane4 + i), dv = __ldg(d4 + c * plane4 + i);
+      q[c][0] = (uint32_t)(uint8_t)__float2int_rz(mul_rn(add_rn(xv.x, dv.x), 255.0f));
+      q[c][1] = (uint32_t)(uint8_t)__float2int_rz(mul_rn(add_rn(xv.y, dv.y), 255.0f));
+      q[c][2] = (uint32_t)(uint8_t)__float2int_rz(mul_rn(add_rn(xv.z, dv.z), 255.0f));
+      q[c][3] = (uint32_t)(uint8_t)__float2int_rz(mul_rn(add_rn(xv.w, dv.w), 255.0f));
+    }
+    // bytes in memory order: p0c0 p0c1 p0c2 p1c0 | p1c1 p1c2 p2c0 p2c1 | p2c2 p3c0 p3c1 p3c2
+    o[3 * i + 0] = q[0][0] | (q[1][0] << 8) | (q[2][0] << 16) | (q[0][1] << 24);
+    o[3 * i + 1] = q[1][1] | (q[2][1] << 8) | (q[0][2] << 16) | (q[1][2] << 24);
+    o[3 * i + 2] = q[2][2] | (q[0][3] << 8) | (q[1][3] << 16) | (q[2][3] << 24);
+  }
+}
+
 }  // namespace
 
 extern "C" {
@@ -278,7 +306,7 @@ int ta_momentum(const float* g, const float* m, const float* scale, float decay,
                 ta_stream_t stream) {
   TA_REQUIRE(g && scale && m_out && B > 0 && n > 0, "ta_momentum: null pointer or empty shape (B=%d n=%lld)", B, (long long)n);
   const bool v4 = (n % 4 == 0) && all_aligned(g, m, m_out);
-  return launch_ew("ta_momentum", (int64_t)B * n, v4, MomentumOp{g, m, scale, m_out, decay, n}, (cudaStream_t)stream);
+  return launch_ew_rows("ta_momentum", B, n, v4, MomentumOp{g, m, scale, m_out, decay, v4 ? n / 4 : n}, (cudaStream_t)stream);
 }
 
 int ta_update_linf(const float* delta, const float* data, const float* dir, const float* alpha_t, float alpha, float eps,
@@ -314,15 +342,15 @@ int ta_normalize_fwd(const float* x, const float* mean, const float* std, float*
                      ta_stream_t stream) {
   TA_REQUIRE(x && mean && std && out && B > 0 && C > 0 && plane > 0, "ta_normalize_fwd: bad arguments");
   const bool v4 = (plane % 4 == 0) && all_aligned(x, out);
-  return launch_ew("ta_normalize_fwd", (int64_t)B * C * plane, v4, NormalizeOp{x, mean, std, out, C, plane, true},
-                   (cudaStream_t)stream);
+  return launch_ew_rows("ta_normalize_fwd", B * C, plane, v4, NormalizeOp{x, mean, std, out, C, v4 ? plane / 4 : plane, true},
+                        (cudaStream_t)stream);
 }
 
 int ta_normalize_bwd(const float* gout, const float* std, float* gin, int B, int C, int64_t plane, ta_stream_t stream) {
   TA_REQUIRE(gout && std && gin && B > 0 && C > 0 && plane > 0, "ta_normalize_bwd: bad arguments");
   const bool v4 = (plane % 4 == 0) && all_aligned(gout, gin);
-  return launch_ew("ta_normalize_bwd", (int64_t)B * C * plane, v4, NormalizeOp{gout, nullptr, std, gin, C, plane, false},
-                   (cudaStream_t)stream);
+  return launch_ew_rows("ta_normalize_bwd", B * C, plane, v4, NormalizeOp{gout, nullptr, std, gin, C, v4 ? plane / 4 : plane, false},
+                        (cudaStream_t)stream);
 }
 
 int ta_sim_fwd(const float* x, float* out, int S, int64_t N, ta_stream_t stream) {
@@ -388,6 +416,15 @@ int ta_add(const float* a, const float* b, float* out, int64_t N, ta_stream_t st
 int ta_quantize_u8(const float* data, const float* delta, uint8_t* out, int B, int C, int64_t plane, int to_nhwc,
                    ta_stream_t stream) {
   TA_REQUIRE(data && delta && out && B > 0 && C > 0 && plane > 0, "ta_quantize_u8: bad arguments");
+  if (C == 3 && to_nhwc && plane % 4 == 0 && all_aligned(data, delta, out) && B <= 65535) {
+    const int64_t plane4 = plane / 4, want = (plane4 + 255) / 256;
+    int64_t per = ((int64_t)sm_count() * 8 + B - 1) / B;
+    if (per < 1) per = 1;
+    dim3 grid((unsigned)(want < per ? want : per), (unsigned)B);
+    quantize_nhwc3_kernel<<<grid, 256, 0, (cudaStream_t)stream>>>(data, delta, out, plane4);
+    count_launch();
+    return check_launch("ta_quantize_u8");
+  }
   const int64_t total = (int64_t)B * plane;
   const int64_t want = (total + 255) / 256, cap = (int64_t)sm_count() * 8;
   quantize_kernel<<<(unsigned)(want < cap ? want : cap), 256, 0, (cudaStream_t)stream>>>(data, delta, out, B, C, plane, to_nhwc);

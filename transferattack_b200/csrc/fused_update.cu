@@ -44,9 +44,10 @@ __device__ __forceinline__ void fused_elem(float g, float m, bool has_m, float d
 
 // ---- strict / fallback path: scale[b] given, flat streaming ---------------------------------------------------
 struct FusedStreamOp {
-  FusedParams p;
-  template <int V> __device__ void run(int64_t i) const {
-    const float mu = __ldg(p.scale + (i * V) / p.n);
+  FusedParams p; int64_t nvec;     // vectors per sample
+  template <int V> __device__ void run(int row, int64_t j) const {
+    const float mu = __ldg(p.scale + row);
+    const int64_t i = (int64_t)row * nvec + j;
     const Vec<V> gv = ldv<V>(p.g, i), xv = ldv<V>(p.data, i);
     const Vec<V> dv = ldv_rw<V>(p.delta, i);
     Vec<V> mv;
@@ -211,7 +212,7 @@ extern "C" int ta_fused_update_linf(const float* g, const float* m, float* m_out
       const cudaError_t e = cudaMemcpyAsync(scale_out, scale, sizeof(float) * (size_t)B, cudaMemcpyDeviceToDevice, s);
       if (e != cudaSuccess) { set_error("ta_fused_update_linf: scale copy failed: %s", cudaGetErrorString(e)); return TA_ECUDA; }
     }
-    return launch_ew("ta_fused_update_linf[stream]", (int64_t)B * n, v4, FusedStreamOp{p}, s);
+    return launch_ew_rows("ta_fused_update_linf[stream]", B, n, v4, FusedStreamOp{p, v4 ? n / 4 : n}, s);
   }
 
   if (mean_mode != TA_MEAN_EXACT) {
@@ -237,7 +238,7 @@ extern "C" int ta_fused_update_linf(const float* g, const float* m, float* m_out
     const int rc = ta_abs_mean_per_sample(g, scale_out, B, n, TA_MEAN_EXACT, nullptr, stream);
     if (rc != TA_OK) return rc;
     p.scale = scale_out;
-    return launch_ew("ta_fused_update_linf[stream]", (int64_t)B * n, false, FusedStreamOp{p}, s);
+    return launch_ew_rows("ta_fused_update_linf[stream]", B, n, false, FusedStreamOp{p, n}, s);
   }
 
   const bool stage = (variant == 0) && slice_bytes <= kMaxStageBytes;

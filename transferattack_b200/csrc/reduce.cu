@@ -28,6 +28,7 @@ __global__ void __launch_bounds__(kThreads) abs_mean_kernel(const float* __restr
   const float* gp = g + (int64_t)blockIdx.y * n;
   const Slice sl = my_slice(nvec);
   double acc = 0.0;
+#pragma unroll 4
   for (int64_t i = sl.begin + threadIdx.x; i < sl.end; i += kThreads) {
     const Vec<V> v = ldv<V>(gp, i);
 #pragma unroll
