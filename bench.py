@@ -438,6 +438,8 @@ def run_kernels(args):
         rows.append({"kernel": name, "bytes_per_elem": bpe, "elems": elems, "median_us": med * 1e3, "min_us": mn * 1e3,
                      "achieved_GBps": gbs, "frac_of_peak": gbs / hbm_peak})
 
+    add("ATen reference: torch.add(x, d, out=) (same harness)", 12, lambda: torch.add(x, d, out=xa))
+    add("ATen reference: tensor.copy_ (same harness)", 8, lambda: xa.copy_(x))
     add("fused_update_linf[cluster, in-kernel mean]", 28, lambda: be.fused_update_linf(g, m, m2, d, d2, x, xa, None, so, 1.0, a, al, 0, 1.0))
     add("fused_update_linf[stream, scale given]", 28, lambda: be.fused_update_linf(g, m, m2, d, d2, x, xa, scale, None, 1.0, a, al, 0, 1.0))
     add("abs_mean_per_sample", 4, lambda: be.abs_mean(g))

@@ -161,53 +161,82 @@ __device__ __forceinline__ float dsmem_ld_f32(const float* local, uint32_t rank)
   return v;
 }
 
-// ---- generic vectorised grid-stride elementwise launcher -----------------------------------------------------
-// F provides:  template <int V> __device__ void run(int64_t i) const;   (i indexes V-wide vectors)
-template <int V, class F>
+// ---- generic vectorised elementwise launchers ------------------------------------------------------------------------
+// Functors come in two shapes:
+//   (a) two-phase (the hot kernels):  template <int V> __device__ L load(i) const;  template <int V> __device__ void apply(i, const L&) const;
+//       the kernel issues the loads of U vectors per thread before the first use (U x #inputs 128-bit loads in flight per
+//       thread — what a streaming kernel needs on HBM3e), then computes and stores. Outputs may alias inputs (same index).
+//   (b) single-phase:                 template <int V> __device__ void run(i) const;      wrapped by OnePhase<F>, U = 1.
+// The grid covers the whole range in one pass (no cap, like ATen's elementwise launches): one batch of U vectors per thread.
+template <class F> struct OnePhase {
+  F f;
+  template <int V> __device__ __forceinline__ int load(int64_t) const { return 0; }
+  template <int V> __device__ __forceinline__ void apply(int64_t i, int) const { f.template run<V>(i); }
+  template <int V> __device__ __forceinline__ int load(int, int64_t) const { return 0; }
+  template <int V> __device__ __forceinline__ void apply(int row, int64_t i, int) const { f.template run<V>(row, i); }
+};
+
+template <int V, int U, class F>
 __global__ void __launch_bounds__(256) ew_kernel(int64_t nvec, F f) {
   const int64_t stride = (int64_t)gridDim.x * blockDim.x;
-  for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < nvec; i += stride) f.template run<V>(i);
+  for (int64_t i0 = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i0 < nvec; i0 += stride * U) {
+    decltype(f.template load<V>(i0)) ld[U];
+#pragma unroll
+    for (int u = 0; u < U; ++u) { const int64_t i = i0 + u * stride; if (i < nvec) ld[u] = f.template load<V>(i); }
+#pragma unroll
+    for (int u = 0; u < U; ++u) { const int64_t i = i0 + u * stride; if (i < nvec) f.template apply<V>(i, ld[u]); }
+  }
 }
 
-// grid sized as a multiple of the SM count (8 resident 256-thread CTAs per SM = full occupancy)
-template <class F>
-int launch_ew(const char* name, int64_t N, bool can_vec4, F f, cudaStream_t s) {
+template <int U, class F>
+int launch_ew2(const char* name, int64_t N, bool can_vec4, F f, cudaStream_t s) {
   if (N <= 0) return TA_OK;
   const int threads = 256;
   const int64_t nvec = can_vec4 ? N / 4 : N;
-  const int64_t want = (nvec + threads - 1) / threads;
-  const int64_t cap = (int64_t)sm_count() * 8;
-  const unsigned grid = (unsigned)(want < cap ? want : cap);
-  if (can_vec4) ew_kernel<4, F><<<grid, threads, 0, s>>>(nvec, f);
-  else ew_kernel<1, F><<<grid, threads, 0, s>>>(nvec, f);
+  int64_t want = (nvec + (int64_t)threads * U - 1) / ((int64_t)threads * U);
+  if (want > 0x7fffffff) want = 0x7fffffff;
+  if (can_vec4) ew_kernel<4, U, F><<<(unsigned)want, threads, 0, s>>>(nvec, f);
+  else ew_kernel<1, U, F><<<(unsigned)want, threads, 0, s>>>(nvec, f);
   count_launch();
   return check_launch(name);
 }
+template <class F>
+int launch_ew(const char* name, int64_t N, bool can_vec4, F f, cudaStream_t s) {
+  return launch_ew2<1>(name, N, can_vec4, OnePhase<F>{f}, s);
+}
 
-// ---- per-row variant: blockIdx.y = row (a sample, or a (sample, channel) plane); the functor gets (row, i) with i the
-// V-wide vector index inside the row, so per-row constants (scale[b], mean[c]) cost no 64-bit division per vector -----
-// F provides:  template <int V> __device__ void run(int row, int64_t i) const;
-template <int V, class F>
+// per-row variant: blockIdx.y = row (a sample, or a (sample, channel) plane); functors get (row, i) with i the V-wide vector
+// index inside the row, so per-row constants (scale[b], mean[c]) cost no 64-bit division per vector
+template <int V, int U, class F>
 __global__ void __launch_bounds__(256) ew_rows_kernel(int64_t nvec_per_row, F f) {
   const int row = blockIdx.y;
   const int64_t stride = (int64_t)gridDim.x * blockDim.x;
-  for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < nvec_per_row; i += stride) f.template run<V>(row, i);
+  for (int64_t i0 = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i0 < nvec_per_row; i0 += stride * U) {
+    decltype(f.template load<V>(row, i0)) ld[U];
+#pragma unroll
+    for (int u = 0; u < U; ++u) { const int64_t i = i0 + u * stride; if (i < nvec_per_row) ld[u] = f.template load<V>(row, i); }
+#pragma unroll
+    for (int u = 0; u < U; ++u) { const int64_t i = i0 + u * stride; if (i < nvec_per_row) f.template apply<V>(row, i, ld[u]); }
+  }
 }
 
-template <class F>
-int launch_ew_rows(const char* name, int rows, int64_t n_per_row, bool can_vec4, F f, cudaStream_t s) {
+template <int U, class F>
+int launch_ew_rows2(const char* name, int rows, int64_t n_per_row, bool can_vec4, F f, cudaStream_t s) {
   if (rows <= 0 || n_per_row <= 0) return TA_OK;
   if (rows > 65535) { set_error("%s: %d rows exceed the grid limit 65535", name, rows); return TA_EINVAL; }
   const int threads = 256;
   const int64_t nvec = can_vec4 ? n_per_row / 4 : n_per_row;
-  const int64_t want = (nvec + threads - 1) / threads;
-  int64_t per_row = ((int64_t)sm_count() * 8 + rows - 1) / rows;      // ~8 resident CTAs per SM over all rows
-  if (per_row < 1) per_row = 1;
-  const dim3 grid((unsigned)(want < per_row ? want : per_row), (unsigned)rows);
-  if (can_vec4) ew_rows_kernel<4, F><<<grid, threads, 0, s>>>(nvec, f);
-  else ew_rows_kernel<1, F><<<grid, threads, 0, s>>>(nvec, f);
+  int64_t want = (nvec + (int64_t)threads * U - 1) / ((int64_t)threads * U);
+  if (want > 0x7fffffff) want = 0x7fffffff;
+  const dim3 grid((unsigned)want, (unsigned)rows);
+  if (can_vec4) ew_rows_kernel<4, U, F><<<grid, threads, 0, s>>>(nvec, f);
+  else ew_rows_kernel<1, U, F><<<grid, threads, 0, s>>>(nvec, f);
   count_launch();
   return check_launch(name);
+}
+template <class F>
+int launch_ew_rows(const char* name, int rows, int64_t n_per_row, bool can_vec4, F f, cudaStream_t s) {
+  return launch_ew_rows2<1>(name, rows, n_per_row, can_vec4, OnePhase<F>{f}, s);
 }
 
 // ---- cluster-wide sum + cluster launch --------------------------------------------------------------------------

@@ -17,39 +17,43 @@ bool all_aligned(P... p) {
 }
 
 // ---- attack.py:128 ---------------------------------------------------------------------------------------
+template <int V> struct MomIn { Vec<V> g, m; float mu; };
 struct MomentumOp {
   const float* g; const float* m; const float* scale; float* out; float decay; int64_t nvec;   // nvec: vectors per sample
-  template <int V> __device__ void run(int row, int64_t j) const {
-    const float mu = __ldg(scale + row);
+  template <int V> __device__ __forceinline__ MomIn<V> load(int row, int64_t j) const {
+    MomIn<V> r;
     const int64_t i = (int64_t)row * nvec + j;
-    const Vec<V> gv = ldv<V>(g, i);
+    r.mu = __ldg(scale + row);
+    r.g = ldv<V>(g, i);
+    if (m) r.m = ldv_rw<V>(m, i);
+    return r;
+  }
+  template <int V> __device__ __forceinline__ void apply(int row, int64_t j, const MomIn<V>& r) const {
     Vec<V> o;
-    if (m) {
-      const Vec<V> mv = ldv_rw<V>(m, i);
 #pragma unroll
-      for (int k = 0; k < V; ++k) o.v[k] = add_rn(mul_rn(mv.v[k], decay), div_rn(gv.v[k], mu));
-    } else {
-#pragma unroll
-      for (int k = 0; k < V; ++k) o.v[k] = add_rn(0.0f, div_rn(gv.v[k], mu));
-    }
-    stv<V>(out, i, o);
+    for (int k = 0; k < V; ++k) o.v[k] = add_rn(m ? mul_rn(r.m.v[k], decay) : 0.0f, div_rn(r.g.v[k], r.mu));
+    stv<V>(out, (int64_t)row * nvec + j, o);
   }
 };
 
 // ---- attack.py:147,152 -------------------------------------------------------------------------------------
+template <int V> struct UpdIn { Vec<V> d, x, g, a; };
 struct UpdateLinfOp {
   const float* delta; const float* data; const float* dir; const float* alpha_t; float* out;
   float alpha, eps, lo, hi; int dir_mode;
-  template <int V> __device__ void run(int64_t i) const {
-    const Vec<V> dv = ldv_rw<V>(delta, i), xv = ldv<V>(data, i), gv = ldv<V>(dir, i);
-    Vec<V> av;
-    if (alpha_t) av = ldv<V>(alpha_t, i);
+  template <int V> __device__ __forceinline__ UpdIn<V> load(int64_t i) const {
+    UpdIn<V> r;
+    r.d = ldv_rw<V>(delta, i); r.x = ldv<V>(data, i); r.g = ldv<V>(dir, i);
+    if (alpha_t) r.a = ldv<V>(alpha_t, i);
+    return r;
+  }
+  template <int V> __device__ __forceinline__ void apply(int64_t i, const UpdIn<V>& r) const {
     Vec<V> o;
 #pragma unroll
     for (int k = 0; k < V; ++k) {
-      const float d = (dir_mode == TA_DIR_SIGN) ? sign_t(gv.v[k]) : gv.v[k];
-      const float a = alpha_t ? av.v[k] : alpha;
-      o.v[k] = project_linf(dv.v[k], mul_rn(a, d), xv.v[k], eps, lo, hi);
+      const float d = (dir_mode == TA_DIR_SIGN) ? sign_t(r.g.v[k]) : r.g.v[k];
+      const float a = alpha_t ? r.a.v[k] : alpha;
+      o.v[k] = project_linf(r.d.v[k], mul_rn(a, d), r.x.v[k], eps, lo, hi);
     }
     stv<V>(out, i, o);
   }
@@ -68,20 +72,24 @@ struct ClampBoxOp {
 };
 
 // ---- attack.py:88 / nifgsm.py:39 / vmifgsm.py:50 ------------------------------------------------------------------
+template <int V> struct StageIn { Vec<V> x, d, n, l; };
 struct StageOp {
   const float* data; const float* delta; const float* noise; const float* look; float* out; float coef;
-  template <int V> __device__ void run(int64_t i) const {
-    const Vec<V> xv = ldv<V>(data, i);
-    Vec<V> dv, nv, lv;
-    if (delta) dv = ldv<V>(delta, i);
-    if (noise) nv = ldv<V>(noise, i);
-    if (look) lv = ldv<V>(look, i);
+  template <int V> __device__ __forceinline__ StageIn<V> load(int64_t i) const {
+    StageIn<V> r;
+    r.x = ldv<V>(data, i);
+    if (delta) r.d = ldv<V>(delta, i);
+    if (noise) r.n = ldv<V>(noise, i);
+    if (look) r.l = ldv<V>(look, i);
+    return r;
+  }
+  template <int V> __device__ __forceinline__ void apply(int64_t i, const StageIn<V>& r) const {
     Vec<V> o;
 #pragma unroll
     for (int k = 0; k < V; ++k) {
-      float x = delta ? add_rn(xv.v[k], dv.v[k]) : xv.v[k];
-      if (noise) x = add_rn(x, nv.v[k]);
-      if (look) x = add_rn(x, mul_rn(coef, lv.v[k]));
+      float x = delta ? add_rn(r.x.v[k], r.d.v[k]) : r.x.v[k];
+      if (noise) x = add_rn(x, r.n.v[k]);
+      if (look) x = add_rn(x, mul_rn(coef, r.l.v[k]));
       o.v[k] = x;
     }
     stv<V>(out, i, o);
@@ -222,16 +230,22 @@ struct LinSampleBwdOp {
 };
 
 // ---- vmifgsm.py:56,58,87 ----------------------------------------------------------------------------------------------------------
+template <int V> struct AccIn { Vec<V> g, a; };
 struct AccumulateOp {
   float* acc; const float* g; int first;
-  template <int V> __device__ void run(int64_t i) const {
-    Vec<V> gv = ldv<V>(g, i);
+  template <int V> __device__ __forceinline__ AccIn<V> load(int64_t i) const {
+    AccIn<V> r;
+    r.g = ldv<V>(g, i);
+    if (!first) r.a = ldv_rw<V>(acc, i);
+    return r;
+  }
+  template <int V> __device__ __forceinline__ void apply(int64_t i, const AccIn<V>& r) const {
+    Vec<V> o = r.g;
     if (!first) {
-      const Vec<V> av = ldv_rw<V>(acc, i);
 #pragma unroll
-      for (int k = 0; k < V; ++k) gv.v[k] = add_rn(av.v[k], gv.v[k]);
+      for (int k = 0; k < V; ++k) o.v[k] = add_rn(r.a.v[k], r.g.v[k]);
     }
-    stv<V>(acc, i, gv);
+    stv<V>(acc, i, o);
   }
 };
 struct VarianceOp {
@@ -306,7 +320,7 @@ int ta_momentum(const float* g, const float* m, const float* scale, float decay,
                 ta_stream_t stream) {
   TA_REQUIRE(g && scale && m_out && B > 0 && n > 0, "ta_momentum: null pointer or empty shape (B=%d n=%lld)", B, (long long)n);
   const bool v4 = (n % 4 == 0) && all_aligned(g, m, m_out);
-  return launch_ew_rows("ta_momentum", B, n, v4, MomentumOp{g, m, scale, m_out, decay, v4 ? n / 4 : n}, (cudaStream_t)stream);
+  return launch_ew_rows2<4>("ta_momentum", B, n, v4, MomentumOp{g, m, scale, m_out, decay, v4 ? n / 4 : n}, (cudaStream_t)stream);
 }
 
 int ta_update_linf(const float* delta, const float* data, const float* dir, const float* alpha_t, float alpha, float eps,
@@ -314,7 +328,7 @@ int ta_update_linf(const float* delta, const float* data, const float* dir, cons
   TA_REQUIRE(delta && data && dir && delta_out && N > 0, "ta_update_linf: null pointer or N=%lld", (long long)N);
   TA_REQUIRE(dir_mode == TA_DIR_SIGN || dir_mode == TA_DIR_RAW, "ta_update_linf: dir_mode %d", dir_mode);
   const bool v4 = (N % 4 == 0) && all_aligned(delta, data, dir, alpha_t, delta_out);
-  return launch_ew("ta_update_linf", N, v4, UpdateLinfOp{delta, data, dir, alpha_t, delta_out, alpha, eps, lo, hi, dir_mode},
+  return launch_ew2<4>("ta_update_linf", N, v4, UpdateLinfOp{delta, data, dir, alpha_t, delta_out, alpha, eps, lo, hi, dir_mode},
                    (cudaStream_t)stream);
 }
 
@@ -328,14 +342,14 @@ int ta_stage_add(const float* data, const float* delta, const float* look, float
                  ta_stream_t stream) {
   TA_REQUIRE(data && out && N > 0, "ta_stage_add: null pointer or N=%lld", (long long)N);
   const bool v4 = (N % 4 == 0) && all_aligned(data, delta, look, out);
-  return launch_ew("ta_stage_add", N, v4, StageOp{data, delta, nullptr, look, out, coef}, (cudaStream_t)stream);
+  return launch_ew2<4>("ta_stage_add", N, v4, StageOp{data, delta, nullptr, look, out, coef}, (cudaStream_t)stream);
 }
 
 int ta_neighbor_stage(const float* data, const float* delta, const float* noise, const float* look, float coef, float* out,
                       int64_t N, ta_stream_t stream) {
   TA_REQUIRE(data && delta && noise && out && N > 0, "ta_neighbor_stage: null pointer or N=%lld", (long long)N);
   const bool v4 = (N % 4 == 0) && all_aligned(data, delta, noise, look, out);
-  return launch_ew("ta_neighbor_stage", N, v4, StageOp{data, delta, noise, look, out, coef}, (cudaStream_t)stream);
+  return launch_ew2<4>("ta_neighbor_stage", N, v4, StageOp{data, delta, noise, look, out, coef}, (cudaStream_t)stream);
 }
 
 int ta_normalize_fwd(const float* x, const float* mean, const float* std, float* out, int B, int C, int64_t plane,
@@ -398,7 +412,7 @@ int ta_lin_sample_bwd(const float* gout, float* gin, int K, int64_t N, ta_stream
 int ta_accumulate(float* acc, const float* g, int first, int64_t N, ta_stream_t stream) {
   TA_REQUIRE(acc && g && N > 0, "ta_accumulate: bad arguments");
   const bool v4 = (N % 4 == 0) && all_aligned(acc, g);
-  return launch_ew("ta_accumulate", N, v4, AccumulateOp{acc, g, first}, (cudaStream_t)stream);
+  return launch_ew2<4>("ta_accumulate", N, v4, AccumulateOp{acc, g, first}, (cudaStream_t)stream);
 }
 
 int ta_variance_finalize(const float* acc, const float* cur, int num_neighbor, float* out, int64_t N, ta_stream_t stream) {

@@ -43,18 +43,23 @@ __device__ __forceinline__ void fused_elem(float g, float m, bool has_m, float d
 }
 
 // ---- strict / fallback path: scale[b] given, flat streaming ---------------------------------------------------
+template <int V> struct FusedIn { Vec<V> g, x, d, m; float mu; };
 struct FusedStreamOp {
   FusedParams p; int64_t nvec;     // vectors per sample
-  template <int V> __device__ void run(int row, int64_t j) const {
-    const float mu = __ldg(p.scale + row);
+  template <int V> __device__ __forceinline__ FusedIn<V> load(int row, int64_t j) const {
+    FusedIn<V> r;
     const int64_t i = (int64_t)row * nvec + j;
-    const Vec<V> gv = ldv<V>(p.g, i), xv = ldv<V>(p.data, i);
-    const Vec<V> dv = ldv_rw<V>(p.delta, i);
-    Vec<V> mv;
-    if (p.m) mv = ldv_rw<V>(p.m, i);
+    r.mu = __ldg(p.scale + row);
+    r.g = ldv<V>(p.g, i); r.x = ldv<V>(p.data, i); r.d = ldv_rw<V>(p.delta, i);
+    if (p.m) r.m = ldv_rw<V>(p.m, i);
+    return r;
+  }
+  template <int V> __device__ __forceinline__ void apply(int row, int64_t j, const FusedIn<V>& r) const {
+    const int64_t i = (int64_t)row * nvec + j;
     Vec<V> mo, dn, xa;
 #pragma unroll
-    for (int k = 0; k < V; ++k) fused_elem(gv.v[k], p.m ? mv.v[k] : 0.0f, p.m != nullptr, dv.v[k], xv.v[k], mu, p, mo.v[k], dn.v[k], xa.v[k]);
+    for (int k = 0; k < V; ++k)
+      fused_elem(r.g.v[k], p.m ? r.m.v[k] : 0.0f, p.m != nullptr, r.d.v[k], r.x.v[k], r.mu, p, mo.v[k], dn.v[k], xa.v[k]);
     stv<V>(p.m_out, i, mo);
     stv<V>(p.delta_out, i, dn);
     if (p.xadv) stv<V>(p.xadv, i, xa);
@@ -212,7 +217,7 @@ extern "C" int ta_fused_update_linf(const float* g, const float* m, float* m_out
       const cudaError_t e = cudaMemcpyAsync(scale_out, scale, sizeof(float) * (size_t)B, cudaMemcpyDeviceToDevice, s);
       if (e != cudaSuccess) { set_error("ta_fused_update_linf: scale copy failed: %s", cudaGetErrorString(e)); return TA_ECUDA; }
     }
-    return launch_ew_rows("ta_fused_update_linf[stream]", B, n, v4, FusedStreamOp{p, v4 ? n / 4 : n}, s);
+    return launch_ew_rows2<2>("ta_fused_update_linf[stream]", B, n, v4, FusedStreamOp{p, v4 ? n / 4 : n}, s);
   }
 
   if (mean_mode != TA_MEAN_EXACT) {
@@ -238,7 +243,7 @@ extern "C" int ta_fused_update_linf(const float* g, const float* m, float* m_out
     const int rc = ta_abs_mean_per_sample(g, scale_out, B, n, TA_MEAN_EXACT, nullptr, stream);
     if (rc != TA_OK) return rc;
     p.scale = scale_out;
-    return launch_ew_rows("ta_fused_update_linf[stream]", B, n, false, FusedStreamOp{p, n}, s);
+    return launch_ew_rows2<2>("ta_fused_update_linf[stream]", B, n, false, FusedStreamOp{p, n}, s);
   }
 
   const bool stage = (variant == 0) && slice_bytes <= kMaxStageBytes;
