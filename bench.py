@@ -391,7 +391,9 @@ def run_ours(args, rank, local_rank, world, dist):
 
 # ------------------------------------------------------------------------------------------------------------------
 def flush_l2(buf):
-    buf.zero_()
+    # displace L2 with CLEAN lines (a read-only pass over 256 MB): a memset would leave 126 MB of dirty lines whose
+    # write-back then competes with the timed kernel for DRAM
+    buf.sum()
 
 
 def time_kernel(fn, iters=20, flush=None):
@@ -463,7 +465,7 @@ def run_kernels(args):
     med, mn = time_kernel(eager_tail, flush=flush)
     rows.append({"kernel": "torch eager tail (14 ATen launches, attack.py:88,128,147-153)", "bytes_per_elem": 128, "elems": N,
                  "median_us": med * 1e3, "min_us": mn * 1e3, "achieved_GBps": 128 * N / (med * 1e-3) / 1e9, "frac_of_peak": None})
-    out = {"hbm_peak_GBps": hbm_peak, "peak_source": peak_src, "batch": B, "l2": "256 MB memset before every timed launch", "rows": rows}
+    out = {"hbm_peak_GBps": hbm_peak, "peak_source": peak_src, "batch": B, "l2": "read-only pass over a 256 MB buffer before every timed launch (clean L2)", "rows": rows}
     os.makedirs(os.path.join(ROOT, "gpurun_out"), exist_ok=True)
     json.dump(out, open(os.path.join(ROOT, "gpurun_out", "kernels.json"), "w"), indent=1)
     for r in rows:

@@ -168,3 +168,42 @@ def test_host_input_device_output_like_reference_main():
     xp = x.pin_memory()
     d2 = make_attack(tab, "mifgsm", net, epoch=2)(xp, y)
     assert torch.equal(d, d2)
+
+
+@pytest.mark.parametrize("name,kw", [("mifgsm", {}), ("nifgsm", {}), ("ifgsm", {}), ("tim", {"epoch": 4}), ("sim", {"epoch": 3}),
+                                     ("mifgsm", {"random_start": True}), ("mifgsm", {"targeted": True})])
+def test_cuda_graph_replay_is_bit_identical(name, kw):
+    """use_cuda_graph replays one captured iteration `epoch` times: same kernels in the same order → same bits, also on
+    the second batch through the cached graph, and against the reference restatement."""
+    net = _net()
+    x, y = _data()
+    lab = torch.stack([y, (y + 1) % 1000]) if kw.get("targeted") else y
+    plain = make_attack(tab, name, net, **kw)
+    seed_all(2); torch.cuda.manual_seed_all(2)
+    d_plain = plain(x, lab)
+    graphed = make_attack(tab, name, net, **kw)
+    graphed.use_cuda_graph = True
+    seed_all(2); torch.cuda.manual_seed_all(2)
+    d_graph = graphed(x, lab)
+    assert torch.equal(d_plain, d_graph)
+    assert len(graphed._graphs) == 1
+    x2, y2 = _data(seed=9)
+    lab2 = torch.stack([y2, (y2 + 1) % 1000]) if kw.get("targeted") else y2
+    seed_all(3); torch.cuda.manual_seed_all(3)
+    d2_plain = plain(x2, lab2)
+    seed_all(3); torch.cuda.manual_seed_all(3)
+    d2_graph = graphed(x2, lab2)
+    assert torch.equal(d2_plain, d2_graph) and len(graphed._graphs) == 1
+    REPORT["graph/" + name + ("_" + "_".join(kw) if kw else "")] = {"bit_identical": True}
+
+
+def test_cuda_graph_is_refused_for_host_rng_transforms():
+    net = _net()
+    x, y = _data(2)
+    atk = make_attack(tab, "dim", net, epoch=2)
+    atk.use_cuda_graph = True
+    seed_all(4); d = atk(x, y)
+    assert not getattr(atk, "_graphs", None)          # DIM draws per call → eager loop
+    ref = make_attack(tab, "dim", net, epoch=2)
+    seed_all(4)
+    assert torch.equal(d, ref(x, y))

@@ -106,7 +106,7 @@ def _try_make(pkg, name, nets, extra):
 @pytest.mark.parametrize("name", GRADIENT + INPUT_T + ENSEMBLE)
 def test_reference_plugin_runs_unchanged_on_this_base(ref, adopted, name):
     x, y = _data(2, 224)
-    nets = [_net(0), _net(3)] if name in ENSEMBLE else _net(0)
+    nets = [_net(0), _net(3), _net(5), _net(7)] if name in ENSEMBLE else _net(0)
     try:
         a_ref = _try_make(ref, name, nets, SMALL)
     except Exception as e:   # missing optional dependency / checkpoint in this container: not a property of the boundary

@@ -47,6 +47,12 @@ class Attack(object):
     mean_mode = os.environ.get("TA_B200_MEAN", "torch")
     #: use the single-launch fused tail in the base loop when the hooks are not overridden
     fuse_update = os.environ.get("TA_B200_FUSE", "1") != "0"
+    #: capture one iteration of the fused loop (staging → surrogate fwd/bwd → fused update) in a CUDA graph and replay it
+    #: `epoch` times per batch: removes the ~550 host launches per iteration, which is what bounds small batches / small
+    #: surrogates. Same kernels, same order → same bits. Off by default (env TA_B200_GRAPH=1).
+    use_cuda_graph = os.environ.get("TA_B200_GRAPH", "0") == "1"
+    #: False for plugins whose transform draws from a host generator per call (DIM, Admix): those cannot be replayed
+    graph_safe = True
 
     def __init__(self, attack, model_name, epsilon, targeted, random_start, norm, loss, device=None):
         """attack.py:12-38 — same arguments, same attributes, same ``Unsupported norm`` exception."""
@@ -112,6 +118,8 @@ class Attack(object):
 
         delta = self.init_delta(data)
         if self._fusable():
+            if self.use_cuda_graph and self.graph_safe and data.is_cuda and ops._test_backend is None:
+                return self._loop_graph(data, label, delta)
             return self._loop_fused(data, label, delta)
 
         momentum = 0
@@ -149,6 +157,60 @@ class Attack(object):
                 ev.append((e0, e1))
             momentum, pre = m_buf, xadv
         return delta.detach()
+
+    # ---- CUDA-graph replay of the fused loop -------------------------------------------------------------
+    def _graph_iteration(self, st):
+        """One iteration on the static buffers `st` (this body is what gets captured)."""
+        x = ops.stage_add(st["data"], st["delta"], precomputed=st["xadv"])
+        logits = self.get_logits(self.transform(x, momentum=st["m"]))
+        loss = self.get_loss(logits, st["label"])
+        grad = self.get_grad(loss, st["delta"])
+        scale = self._torch_abs_mean(grad) if self.mean_mode == 'torch' else None
+        with torch.no_grad():
+            ops.backend().fused_update_linf(grad, st["m"], st["m"], st["delta"], st["delta"], st["data"], st["xadv"], scale,
+                                            st["scale_out"], self.decay, self.alpha, self.epsilon, img_min, img_max,
+                                            _lib.TA_MEAN_EXACT)
+
+    def _graph_reset(self, st, data, label, delta0):
+        with torch.no_grad():
+            st["data"].copy_(data)
+            st["label"].copy_(label)
+            st["delta"].copy_(delta0)
+            st["m"].zero_()          # momentum * decay with momentum = +0 is the reference's first-iteration `0 * decay`
+            ops.backend().stage_add(st["data"], st["delta"], out=st["xadv"])
+
+    def _graph_for(self, data, label, delta0):
+        key = (tuple(data.shape), str(data.device), tuple(label.shape), self.mean_mode, float(self.alpha), float(self.decay),
+               float(self.epsilon), bool(self.targeted))
+        cache = self.__dict__.setdefault("_graphs", {})
+        st = cache.get(key)
+        if st is not None:
+            return st
+        st = {"data": torch.empty_like(data), "label": torch.empty_like(label),
+              "delta": torch.zeros_like(data).requires_grad_(True), "m": torch.zeros_like(data),
+              "xadv": torch.empty_like(data), "scale_out": torch.empty(data.shape[0], device=data.device, dtype=torch.float32)}
+        self._graph_reset(st, data, label, delta0)
+        cur = torch.cuda.current_stream(data.device)
+        side = torch.cuda.Stream(device=data.device)
+        side.wait_stream(cur)
+        with torch.cuda.stream(side):          # warm-up off the capture: cuDNN heuristics, workspaces, our smem attributes
+            for _ in range(3):
+                self._graph_iteration(st)
+        cur.wait_stream(side)
+        torch.cuda.synchronize(data.device)
+        graph = torch.cuda.CUDAGraph()
+        with torch.cuda.graph(graph):
+            self._graph_iteration(st)
+        st["graph"] = graph
+        cache[key] = st
+        return st
+
+    def _loop_graph(self, data, label, delta0):
+        st = self._graph_for(data, label, delta0.detach())
+        self._graph_reset(st, data, label, delta0.detach())
+        for _ in range(self.epoch):
+            st["graph"].replay()
+        return st["delta"].detach().clone()
 
     # ------------------------------------------------------------------------------------------------
     def get_logits(self, x, **kwargs):

@@ -178,13 +178,14 @@ template <class F> struct OnePhase {
 
 template <int V, int U, class F>
 __global__ void __launch_bounds__(256) ew_kernel(int64_t nvec, F f) {
-  const int64_t stride = (int64_t)gridDim.x * blockDim.x;
-  for (int64_t i0 = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i0 < nvec; i0 += stride * U) {
+  // each CTA owns U * blockDim consecutive vectors per step (contiguous 4 KB pieces per stream: DRAM-page friendly)
+  const int64_t step = (int64_t)gridDim.x * blockDim.x * U;
+  for (int64_t i0 = (int64_t)blockIdx.x * blockDim.x * U + threadIdx.x; i0 < nvec; i0 += step) {
     decltype(f.template load<V>(i0)) ld[U];
 #pragma unroll
-    for (int u = 0; u < U; ++u) { const int64_t i = i0 + u * stride; if (i < nvec) ld[u] = f.template load<V>(i); }
+    for (int u = 0; u < U; ++u) { const int64_t i = i0 + u * (int64_t)blockDim.x; if (i < nvec) ld[u] = f.template load<V>(i); }
 #pragma unroll
-    for (int u = 0; u < U; ++u) { const int64_t i = i0 + u * stride; if (i < nvec) f.template apply<V>(i, ld[u]); }
+    for (int u = 0; u < U; ++u) { const int64_t i = i0 + u * (int64_t)blockDim.x; if (i < nvec) f.template apply<V>(i, ld[u]); }
   }
 }
 
@@ -210,13 +211,13 @@ int launch_ew(const char* name, int64_t N, bool can_vec4, F f, cudaStream_t s) {
 template <int V, int U, class F>
 __global__ void __launch_bounds__(256) ew_rows_kernel(int64_t nvec_per_row, F f) {
   const int row = blockIdx.y;
-  const int64_t stride = (int64_t)gridDim.x * blockDim.x;
-  for (int64_t i0 = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i0 < nvec_per_row; i0 += stride * U) {
+  const int64_t step = (int64_t)gridDim.x * blockDim.x * U;
+  for (int64_t i0 = (int64_t)blockIdx.x * blockDim.x * U + threadIdx.x; i0 < nvec_per_row; i0 += step) {
     decltype(f.template load<V>(row, i0)) ld[U];
 #pragma unroll
-    for (int u = 0; u < U; ++u) { const int64_t i = i0 + u * stride; if (i < nvec_per_row) ld[u] = f.template load<V>(row, i); }
+    for (int u = 0; u < U; ++u) { const int64_t i = i0 + u * (int64_t)blockDim.x; if (i < nvec_per_row) ld[u] = f.template load<V>(row, i); }
 #pragma unroll
-    for (int u = 0; u < U; ++u) { const int64_t i = i0 + u * stride; if (i < nvec_per_row) f.template apply<V>(row, i, ld[u]); }
+    for (int u = 0; u < U; ++u) { const int64_t i = i0 + u * (int64_t)blockDim.x; if (i < nvec_per_row) f.template apply<V>(row, i, ld[u]); }
   }
 }
 
@@ -253,7 +254,26 @@ __device__ __forceinline__ double cluster_allreduce_sum(double v, double* s_scra
   return tot;
 }
 
-int pick_cluster(int64_t n, int threads);   // CTAs per sample for the per-sample reduction kernels (<= 8)
+int pick_cluster(int64_t n, int threads);
+
+// Opt a kernel in to `bytes` of dynamic shared memory (> 48 KB needs it) once per (kernel, device): the attribute call is
+// skipped when an equal or larger size was granted before, so steady-state launches (and CUDA-graph captures) issue none.
+struct SmemOptIn { size_t granted[64]; };
+template <class K>
+int ensure_dyn_smem(const char* who, K kernel, size_t bytes, SmemOptIn& st) {
+  if (bytes <= 48 * 1024) return TA_OK;
+  int dev = 0;
+  if (cudaGetDevice(&dev) != cudaSuccess || dev < 0 || dev >= 64) dev = 0;
+  if (st.granted[dev] >= bytes) return TA_OK;
+  const cudaError_t e = cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)bytes);
+  if (e != cudaSuccess) {
+    set_error("%s: cannot reserve %zu B of shared memory: %s", who, bytes, cudaGetErrorString(e));
+    cudaGetLastError();
+    return TA_ECUDA;
+  }
+  st.granted[dev] = bytes;
+  return TA_OK;
+}   // CTAs per sample for the per-sample reduction kernels (<= 8)
 
 template <class T> struct ident { using type = T; };
 

@@ -297,10 +297,9 @@ int ta_dim_fwd(const float* x, float* out, int planes, int S, int rnd, int R, in
                       sizeof(float) * ((size_t)gm.src_rows_max * rnd + (size_t)gm.y1_rows_max * rnd);
   TA_REQUIRE(smem <= 200 * 1024, "ta_dim_fwd: image size S=%d needs %zu B of shared memory per CTA", S, smem);
   auto k = can_tma ? dim_fwd_kernel<true> : dim_fwd_kernel<false>;
-  if (smem > 48 * 1024) {
-    const cudaError_t e = cudaFuncSetAttribute(k, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
-    if (e != cudaSuccess) { set_error("ta_dim_fwd: smem attribute: %s", cudaGetErrorString(e)); cudaGetLastError(); return TA_ECUDA; }
-  }
+  static SmemOptIn optin_tma = {}, optin_ldg = {};
+  rc = ensure_dyn_smem("ta_dim_fwd", k, smem, can_tma ? optin_tma : optin_ldg);
+  if (rc != TA_OK) return rc;
   dim3 grid((unsigned)((S + RB - 1) / RB), (unsigned)planes);
   k<<<grid, kThreads, smem, (cudaStream_t)stream>>>(x, out, gm);
   count_launch();
@@ -319,10 +318,9 @@ int ta_dim_bwd(const float* gout, float* gin, int planes, int S, int rnd, int R,
   const size_t smem = sizeof(Tap) * (size_t)(S + rnd) + sizeof(int) * (size_t)(2 * R + 2 * S) +
                       sizeof(float) * (u_elems + (size_t)gm.y1_rows_max * rnd);
   TA_REQUIRE(smem <= 200 * 1024, "ta_dim_bwd: image size S=%d needs %zu B of shared memory per CTA", S, smem);
-  if (smem > 48 * 1024) {
-    const cudaError_t e = cudaFuncSetAttribute(dim_bwd_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
-    if (e != cudaSuccess) { set_error("ta_dim_bwd: smem attribute: %s", cudaGetErrorString(e)); cudaGetLastError(); return TA_ECUDA; }
-  }
+  static SmemOptIn optin = {};
+  rc = ensure_dyn_smem("ta_dim_bwd", dim_bwd_kernel, smem, optin);
+  if (rc != TA_OK) return rc;
   dim3 grid((unsigned)((S + RB - 1) / RB), (unsigned)planes);
   dim_bwd_kernel<<<grid, kThreads, smem, (cudaStream_t)stream>>>(gout, gin, gm);
   count_launch();

@@ -148,15 +148,17 @@ __global__ void __launch_bounds__(kBandThreads) dwconv_sep_band_kernel(const flo
   // valid input rows of this band: image rows [ya, yb)
   const int ya = max(y0 - R, 0), yb = min(y0 + BH + R, H);
   if (tid == 0) { mbar_init(&s_bar, 1); mbar_fence_init(); }
-  // zero the margins of every row and the rows that fall outside the image (disjoint from the TMA destinations)
+  // zero the margins of every row and the rows that fall outside the image (disjoint from the TMA destinations); only the
+  // first / last band of a plane has such rows: [0, top_inv) and [rows - bot_inv, rows)
   for (int e = tid; e < rows * 2 * PADX; e += kBandThreads) {
-    const int r = e / (2 * PADX), q = e % (2 * PADX);
+    const int r = e / (2 * PADX), q = e % (2 * PADX);       // constants: shifts / masks
     s_in[r * WP + (q < PADX ? q : W + q)] = 0.0f;
   }
-  for (int r = 0; r < rows; ++r) {
-    const int yy = y0 - R + r;
-    if (yy < 0 || yy >= H)
-      for (int x = tid; x < W; x += kBandThreads) s_in[r * WP + PADX + x] = 0.0f;
+  const int top_inv = ya - (y0 - R), bot_inv = (y0 + BH + R) - yb;
+  for (int e = tid; e < (top_inv + bot_inv) * W; e += kBandThreads) {
+    const int k = e / W, x = e - k * W;
+    const int r = k < top_inv ? k : rows - bot_inv + (k - top_inv);
+    s_in[r * WP + PADX + x] = 0.0f;
   }
   __syncthreads();
   if (tid == 0) {
@@ -167,8 +169,10 @@ __global__ void __launch_bounds__(kBandThreads) dwconv_sep_band_kernel(const flo
 
   // row pass: tmp[r][x] = sum_j krow[j] * in[r][x + j - R]
   const int groups = W >> 2;
-  for (int e = tid; e < rows * groups; e += kBandThreads) {
-    const int r = e / groups, xg = e % groups;
+  const int dq = kBandThreads / groups, dr = kBandThreads % groups;   // advancing e by the block size without a division
+  int r = tid / groups, xg = tid % groups;
+  for (int e = tid; e < rows * groups; e += kBandThreads, r += dq, xg += dr) {
+    if (xg >= groups) { xg -= groups; ++r; }
     // outputs x = 4xg..4xg+3 read padded columns 4xg + (PADX - R) + [0, KS + 3)
     const float4* row4 = reinterpret_cast<const float4*>(s_in + r * WP + 4 * xg);
     float v[4 * NV];
@@ -188,8 +192,10 @@ __global__ void __launch_bounds__(kBandThreads) dwconv_sep_band_kernel(const flo
   __syncthreads();
 
   // column pass: out[y][x] = sum_i kcol[i] * tmp[y + i][x]; item = (4 rows, 1 column)
-  for (int e = tid; e < (BH / 4) * W; e += kBandThreads) {
-    const int yg = e / W, x = e % W;
+  const int cq = kBandThreads / W, cr = kBandThreads % W;
+  int yg = tid / W, x = tid % W;
+  for (int e = tid; e < (BH / 4) * W; e += kBandThreads, yg += cq, x += cr) {
+    if (x >= W) { x -= W; ++yg; }
     float v[KS + 3];
 #pragma unroll
     for (int t = 0; t < KS + 3; ++t) v[t] = s_tmp[(4 * yg + t) * W + x];
@@ -211,10 +217,9 @@ int launch_band(const float* g, const float* kcol, const float* krow, float* out
   constexpr int R = KS / 2, PADX = (R + 3) & ~3;
   const size_t smem = sizeof(float) * ((size_t)(BH + KS - 1) * (W + 2 * PADX) + (size_t)(BH + KS - 1) * W);
   auto k = dwconv_sep_band_kernel<KS>;
-  if (smem > 48 * 1024) {
-    const cudaError_t e = cudaFuncSetAttribute(k, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
-    if (e != cudaSuccess) { set_error("ta_dwconv2d_sep: smem attribute: %s", cudaGetErrorString(e)); cudaGetLastError(); return TA_ECUDA; }
-  }
+  static SmemOptIn optin = {};
+  const int rc = ensure_dyn_smem("ta_dwconv2d_sep", k, smem, optin);
+  if (rc != TA_OK) return rc;
   dim3 grid((unsigned)((H + BH - 1) / BH), (unsigned)(B * C));
   k<<<grid, kBandThreads, smem, s>>>(g, kcol, krow, out, C, H, W);
   count_launch();

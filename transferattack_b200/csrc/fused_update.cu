@@ -177,20 +177,21 @@ __global__ void __launch_bounds__(THREADS) fused_cluster_kernel(FusedParams p) {
 template <int THREADS, int U, bool STAGE>
 int launch_fused(const FusedParams& p, int B, int cl, size_t smem, cudaStream_t s) {
   auto k = fused_cluster_kernel<THREADS, U, STAGE>;
-  if (smem > 48 * 1024) {
-    const cudaError_t e = cudaFuncSetAttribute(k, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
-    if (e != cudaSuccess) {
-      set_error("ta_fused_update_linf: cannot reserve %zu B of shared memory: %s", smem, cudaGetErrorString(e));
-      cudaGetLastError();
-      return TA_ECUDA;
-    }
-  }
+  static SmemOptIn optin = {};
+  static bool nonportable[64] = {};
+  int rc = ensure_dyn_smem("ta_fused_update_linf", k, smem, optin);
+  if (rc != TA_OK) return rc;
   if (cl > 8) {
-    const cudaError_t e = cudaFuncSetAttribute(k, cudaFuncAttributeNonPortableClusterSizeAllowed, 1);
-    if (e != cudaSuccess) {
-      set_error("ta_fused_update_linf: cluster size %d not allowed: %s", cl, cudaGetErrorString(e));
-      cudaGetLastError();
-      return TA_ECUDA;
+    int dev = 0;
+    if (cudaGetDevice(&dev) != cudaSuccess || dev < 0 || dev >= 64) dev = 0;
+    if (!nonportable[dev]) {
+      const cudaError_t e = cudaFuncSetAttribute(k, cudaFuncAttributeNonPortableClusterSizeAllowed, 1);
+      if (e != cudaSuccess) {
+        set_error("ta_fused_update_linf: cluster size %d not allowed: %s", cl, cudaGetErrorString(e));
+        cudaGetLastError();
+        return TA_ECUDA;
+      }
+      nonportable[dev] = true;
     }
   }
   return launch_cluster("ta_fused_update_linf", k, cl, B, THREADS, smem, s, p);

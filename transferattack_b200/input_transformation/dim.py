@@ -12,6 +12,8 @@ from ..gradient.mifgsm import MIFGSM
 
 
 class DIM(MIFGSM):
+    graph_safe = False      # draws host-generator numbers on every call → not replayable from a CUDA graph
+
     def __init__(self, model_name, epsilon=16/255, alpha=1.6/255, epoch=10, decay=1., resize_rate=1.1, diversity_prob=0.5, targeted=False,
                  random_start=False, norm='linfty', loss='crossentropy', device=None, attack='DIM', **kwargs):
         super().__init__(model_name, epsilon, alpha, epoch, decay, targeted, random_start, norm, loss, device, attack)
