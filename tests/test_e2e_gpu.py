@@ -207,3 +207,33 @@ def test_cuda_graph_is_refused_for_host_rng_transforms():
     ref = make_attack(tab, "dim", net, epoch=2)
     seed_all(4)
     assert torch.equal(d, ref(x, y))
+
+
+def test_cli_attack_and_eval_modes(tmp_path):
+    """main.py with the reference's flags on a tiny synthetic dataset (random-weight models: no network here): PNGs come out
+    with the right shape and stay inside the epsilon ball around the inputs after uint8 truncation; --eval prints an ASR row."""
+    import subprocess
+    import sys
+    from PIL import Image
+    inp, out = tmp_path / "data", tmp_path / "adv"
+    (inp / "images").mkdir(parents=True)
+    rng = np.random.default_rng(0)
+    names = ["img%d.png" % i for i in range(6)]
+    for n in names:
+        Image.fromarray(rng.integers(0, 256, (224, 224, 3), dtype=np.uint8)).save(inp / "images" / n)
+    with open(inp / "labels.csv", "w") as f:
+        f.write("filename,label,targeted_label\n")
+        for i, n in enumerate(names):
+            f.write("%s,%d,%d\n" % (n, i * 7, i * 7 + 1))
+    cmd = [sys.executable, os.path.join(ROOT, "main.py"), "--input_dir", str(inp), "--output_dir", str(out), "--attack", "mifgsm",
+           "--model", "resnet18", "--epoch", "2", "--batchsize", "4", "--random_weights", "--num_workers", "0"]
+    r = subprocess.run(cmd, capture_output=True, text=True, timeout=600)
+    assert r.returncode == 0, r.stderr[-2000:]
+    for n in names:
+        a = np.array(Image.open(out / n)).astype(np.int32)
+        b = np.array(Image.open(inp / "images" / n)).astype(np.int32)
+        assert a.shape == (224, 224, 3)
+        assert np.abs(a - b).max() <= 17 and np.abs(a - b).max() >= 1      # eps = 16/255, truncation adds < 1
+    r = subprocess.run(cmd + ["--eval"], capture_output=True, text=True, timeout=900, cwd=str(tmp_path))
+    assert r.returncode == 0, r.stderr[-2000:]
+    assert "resnet50:" in r.stdout and r.stdout.strip().splitlines()[-1].startswith("|")

@@ -48,9 +48,11 @@ class Attack(object):
     #: use the single-launch fused tail in the base loop when the hooks are not overridden
     fuse_update = os.environ.get("TA_B200_FUSE", "1") != "0"
     #: capture one iteration of the fused loop (staging → surrogate fwd/bwd → fused update) in a CUDA graph and replay it
-    #: `epoch` times per batch: removes the ~550 host launches per iteration, which is what bounds small batches / small
-    #: surrogates. Same kernels, same order → same bits. Off by default (env TA_B200_GRAPH=1).
-    use_cuda_graph = os.environ.get("TA_B200_GRAPH", "0") == "1"
+    #: `epoch` times per batch: removes the ~550 host launches per iteration (measured on B200, profiles/graph_vs_eager_r1.json:
+    #: +10 % at ResNet-50 B=64, 2.0x at B=8). Same kernels, same order → same bits (tests/test_e2e_gpu.py). On by default;
+    #: a surrogate that cannot be captured (host syncs, data-dependent control flow) makes the loop fall back to launching
+    #: the very same kernels eagerly. Env TA_B200_GRAPH=0 disables.
+    use_cuda_graph = os.environ.get("TA_B200_GRAPH", "1") == "1"
     #: False for plugins whose transform draws from a host generator per call (DIM, Admix): those cannot be replayed
     graph_safe = True
 
@@ -118,8 +120,14 @@ class Attack(object):
 
         delta = self.init_delta(data)
         if self._fusable():
-            if self.use_cuda_graph and self.graph_safe and data.is_cuda and ops._test_backend is None:
-                return self._loop_graph(data, label, delta)
+            if (self.use_cuda_graph and self.graph_safe and data.is_cuda and ops._test_backend is None
+                    and getattr(self, "_kernel_events", None) is None and not self.__dict__.get("_graph_failed", False)):
+                try:
+                    return self._loop_graph(data, label, delta)
+                except RuntimeError as e:        # capture refused (e.g. the surrogate synchronises): eager launches from now on
+                    self._graph_failed = True
+                    self._graph_error = str(e)
+                    torch.cuda.synchronize(data.device)
             return self._loop_fused(data, label, delta)
 
         momentum = 0

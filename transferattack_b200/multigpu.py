@@ -145,5 +145,6 @@ def make_ens_attack(attack_cls, member, group=None, **kwargs):
     reference's documented override point, attack.py:40-65). The base ``Attack`` treats ``ShardedEnsembleModel`` like any
     module; ``device`` is taken from the member."""
     model = ShardedEnsembleModel(member, group)
-    P = type("Sharded" + attack_cls.__name__, (attack_cls,), {"load_model": lambda self, _n: model})
+    # collectives inside forward/backward: keep the loop eager (NCCL inside a captured graph is not exercised here)
+    P = type("Sharded" + attack_cls.__name__, (attack_cls,), {"load_model": lambda self, _n: model, "graph_safe": False})
     return P(model_name="sharded-ensemble", device=model.device, **kwargs)
