@@ -452,6 +452,12 @@ def run_kernels(args):
     add("ATen reference: tensor.copy_ (same harness)", 8, lambda: xa.copy_(x))
     add("fused_update_linf[cluster, in-kernel mean]", 28, lambda: be.fused_update_linf(g, m, m2, d, d2, x, xa, None, so, 1.0, a, al, 0, 1.0))
     add("fused_update_linf[stream, scale given]", 28, lambda: be.fused_update_linf(g, m, m2, d, d2, x, xa, scale, None, 1.0, a, al, 0, 1.0))
+    for cap in (0, 4, 8, 16):
+        for un in (1, 2, 4):
+            _lib.tune_set("stream.cap", cap); _lib.tune_set("stream.unroll", un)
+            add("  fused stream variant cap=%d unroll=%d" % (cap, un), 28,
+                lambda: be.fused_update_linf(g, m, m2, d, d2, x, xa, scale, None, 1.0, a, al, 0, 1.0))
+    _lib.tune_set("stream.cap", 8); _lib.tune_set("stream.unroll", 1)
     add("abs_mean_per_sample", 4, lambda: be.abs_mean(g))
     add("momentum", 12, lambda: be.momentum(g, m, scale, 1.0, out=m2))
     add("update_linf", 16, lambda: be.update_linf(d, x, m, a, al, 0, 1.0, out=d2))

@@ -40,9 +40,8 @@ enum {
 
 /* how ta_abs_mean_per_sample / ta_fused_update_linf form mean|g| */
 enum {
-  TA_MEAN_EXACT = 0,    /* fp64 accumulation, mean = (float)(sum / n): order-independent up to the final rounding */
-  TA_MEAN_ATEN = 1      /* replays ATen's CUDA reduction order for sum(|g|) over a contiguous row of n floats
-                           followed by `* (float)(1/n)` (torch.mean on sm_100, 148 SMs) */
+  TA_MEAN_EXACT = 0     /* fp64 accumulation, mean = (float)(sum / n): order-independent up to the final rounding.
+                           (Strict parity with torch's fp32 tree sum is obtained by passing torch's own result as `scale`.) */
 };
 
 /* direction modes of ta_update_linf */
@@ -68,7 +67,7 @@ int ta_tune_set(const char* key, int value);
 /* ---- get_momentum  (attack.py:124-128) ----------------------------------------------
  *   momentum * decay + grad / mean_{C,H,W}(|grad|)                                       */
 
-/* mean_out[b] = mean over the sample of |g|.  mode: TA_MEAN_EXACT or TA_MEAN_ATEN.
+/* mean_out[b] = mean over the sample of |g|.  mode: TA_MEAN_EXACT.
  * ws: caller-provided scratch of ta_abs_mean_ws_bytes(B, n) bytes (may be NULL when that is 0). */
 int64_t ta_abs_mean_ws_bytes(int B, int64_t n);
 int ta_abs_mean_per_sample(const float* g, float* mean_out, int B, int64_t n, int mode,
@@ -117,6 +116,20 @@ int ta_fused_update_linf(const float* g, const float* m, float* m_out,
                          float* xadv_out, const float* scale, float* scale_out, int mean_mode,
                          float decay, float alpha, float eps, float lo, float hi,
                          int B, int64_t n, ta_stream_t stream);
+
+/* ---- ENS with one surrogate per GPU (ensemble/ens.py:31-36 + utils.py:94-100, new multi-GPU functionality) -----------
+ *   The gradient reduce-scatter, the fused update and the all-gather of the next model input as ONE kernel over NVLink
+ *   peer memory. Rank r owns samples [b0, b0+Bown). g_peers[k] / xadv_peers[k] (HOST arrays of K device pointers valid in
+ *   this process: symmetric / IPC-mapped memory) are rank k's FULL [B, n] gradient and model-input buffers.
+ *   For the owned samples: g = (((g_{K-1} + g_{K-2}) + ...) + g_0)  — the order autograd accumulates the members'
+ *   gradients on one device — then ta_fused_update_linf's arithmetic; x_adv is stored into every rank's buffer, m' and
+ *   delta' (full-batch pointers, only the owned rows are touched) stay local. The caller orders it across GPUs with a
+ *   barrier before (all gradients written) and after (all x_adv visible) on the same stream. K <= 8.                 */
+int ta_fused_allreduce_update_linf(const float* const* g_peers, float* const* xadv_peers, int K,
+                                   const float* m, float* m_out, const float* delta, float* delta_out,
+                                   const float* data, const float* scale, float* scale_out, int mean_mode,
+                                   float decay, float alpha, float eps, float lo, float hi,
+                                   int b0, int Bown, int64_t n, ta_stream_t stream);
 
 /* ---- model-input staging (attack.py:88, gradient/nifgsm.py:35-39) -------------------------
  *   out = data + delta                         (look == NULL)

@@ -57,6 +57,12 @@ def _worker(rank, world, init_file, out_dir, case):
             member = tab.utils.wrap_model(_net("resnet18" if rank == 0 else "mobilenet_v2", 0 if rank == 0 else 3, dev))
             atk = multigpu.make_ens_attack(tab.load_attack_class("ens"), member, epoch=4)
             out = atk(x, y)
+        elif case == "p2p":
+            member = tab.utils.wrap_model(_net("resnet18" if rank == 0 else "mobilenet_v2", 0 if rank == 0 else 3, dev))
+            run = multigpu.make_fused_p2p_ens(tab.load_attack_class("ens"), member, epoch=4)
+            out = run(x, y)
+            out2 = run(*_data(4))                       # second batch through the cached symmetric buffers
+            assert torch.equal(out, out2)
         np.save(os.path.join(out_dir, "%s_rank%d.npy" % (case, rank)), out.detach().cpu().numpy())
     finally:
         dist.destroy_process_group()
@@ -110,3 +116,20 @@ def test_sharded_ensemble_equals_single_device_ensemble():
     nets = [_net("resnet18", 0, "cuda:0"), _net("mobilenet_v2", 3, "cuda:0")]
     ref = make_attack(tab, "ens", nets, epoch=4)(x, y).cpu().numpy()
     assert np.array_equal(outs[0], ref)
+
+
+def test_fused_p2p_ensemble_equals_single_device_ensemble():
+    """ta_fused_allreduce_update_linf: reduce-scatter + update + all-gather in one kernel over NVLink peer memory."""
+    _need2()
+    import transferattack_b200 as tab
+    from helpers import make_attack
+    outs = _run("p2p")
+    assert np.array_equal(outs[0], outs[1])
+    torch.backends.cudnn.benchmark = False
+    torch.backends.cudnn.deterministic = True
+    x, y = _data()
+    nets = [_net("resnet18", 0, "cuda:0"), _net("mobilenet_v2", 3, "cuda:0")]
+    atk = make_attack(tab, "ens", nets, epoch=4)
+    atk.mean_mode = "exact"
+    ref = atk(x, y).cpu().numpy()
+    assert np.array_equal(outs[0], ref), int((outs[0] != ref).sum())

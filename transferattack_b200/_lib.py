@@ -10,7 +10,7 @@ _HERE = os.path.dirname(os.path.abspath(__file__))
 SO_PATH = os.path.join(_HERE, "libta_b200.so")
 
 TA_OK, TA_EINVAL, TA_ECUDA, TA_EUNSUPPORTED = 0, -1, -2, -3
-TA_MEAN_EXACT, TA_MEAN_ATEN = 0, 1
+TA_MEAN_EXACT = 0
 TA_DIR_SIGN, TA_DIR_RAW = 0, 1
 
 _p = ctypes.c_void_p
@@ -34,6 +34,8 @@ SIGNATURES = {
     "ta_clamp_box": (_i, [_p, _p, _f, _f, _p, _l, _p]),
     "ta_init_l2_scale": (_i, [_p, _p, _p, _f, _f, _f, _p, _i, _l, _p, _p]),
     "ta_fused_update_linf": (_i, [_p, _p, _p, _p, _p, _p, _p, _p, _p, _i, _f, _f, _f, _f, _f, _i, _l, _p]),
+    "ta_fused_allreduce_update_linf": (_i, [ctypes.POINTER(_p), ctypes.POINTER(_p), _i, _p, _p, _p, _p, _p, _p, _p, _i,
+                                            _f, _f, _f, _f, _f, _i, _i, _l, _p]),
     "ta_stage_add": (_i, [_p, _p, _p, _f, _p, _l, _p]),
     "ta_normalize_fwd": (_i, [_p, _p, _p, _p, _i, _i, _l, _p]),
     "ta_normalize_bwd": (_i, [_p, _p, _p, _i, _i, _l, _p]),

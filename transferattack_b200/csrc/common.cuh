@@ -221,14 +221,20 @@ __global__ void __launch_bounds__(256) ew_rows_kernel(int64_t nvec_per_row, F f)
   }
 }
 
+// cap_per_sm > 0: persistent launch — at most cap_per_sm resident CTAs per SM over all rows, each looping over its row
 template <int U, class F>
-int launch_ew_rows2(const char* name, int rows, int64_t n_per_row, bool can_vec4, F f, cudaStream_t s) {
+int launch_ew_rows2(const char* name, int rows, int64_t n_per_row, bool can_vec4, F f, cudaStream_t s, int cap_per_sm = 0) {
   if (rows <= 0 || n_per_row <= 0) return TA_OK;
   if (rows > 65535) { set_error("%s: %d rows exceed the grid limit 65535", name, rows); return TA_EINVAL; }
   const int threads = 256;
   const int64_t nvec = can_vec4 ? n_per_row / 4 : n_per_row;
   int64_t want = (nvec + (int64_t)threads * U - 1) / ((int64_t)threads * U);
   if (want > 0x7fffffff) want = 0x7fffffff;
+  if (cap_per_sm > 0) {
+    int64_t per_row = ((int64_t)sm_count() * cap_per_sm + rows - 1) / rows;
+    if (per_row < 1) per_row = 1;
+    if (want > per_row) want = per_row;
+  }
   const dim3 grid((unsigned)want, (unsigned)rows);
   if (can_vec4) ew_rows_kernel<4, U, F><<<grid, threads, 0, s>>>(nvec, f);
   else ew_rows_kernel<1, U, F><<<grid, threads, 0, s>>>(nvec, f);

@@ -197,6 +197,113 @@ int launch_fused(const FusedParams& p, int B, int cl, size_t smem, cudaStream_t 
   return launch_cluster("ta_fused_update_linf", k, cl, B, THREADS, smem, s, p);
 }
 
+
+// ---- ENS, one surrogate per GPU: reduce-scatter + fused update + all-gather in ONE kernel over NVLink peer memory ------------
+// Rank r owns the samples [b0, b0 + Bown). For those samples the kernel
+//   reads the K per-rank gradient buffers (K-1 of them are PEER memory mapped over NVLink) and sums them in the order
+//   autograd accumulates the members' gradients on one device (k = K-1 first, then K-2, ... 0),
+//   runs exactly ta_fused_update_linf's arithmetic (cluster per sample, summed g kept in shared memory),
+//   and stores x_adv = x + delta' into EVERY rank's model-input buffer (K-1 remote stores per element),
+// i.e. the gradient reduce-scatter, the update and the all-gather of the next model input are one launch; m' and delta' stay
+// local to the owner. Cross-GPU ordering (all gradients written before / all x_adv visible after) is the caller's two
+// symmetric-memory barriers on the same stream. L1 is invalidated at every kernel launch, and peer lines bypass the local L2,
+// so plain loads see the peers' fresh data.
+constexpr int kMaxPeers = 8;
+struct PeerPtrs { const float* g[kMaxPeers]; float* x[kMaxPeers]; int K; };
+
+template <int THREADS, int U>
+__global__ void __launch_bounds__(THREADS) fused_p2p_kernel(FusedParams p, PeerPtrs pp, int b0) {
+  extern __shared__ __align__(128) unsigned char smem_raw[];
+  __shared__ double s_scratch[32];
+  __shared__ double s_part;
+  const int tid = threadIdx.x;
+  const int K = pp.K;
+  const int64_t nvec = p.n >> 2;
+  const int64_t nr = cluster_nctarank(), rank = cluster_ctarank();
+  const int64_t per = (nvec + nr - 1) / nr;
+  const int64_t begin = rank * per < nvec ? rank * per : nvec;
+  const int64_t end = (rank + 1) * per < nvec ? (rank + 1) * per : nvec;
+  const int64_t cnt = end - begin;
+  const int64_t off = (int64_t)(b0 + blockIdx.y) * nvec + begin;       // slice start (vectors) in the FULL batch
+  float4* sg4 = reinterpret_cast<float4*>(smem_raw);
+
+  // phase A: g = sum over ranks (descending rank order), kept in shared memory; sum |g| in fp64
+  double acc = 0.0;
+  for (int64_t i0 = tid; i0 < cnt; i0 += (int64_t)THREADS * U) {
+    float4 v[U];
+#pragma unroll
+    for (int u = 0; u < U; ++u) {
+      const int64_t i = i0 + (int64_t)u * THREADS;
+      if (i < cnt) v[u] = reinterpret_cast<const float4*>(pp.g[K - 1])[off + i];
+    }
+    for (int k = K - 2; k >= 0; --k) {
+      float4 w[U];
+#pragma unroll
+      for (int u = 0; u < U; ++u) {
+        const int64_t i = i0 + (int64_t)u * THREADS;
+        if (i < cnt) w[u] = reinterpret_cast<const float4*>(pp.g[k])[off + i];
+      }
+#pragma unroll
+      for (int u = 0; u < U; ++u) {
+        v[u].x = add_rn(v[u].x, w[u].x); v[u].y = add_rn(v[u].y, w[u].y); v[u].z = add_rn(v[u].z, w[u].z); v[u].w = add_rn(v[u].w, w[u].w);
+      }
+    }
+#pragma unroll
+    for (int u = 0; u < U; ++u) {
+      const int64_t i = i0 + (int64_t)u * THREADS;
+      if (i < cnt) {
+        sg4[i] = v[u];
+        acc += (double)fabsf(v[u].x); acc += (double)fabsf(v[u].y); acc += (double)fabsf(v[u].z); acc += (double)fabsf(v[u].w);
+      }
+    }
+  }
+  const double part = block_sum(acc, s_scratch);
+  if (tid == 0) s_part = part;
+  cluster_sync_all();
+  double tot = 0.0;
+  for (uint32_t r = 0; r < (uint32_t)nr; ++r) tot += dsmem_ld_f64(&s_part, r);
+  cluster_arrive();
+  float mu = (float)(tot / (double)p.n);
+  if (p.scale) mu = __ldg(p.scale + b0 + blockIdx.y);
+  if (rank == 0 && tid == 0 && p.scale_out) p.scale_out[b0 + blockIdx.y] = mu;
+
+  // phase B
+  const bool has_m = p.m != nullptr;
+  const float4* m4 = reinterpret_cast<const float4*>(p.m) + off;
+  const float4* d4 = reinterpret_cast<const float4*>(p.delta) + off;
+  const float4* x4 = reinterpret_cast<const float4*>(p.data) + off;
+  float4* mo4 = reinterpret_cast<float4*>(p.m_out) + off;
+  float4* do4 = reinterpret_cast<float4*>(p.delta_out) + off;
+  for (int64_t i0 = tid; i0 < cnt; i0 += (int64_t)THREADS * U) {
+    float4 mv[U], dv[U], xv[U];
+#pragma unroll
+    for (int u = 0; u < U; ++u) {
+      const int64_t i = i0 + (int64_t)u * THREADS;
+      if (i < cnt) {
+        xv[u] = __ldg(x4 + i);
+        dv[u] = d4[i];
+        mv[u] = has_m ? m4[i] : make_float4(0.f, 0.f, 0.f, 0.f);
+      }
+    }
+#pragma unroll
+    for (int u = 0; u < U; ++u) {
+      const int64_t i = i0 + (int64_t)u * THREADS;
+      if (i < cnt) {
+        const float4 gv = sg4[i];
+        float4 mo, dn, xa;
+        fused_elem(gv.x, mv[u].x, has_m, dv[u].x, xv[u].x, mu, p, mo.x, dn.x, xa.x);
+        fused_elem(gv.y, mv[u].y, has_m, dv[u].y, xv[u].y, mu, p, mo.y, dn.y, xa.y);
+        fused_elem(gv.z, mv[u].z, has_m, dv[u].z, xv[u].z, mu, p, mo.z, dn.z, xa.z);
+        fused_elem(gv.w, mv[u].w, has_m, dv[u].w, xv[u].w, mu, p, mo.w, dn.w, xa.w);
+        mo4[i] = mo;
+        do4[i] = dn;
+        for (int k = 0; k < K; ++k) reinterpret_cast<float4*>(pp.x[k])[off + i] = xa;      // local + K-1 peers over NVLink
+      }
+    }
+  }
+  cluster_wait();
+}
+
 constexpr size_t kMaxStageBytes = 200 * 1024;   // per-CTA g slice bound (227 KB/SM minus static + system use)
 
 }  // namespace
@@ -218,7 +325,13 @@ extern "C" int ta_fused_update_linf(const float* g, const float* m, float* m_out
       const cudaError_t e = cudaMemcpyAsync(scale_out, scale, sizeof(float) * (size_t)B, cudaMemcpyDeviceToDevice, s);
       if (e != cudaSuccess) { set_error("ta_fused_update_linf: scale copy failed: %s", cudaGetErrorString(e)); return TA_ECUDA; }
     }
-    return launch_ew_rows2<2>("ta_fused_update_linf[stream]", B, n, v4, FusedStreamOp{p, v4 ? n / 4 : n}, s);
+    const FusedStreamOp op{p, v4 ? n / 4 : n};
+    const int cap = tune_get("stream.cap", 8);          // resident CTAs per SM (0 = one batch per thread, no loop)
+    switch (tune_get("stream.unroll", 1)) {
+      case 4: return launch_ew_rows2<4>("ta_fused_update_linf[stream]", B, n, v4, op, s, cap);
+      case 2: return launch_ew_rows2<2>("ta_fused_update_linf[stream]", B, n, v4, op, s, cap);
+      default: return launch_ew_rows2<1>("ta_fused_update_linf[stream]", B, n, v4, op, s, cap);
+    }
   }
 
   if (mean_mode != TA_MEAN_EXACT) {
@@ -261,4 +374,45 @@ extern "C" int ta_fused_update_linf(const float* g, const float* m, float* m_out
 #undef TA_FUSED_CASE
   set_error("ta_fused_update_linf: unsupported tuning threads=%d unroll=%d", threads, unroll);
   return TA_EUNSUPPORTED;
+}
+
+extern "C" int ta_fused_allreduce_update_linf(const float* const* g_peers, float* const* xadv_peers, int K, const float* m,
+                                              float* m_out, const float* delta, float* delta_out, const float* data,
+                                              const float* scale, float* scale_out, int mean_mode, float decay, float alpha,
+                                              float eps, float lo, float hi, int b0, int Bown, int64_t n, ta_stream_t stream) {
+  TA_REQUIRE(g_peers && xadv_peers && K >= 1 && K <= kMaxPeers, "ta_fused_allreduce_update_linf: K=%d (1..%d)", K, kMaxPeers);
+  TA_REQUIRE(m_out && delta && delta_out && data && b0 >= 0 && n > 0, "ta_fused_allreduce_update_linf: null pointer or bad shape");
+  if (Bown <= 0) return TA_OK;
+  TA_REQUIRE(Bown <= 65535, "ta_fused_allreduce_update_linf: Bown=%d exceeds 65535", Bown);
+  if (mean_mode != TA_MEAN_EXACT) { set_error("ta_fused_allreduce_update_linf: mean_mode %d not available", mean_mode); return TA_EUNSUPPORTED; }
+  PeerPtrs pp;
+  pp.K = K;
+  bool ok = (n % 4 == 0) && aligned16(m) && aligned16(m_out) && aligned16(delta) && aligned16(delta_out) && aligned16(data);
+  for (int k = 0; k < kMaxPeers; ++k) {
+    pp.g[k] = k < K ? g_peers[k] : nullptr;
+    pp.x[k] = k < K ? xadv_peers[k] : nullptr;
+    if (k < K) { TA_REQUIRE(pp.g[k] && pp.x[k], "ta_fused_allreduce_update_linf: null peer pointer %d", k); ok = ok && aligned16(pp.g[k]) && aligned16(pp.x[k]); }
+  }
+  TA_REQUIRE(ok, "ta_fused_allreduce_update_linf: needs n %% 4 == 0 and 16-byte aligned buffers");
+  FusedParams p{nullptr, m, m_out, delta, delta_out, data, nullptr, scale, scale_out, decay, alpha, eps, lo, hi, n};
+  const int64_t nvec = n / 4;
+  int cl = tune_get("fused.cluster", 0);
+  if (cl <= 0) { cl = 1; while (cl < 8 && n / (cl * 2) >= 2048) cl *= 2; }
+  size_t slice = (size_t)((nvec + cl - 1) / cl) * 16;
+  while (slice > kMaxStageBytes && cl < 16) { cl *= 2; slice = (size_t)((nvec + cl - 1) / cl) * 16; }
+  if (slice > kMaxStageBytes) { set_error("ta_fused_allreduce_update_linf: sample of %lld elements does not fit a 16-CTA cluster", (long long)n); return TA_EUNSUPPORTED; }
+  auto k = fused_p2p_kernel<512, 2>;
+  static SmemOptIn optin = {};
+  static bool nonportable[64] = {};
+  int rc = ensure_dyn_smem("ta_fused_allreduce_update_linf", k, slice, optin);
+  if (rc != TA_OK) return rc;
+  if (cl > 8) {
+    int dev = 0;
+    if (cudaGetDevice(&dev) != cudaSuccess || dev < 0 || dev >= 64) dev = 0;
+    if (!nonportable[dev]) {
+      if (cudaFuncSetAttribute(k, cudaFuncAttributeNonPortableClusterSizeAllowed, 1) != cudaSuccess) { set_error("cluster 16 not allowed"); cudaGetLastError(); return TA_ECUDA; }
+      nonportable[dev] = true;
+    }
+  }
+  return launch_cluster("ta_fused_allreduce_update_linf", k, cl, Bown, 512, slice, (cudaStream_t)stream, p, pp, b0);
 }

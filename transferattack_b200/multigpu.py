@@ -148,3 +148,122 @@ def make_ens_attack(attack_cls, member, group=None, **kwargs):
     # collectives inside forward/backward: keep the loop eager (NCCL inside a captured graph is not exercised here)
     P = type("Sharded" + attack_cls.__name__, (attack_cls,), {"load_model": lambda self, _n: model, "graph_safe": False})
     return P(model_name="sharded-ensemble", device=model.device, **kwargs)
+
+
+# =====================================================================================================================
+# 3. ENS with the collective FUSED into the update: one kernel does reduce-scatter + update + all-gather over NVLink
+# =====================================================================================================================
+class _GatherMeanLogits(torch.autograd.Function):
+    """forward: all_gather the K members' logits and average them with the reference's own ops — torch.mean(torch.stack(...))
+    (utils.py:97-99) — so the mean is bit-identical to the single-device EnsembleModel for any K; backward: gout / K."""
+
+    @staticmethod
+    def forward(ctx, logits, group, K):
+        ctx.K = K
+        parts = [torch.empty_like(logits) for _ in range(K)]
+        dist.all_gather(parts, logits.detach().contiguous(), group=group)
+        return torch.mean(torch.stack(parts, dim=0), dim=0)
+
+    @staticmethod
+    def backward(ctx, gout):
+        return gout / ctx.K, None, None
+
+
+def _symm():
+    import torch.distributed._symmetric_memory as symm_mem
+    return symm_mem
+
+
+class FusedP2PEnsembleLoop:
+    """The ENS iteration with one surrogate per GPU where the gradient exchange is fused into the update kernel
+    (``ta_fused_allreduce_update_linf``): every rank forwards/backwards the FULL batch through its own member, publishes its
+    input gradient in symmetric (peer-mapped) memory, and then updates only the samples it OWNS — reading the K gradients of
+    those samples straight from the peers over NVLink, and writing the next model input into every peer's buffer.
+    Per GPU and iteration that is (K-1)/K * |g| in and (K-1)/K * |x| out over NVLink — the volume of reduce-scatter +
+    all-gather — with no separate collective kernels and no replicated update. `mean|g|` is formed in the kernel
+    (mean_mode 'exact'); the gradient sum follows autograd's accumulation order, the logits mean uses the reference's own
+    ops, so for any K the result equals the single-device EnsembleModel run with mean_mode='exact' bit for bit."""
+
+    def __init__(self, attacker, group=None):
+        self.atk = attacker
+        self.group = group if group is not None else dist.group.WORLD
+        self.rank, self.K = dist.get_rank(self.group), dist.get_world_size(self.group)
+        self._state = {}
+
+    def _buffers(self, data):
+        key = (tuple(data.shape), str(data.device))
+        st = self._state.get(key)
+        if st is not None:
+            return st
+        symm_mem = _symm()
+        if hasattr(symm_mem, "enable_symm_mem_for_group"):
+            try:
+                symm_mem.enable_symm_mem_for_group(self.group.group_name)
+            except Exception:
+                pass
+        G = symm_mem.empty(*data.shape, dtype=torch.float32, device=data.device)
+        X = symm_mem.empty(*data.shape, dtype=torch.float32, device=data.device)
+        hg = symm_mem.rendezvous(G, self.group)
+        hx = symm_mem.rendezvous(X, self.group)
+        import ctypes
+        st = {"G": G, "X": X, "hg": hg, "hx": hx,
+              "g_ptrs": (ctypes.c_void_p * self.K)(*[int(p) for p in hg.buffer_ptrs]),
+              "x_ptrs": (ctypes.c_void_p * self.K)(*[int(p) for p in hx.buffer_ptrs]),
+              "m": torch.zeros_like(data), "scale_out": torch.zeros(data.shape[0], device=data.device, dtype=torch.float32)}
+        self._state[key] = st
+        return st
+
+    def __call__(self, data, label):
+        from . import _lib, ops
+        from .utils import img_max, img_min
+        atk = self.atk
+        atk.model.eval()
+        if atk.targeted:
+            assert len(label) == 2
+            label = label[1]
+        if atk.norm != 'linfty':
+            raise RuntimeError("the fused P2P ensemble loop implements the L-inf update")
+        data = atk._to_device(data).contiguous()
+        label = atk._to_device(label)
+        B = data.shape[0]
+        n = data.numel() // B
+        lo, hi = shard_bounds(B, self.rank, self.K)
+        st = self._buffers(data)
+        be = ops.backend()
+        lib = _lib.load()
+        delta = atk.init_delta(data).detach()
+        if atk.random_start:
+            dist.broadcast(delta, src=dist.get_global_rank(self.group, 0), group=self.group)      # one draw for all ranks
+        st["m"].zero_()
+        be.stage_add(data, delta, out=st["X"])
+        st["hx"].barrier(channel=0)
+        stream = torch.cuda.current_stream(data.device)
+        for _ in range(atk.epoch):
+            x_leaf = st["X"].detach().requires_grad_(True)
+            logits = _GatherMeanLogits.apply(atk.get_logits(atk.transform(x_leaf, momentum=0)), self.group, self.K)
+            loss = atk.get_loss(logits, label)
+            g = torch.autograd.grad(loss, x_leaf)[0]
+            st["G"].copy_(g)
+            st["hg"].barrier(channel=0)                     # every rank's gradient is published
+            _lib.check(lib.ta_fused_allreduce_update_linf(
+                st["g_ptrs"], st["x_ptrs"], self.K, st["m"].data_ptr(), st["m"].data_ptr(), delta.data_ptr(), delta.data_ptr(),
+                data.data_ptr(), None, st["scale_out"].data_ptr(), _lib.TA_MEAN_EXACT, float(atk.decay), float(atk.alpha),
+                float(atk.epsilon), float(img_min), float(img_max), lo, hi - lo, n, stream.cuda_stream), "ta_fused_allreduce_update_linf")
+            st["hx"].barrier(channel=0)                     # every owner's x_adv rows are visible everywhere
+        # hand every rank the full perturbation (after the attack; not on the per-iteration path)
+        sizes = [h - l for l, h in (shard_bounds(B, r, self.K) for r in range(self.K))]
+        widest = max(sizes)
+        mine = torch.zeros((widest,) + tuple(data.shape[1:]), dtype=torch.float32, device=data.device)
+        mine[:hi - lo] = delta[lo:hi]
+        parts = [torch.empty_like(mine) for _ in range(self.K)]
+        dist.all_gather(parts, mine, group=self.group)
+        return torch.cat([p[:s] for p, s in zip(parts, sizes)], dim=0)
+
+
+def make_fused_p2p_ens(attack_cls, member, group=None, **kwargs):
+    """ENS-style attack (`attack_cls`, e.g. transferattack_b200.ensemble.ens.ENS) with this rank's `member` as its surrogate,
+    run through FusedP2PEnsembleLoop. Returns a callable (data, label) → full perturbation."""
+    P = type("P2P" + attack_cls.__name__, (attack_cls,), {"load_model": lambda self, _n: member, "graph_safe": False})
+    atk = P(model_name="p2p-ensemble-member", device=next(member.parameters()).device, **kwargs)
+    atk.mean_mode = 'exact'
+    return FusedP2PEnsembleLoop(atk, group)
