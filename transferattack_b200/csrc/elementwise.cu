@@ -320,7 +320,7 @@ int ta_momentum(const float* g, const float* m, const float* scale, float decay,
                 ta_stream_t stream) {
   TA_REQUIRE(g && scale && m_out && B > 0 && n > 0, "ta_momentum: null pointer or empty shape (B=%d n=%lld)", B, (long long)n);
   const bool v4 = (n % 4 == 0) && all_aligned(g, m, m_out);
-  return launch_ew_rows2<4>("ta_momentum", B, n, v4, MomentumOp{g, m, scale, m_out, decay, v4 ? n / 4 : n}, (cudaStream_t)stream);
+  return launch_ew_rows2<1>("ta_momentum", B, n, v4, MomentumOp{g, m, scale, m_out, decay, v4 ? n / 4 : n}, (cudaStream_t)stream);
 }
 
 int ta_update_linf(const float* delta, const float* data, const float* dir, const float* alpha_t, float alpha, float eps,
@@ -328,7 +328,7 @@ int ta_update_linf(const float* delta, const float* data, const float* dir, cons
   TA_REQUIRE(delta && data && dir && delta_out && N > 0, "ta_update_linf: null pointer or N=%lld", (long long)N);
   TA_REQUIRE(dir_mode == TA_DIR_SIGN || dir_mode == TA_DIR_RAW, "ta_update_linf: dir_mode %d", dir_mode);
   const bool v4 = (N % 4 == 0) && all_aligned(delta, data, dir, alpha_t, delta_out);
-  return launch_ew2<4>("ta_update_linf", N, v4, UpdateLinfOp{delta, data, dir, alpha_t, delta_out, alpha, eps, lo, hi, dir_mode},
+  return launch_ew2<1>("ta_update_linf", N, v4, UpdateLinfOp{delta, data, dir, alpha_t, delta_out, alpha, eps, lo, hi, dir_mode},
                    (cudaStream_t)stream);
 }
 
@@ -342,14 +342,14 @@ int ta_stage_add(const float* data, const float* delta, const float* look, float
                  ta_stream_t stream) {
   TA_REQUIRE(data && out && N > 0, "ta_stage_add: null pointer or N=%lld", (long long)N);
   const bool v4 = (N % 4 == 0) && all_aligned(data, delta, look, out);
-  return launch_ew2<4>("ta_stage_add", N, v4, StageOp{data, delta, nullptr, look, out, coef}, (cudaStream_t)stream);
+  return launch_ew2<1>("ta_stage_add", N, v4, StageOp{data, delta, nullptr, look, out, coef}, (cudaStream_t)stream);
 }
 
 int ta_neighbor_stage(const float* data, const float* delta, const float* noise, const float* look, float coef, float* out,
                       int64_t N, ta_stream_t stream) {
   TA_REQUIRE(data && delta && noise && out && N > 0, "ta_neighbor_stage: null pointer or N=%lld", (long long)N);
   const bool v4 = (N % 4 == 0) && all_aligned(data, delta, noise, look, out);
-  return launch_ew2<4>("ta_neighbor_stage", N, v4, StageOp{data, delta, noise, look, out, coef}, (cudaStream_t)stream);
+  return launch_ew2<1>("ta_neighbor_stage", N, v4, StageOp{data, delta, noise, look, out, coef}, (cudaStream_t)stream);
 }
 
 int ta_normalize_fwd(const float* x, const float* mean, const float* std, float* out, int B, int C, int64_t plane,
@@ -412,7 +412,7 @@ int ta_lin_sample_bwd(const float* gout, float* gin, int K, int64_t N, ta_stream
 int ta_accumulate(float* acc, const float* g, int first, int64_t N, ta_stream_t stream) {
   TA_REQUIRE(acc && g && N > 0, "ta_accumulate: bad arguments");
   const bool v4 = (N % 4 == 0) && all_aligned(acc, g);
-  return launch_ew2<4>("ta_accumulate", N, v4, AccumulateOp{acc, g, first}, (cudaStream_t)stream);
+  return launch_ew2<1>("ta_accumulate", N, v4, AccumulateOp{acc, g, first}, (cudaStream_t)stream);
 }
 
 int ta_variance_finalize(const float* acc, const float* cur, int num_neighbor, float* out, int64_t N, ta_stream_t stream) {

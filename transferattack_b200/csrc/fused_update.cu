@@ -326,7 +326,7 @@ extern "C" int ta_fused_update_linf(const float* g, const float* m, float* m_out
       if (e != cudaSuccess) { set_error("ta_fused_update_linf: scale copy failed: %s", cudaGetErrorString(e)); return TA_ECUDA; }
     }
     const FusedStreamOp op{p, v4 ? n / 4 : n};
-    const int cap = tune_get("stream.cap", 8);          // resident CTAs per SM (0 = one batch per thread, no loop)
+    const int cap = tune_get("stream.cap", 0);          // resident CTAs per SM (0 = one batch per thread, no loop)
     switch (tune_get("stream.unroll", 1)) {
       case 4: return launch_ew_rows2<4>("ta_fused_update_linf[stream]", B, n, v4, op, s, cap);
       case 2: return launch_ew_rows2<2>("ta_fused_update_linf[stream]", B, n, v4, op, s, cap);
@@ -365,8 +365,10 @@ extern "C" int ta_fused_update_linf(const float* g, const float* m, float* m_out
 #define TA_FUSED_CASE(T, U_)                                                        \
   if (threads == T && unroll == U_)                                                 \
     return stage ? launch_fused<T, U_, true>(p, B, cl, smem, s) : launch_fused<T, U_, false>(p, B, cl, 0, s);
+  TA_FUSED_CASE(256, 1)
   TA_FUSED_CASE(256, 2)
   TA_FUSED_CASE(256, 4)
+  TA_FUSED_CASE(512, 1)
   TA_FUSED_CASE(512, 2)
   TA_FUSED_CASE(512, 4)
   TA_FUSED_CASE(1024, 1)
