@@ -1,4 +1,3 @@
 #!/bin/bash
 mkdir -p gpurun_out
-echo "== kernel table (gpu0)"; CUDA_VISIBLE_DEVICES=0 timeout 300 python bench.py --kernels > gpurun_out/kernels.log 2>&1; echo "rc=$?"; tail -32 gpurun_out/kernels.log
-echo "== multigpu tests"; timeout 900 python -m pytest tests/test_multigpu_gpu.py -m gpu -q --timeout 600 --timeout-method thread -p no:cacheprovider -k "p2p" > gpurun_out/pytest_multigpu_p2p.log 2>&1; echo "rc=$?"; tail -25 gpurun_out/pytest_multigpu_p2p.log
+echo "== bench ens K=2"; timeout 900 python -m torch.distributed.run --nnodes=1 --nproc-per-node 2 --master-addr 127.0.0.1 --master-port 29521 tools/bench_ens.py --batch 64 --steps 5 > gpurun_out/bench_ens2.log 2>&1; echo "rc=$?"; tail -3 gpurun_out/bench_ens2.log | cut -c1-1200
