@@ -68,6 +68,42 @@ def main():
     out["p2p"] = {"ms_per_attack": ms, "images_per_s": args.batch / ms * 1e3}
     out["p2p_vs_nccl_mismatch"] = int((d_p2p != d_nccl).sum())
 
+    # the exchange + update step in isolation (same gradient tensor on every rank; median of 20 after 5 warm-ups)
+    from transferattack_b200 import _lib, ops
+    be = ops.backend(); lib = _lib.load()
+    gfull = torch.randn_like(x) * 1e-4
+    m = torch.zeros_like(x); d = torch.zeros_like(x); xa = torch.empty_like(x); so = torch.empty(args.batch, device=dev)
+    st = a_p2p._buffers(x)
+    lo, hi = multigpu.shard_bounds(args.batch, rank, K)
+    n = x[0].numel()
+    stream = torch.cuda.current_stream(dev)
+
+    def step_nccl():
+        gg = gfull.clone()
+        dist.all_reduce(gg)
+        be.fused_update_linf(gg, m, m, d, d, x, xa, None, so, 1.0, 1.6 / 255, 16 / 255, 0, 1.0)
+
+    def step_p2p():
+        st["G"].copy_(gfull)
+        st["hg"].barrier(channel=0)
+        _lib.check(lib.ta_fused_allreduce_update_linf(st["g_ptrs"], st["x_ptrs"], K, m.data_ptr(), m.data_ptr(), d.data_ptr(), d.data_ptr(),
+                                                      x.data_ptr(), None, so.data_ptr(), 0, 1.0, 1.6 / 255, 16 / 255, 0.0, 1.0, lo, hi - lo, n,
+                                                      stream.cuda_stream), "p2p")
+        st["hx"].barrier(channel=0)
+
+    for name, fn in (("nccl_allreduce_plus_update_us", step_nccl), ("p2p_fused_us", step_p2p)):
+        for _ in range(5):
+            fn()
+        ts = []
+        for _ in range(20):
+            dist.barrier(); torch.cuda.synchronize(dev)
+            a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            a.record(); fn(); b.record(); torch.cuda.synchronize(dev)
+            t = torch.tensor([a.elapsed_time(b)], device=dev, dtype=torch.float64)
+            dist.all_reduce(t, op=dist.ReduceOp.MAX)
+            ts.append(float(t.item()) * 1e3)
+        out[name] = sorted(ts)[len(ts) // 2]
+
     # the reference's layout: every member on one device, sequentially (rank 0 measures, the others idle)
     if rank == 0:
         nets = [tab.utils.wrap_model(net(MODELS[k], k, dev)) for k in range(K)]

@@ -196,11 +196,6 @@ class FusedP2PEnsembleLoop:
         if st is not None:
             return st
         symm_mem = _symm()
-        if hasattr(symm_mem, "enable_symm_mem_for_group"):
-            try:
-                symm_mem.enable_symm_mem_for_group(self.group.group_name)
-            except Exception:
-                pass
         G = symm_mem.empty(*data.shape, dtype=torch.float32, device=data.device)
         X = symm_mem.empty(*data.shape, dtype=torch.float32, device=data.device)
         hg = symm_mem.rendezvous(G, self.group)
