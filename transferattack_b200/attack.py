@@ -55,6 +55,8 @@ class Attack(object):
     use_cuda_graph = os.environ.get("TA_B200_GRAPH", "1") == "1"
     #: False for plugins whose transform draws from a host generator per call (DIM, Admix): those cannot be replayed
     graph_safe = True
+    #: captured graphs kept per attacker (one per batch shape); the oldest is dropped beyond this
+    max_cached_graphs = 4
 
     def __init__(self, attack, model_name, epsilon, targeted, random_start, norm, loss, device=None):
         """attack.py:12-38 — same arguments, same attributes, same ``Unsupported norm`` exception."""
@@ -189,11 +191,13 @@ class Attack(object):
 
     def _graph_for(self, data, label, delta0):
         key = (tuple(data.shape), str(data.device), tuple(label.shape), self.mean_mode, float(self.alpha), float(self.decay),
-               float(self.epsilon), bool(self.targeted))
+               float(self.epsilon), bool(self.targeted), id(self.model))
         cache = self.__dict__.setdefault("_graphs", {})
         st = cache.get(key)
         if st is not None:
             return st
+        while len(cache) >= self.max_cached_graphs:      # each graph pins its static buffers + the surrogate's activation pool
+            cache.pop(next(iter(cache)))
         st = {"data": torch.empty_like(data), "label": torch.empty_like(label),
               "delta": torch.zeros_like(data).requires_grad_(True), "m": torch.zeros_like(data),
               "xadv": torch.empty_like(data), "scale_out": torch.empty(data.shape[0], device=data.device, dtype=torch.float32)}
