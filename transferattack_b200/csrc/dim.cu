@@ -164,22 +164,9 @@ __device__ __forceinline__ float tap_w(const Tap& t, int i) {
   return w;
 }
 
-constexpr int kMaxW = 4;   // entries of one inverse range kept as a weight table (bilinear at DIM's resize rates needs <= 4)
+constexpr int kMaxW = 6;   // weights of one inverse range kept in registers (bilinear at DIM's rates needs <= 4)
 
-// inverse tap table entry: input index p is read by the outputs lo .. lo+cnt-1 with weights w[0..cnt)
-struct Inv { int lo, cnt; float w[kMaxW]; };
-
-__device__ __forceinline__ Inv make_inv(const Tap* taps, const int* lo_tab, const int* hi_tab, int p) {
-  Inv v;
-  v.lo = lo_tab[p];
-  v.cnt = hi_tab[p] - v.lo + 1;
-  if (v.cnt < 0) v.cnt = 0;
-#pragma unroll
-  for (int k = 0; k < kMaxW; ++k) v.w[k] = (k < v.cnt) ? tap_w(taps[v.lo + k], p) : 0.0f;
-  return v;
-}
-
-// smem: [taps2: S][taps1: rnd][inv2 lo/hi: 2R ints][inv1 lo/hi: 2S ints][t2: R Inv][t1: S Inv][bufU: max(nq*S, RB*rnd)][bufG: nq*rnd]
+// smem: [taps2: S][taps1: rnd][inv2 lo/hi: 2R ints][inv1 lo/hi: 2S ints][bufU: max(nq*S, RB*rnd)][bufG: nq*rnd]
 __global__ void __launch_bounds__(kThreads) dim_bwd_kernel(const float* __restrict__ gout, float* __restrict__ gin, DimGeom gm) {
   extern __shared__ __align__(128) unsigned char smem_raw[];
   const int S = gm.S, rnd = gm.rnd, R = gm.R, top = gm.top, left = gm.left;
@@ -189,9 +176,7 @@ __global__ void __launch_bounds__(kThreads) dim_bwd_kernel(const float* __restri
   int* inv2_hi = inv2_lo + R;
   int* inv1_lo = inv2_hi + R;
   int* inv1_hi = inv1_lo + S;
-  Inv* t2 = reinterpret_cast<Inv*>(inv1_hi + S);
-  Inv* t1 = t2 + R;
-  float* bufU = reinterpret_cast<float*>(t1 + S);
+  float* bufU = reinterpret_cast<float*>(inv1_hi + S);
   const size_t u_elems = (size_t)gm.y1_rows_max * S > (size_t)RB * rnd ? (size_t)gm.y1_rows_max * S : (size_t)RB * rnd;
   float* bufG = bufU + u_elems;
 
@@ -217,11 +202,6 @@ __global__ void __launch_bounds__(kThreads) dim_bwd_kernel(const float* __restri
     atomicMin(&inv1_lo[taps1[q].i1], q); atomicMax(&inv1_hi[taps1[q].i0], q);
   }
   __syncthreads();
-  // weight tables; `wide` = some range longer than the table (extreme resize rates) → generic loops below
-  int wide_local = 0;
-  for (int p = tid; p < R; p += kThreads) { t2[p] = make_inv(taps2, inv2_lo, inv2_hi, p); wide_local |= t2[p].cnt > kMaxW; }
-  for (int p = tid; p < S; p += kThreads) { t1[p] = make_inv(taps1, inv1_lo, inv1_hi, p); wide_local |= t1[p].cnt > kMaxW; }
-  const bool wide = __syncthreads_or(wide_local) != 0;
 
   // y1 rows feeding this band of source rows
   int q0 = 0x7fffffff, q1 = -1;
@@ -234,14 +214,7 @@ __global__ void __launch_bounds__(kThreads) dim_bwd_kernel(const float* __restri
       for (int q = q0; q <= q1; ++q) {
         const int py = q + top;
         float acc = 0.0f;
-        if (!wide) {
-          const Inv v = t2[py];                      // warp-uniform broadcast
-          const float* col = gp + (int64_t)v.lo * S + ox;
-#pragma unroll
-          for (int k = 0; k < kMaxW; ++k) if (k < v.cnt) acc = fmaf(v.w[k], __ldg(col + (int64_t)k * S), acc);
-        } else {
-          for (int oy = inv2_lo[py]; oy <= inv2_hi[py]; ++oy) acc = fmaf(tap_w(taps2[oy], py), __ldg(gp + (int64_t)oy * S + ox), acc);
-        }
+        for (int oy = inv2_lo[py]; oy <= inv2_hi[py]; ++oy) acc = fmaf(tap_w(taps2[oy], py), __ldg(gp + (int64_t)oy * S + ox), acc);
         bufU[(q - q0) * S + ox] = acc;
       }
     }
@@ -249,16 +222,16 @@ __global__ void __launch_bounds__(kThreads) dim_bwd_kernel(const float* __restri
     // pass b (adjoint of T2's h-lerp, cropped to the pad window): g1[q][qx] = sum_{ox reads y2 col qx+left} wx * U[q][ox]
     for (int qx = tid; qx < rnd; qx += kThreads) {
       const int px = qx + left;
-      const Inv v = t2[px];
+      const int lo = inv2_lo[px], cnt = inv2_hi[px] - lo + 1;
+      float w[kMaxW];
+#pragma unroll
+      for (int k = 0; k < kMaxW; ++k) w[k] = (k < cnt) ? tap_w(taps2[lo + k], px) : 0.0f;
       for (int q = q0; q <= q1; ++q) {
         const float* row = bufU + (q - q0) * S;
         float acc = 0.0f;
-        if (!wide) {
 #pragma unroll
-          for (int k = 0; k < kMaxW; ++k) if (k < v.cnt) acc = fmaf(v.w[k], row[v.lo + k], acc);
-        } else {
-          for (int ox = inv2_lo[px]; ox <= inv2_hi[px]; ++ox) acc = fmaf(tap_w(taps2[ox], px), row[ox], acc);
-        }
+        for (int k = 0; k < kMaxW; ++k) if (k < cnt) acc = fmaf(w[k], row[lo + k], acc);
+        for (int k = kMaxW; k < cnt; ++k) acc = fmaf(tap_w(taps2[lo + k], px), row[lo + k], acc);
         bufG[(q - q0) * rnd + qx] = acc;
       }
     }
@@ -268,32 +241,24 @@ __global__ void __launch_bounds__(kThreads) dim_bwd_kernel(const float* __restri
   for (int qx = tid; qx < rnd; qx += kThreads) {
     for (int sy = sy0; sy <= sy1; ++sy) {
       float acc = 0.0f;
-      if (any) {
-        if (!wide) {
-          const Inv v = t1[sy];
-          const float* col = bufG + (v.lo - q0) * rnd + qx;
-#pragma unroll
-          for (int k = 0; k < kMaxW; ++k) if (k < v.cnt) acc = fmaf(v.w[k], col[k * rnd], acc);
-        } else {
-          for (int q = inv1_lo[sy]; q <= inv1_hi[sy]; ++q) acc = fmaf(tap_w(taps1[q], sy), bufG[(q - q0) * rnd + qx], acc);
-        }
-      }
+      if (any)
+        for (int q = inv1_lo[sy]; q <= inv1_hi[sy]; ++q) acc = fmaf(tap_w(taps1[q], sy), bufG[(q - q0) * rnd + qx], acc);
       bufU[(sy - sy0) * rnd + qx] = acc;
     }
   }
   __syncthreads();
   // pass d (adjoint of T1's h-lerp): gin[sy][sx] = sum_{qx reads source col sx} wx * V[sy][qx]     (coalesced stores)
   for (int sx = tid; sx < S; sx += kThreads) {
-    const Inv v = t1[sx];
+    const int lo = inv1_lo[sx], cnt = inv1_hi[sx] - lo + 1;
+    float w[kMaxW];
+#pragma unroll
+    for (int k = 0; k < kMaxW; ++k) w[k] = (k < cnt) ? tap_w(taps1[lo + k], sx) : 0.0f;
     for (int sy = sy0; sy <= sy1; ++sy) {
       const float* row = bufU + (sy - sy0) * rnd;
       float acc = 0.0f;
-      if (!wide) {
 #pragma unroll
-        for (int k = 0; k < kMaxW; ++k) if (k < v.cnt) acc = fmaf(v.w[k], row[v.lo + k], acc);
-      } else {
-        for (int qx = inv1_lo[sx]; qx <= inv1_hi[sx]; ++qx) acc = fmaf(tap_w(taps1[qx], sx), row[qx], acc);
-      }
+      for (int k = 0; k < kMaxW; ++k) if (k < cnt) acc = fmaf(w[k], row[lo + k], acc);
+      for (int k = kMaxW; k < cnt; ++k) acc = fmaf(tap_w(taps1[lo + k], sx), row[lo + k], acc);
       ip[(int64_t)sy * S + sx] = acc;
     }
   }
@@ -350,7 +315,7 @@ int ta_dim_bwd(const float* gout, float* gin, int planes, int S, int rnd, int R,
   gm.y1_rows_max = (int)((double)(RB + 1) * (double)rnd / (double)S) + 3;
   if (gm.y1_rows_max > rnd) gm.y1_rows_max = rnd;
   const size_t u_elems = (size_t)gm.y1_rows_max * S > (size_t)RB * rnd ? (size_t)gm.y1_rows_max * S : (size_t)RB * rnd;
-  const size_t smem = sizeof(Tap) * (size_t)(S + rnd) + sizeof(int) * (size_t)(2 * R + 2 * S) + sizeof(Inv) * (size_t)(R + S) +
+  const size_t smem = sizeof(Tap) * (size_t)(S + rnd) + sizeof(int) * (size_t)(2 * R + 2 * S) +
                       sizeof(float) * (u_elems + (size_t)gm.y1_rows_max * rnd);
   TA_REQUIRE(smem <= 200 * 1024, "ta_dim_bwd: image size S=%d needs %zu B of shared memory per CTA", S, smem);
   static SmemOptIn optin = {};
