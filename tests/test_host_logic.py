@@ -230,3 +230,22 @@ def test_save_images_quantisation(tmp_path):
     save_images(str(tmp_path), torch.from_numpy(M["q_data"] + M["q_delta"]), ["a.png", "b.png"])
     u8 = np.stack([np.array(Image.open(tmp_path / f)) for f in ["a.png", "b.png"]])
     assert np.array_equal(u8, M["q_u8"])
+
+
+def test_graph_capture_is_opt_in_per_hook_owner():
+    """A CUDA graph replays what ran at capture time; a transform that flips a host coin per call must therefore never
+    be captured. Every class defining a loop hook has to declare graph_safe itself — inheriting the flag is not enough."""
+    ok = {n: make_attack(tab, n, [tiny_net(0), tiny_net(1)] if n == "ens" else tiny_net(0))._graph_ok() for n in tab.attack_zoo}
+    assert ok == {"fgsm": True, "ifgsm": True, "mifgsm": True, "nifgsm": True, "tim": True, "sim": True, "ens": True,
+                  "dim": False, "admix": False, "ditimi": False, "vmifgsm": False, "vnifgsm": False, "emifgsm": False}
+    base = tab.load_attack_class("mifgsm")
+
+    class Custom(base):                          # a user plugin overriding a hook without declaring anything
+        def transform(self, x, **kw):
+            return x if torch.rand(1) > 0.5 else x.flip(-1)
+    assert not make_attack(tab, Custom, tiny_net(0))._graph_ok()
+
+    class OnlyCtor(base):                        # overriding non-hook members keeps the parent's verdict
+        def load_model(self, n):
+            return super().load_model(n)
+    assert make_attack(tab, OnlyCtor, tiny_net(0))._graph_ok()

@@ -128,3 +128,12 @@ def test_reference_plugin_runs_unchanged_on_this_base(ref, adopted, name):
     d_new = a_new(x, y)
     assert d_new.shape == d_ref.shape
     assert bits_equal(d_new.detach().numpy(), d_ref.detach().numpy()), (name, n_diff_bits(d_new.detach().numpy(), d_ref.detach().numpy()))
+
+
+def test_reference_plugins_are_never_graph_captured_unless_hook_free(adopted):
+    """The reference's dim.py / tim.py define hooks (host coin flip; F.conv2d) and know nothing about CUDA graphs: on this base
+    they stay eager. Its mifgsm.py only configures the base loop, whose hooks are ours → capturable."""
+    assert make_attack(adopted, "mifgsm", _net())._graph_ok()
+    assert make_attack(adopted, "ifgsm", _net())._graph_ok()
+    for name in ("dim", "tim", "sim", "nifgsm", "admix"):
+        assert not make_attack(adopted, name, _net())._graph_ok(), name

@@ -53,7 +53,10 @@ class Attack(object):
     #: a surrogate that cannot be captured (host syncs, data-dependent control flow) makes the loop fall back to launching
     #: the very same kernels eagerly. Env TA_B200_GRAPH=0 disables.
     use_cuda_graph = os.environ.get("TA_B200_GRAPH", "1") == "1"
-    #: False for plugins whose transform draws from a host generator per call (DIM, Admix): those cannot be replayed
+    #: Declared (in the class BODY) by every class that defines loop hooks which are safe to capture once and replay:
+    #: no host-side random draws or data-dependent Python control flow per call. A hook defined by a class that does not
+    #: declare it — e.g. the reference's own dim.py on this base, whose transform flips a host coin per call — keeps the
+    #: loop eager, so capture can never freeze such a decision into a graph.
     graph_safe = True
     #: captured graphs kept per attacker (one per batch shape); the oldest is dropped beyond this
     max_cached_graphs = 4
@@ -102,6 +105,16 @@ class Attack(object):
             return t
         return t.to(self.device, non_blocking=t.is_pinned() if not t.is_cuda else False)
 
+    _GRAPH_HOOKS = ("forward", "transform", "get_logits", "get_loss", "get_grad", "get_momentum", "update_delta", "init_delta")
+
+    def _graph_ok(self):
+        """every loop hook in effect is defined by a class that itself declares graph_safe = True"""
+        for hook in self._GRAPH_HOOKS:
+            owner = next(c for c in type(self).__mro__ if hook in c.__dict__)
+            if not owner.__dict__.get("graph_safe", False):
+                return False
+        return True
+
     def _fusable(self):
         cls = type(self)
         return (self.fuse_update and self.norm == 'linfty'
@@ -122,7 +135,7 @@ class Attack(object):
 
         delta = self.init_delta(data)
         if self._fusable():
-            if (self.use_cuda_graph and self.graph_safe and data.is_cuda and ops._test_backend is None
+            if (self.use_cuda_graph and self._graph_ok() and data.is_cuda and ops._test_backend is None
                     and getattr(self, "_kernel_events", None) is None and not self.__dict__.get("_graph_failed", False)):
                 try:
                     return self._loop_graph(data, label, delta)

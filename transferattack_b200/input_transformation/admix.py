@@ -10,7 +10,7 @@ from ..gradient.mifgsm import MIFGSM
 
 
 class Admix(MIFGSM):
-    graph_safe = False      # draws host-generator numbers on every call → not replayable from a CUDA graph
+    graph_safe = False      # transform draws host-generator numbers on every call → never captured into a CUDA graph
 
     def __init__(self, model_name, epsilon=16/255, alpha=1.6/255, epoch=10, decay=1., num_scale=5, num_admix=3, admix_strength=0.2,
                  targeted=False, random_start=False, norm='linfty', loss='crossentropy', device=None, attack='Admix', **kwargs):

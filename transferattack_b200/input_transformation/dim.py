@@ -12,7 +12,7 @@ from ..gradient.mifgsm import MIFGSM
 
 
 class DIM(MIFGSM):
-    graph_safe = False      # draws host-generator numbers on every call → not replayable from a CUDA graph
+    graph_safe = False      # transform draws host-generator numbers on every call → never captured into a CUDA graph
 
     def __init__(self, model_name, epsilon=16/255, alpha=1.6/255, epoch=10, decay=1., resize_rate=1.1, diversity_prob=0.5, targeted=False,
                  random_start=False, norm='linfty', loss='crossentropy', device=None, attack='DIM', **kwargs):

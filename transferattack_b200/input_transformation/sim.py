@@ -7,6 +7,8 @@ from ..gradient.mifgsm import MIFGSM
 
 
 class SIM(MIFGSM):
+    graph_safe = True       # hooks defined here are deterministic device code → capturable (attack.py: _graph_ok)
+
     def __init__(self, model_name, epsilon=16/255, alpha=1.6/255, epoch=10, decay=1., num_scale=5, targeted=False, random_start=False,
                  norm='linfty', loss='crossentropy', device=None, attack='SIM', **kwargs):
         super().__init__(model_name, epsilon, alpha, epoch, decay, targeted, random_start, norm, loss, device, attack)

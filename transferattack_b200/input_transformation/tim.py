@@ -33,6 +33,8 @@ def make_kernel(kernel_type, kernel_size, nsig=3):
 
 
 class TIM(MIFGSM):
+    graph_safe = True       # hooks defined here are deterministic device code → capturable (attack.py: _graph_ok)
+
     conv_mode = 'separable'     # 'separable' | 'direct'
 
     def __init__(self, model_name, epsilon=16/255, alpha=1.6/255, epoch=10, decay=1., kernel_type='gaussian', kernel_size=15, targeted=False,

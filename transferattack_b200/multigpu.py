@@ -146,7 +146,7 @@ def make_ens_attack(attack_cls, member, group=None, **kwargs):
     module; ``device`` is taken from the member."""
     model = ShardedEnsembleModel(member, group)
     # collectives inside forward/backward: keep the loop eager (NCCL inside a captured graph is not exercised here)
-    P = type("Sharded" + attack_cls.__name__, (attack_cls,), {"load_model": lambda self, _n: model, "graph_safe": False})
+    P = type("Sharded" + attack_cls.__name__, (attack_cls,), {"load_model": lambda self, _n: model, "use_cuda_graph": False})
     return P(model_name="sharded-ensemble", device=model.device, **kwargs)
 
 
@@ -258,7 +258,7 @@ class FusedP2PEnsembleLoop:
 def make_fused_p2p_ens(attack_cls, member, group=None, **kwargs):
     """ENS-style attack (`attack_cls`, e.g. transferattack_b200.ensemble.ens.ENS) with this rank's `member` as its surrogate,
     run through FusedP2PEnsembleLoop. Returns a callable (data, label) → full perturbation."""
-    P = type("P2P" + attack_cls.__name__, (attack_cls,), {"load_model": lambda self, _n: member, "graph_safe": False})
+    P = type("P2P" + attack_cls.__name__, (attack_cls,), {"load_model": lambda self, _n: member, "use_cuda_graph": False})
     atk = P(model_name="p2p-ensemble-member", device=next(member.parameters()).device, **kwargs)
     atk.mean_mode = 'exact'
     return FusedP2PEnsembleLoop(atk, group)
