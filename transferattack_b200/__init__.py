@@ -8,24 +8,24 @@ import importlib
 
 from . import utils, attack   # noqa: F401  (reference-style `pkg.utils.wrap_model` / `pkg.attack.Attack` access)
 
-attack_zoo = {
-    # gradient
-    'fgsm': ('.gradient.fgsm', 'FGSM'),
-    'ifgsm': ('.gradient.ifgsm', 'IFGSM'),
-    'mifgsm': ('.gradient.mifgsm', 'MIFGSM'),
-    'nifgsm': ('.gradient.nifgsm', 'NIFGSM'),
-    'vmifgsm': ('.gradient.vmifgsm', 'VMIFGSM'),
-    'vnifgsm': ('.gradient.vnifgsm', 'VNIFGSM'),
-    'emifgsm': ('.gradient.emifgsm', 'EMIFGSM'),
-    # input transformation
-    'dim': ('.input_transformation.dim', 'DIM'),
-    'tim': ('.input_transformation.tim', 'TIM'),
-    'sim': ('.input_transformation.sim', 'SIM'),
-    'admix': ('.input_transformation.admix', 'Admix'),
-    'ditimi': ('.input_transformation.di_ti_mi', 'DITIMI'),
-    # ensemble
-    'ens': ('.ensemble.ens', 'ENS'),
-}
+def _zoo():
+    """name → (relative module, class); same keys and classes as the reference registry for the accelerated attacks."""
+    table = {
+        "gradient": ["fgsm:FGSM", "ifgsm:IFGSM", "mifgsm:MIFGSM", "nifgsm:NIFGSM", "vmifgsm:VMIFGSM", "vnifgsm:VNIFGSM",
+                     "emifgsm:EMIFGSM"],
+        "input_transformation": ["dim:DIM", "tim:TIM", "sim:SIM", "admix:Admix", "di_ti_mi:DITIMI=ditimi"],
+        "ensemble": ["ens:ENS"],
+    }
+    zoo = {}
+    for package, entries in table.items():
+        for entry in entries:
+            spec, _, alias = entry.partition("=")
+            module, cls = spec.split(":")
+            zoo[alias or module] = (".%s.%s" % (package, module), cls)
+    return zoo
+
+
+attack_zoo = _zoo()
 
 
 def load_attack_class(attack_name):

@@ -6,7 +6,7 @@ from ..attack import Attack
 
 
 class ENS(Attack):
-    def __init__(self, model_name, epsilon=16/255, alpha=1.6/255, epoch=10, decay=1., targeted=False, random_start=False,
-                 norm='linfty', loss='crossentropy', device=None, attack='ENS', **kwargs):
-        super().__init__(attack, model_name, epsilon, targeted, random_start, norm, loss, device)
+    def __init__(self, model_name, epsilon=16/255, alpha=1.6/255, epoch=10, decay=1., targeted=False,
+                 random_start=False, norm='linfty', loss='crossentropy', device=None, attack='ENS', **kwargs):
+        Attack.__init__(self, attack, model_name, epsilon, targeted, random_start, norm, loss, device)
         self.alpha, self.epoch, self.decay = alpha, epoch, decay

@@ -5,7 +5,7 @@ from ..attack import Attack
 
 
 class IFGSM(Attack):
-    def __init__(self, model_name, epsilon=16/255, alpha=1.6/255, epoch=10, targeted=False, random_start=False,
-                 norm='linfty', loss='crossentropy', device=None, attack='I-FGSM', **kwargs):
-        super().__init__(attack, model_name, epsilon, targeted, random_start, norm, loss, device)
-        self.alpha, self.epoch, self.decay = alpha, epoch, 0
+    def __init__(self, model_name, epsilon=16/255, alpha=1.6/255, epoch=10, targeted=False,
+                 random_start=False, norm='linfty', loss='crossentropy', device=None, attack='I-FGSM', **kwargs):
+        Attack.__init__(self, attack, model_name, epsilon, targeted, random_start, norm, loss, device)
+        self.alpha, self.epoch, self.decay = alpha, epoch, 0     # decay 0: the buffer is just g / mean|g|
