@@ -464,9 +464,20 @@ def run_kernels(args):
     add("stage_add", 12, lambda: be.stage_add(x, d, out=xa))
     add("sim_fwd S=5", 24, lambda: be.sim(x, 5, True))
     add("sim_bwd S=5", 24, lambda: be.sim(g5, 5, False))
-    add("dim_fwd", 8, lambda: be.dim(x, 235, 246, 5, 6, True))
-    add("dim_bwd", 8, lambda: be.dim(g, 235, 246, 5, 6, False))
-    add("dwconv2d_sep k=15", 8, lambda: be.dwconv2d_sep(g, kc3, kr3))
+    for impl, tag in ((1, "direct 2-phase, host tap tables"), (0, "4-pass")):
+        _lib.tune_set("dim.impl", impl)
+        add("dim_fwd [%s]" % tag, 8, lambda: be.dim(x, 235, 246, 5, 6, True))
+        add("dim_bwd [%s]" % tag, 8, lambda: be.dim(g, 235, 246, 5, 6, False))
+    _lib.tune_set("dim.impl", 1)
+    hc, hr = kc3.cpu().numpy(), kr3.cpu().numpy()
+    add("dwconv2d_sep k=15 [register-sliding, factors as kernel parameters]", 8, lambda: be.dwconv2d_sep(g, kc3, kr3, host=(hc, hr)))
+    _lib.tune_set("tim.bh", 56)
+    add("dwconv2d_sep k=15 [register-sliding, parameters, band 56]", 8, lambda: be.dwconv2d_sep(g, kc3, kr3, host=(hc, hr)))
+    _lib.tune_set("tim.bh", 32)
+    add("dwconv2d_sep k=15 [register-sliding, factors from device arrays]", 8, lambda: be.dwconv2d_sep(g, kc3, kr3))
+    _lib.tune_set("tim.band", 1)
+    add("dwconv2d_sep k=15 [two-pass band kernel]", 8, lambda: be.dwconv2d_sep(g, kc3, kr3))
+    _lib.tune_set("tim.band", 2)
     add("dwconv2d k=15 (direct)", 8, lambda: be.dwconv2d(g, k3))
     add("accumulate", 12, lambda: be.accumulate(m2, g, False))
     add("quantize_u8", 9, lambda: be.quantize_u8(x, d, True))

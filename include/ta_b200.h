@@ -179,6 +179,11 @@ int ta_dwconv2d(const float* g, const float* k, int ks, float* out, int B, int C
                 ta_stream_t stream);
 int ta_dwconv2d_sep(const float* g, const float* kcol, const float* krow, int ks, float* out,
                     int B, int C, int H, int W, ta_stream_t stream);
+/* Same operation with the factors given as HOST arrays [C, ks] (read during the call): when all channels share them (every
+ * kernel tim.py generates) and W % 4 == 0, 32 <= W <= 512, ks in {3,5,7,15}, they travel as kernel parameters and feed the
+ * FMAs from the constant bank; any other request returns TA_EUNSUPPORTED (use ta_dwconv2d_sep). Bit-identical results.  */
+int ta_dwconv2d_sep_hw(const float* g, const float* kcol_host, const float* krow_host, int ks,
+                       float* out, int B, int C, int H, int W, ta_stream_t stream);
 
 /* ---- EMI (gradient/emifgsm.py:53-58, 86-103) ---------------------------------------------------------
  *   out[k*N + i] = x[i] + coef[k] * gbar[i]  (coef[k] = (float)(factor_k * alpha), host array, K <= 32)

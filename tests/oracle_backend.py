@@ -108,7 +108,7 @@ class OracleBackend:
         self._log("dwconv2d")
         return _t(oracle.dwconv2d(_np(g), _np(k)))
 
-    def dwconv2d_sep(self, g, kcol, krow):
+    def dwconv2d_sep(self, g, kcol, krow, host=None):
         self._log("dwconv2d_sep")
         return _t(oracle.dwconv2d_sep(_np(g), _np(kcol), _np(krow)))
 

@@ -158,8 +158,17 @@ def _dim_cases():
     return D, sorted({k.rsplit("_", 1)[0] for k in D.files})
 
 
+@pytest.fixture(params=[1, 0], ids=["direct", "fourpass"])
+def dim_impl(request):
+    """Both generations of the DIM kernels (csrc/dim_direct.cu = default, csrc/dim.cu) must meet the same parity bar."""
+    from transferattack_b200 import _lib
+    _lib.tune_set("dim.impl", request.param)
+    yield request.param
+    _lib.tune_set("dim.impl", 1)
+
+
 @pytest.mark.parametrize("tma", [1, 0])
-def test_dim_forward(be, tma):
+def test_dim_forward(be, tma, dim_impl):
     from transferattack_b200 import _lib
     _lib.tune_set("dim.tma", tma)
     try:
@@ -177,7 +186,7 @@ def test_dim_forward(be, tma):
         _lib.tune_set("dim.blend", 1)
 
 
-def test_dim_forward_bit_identical_to_torch_cuda(be):
+def test_dim_forward_bit_identical_to_torch_cuda(be, dim_impl):
     """The reference runs F.interpolate / F.pad / F.interpolate on the GPU; with the default blend (the FMA contraction of
     torch's own CUDA kernel) ta_dim_fwd reproduces that chain bit for bit. The adjoint is compared with autograd's
     (atomicAdd scatter) result at rounding level."""
@@ -195,7 +204,7 @@ def test_dim_forward_bit_identical_to_torch_cuda(be):
         assert float((gin - gin_ref).abs().max()) <= 2e-6 * max(1.0, float(gin_ref.abs().max()))
 
 
-def test_dim_backward(be):
+def test_dim_backward(be, dim_impl):
     D, cases = _dim_cases()
     for c in cases:
         rnd, R, top, left, _ = [int(v) for v in D[c + "_params"]]
@@ -204,7 +213,7 @@ def test_dim_backward(be):
         np.testing.assert_allclose(gin, D[c + "_gin"], rtol=0, atol=3e-6, err_msg=c)
 
 
-def test_dim_edge_geometries(be):
+def test_dim_edge_geometries(be, dim_impl):
     rng = np.random.default_rng(3)
     for S, rate in [(224, 1.1), (299, 1.1), (64, 1.5), (33, 1.2), (16, 2.0)]:
         R = int(S * rate)
@@ -248,6 +257,42 @@ def test_tim_generic_kernel_sizes(be):
         assert bits_equal(npy(be.dwconv2d(cu(x), cu(k))), oracle.dwconv2d(x, k.reshape(2, 1, ks, ks))), ks
         kc, kr = rng.random((2, ks), dtype=np.float32), rng.random((2, ks), dtype=np.float32)
         assert bits_equal(npy(be.dwconv2d_sep(cu(x), cu(kc), cu(kr))), oracle.dwconv2d_sep(x, kc, kr)), ks
+
+
+@pytest.mark.parametrize("ks", [3, 5, 7, 15])
+def test_tim_sep_all_launch_paths_bit_identical(be, ks):
+    """The separable convolution has four launch paths (register-sliding with the factors as kernel parameters or loaded
+    from device arrays, band height 32 / 56; two-pass band kernel; 32x32 tiles): all must equal the C oracle bit for bit,
+    including ragged heights (last band partly / wholly outside the image) and channel-specific factors."""
+    from transferattack_b200 import _lib
+    rng = np.random.default_rng(ks)
+    shapes = [(2, 3, 224, 224), (1, 2, 64, 32), (1, 3, 40, 36), (1, 1, 33, 32), (1, 2, 20, 32), (1, 1, 100, 512), (1, 2, 70, 40)]
+    try:
+        for shp in shapes:
+            x = rng.standard_normal(shp).astype(np.float32)
+            C = shp[1]
+            k1c, k1r = rng.random(ks, dtype=np.float32), rng.random(ks, dtype=np.float32)
+            shared = (np.stack([k1c] * C), np.stack([k1r] * C))
+            distinct = (rng.random((C, ks), dtype=np.float32), rng.random((C, ks), dtype=np.float32))
+            for kc, kr in (shared, distinct):
+                want = oracle.dwconv2d_sep(x, kc, kr)
+                for band, bh in ((2, 32), (2, 56), (1, 32), (0, 32)):
+                    _lib.tune_set("tim.band", band); _lib.tune_set("tim.bh", bh)
+                    got = npy(be.dwconv2d_sep(cu(x), cu(kc), cu(kr)))
+                    assert bits_equal(got, want), (shp, "device factors", band, bh)
+                    got = npy(be.dwconv2d_sep(cu(x), cu(kc), cu(kr), host=(kc, kr)))
+                    assert bits_equal(got, want), (shp, "host factors", band, bh)
+    finally:
+        _lib.tune_set("tim.band", 2); _lib.tune_set("tim.bh", 32)
+
+
+def test_tim_sep_hw_refuses_what_it_cannot_serve(be):
+    from transferattack_b200 import _lib
+    lib = _lib.load()
+    x = torch.zeros(1, 3, 30, 30, device="cuda"); out = torch.empty_like(x)       # W % 4 != 0
+    k = np.ones((3, 15), np.float32)
+    rc = lib.ta_dwconv2d_sep_hw(x.data_ptr(), k.ctypes.data, k.ctypes.data, 15, out.data_ptr(), 1, 3, 30, 30, None)
+    assert rc == _lib.TA_EUNSUPPORTED and "ta_dwconv2d_sep_hw" in _lib.last_error()
 
 
 # ---------------------------------------------------------------------------------------------- reductions + fused

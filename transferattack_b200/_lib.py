@@ -47,6 +47,7 @@ SIGNATURES = {
     "ta_dim_bwd": (_i, [_p, _p, _i, _i, _i, _i, _i, _i, _p]),
     "ta_dwconv2d": (_i, [_p, _p, _i, _p, _i, _i, _i, _i, _p]),
     "ta_dwconv2d_sep": (_i, [_p, _p, _p, _i, _p, _i, _i, _i, _i, _p]),
+    "ta_dwconv2d_sep_hw": (_i, [_p, _p, _p, _i, _p, _i, _i, _i, _i, _p]),
     "ta_lin_sample_fwd": (_i, [_p, _p, ctypes.POINTER(_f), _i, _p, _l, _p]),
     "ta_lin_sample_bwd": (_i, [_p, _p, _i, _l, _p]),
     "ta_neighbor_stage": (_i, [_p, _p, _p, _p, _f, _p, _l, _p]),

@@ -20,6 +20,7 @@
 // Adjoint: the four passes transposed — vertical gather from gout, horizontal gather, (crop = the pad's adjoint),
 // vertical gather, horizontal gather — with inverse tap ranges built in shared memory; fixed ascending summation order.
 #include "common.cuh"
+#include "dim_direct.cuh"
 
 using namespace ta;
 
@@ -285,6 +286,10 @@ int ta_dim_fwd(const float* x, float* out, int planes, int S, int rnd, int R, in
   TA_REQUIRE(x && out, "ta_dim_fwd: null pointer");
   int rc = check_geom("ta_dim_fwd", planes, S, rnd, R, pad_top, pad_left);
   if (rc != TA_OK) return rc;
+  // dim.impl: 1 (default) = direct two-phase kernels with host-built tap tables (dim_direct.cu), 0 = four-pass kernels below
+  if (tune_get("dim.impl", 1) != 0 && dim_direct_ok(S, rnd, R))
+    return dim_fwd_direct(x, out, planes, S, rnd, R, pad_top, pad_left, tune_get("dim.blend", 1),
+                          (S % 4 == 0) && aligned16(x) && tune_get("dim.tma", 1) != 0, (cudaStream_t)stream);
   DimGeom gm{S, rnd, R, pad_top, pad_left, 0, 0, 0, tune_get("dim.blend", 1)};
   gm.t2_rows_max = band_rows(RB, R, S);
   if (gm.t2_rows_max > R) gm.t2_rows_max = R;
@@ -310,6 +315,9 @@ int ta_dim_bwd(const float* gout, float* gin, int planes, int S, int rnd, int R,
   TA_REQUIRE(gout && gin, "ta_dim_bwd: null pointer");
   int rc = check_geom("ta_dim_bwd", planes, S, rnd, R, pad_top, pad_left);
   if (rc != TA_OK) return rc;
+  if (tune_get("dim.impl", 1) != 0 && dim_direct_ok(S, rnd, R))
+    return dim_bwd_direct(gout, gin, planes, S, rnd, R, pad_top, pad_left,
+                          (S % 4 == 0) && aligned16(gout) && tune_get("dim.tma", 1) != 0, (cudaStream_t)stream);
   DimGeom gm{S, rnd, R, pad_top, pad_left, 0, 0, 0, 0};
   // y1 rows reading RB consecutive source rows of the S -> rnd resize
   gm.y1_rows_max = (int)((double)(RB + 1) * (double)rnd / (double)S) + 3;

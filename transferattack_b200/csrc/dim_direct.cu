@@ -1,0 +1,397 @@
+// dim_direct.cu — second-generation DIM kernels (input_transformation/dim.py:42-68): same arithmetic as dim.cu
+// (ATen's bilinear expression with the contraction torch's CUDA build uses — bit-identical forward), different
+// organisation. ncu on the four-pass kernels of dim.cu showed them instruction-issue-bound (IPC 2.6, > 100 issued
+// instructions per output element, 37 % of them integer address arithmetic; profiles/ncu_tim_dim_r1.md). Here:
+//
+//  * every 1-D tap ((i0, i1, l1) per destination index) and every inverse range is computed ONCE on the host per call
+//    (470 entries for 224 -> rnd -> 246 -> 224) and travels as a __grid_constant__ kernel parameter (8.7 / 13 KB): the
+//    row loops index it with a warp-uniform counter, so row taps, row offsets and loop control live in UNIFORM registers
+//    (ULDC / UIMAD on the uniform datapath) and shared-memory loads use [thread column + uniform row offset] addressing
+//    with no per-thread integer arithmetic;
+//  * forward = two phases instead of four passes: y1 band (direct 4-tap bilinear from the bulk-TMA-staged source rows)
+//    -> shared memory (with one zero row and one zero column appended: that IS the zero padding, no predicates),
+//    then out band (direct 4-tap bilinear from y1) -> coalesced global stores. hlerp/vlerp are evaluated exactly as in
+//    dim.cu, so the result is bit-identical to it, to the C oracle and to torch's CUDA kernels;
+//  * adjoint = the two phases transposed, each as "horizontal gather, then vertical scatter into two rotating register
+//    accumulators": a thread owns one column, walks the rows of the incoming gradient once, forms the horizontal
+//    inverse-range sum (<= 3 taps, weights in registers) and adds l0*h / l1*h to the two destination rows the current row
+//    feeds; a destination row is complete when the (monotone) tap index moves past it and is written exactly once.
+//    Deterministic (fixed ascending order), no atomics, no intermediate pass through shared memory except g1.
+#include "common.cuh"
+#include "dim_direct.cuh"
+
+#include <string.h>
+
+using namespace ta;
+
+namespace {
+
+constexpr int RB = 16;          // destination rows per CTA
+constexpr int kThreads = 256;
+constexpr int kMaxW = 3;        // inverse-range weights kept in registers (bilinear at DIM's rates needs <= 3)
+
+struct Geo { int S, rnd, R, top, left, a_rows, c_rows; };
+
+__device__ __forceinline__ int tap_i0(const TapE& e) { return e.i01 & 0xffff; }
+__device__ __forceinline__ int tap_i1(const TapE& e) { return (int)((unsigned)e.i01 >> 16); }
+
+// ATen: hl0*(wl0*p00 + wl1*p01) + hl1*(wl0*p10 + wl1*p11) with the FMA contraction of torch's CUDA build (dim.cu mode 1);
+// MODE 0: every product and sum rounded separately; 2-4: the other contraction orders (diagnostic).
+template <int MODE>
+__device__ __forceinline__ float hl(float w0, float w1, float a, float b) {
+  if (MODE == 0) return add_rn(mul_rn(w0, a), mul_rn(w1, b));
+  if (MODE == 1 || MODE == 3) return fmaf(w0, a, mul_rn(w1, b));
+  return fmaf(w1, b, mul_rn(w0, a));
+}
+template <int MODE>
+__device__ __forceinline__ float vl(float h0, float h1, float t, float b) {
+  if (MODE == 0) return add_rn(mul_rn(h0, t), mul_rn(h1, b));
+  if (MODE == 1 || MODE == 4) return fmaf(h0, t, mul_rn(h1, b));
+  return fmaf(h1, b, mul_rn(h0, t));
+}
+
+// ---- forward ---------------------------------------------------------------------------------------------------------
+// Row descriptor of one destination row inside a band: BYTE offsets of its two source rows in the staging buffer (the
+// zero row for padding) and the vertical weight. Built once per CTA by one thread per row, read back as one broadcast
+// LDS.128 per row: the row loops then need 4 integer adds per element and no multiplies, compares or table decoding.
+struct __align__(16) RowD { int offa, offb; float l1; int pad; };
+
+__device__ __forceinline__ float lds_f32(uint32_t addr) {
+  float v;
+  asm volatile("ld.shared.f32 %0, [%1];" : "=f"(v) : "r"(addr));
+  return v;
+}
+__device__ __forceinline__ void sts_f32(uint32_t addr, float v) {
+  asm volatile("st.shared.f32 [%0], %1;" ::"r"(addr), "f"(v) : "memory");
+}
+
+// smem: bufA [a_rows * S] source band (offset 0: the bulk-TMA destination) | bufC [(c_rows + 1) * (rnd + 1)] y1 band,
+// row nq and column rnd are zero | descA [c_rows] | descB [RB]
+template <int MODE, bool TMA_STAGE>
+__global__ void __launch_bounds__(kThreads) dim_fwd_direct_kernel(const float* __restrict__ x, float* __restrict__ out,
+                                                                  const __grid_constant__ DimTabF tab, const Geo gm) {
+  extern __shared__ __align__(128) unsigned char smem_raw[];
+  __shared__ __align__(8) uint64_t s_bar;
+  const int S = gm.S, rnd = gm.rnd, top = gm.top, left = gm.left;
+  const int CP = rnd + 1;
+  float* bufA = reinterpret_cast<float*>(smem_raw);
+  float* bufC = bufA + (size_t)gm.a_rows * S;
+  RowD* descA = reinterpret_cast<RowD*>(smem_raw + (((size_t)gm.a_rows * S + (size_t)(gm.c_rows + 1) * CP) * 4 + 15 & ~(size_t)15));
+  RowD* descB = descA + gm.c_rows;
+
+  const int tid = threadIdx.x;
+  const int oy0 = blockIdx.x * RB;
+  const int oy1 = min(oy0 + RB, S) - 1;                 // inclusive
+  const int nb = oy1 - oy0 + 1;
+  const float* xp = x + (int64_t)blockIdx.y * S * S;
+  float* op = out + (int64_t)blockIdx.y * S * S;
+
+  // rows of y2 (padded), y1 and x this band depends on; the y1 range is empty when the band maps entirely into the padding
+  const int pr0 = tap_i0(tab.t2[oy0]), pr1 = tap_i1(tab.t2[oy1]);
+  const int q0 = max(pr0 - top, 0), q1 = min(pr1 - top, rnd - 1);
+  const bool any = q0 <= q1;
+  const int nq = any ? q1 - q0 + 1 : 0;
+  int sr0 = 0, nsr = 0;
+  if (any) { sr0 = tap_i0(tab.t1[q0]); nsr = tap_i1(tab.t1[q1]) - sr0 + 1; }
+
+  if (TMA_STAGE) {
+    if (tid == 0) {
+      mbar_init(&s_bar, 1);
+      mbar_fence_init();
+      if (any) {
+        const uint32_t bytes = (uint32_t)(nsr * S * 4);
+        mbar_expect_tx(&s_bar, bytes);
+        tma_bulk_g2s(bufA, xp + (int64_t)sr0 * S, bytes, &s_bar);
+      }
+    }
+  } else if (any) {
+    const float* src = xp + (int64_t)sr0 * S;
+    for (int e = tid; e < nsr * S; e += kThreads) bufA[e] = __ldg(src + e);
+  }
+  // zero row nq and zero column rnd of the y1 band; row descriptors
+  for (int e = tid; e < CP; e += kThreads) bufC[nq * CP + e] = 0.0f;
+  for (int e = tid; e < nq; e += kThreads) bufC[e * CP + rnd] = 0.0f;
+  for (int q = tid; q < nq; q += kThreads) {
+    const TapE th = tab.t1[q0 + q];
+    descA[q] = RowD{(tap_i0(th) - sr0) * S * 4, (tap_i1(th) - sr0) * S * 4, th.l1, 0};
+  }
+  for (int r = tid; r < nb; r += kThreads) {
+    const TapE th = tab.t2[oy0 + r];
+    const int ya = tap_i0(th) - top - q0, yb = tap_i1(th) - top - q0;
+    descB[r] = RowD{((ya >= 0 && ya < nq) ? ya : nq) * CP * 4, ((yb >= 0 && yb < nq) ? yb : nq) * CP * 4, th.l1, 0};
+  }
+  __syncthreads();
+
+  if (any) {
+    if (TMA_STAGE) mbar_wait(&s_bar, 0);
+    // phase A: y1[q][qx] for q in [q0, q1]; inactive lanes of the last column chunk recompute column rnd-1 (same value,
+    // same address) so that the loop stays convergent
+    for (int c0 = 0; c0 < rnd; c0 += kThreads) {
+      const int col = min(c0 + tid, rnd - 1);
+      const TapE tw = tab.t1[col];
+      const float wl1 = tw.l1, wl0 = sub_rn(1.0f, wl1);
+      const uint32_t ca = smem_u32(bufA + tap_i0(tw)), cb = smem_u32(bufA + tap_i1(tw));
+      uint32_t dst = smem_u32(bufC + col);
+      const RowD* d = descA;
+#pragma unroll 4
+      for (int q = 0; q < nq; ++q, ++d, dst += (uint32_t)CP * 4) {
+        const int4 dd = *reinterpret_cast<const int4*>(d);
+        const float hl1 = __int_as_float(dd.z), hl0 = sub_rn(1.0f, hl1);
+        const float t = hl<MODE>(wl0, wl1, lds_f32(ca + dd.x), lds_f32(cb + dd.x));
+        const float b = hl<MODE>(wl0, wl1, lds_f32(ca + dd.y), lds_f32(cb + dd.y));
+        sts_f32(dst, vl<MODE>(hl0, hl1, t, b));
+      }
+    }
+  }
+  __syncthreads();
+  // phase B: out[oy][ox] for oy in [oy0, oy1]
+  for (int c0 = 0; c0 < S; c0 += kThreads) {
+    const int col = min(c0 + tid, S - 1);
+    const TapE tw = tab.t2[col];
+    const float wl1 = tw.l1, wl0 = sub_rn(1.0f, wl1);
+    const int xa = tap_i0(tw) - left, xb = tap_i1(tw) - left;
+    const uint32_t ca = smem_u32(bufC + ((xa >= 0 && xa < rnd) ? xa : rnd)), cb = smem_u32(bufC + ((xb >= 0 && xb < rnd) ? xb : rnd));
+    float* o = op + (int64_t)oy0 * S + col;
+    const RowD* d = descB;
+#pragma unroll 4
+    for (int r = 0; r < nb; ++r, ++d, o += S) {
+      const int4 dd = *reinterpret_cast<const int4*>(d);
+      const float hl1 = __int_as_float(dd.z), hl0 = sub_rn(1.0f, hl1);
+      const float t = hl<MODE>(wl0, wl1, lds_f32(ca + dd.x), lds_f32(cb + dd.x));
+      const float b = hl<MODE>(wl0, wl1, lds_f32(ca + dd.y), lds_f32(cb + dd.y));
+      *o = vl<MODE>(hl0, hl1, t, b);
+    }
+  }
+}
+
+// ---- adjoint ---------------------------------------------------------------------------------------------------------
+// weight with which tap `t` (of some destination index) reads source index `i`: l0 if i0 == i, plus l1 if i1 == i
+__device__ __forceinline__ float tap_w(const TapE& t, int i) {
+  float w = 0.0f;
+  if (tap_i0(t) == i) w = sub_rn(1.0f, t.l1);
+  if (tap_i1(t) == i) w = add_rn(w, t.l1);
+  return w;
+}
+
+// One "horizontal gather + vertical scatter" sweep. The thread owns destination column `col` (weights w[], first source
+// column lo, count cnt) and walks source rows r = 0..nrows-1 of the staged band at shared address `src` (pitch bytes);
+// desc[r] = {i0, i1, l1} of the destination-tap that row r is (decoded once per CTA), feeding destination rows i0 / i1
+// with l0 / l1. emit(row, value) is called exactly once for every destination row in [emit_lo, emit_hi], ascending.
+struct __align__(16) RowT { int i0, i1; float l1; int pad; };
+
+template <class Emit>
+__device__ __forceinline__ void gather_scatter(uint32_t src, uint32_t pitch_bytes, int nrows, const RowT* __restrict__ desc,
+                                               const TapE* __restrict__ th_tab, int lo, int cnt, int col,
+                                               const float (&w)[kMaxW], int emit_lo, int emit_hi, Emit emit) {
+  int pcur = nrows > 0 ? desc[0].i0 : emit_hi + 1;
+  for (int p = emit_lo; p < pcur && p <= emit_hi; ++p) emit(p, 0.0f);
+  float accA = 0.0f, accB = 0.0f;
+  uint32_t sp = src + (uint32_t)lo * 4;
+  const unsigned span = (unsigned)(emit_hi - emit_lo);
+  for (int r = 0; r < nrows; ++r, sp += pitch_bytes) {
+    const int4 e = *reinterpret_cast<const int4*>(desc + r);
+    float h = 0.0f;
+#pragma unroll
+    for (int k = 0; k < kMaxW; ++k) if (k < cnt) h = fmaf(w[k], lds_f32(sp + 4 * k), h);
+    for (int k = kMaxW; k < cnt; ++k) h = fmaf(tap_w(th_tab[lo + k], col), lds_f32(sp + 4 * k), h);
+    while (pcur < e.x) {                             // rows the monotone tap index has moved past are complete
+      if ((unsigned)(pcur - emit_lo) <= span) emit(pcur, accA);
+      accA = accB; accB = 0.0f; ++pcur;
+    }
+    const float l1 = __int_as_float(e.z), l0 = sub_rn(1.0f, l1);
+    accA = fmaf(l0, h, accA);
+    if (e.y == e.x) accA = fmaf(l1, h, accA); else accB = fmaf(l1, h, accB);
+  }
+  if (nrows > 0) {
+    if ((unsigned)(pcur - emit_lo) <= span) emit(pcur, accA);
+    if ((unsigned)(pcur + 1 - emit_lo) <= span) emit(pcur + 1, accB);
+    for (int p = max(pcur + 2, emit_lo); p <= emit_hi; ++p) emit(p, 0.0f);
+  }
+}
+
+// smem: bufU [u_rows * S] gout band (offset 0: the bulk-TMA destination) | bufG [g_rows * rnd] g1 band | descU [u_rows] |
+// descQ [g_rows]
+template <bool TMA_STAGE>
+__global__ void __launch_bounds__(kThreads) dim_bwd_direct_kernel(const float* __restrict__ gout, float* __restrict__ gin,
+                                                                  const __grid_constant__ DimTabB tab, const Geo gm) {
+  extern __shared__ __align__(128) unsigned char smem_raw[];
+  __shared__ __align__(8) uint64_t s_bar;
+  const int S = gm.S, rnd = gm.rnd, top = gm.top, left = gm.left;
+  float* bufU = reinterpret_cast<float*>(smem_raw);
+  float* bufG = bufU + (size_t)gm.a_rows * S;
+  RowT* descU = reinterpret_cast<RowT*>(smem_raw + ((((size_t)gm.a_rows * S + (size_t)gm.c_rows * rnd) * 4 + 15) & ~(size_t)15));
+  RowT* descQ = descU + gm.a_rows;
+
+  const int tid = threadIdx.x;
+  const int sy0 = blockIdx.x * RB;
+  const int sy1 = min(sy0 + RB, S) - 1;
+  const float* gp = gout + (int64_t)blockIdx.y * S * S;
+  float* ip = gin + (int64_t)blockIdx.y * S * S;
+
+  // y1 rows feeding this band of source rows, then the gout rows feeding those (scans over the host's inverse ranges)
+  int q0 = 0x7fffffff, q1 = -1;
+  for (int sy = sy0; sy <= sy1; ++sy) {
+    const InvE iv = tab.inv1[sy];
+    if (iv.cnt > 0) { q0 = min(q0, (int)iv.lo); q1 = max(q1, (int)iv.lo + iv.cnt - 1); }
+  }
+  const bool any = q0 <= q1;
+  const int nq = any ? q1 - q0 + 1 : 0;
+  if (!any) q0 = 0;
+  int oyA = 0x7fffffff, oyB = -1;
+  for (int q = 0; q < nq; ++q) {
+    const InvE iv = tab.inv2[q0 + q + top];
+    if (iv.cnt > 0) { oyA = min(oyA, (int)iv.lo); oyB = max(oyB, (int)iv.lo + iv.cnt - 1); }
+  }
+  const int nu = oyA <= oyB ? oyB - oyA + 1 : 0;
+  if (nu == 0) oyA = 0;
+
+  if (TMA_STAGE) {
+    if (tid == 0) {
+      mbar_init(&s_bar, 1);
+      mbar_fence_init();
+      if (nu > 0) {
+        const uint32_t bytes = (uint32_t)(nu * S * 4);
+        mbar_expect_tx(&s_bar, bytes);
+        tma_bulk_g2s(bufU, gp + (int64_t)oyA * S, bytes, &s_bar);
+      }
+    }
+  } else {
+    const float* src = gp + (int64_t)oyA * S;
+    for (int e = tid; e < nu * S; e += kThreads) bufU[e] = __ldg(src + e);
+  }
+  for (int r = tid; r < nu; r += kThreads) { const TapE t = tab.t2[oyA + r]; descU[r] = RowT{tap_i0(t), tap_i1(t), t.l1, 0}; }
+  for (int q = tid; q < nq; q += kThreads) { const TapE t = tab.t1[q0 + q]; descQ[q] = RowT{tap_i0(t), tap_i1(t), t.l1, 0}; }
+  __syncthreads();
+  if (TMA_STAGE && nu > 0) mbar_wait(&s_bar, 0);
+
+  // phase B^T: g1[q][qx], q in [q0, q1]: gather over output columns, scatter over y2 rows (crop = the pad's adjoint)
+  for (int col = tid; col < rnd && any; col += kThreads) {
+    const int px = col + left;
+    const InvE iv = tab.inv2[px];
+    float w[kMaxW];
+#pragma unroll
+    for (int k = 0; k < kMaxW; ++k) w[k] = (k < iv.cnt) ? tap_w(tab.t2[iv.lo + k], px) : 0.0f;
+    const uint32_t g1 = smem_u32(bufG + col);
+    const int base = top + q0;
+    gather_scatter(smem_u32(bufU), (uint32_t)S * 4, nu, descU, tab.t2, iv.lo, iv.cnt, px, w, q0 + top, q1 + top,
+                   [&](int p, float v) { sts_f32(g1 + (uint32_t)((p - base) * rnd) * 4, v); });
+  }
+  __syncthreads();
+  // phase A^T: gin[sy][sx], sy in [sy0, sy1]: gather over y1 columns, scatter over source rows (coalesced stores)
+  for (int col = tid; col < S; col += kThreads) {
+    const InvE iv = tab.inv1[col];
+    float w[kMaxW];
+#pragma unroll
+    for (int k = 0; k < kMaxW; ++k) w[k] = (k < iv.cnt) ? tap_w(tab.t1[iv.lo + k], col) : 0.0f;
+    float* o = ip + col;
+    gather_scatter(smem_u32(bufG), (uint32_t)rnd * 4, nq, descQ, tab.t1, iv.lo, iv.cnt, col, w, sy0, sy1,
+                   [&](int s, float v) { o[(int64_t)s * S] = v; });
+  }
+}
+
+// ---- host: tables ------------------------------------------------------------------------------------------------------
+void host_taps(int in, int out, TapE* t) {           // ATen area_pixel_compute_source_index, align_corners=False
+  const float scale = (float)in / (float)out;
+  for (int d = 0; d < out; ++d) {
+    float src = fmaf(scale, (float)d + 0.5f, -0.5f);
+    if (src < 0.0f) src = 0.0f;
+    const int i0 = (int)src;
+    const int i1 = i0 + ((i0 < in - 1) ? 1 : 0);
+    t[d].l1 = src - (float)i0;
+    t[d].i01 = i0 | (i1 << 16);
+  }
+}
+void host_inverse(const TapE* t, int out, int in, InvE* inv) {
+  for (int i = 0; i < in; ++i) { inv[i].lo = 0; inv[i].cnt = 0; }
+  for (int d = 0; d < out; ++d) {
+    const int idx[2] = {t[d].i01 & 0xffff, (int)((unsigned)t[d].i01 >> 16)};
+    for (int k = 0; k < 2; ++k) {
+      InvE& e = inv[idx[k]];
+      if (e.cnt == 0) { e.lo = (short)d; e.cnt = 1; }
+      else e.cnt = (short)(d - e.lo + 1);             // d ascends: [lo, d] (taps are monotone: everything inside touches it)
+    }
+  }
+}
+inline int h_i0(const TapE& e) { return e.i01 & 0xffff; }
+inline int h_i1(const TapE& e) { return (int)((unsigned)e.i01 >> 16); }
+
+}  // namespace
+
+namespace ta {
+
+bool dim_direct_ok(int S, int rnd, int R) { return S <= kDimMaxS && R <= kDimMaxR && rnd <= kDimMaxR && S >= 1; }
+
+int dim_fwd_direct(const float* x, float* out, int planes, int S, int rnd, int R, int top, int left, int blend, bool tma,
+                   cudaStream_t stream) {
+  static thread_local DimTabF tab;
+  host_taps(R, S, tab.t2);
+  host_taps(S, rnd, tab.t1);
+  // exact band maxima (rows of y1 and of the source one band needs)
+  int c_rows = 0, a_rows = 1;
+  for (int oy0 = 0; oy0 < S; oy0 += RB) {
+    const int oy1 = (oy0 + RB < S ? oy0 + RB : S) - 1;
+    const int pr0 = h_i0(tab.t2[oy0]), pr1 = h_i1(tab.t2[oy1]);
+    const int q0 = pr0 - top > 0 ? pr0 - top : 0, q1 = pr1 - top < rnd - 1 ? pr1 - top : rnd - 1;
+    if (q0 > q1) continue;
+    if (q1 - q0 + 1 > c_rows) c_rows = q1 - q0 + 1;
+    const int nsr = h_i1(tab.t1[q1]) - h_i0(tab.t1[q0]) + 1;
+    if (nsr > a_rows) a_rows = nsr;
+  }
+  Geo gm{S, rnd, R, top, left, a_rows, c_rows};
+  const size_t smem = ((sizeof(float) * ((size_t)a_rows * S + (size_t)(c_rows + 1) * (rnd + 1)) + 15) & ~(size_t)15) + 16 * (size_t)(c_rows + RB);
+  TA_REQUIRE(smem <= 200 * 1024, "ta_dim_fwd: image size S=%d needs %zu B of shared memory per CTA", S, smem);
+  void (*k)(const float*, float*, const DimTabF, const Geo);
+  int slot;
+  if (blend == 1) { k = tma ? dim_fwd_direct_kernel<1, true> : dim_fwd_direct_kernel<1, false>; slot = tma ? 0 : 1; }
+  else if (blend == 0) { k = tma ? dim_fwd_direct_kernel<0, true> : dim_fwd_direct_kernel<0, false>; slot = tma ? 2 : 3; }
+  else if (blend == 2) { k = tma ? dim_fwd_direct_kernel<2, true> : dim_fwd_direct_kernel<2, false>; slot = tma ? 4 : 5; }
+  else if (blend == 3) { k = tma ? dim_fwd_direct_kernel<3, true> : dim_fwd_direct_kernel<3, false>; slot = tma ? 6 : 7; }
+  else { k = tma ? dim_fwd_direct_kernel<4, true> : dim_fwd_direct_kernel<4, false>; slot = tma ? 8 : 9; }
+  static SmemOptIn optin[10] = {};
+  const int rc = ensure_dyn_smem("ta_dim_fwd", k, smem, optin[slot]);
+  if (rc != TA_OK) return rc;
+  dim3 grid((unsigned)((S + RB - 1) / RB), (unsigned)planes);
+  k<<<grid, kThreads, smem, stream>>>(x, out, tab, gm);
+  count_launch();
+  return check_launch("ta_dim_fwd[direct]");
+}
+
+int dim_bwd_direct(const float* gout, float* gin, int planes, int S, int rnd, int R, int top, int left, bool tma,
+                   cudaStream_t stream) {
+  static thread_local DimTabB tab;
+  host_taps(R, S, tab.t2);
+  host_taps(S, rnd, tab.t1);
+  host_inverse(tab.t2, S, R, tab.inv2);
+  host_inverse(tab.t1, rnd, S, tab.inv1);
+  int g_rows = 1, u_rows = 1;
+  for (int sy0 = 0; sy0 < S; sy0 += RB) {
+    const int sy1 = (sy0 + RB < S ? sy0 + RB : S) - 1;
+    int q0 = 0x7fffffff, q1 = -1;
+    for (int sy = sy0; sy <= sy1; ++sy)
+      if (tab.inv1[sy].cnt > 0) {
+        if (tab.inv1[sy].lo < q0) q0 = tab.inv1[sy].lo;
+        if (tab.inv1[sy].lo + tab.inv1[sy].cnt - 1 > q1) q1 = tab.inv1[sy].lo + tab.inv1[sy].cnt - 1;
+      }
+    if (q0 > q1) continue;
+    if (q1 - q0 + 1 > g_rows) g_rows = q1 - q0 + 1;
+    int a = 0x7fffffff, b = -1;
+    for (int q = q0; q <= q1; ++q) {
+      const InvE& iv = tab.inv2[q + top];
+      if (iv.cnt > 0) { if (iv.lo < a) a = iv.lo; if (iv.lo + iv.cnt - 1 > b) b = iv.lo + iv.cnt - 1; }
+    }
+    if (a <= b && b - a + 1 > u_rows) u_rows = b - a + 1;
+  }
+  Geo gm{S, rnd, R, top, left, u_rows, g_rows};
+  const size_t smem = ((sizeof(float) * ((size_t)u_rows * S + (size_t)g_rows * rnd) + 15) & ~(size_t)15) + 16 * (size_t)(u_rows + g_rows);
+  TA_REQUIRE(smem <= 200 * 1024, "ta_dim_bwd: image size S=%d needs %zu B of shared memory per CTA", S, smem);
+  auto k = tma ? dim_bwd_direct_kernel<true> : dim_bwd_direct_kernel<false>;
+  static SmemOptIn optin[2] = {};
+  const int rc = ensure_dyn_smem("ta_dim_bwd", k, smem, optin[tma ? 0 : 1]);
+  if (rc != TA_OK) return rc;
+  dim3 grid((unsigned)((S + RB - 1) / RB), (unsigned)planes);
+  k<<<grid, kThreads, smem, stream>>>(gout, gin, tab, gm);
+  count_launch();
+  return check_launch("ta_dim_bwd[direct]");
+}
+
+}  // namespace ta

@@ -12,6 +12,8 @@
 // (bank-conflict-free 4-wide register blocking); zero padding comes from the guarded tile load.
 #include "common.cuh"
 
+#include <string.h>
+
 using namespace ta;
 
 namespace {
@@ -226,6 +228,159 @@ int launch_band(const float* g, const float* kcol, const float* krow, float* out
   return check_launch("ta_dwconv2d_sep[band]");
 }
 
+// ---- register-sliding variant of the separable convolution (default for the TIM hot case) ---------------------------------
+// One CTA = one band of BH output rows x the full width of one plane, ONE thread per 4 adjacent columns. The band's
+// BH + KS - 1 input rows are staged exactly like the band kernel (one bulk-TMA copy per image row into a zero-margined
+// layout), but in chunks of CH rows with one mbarrier each, so the first rows are consumed while the rest are in flight.
+// A thread then walks down the band ONCE: for input row r it forms the row pass of its 4 columns in registers
+// (5 x LDS.128, KS x 4 FMA) and immediately scatters that value into the KS output rows it contributes to,
+//   acc[(r - i) mod KS] = fma(kcol[i], tmp_r, acc[(r - i) mod KS]),  i = 0..KS-1,
+// a rotating file of KS x 4 accumulators whose slot index is static because the row loop is unrolled KS-fold. Output row
+// y = r - (KS-1) is complete after input row r and leaves as one 128-bit store. The intermediate never touches shared
+// memory, there is no second pass, no per-item index arithmetic, and per output the FMA chain still runs tap 0..KS-1 from
+// 0 in both directions → bit-identical to the band / tile kernels and to orc_dwconv2d_sep.
+// PW = true: the weights are kernel parameters (constant bank operands of the FMAs, no registers) — used when the host knows
+// them (ta_dwconv2d_sep_hw); PW = false: loaded once per thread from the device arrays.
+template <int KS> struct SepWeights { float kr[KS]; float kc[KS]; };
+
+template <int KS> struct RsGeom {
+  static constexpr int R = KS / 2;
+  static constexpr int PADX = (R + 3) & ~3;
+  static constexpr int OFF = PADX - R;                    // first padded column read by output column 0
+  static constexpr int NV = (OFF + KS + 3 + 3) / 4;       // float4 loads covering the 4-output window
+  static constexpr int M = (8 + KS - 1) / KS;             // chunk = M * KS rows (>= 8)
+  static constexpr int CH = M * KS;
+};
+
+template <int KS, int BHR, bool PW>
+__global__ void __launch_bounds__(128) dwconv_sep_rs_kernel(const float* __restrict__ g, const float* __restrict__ kcol,
+                                                            const float* __restrict__ krow,
+                                                            const __grid_constant__ SepWeights<KS> wp, float* __restrict__ out,
+                                                            int C, int H, int W) {
+  using G = RsGeom<KS>;
+  constexpr int R = G::R, PADX = G::PADX, OFF = G::OFF, NV = G::NV, CH = G::CH;
+  constexpr int ROWS = BHR + KS - 1;
+  constexpr int NCH = (ROWS + CH - 1) / CH;
+  extern __shared__ __align__(128) unsigned char smem_raw[];
+  __shared__ __align__(8) uint64_t s_bar[NCH];
+  const int WP = W + 2 * PADX;
+  float* s_in = reinterpret_cast<float*>(smem_raw);            // [ROWS][WP]
+  const int tid = threadIdx.x;
+  const int plane = blockIdx.y;
+  const int y0 = blockIdx.x * BHR;
+  const float* gp = g + (int64_t)plane * H * W;
+
+  const int ya = max(y0 - R, 0), yb = min(y0 + BHR + R, H);     // valid image rows of this band
+  const int top_inv = ya - (y0 - R);                            // band rows [0, top_inv) and [ROWS - bot_inv, ROWS) are padding
+  const int bot_inv = (y0 + BHR + R) - yb;
+  if (tid == 0) {
+#pragma unroll
+    for (int c = 0; c < NCH; ++c) mbar_init(&s_bar[c], 1);
+    mbar_fence_init();
+#pragma unroll
+    for (int c = 0; c < NCH; ++c) {
+      const int ra = max(c * CH, top_inv), rb = min(min((c + 1) * CH, ROWS), ROWS - bot_inv);
+      mbar_expect_tx(&s_bar[c], (uint32_t)(max(rb - ra, 0) * W * 4));
+      for (int r = ra; r < rb; ++r)
+        tma_bulk_g2s(s_in + r * WP + PADX, gp + (int64_t)(y0 - R + r) * W, (uint32_t)(W * 4), &s_bar[c]);
+    }
+  }
+  // zero margins of every row, and the rows outside the image (disjoint from every TMA destination)
+  {
+    const float4 z = make_float4(0.f, 0.f, 0.f, 0.f);
+    constexpr int MV = PADX / 4;                              // float4s per margin
+    for (int e = tid; e < ROWS * 2 * MV; e += blockDim.x) {
+      const int r = e / (2 * MV), q = e % (2 * MV);
+      *reinterpret_cast<float4*>(s_in + r * WP + (q < MV ? 4 * q : W + PADX + 4 * (q - MV))) = z;
+    }
+    const int wv = W >> 2;
+    for (int e = tid; e < (top_inv + bot_inv) * wv; e += blockDim.x) {
+      const int k = e / wv, x4 = e - k * wv;
+      const int r = k < top_inv ? k : ROWS - bot_inv + (k - top_inv);
+      *reinterpret_cast<float4*>(s_in + r * WP + PADX + 4 * x4) = z;
+    }
+  }
+  __syncthreads();     // barrier inits + zero fill visible to everyone
+  if (4 * tid >= W) return;
+
+  float wr[PW ? 1 : KS], wc[PW ? 1 : KS];
+  if (!PW) {
+    const int c = plane % C;
+#pragma unroll
+    for (int j = 0; j < KS; ++j) { wr[j] = __ldg(krow + c * KS + j); wc[j] = __ldg(kcol + c * KS + j); }
+  }
+  float acc[KS][4];
+#pragma unroll
+  for (int s = 0; s < KS; ++s) { acc[s][0] = 0.f; acc[s][1] = 0.f; acc[s][2] = 0.f; acc[s][3] = 0.f; }
+
+  const float* sp = s_in + 4 * tid;                               // this thread's window in band row r (advanced per row)
+  int yl = -(KS - 1);                                             // band-local output row completed by band row r
+  const unsigned ylim = (unsigned)min(BHR, H - y0);               // rows of this band inside the image
+  float* op = out + (int64_t)plane * H * W + (int64_t)(y0 + yl) * W + 4 * tid;
+#pragma unroll 1
+  for (int ch = 0; ch < NCH; ++ch) {
+    mbar_wait(&s_bar[ch], 0);
+#pragma unroll
+    for (int rr = 0; rr < CH; ++rr) {
+      if (ch * CH + rr < ROWS) {
+        const float4* row4 = reinterpret_cast<const float4*>(sp);
+        float v[4 * NV];
+#pragma unroll
+        for (int t = 0; t < NV; ++t) {
+          const float4 q = row4[t];
+          v[4 * t] = q.x; v[4 * t + 1] = q.y; v[4 * t + 2] = q.z; v[4 * t + 3] = q.w;
+        }
+        float t0 = 0.f, t1 = 0.f, t2 = 0.f, t3 = 0.f;
+#pragma unroll
+        for (int j = 0; j < KS; ++j) {
+          const float w = PW ? wp.kr[j] : wr[j];
+          t0 = fmaf(w, v[OFF + j], t0); t1 = fmaf(w, v[OFF + j + 1], t1);
+          t2 = fmaf(w, v[OFF + j + 2], t2); t3 = fmaf(w, v[OFF + j + 3], t3);
+        }
+#pragma unroll
+        for (int i = 0; i < KS; ++i) {
+          const int s = ((rr - i) % KS + KS) % KS;            // static: CH is a multiple of KS
+          const float w = PW ? wp.kc[i] : wc[i];
+          acc[s][0] = fmaf(w, t0, acc[s][0]); acc[s][1] = fmaf(w, t1, acc[s][1]);
+          acc[s][2] = fmaf(w, t2, acc[s][2]); acc[s][3] = fmaf(w, t3, acc[s][3]);
+        }
+        const int sc = (rr + 1) % KS;                         // slot of output row r - (KS-1): complete now
+        if ((unsigned)yl < ylim)                              // false for the KS-1 warm-up rows (yl < 0) and past the image
+          *reinterpret_cast<float4*>(op) = make_float4(acc[sc][0], acc[sc][1], acc[sc][2], acc[sc][3]);
+        acc[sc][0] = 0.f; acc[sc][1] = 0.f; acc[sc][2] = 0.f; acc[sc][3] = 0.f;
+        sp += WP; op += W; ++yl;
+      }
+    }
+  }
+}
+
+template <int KS, int BHR, bool PW>
+int launch_rs(const float* g, const float* kcol, const float* krow, const SepWeights<KS>& wp, float* out, int B, int C, int H,
+              int W, cudaStream_t s) {
+  using G = RsGeom<KS>;
+  const size_t smem = sizeof(float) * (size_t)(BHR + KS - 1) * (W + 2 * G::PADX);
+  auto k = dwconv_sep_rs_kernel<KS, BHR, PW>;
+  static SmemOptIn optin = {};
+  const int rc = ensure_dyn_smem("ta_dwconv2d_sep", k, smem, optin);
+  if (rc != TA_OK) return rc;
+  const int threads = (((W + 3) / 4) + 31) & ~31;
+  dim3 grid((unsigned)((H + BHR - 1) / BHR), (unsigned)(B * C));
+  k<<<grid, threads, smem, s>>>(g, kcol, krow, wp, out, C, H, W);
+  count_launch();
+  return check_launch("ta_dwconv2d_sep[rs]");
+}
+
+template <int KS, bool PW>
+int launch_rs_bh(const float* g, const float* kcol, const float* krow, const SepWeights<KS>& wp, float* out, int B, int C,
+                 int H, int W, cudaStream_t s) {
+  if (tune_get("tim.bh", 32) == 56) return launch_rs<KS, 56, PW>(g, kcol, krow, wp, out, B, C, H, W, s);
+  return launch_rs<KS, 32, PW>(g, kcol, krow, wp, out, B, C, H, W, s);
+}
+
+inline bool rs_ok(const void* g, const void* out, int ks, int W) {
+  return (W % 4 == 0) && W >= 32 && W <= 512 && aligned16(g) && aligned16(out) && (ks == 3 || ks == 5 || ks == 7 || ks == 15);
+}
+
 template <int KS>
 __global__ void __launch_bounds__(kThreads) dwconv2d_kernel(const float* __restrict__ g, const float* __restrict__ k, int ks_rt,
                                                             float* __restrict__ out, int C, int H, int W) {
@@ -299,8 +454,19 @@ int ta_dwconv2d_sep(const float* g, const float* kcol, const float* krow, int ks
   int rc = check_conv("ta_dwconv2d_sep", g, kcol, out, ks, B, C, H, W);
   if (rc != TA_OK) return rc;
   TA_REQUIRE(krow, "ta_dwconv2d_sep: null krow");
-  // hot case (TIM on 224 / 299-class images): full-width bands staged by bulk-TMA
-  if ((W % 4 == 0) && W >= 32 && W <= 512 && aligned16(g) && tune_get("tim.band", 1) != 0) {
+  // hot case (TIM on 224-class images): full-width bands staged by bulk-TMA; tim.band: 2 = register-sliding kernel
+  // (default), 1 = two-pass band kernel, 0 = 32x32 tiles
+  const int mode = tune_get("tim.band", 2);
+  if (mode == 2 && rs_ok(g, out, ks, W)) {
+    cudaStream_t bs = (cudaStream_t)stream;
+    switch (ks) {
+      case 3: return launch_rs_bh<3, false>(g, kcol, krow, SepWeights<3>{}, out, B, C, H, W, bs);
+      case 5: return launch_rs_bh<5, false>(g, kcol, krow, SepWeights<5>{}, out, B, C, H, W, bs);
+      case 7: return launch_rs_bh<7, false>(g, kcol, krow, SepWeights<7>{}, out, B, C, H, W, bs);
+      default: return launch_rs_bh<15, false>(g, kcol, krow, SepWeights<15>{}, out, B, C, H, W, bs);
+    }
+  }
+  if ((W % 4 == 0) && W >= 32 && W <= 512 && aligned16(g) && mode != 0) {
     cudaStream_t bs = (cudaStream_t)stream;
     switch (ks) {
       case 3: return launch_band<3>(g, kcol, krow, out, B, C, H, W, bs);
@@ -326,6 +492,38 @@ int ta_dwconv2d_sep(const float* g, const float* kcol, const float* krow, int ks
 #undef TA_SEP_CASE
   count_launch();
   return check_launch("ta_dwconv2d_sep");
+}
+
+// Host-weight form: kcol_host / krow_host are HOST arrays [C, ks] read during the call (like ta_lin_sample_fwd's table).
+// When every channel carries the same factors (all of tim.py's kernels) and the shape is the hot one, the weights travel
+// as kernel parameters and feed the FMAs from the constant bank; otherwise returns TA_EUNSUPPORTED and the caller uses
+// ta_dwconv2d_sep with device arrays.
+int ta_dwconv2d_sep_hw(const float* g, const float* kcol_host, const float* krow_host, int ks, float* out, int B, int C,
+                       int H, int W, ta_stream_t stream) {
+  int rc = check_conv("ta_dwconv2d_sep_hw", g, kcol_host, out, ks, B, C, H, W);
+  if (rc != TA_OK) return rc;
+  TA_REQUIRE(krow_host, "ta_dwconv2d_sep_hw: null krow_host");
+  bool same = true;
+  for (int c = 1; c < C && same; ++c)
+    for (int j = 0; j < ks; ++j)
+      if (memcmp(&kcol_host[c * ks + j], &kcol_host[j], 4) != 0 || memcmp(&krow_host[c * ks + j], &krow_host[j], 4) != 0) { same = false; break; }
+  if (!same || !rs_ok(g, out, ks, W)) {
+    set_error("ta_dwconv2d_sep_hw: needs channel-shared factors, ks in {3,5,7,15}, W %% 4 == 0, 32 <= W <= 512, 16-B aligned tensors");
+    return TA_EUNSUPPORTED;
+  }
+  cudaStream_t bs = (cudaStream_t)stream;
+#define TA_HW_CASE(K)                                                                     \
+  case K: {                                                                               \
+    SepWeights<K> w;                                                                      \
+    for (int j = 0; j < K; ++j) { w.kr[j] = krow_host[j]; w.kc[j] = kcol_host[j]; }      \
+    return launch_rs_bh<K, true>(g, nullptr, nullptr, w, out, B, C, H, W, bs);            \
+  }
+  switch (ks) {
+    TA_HW_CASE(3) TA_HW_CASE(5) TA_HW_CASE(7) TA_HW_CASE(15)
+    default: break;
+  }
+#undef TA_HW_CASE
+  return TA_EUNSUPPORTED;
 }
 
 int ta_dwconv2d(const float* g, const float* k, int ks, float* out, int B, int C, int H, int W, ta_stream_t stream) {

@@ -45,14 +45,15 @@ class TIM(MIFGSM):
     def generate_kernel(self, kernel_type, kernel_size, nsig=3):
         k2d, kcol, krow = make_kernel(kernel_type, kernel_size, nsig)
         kernel = torch.from_numpy(k2d).to(self.device)
-        self._sep = (kernel, torch.from_numpy(np.stack([kcol] * 3)).to(self.device), torch.from_numpy(np.stack([krow] * 3)).to(self.device))
+        hc, hr = np.stack([kcol] * 3), np.stack([krow] * 3)
+        self._sep = (kernel, torch.from_numpy(hc).to(self.device), torch.from_numpy(hr).to(self.device), (hc, hr))
         return kernel
 
     def smooth(self, grad):
         be = ops.backend()
         sep = getattr(self, '_sep', None)
         if self.conv_mode == 'separable' and sep is not None and sep[0] is self.kernel and grad.shape[1] == 3:
-            return be.dwconv2d_sep(grad, sep[1], sep[2])
+            return be.dwconv2d_sep(grad, sep[1], sep[2], host=sep[3])
         return be.dwconv2d(grad, self.kernel.reshape(self.kernel.shape[0], self.kernel.shape[-2], self.kernel.shape[-1]))
 
     def get_grad(self, loss, delta, **kwargs):

@@ -8,6 +8,8 @@ control flow can be unit-tested on a box without a GPU; nothing in this package 
 """
 import ctypes
 
+import numpy as np
+
 import torch
 
 from . import _lib
@@ -194,10 +196,20 @@ class CudaBackend:
             _lib.check(self.lib.ta_dwconv2d(_ptr(g), _ptr(k), ks, _ptr(out), B, C, H, W, _stream()), "ta_dwconv2d")
         return out
 
-    def dwconv2d_sep(self, g, kcol, krow):
-        g = _f32c(g, "grad"); kcol = _f32c(kcol, "kcol"); krow = _f32c(krow, "krow"); B, C, H, W = g.shape; ks = kcol.shape[-1]
+    def dwconv2d_sep(self, g, kcol, krow, host=None):
+        """host = (kcol, krow) as numpy [C, ks] copies of the same factors: lets the library pass them as kernel parameters
+        (ta_dwconv2d_sep_hw) for the shapes it supports; bit-identical either way."""
+        g = _f32c(g, "grad"); B, C, H, W = g.shape
         out = torch.empty_like(g)
         with _DeviceOf(g):
+            if host is not None:
+                hc = np.ascontiguousarray(host[0], np.float32); hr = np.ascontiguousarray(host[1], np.float32)
+                rc = self.lib.ta_dwconv2d_sep_hw(_ptr(g), hc.ctypes.data, hr.ctypes.data, hc.shape[-1], _ptr(out), B, C, H, W, _stream())
+                if rc == _lib.TA_OK:
+                    return out
+                if rc != _lib.TA_EUNSUPPORTED:
+                    _lib.check(rc, "ta_dwconv2d_sep_hw")
+            kcol = _f32c(kcol, "kcol"); krow = _f32c(krow, "krow"); ks = kcol.shape[-1]
             _lib.check(self.lib.ta_dwconv2d_sep(_ptr(g), _ptr(kcol), _ptr(krow), ks, _ptr(out), B, C, H, W, _stream()), "ta_dwconv2d_sep")
         return out
 
