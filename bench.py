@@ -470,14 +470,17 @@ def run_kernels(args):
         add("dim_bwd [%s]" % tag, 8, lambda: be.dim(g, 235, 246, 5, 6, False))
     _lib.tune_set("dim.impl", 1)
     hc, hr = kc3.cpu().numpy(), kr3.cpu().numpy()
-    add("dwconv2d_sep k=15 [register-sliding, factors as kernel parameters]", 8, lambda: be.dwconv2d_sep(g, kc3, kr3, host=(hc, hr)))
-    _lib.tune_set("tim.bh", 56)
-    add("dwconv2d_sep k=15 [register-sliding, parameters, band 56]", 8, lambda: be.dwconv2d_sep(g, kc3, kr3, host=(hc, hr)))
-    _lib.tune_set("tim.bh", 32)
-    add("dwconv2d_sep k=15 [register-sliding, factors from device arrays]", 8, lambda: be.dwconv2d_sep(g, kc3, kr3))
+    for band, f2, tag in ((3, 1, "register-sliding from global memory, FFMA2"), (3, 0, "register-sliding from global memory, FFMA"),
+                          (2, 0, "register-sliding from TMA-staged smem")):
+        _lib.tune_set("tim.band", band); _lib.tune_set("tim.f2", f2)
+        add("dwconv2d_sep k=15 [%s, factors as kernel parameters]" % tag, 8, lambda: be.dwconv2d_sep(g, kc3, kr3, host=(hc, hr)))
+        _lib.tune_set("tim.bh", 56)
+        add("dwconv2d_sep k=15 [%s, parameters, band 56]" % tag, 8, lambda: be.dwconv2d_sep(g, kc3, kr3, host=(hc, hr)))
+        _lib.tune_set("tim.bh", 32)
+        add("dwconv2d_sep k=15 [%s, factors from device arrays]" % tag, 8, lambda: be.dwconv2d_sep(g, kc3, kr3))
     _lib.tune_set("tim.band", 1)
     add("dwconv2d_sep k=15 [two-pass band kernel]", 8, lambda: be.dwconv2d_sep(g, kc3, kr3))
-    _lib.tune_set("tim.band", 2)
+    _lib.tune_set("tim.band", 3); _lib.tune_set("tim.f2", 1)
     add("dwconv2d k=15 (direct)", 8, lambda: be.dwconv2d(g, k3))
     add("accumulate", 12, lambda: be.accumulate(m2, g, False))
     add("quantize_u8", 9, lambda: be.quantize_u8(x, d, True))

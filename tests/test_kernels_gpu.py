@@ -261,8 +261,9 @@ def test_tim_generic_kernel_sizes(be):
 
 @pytest.mark.parametrize("ks", [3, 5, 7, 15])
 def test_tim_sep_all_launch_paths_bit_identical(be, ks):
-    """The separable convolution has four launch paths (register-sliding with the factors as kernel parameters or loaded
-    from device arrays, band height 32 / 56; two-pass band kernel; 32x32 tiles): all must equal the C oracle bit for bit,
+    """The separable convolution has several launch paths (register-sliding fed from global memory or from bulk-TMA-staged
+    shared memory, each with the factors as kernel parameters or loaded from device arrays, band height 32 / 56; two-pass
+    band kernel; 32x32 tiles): all must equal the C oracle bit for bit,
     including ragged heights (last band partly / wholly outside the image) and channel-specific factors."""
     from transferattack_b200 import _lib
     rng = np.random.default_rng(ks)
@@ -276,14 +277,14 @@ def test_tim_sep_all_launch_paths_bit_identical(be, ks):
             distinct = (rng.random((C, ks), dtype=np.float32), rng.random((C, ks), dtype=np.float32))
             for kc, kr in (shared, distinct):
                 want = oracle.dwconv2d_sep(x, kc, kr)
-                for band, bh in ((2, 32), (2, 56), (1, 32), (0, 32)):
-                    _lib.tune_set("tim.band", band); _lib.tune_set("tim.bh", bh)
+                for band, bh, f2 in ((3, 32, 1), (3, 56, 1), (3, 32, 0), (3, 56, 0), (2, 32, 0), (2, 56, 0), (1, 32, 0), (0, 32, 0)):
+                    _lib.tune_set("tim.band", band); _lib.tune_set("tim.bh", bh); _lib.tune_set("tim.f2", f2)
                     got = npy(be.dwconv2d_sep(cu(x), cu(kc), cu(kr)))
-                    assert bits_equal(got, want), (shp, "device factors", band, bh)
+                    assert bits_equal(got, want), (shp, "device factors", band, bh, f2)
                     got = npy(be.dwconv2d_sep(cu(x), cu(kc), cu(kr), host=(kc, kr)))
-                    assert bits_equal(got, want), (shp, "host factors", band, bh)
+                    assert bits_equal(got, want), (shp, "host factors", band, bh, f2)
     finally:
-        _lib.tune_set("tim.band", 2); _lib.tune_set("tim.bh", 32)
+        _lib.tune_set("tim.band", 3); _lib.tune_set("tim.bh", 32); _lib.tune_set("tim.f2", 1)
 
 
 def test_tim_sep_hw_refuses_what_it_cannot_serve(be):

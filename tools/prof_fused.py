@@ -21,6 +21,16 @@ for it in range(6):
         be.fused_update_linf(g, m, m2, d, d2, x, xa, scale, None, 1.0, 1.6 / 255, 16 / 255, 0, 1.0)
     elif which == "dim":
         be.dim(x, 235, 246, 5, 6, True); be.dim(g, 235, 246, 5, 6, False)
+    elif which == "timdim":      # one launch each: TIM with factors as parameters / from device arrays, DIM forward, DIM adjoint
+        import numpy as np
+        import transferattack_b200.input_transformation.tim as tim
+        k2d, kcol, krow = tim.make_kernel("gaussian", 15)
+        hc, hr = np.stack([kcol] * 3), np.stack([krow] * 3)
+        kc3, kr3 = torch.from_numpy(hc).cuda(), torch.from_numpy(hr).cuda()
+        be.dwconv2d_sep(g, kc3, kr3, host=(hc, hr)); flush.sum()
+        be.dwconv2d_sep(g, kc3, kr3); flush.sum()
+        be.dim(x, 235, 246, 5, 6, True); flush.sum()
+        be.dim(g, 235, 246, 5, 6, False)
     elif which == "tim":
         import numpy as np
         import transferattack_b200.input_transformation.tim as tim

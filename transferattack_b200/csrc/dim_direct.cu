@@ -26,7 +26,7 @@ using namespace ta;
 
 namespace {
 
-constexpr int RB = 16;          // destination rows per CTA
+constexpr int RB = kDimRB;      // destination rows per CTA
 constexpr int kThreads = 256;
 constexpr int kMaxW = 3;        // inverse-range weights kept in registers (bilinear at DIM's rates needs <= 3)
 
@@ -183,17 +183,30 @@ template <class Emit>
 __device__ __forceinline__ void gather_scatter(uint32_t src, uint32_t pitch_bytes, int nrows, const RowT* __restrict__ desc,
                                                const TapE* __restrict__ th_tab, int lo, int cnt, int col,
                                                const float (&w)[kMaxW], int emit_lo, int emit_hi, Emit emit) {
+  asm volatile("" : "+r"(pitch_bytes));                  // keep the pitch in a register (else re-read from the constant bank per row)
   int pcur = nrows > 0 ? desc[0].i0 : emit_hi + 1;
   for (int p = emit_lo; p < pcur && p <= emit_hi; ++p) emit(p, 0.0f);
   float accA = 0.0f, accB = 0.0f;
   uint32_t sp = src + (uint32_t)lo * 4;
   const unsigned span = (unsigned)(emit_hi - emit_lo);
-  for (int r = 0; r < nrows; ++r, sp += pitch_bytes) {
-    const int4 e = *reinterpret_cast<const int4*>(desc + r);
+  // software pipeline: the taps of row r + 1 and its descriptor are requested before row r is consumed
+  float nx[kMaxW];
+  int4 ne = make_int4(0, 0, 0, 0);
+#pragma unroll
+  for (int k = 0; k < kMaxW; ++k) nx[k] = (nrows > 0 && k < cnt) ? lds_f32(sp + 4 * k) : 0.0f;
+  if (nrows > 0) ne = *reinterpret_cast<const int4*>(desc);
+  for (int r = 0; r < nrows; ++r) {
+    const int4 e = ne;
     float h = 0.0f;
 #pragma unroll
-    for (int k = 0; k < kMaxW; ++k) if (k < cnt) h = fmaf(w[k], lds_f32(sp + 4 * k), h);
+    for (int k = 0; k < kMaxW; ++k) if (k < cnt) h = fmaf(w[k], nx[k], h);
     for (int k = kMaxW; k < cnt; ++k) h = fmaf(tap_w(th_tab[lo + k], col), lds_f32(sp + 4 * k), h);
+    sp += pitch_bytes;
+    if (r + 1 < nrows) {
+#pragma unroll
+      for (int k = 0; k < kMaxW; ++k) if (k < cnt) nx[k] = lds_f32(sp + 4 * k);
+      ne = *reinterpret_cast<const int4*>(desc + r + 1);
+    }
     while (pcur < e.x) {                             // rows the monotone tap index has moved past are complete
       if ((unsigned)(pcur - emit_lo) <= span) emit(pcur, accA);
       accA = accB; accB = 0.0f; ++pcur;
@@ -228,22 +241,11 @@ __global__ void __launch_bounds__(kThreads) dim_bwd_direct_kernel(const float* _
   const float* gp = gout + (int64_t)blockIdx.y * S * S;
   float* ip = gin + (int64_t)blockIdx.y * S * S;
 
-  // y1 rows feeding this band of source rows, then the gout rows feeding those (scans over the host's inverse ranges)
-  int q0 = 0x7fffffff, q1 = -1;
-  for (int sy = sy0; sy <= sy1; ++sy) {
-    const InvE iv = tab.inv1[sy];
-    if (iv.cnt > 0) { q0 = min(q0, (int)iv.lo); q1 = max(q1, (int)iv.lo + iv.cnt - 1); }
-  }
-  const bool any = q0 <= q1;
-  const int nq = any ? q1 - q0 + 1 : 0;
-  if (!any) q0 = 0;
-  int oyA = 0x7fffffff, oyB = -1;
-  for (int q = 0; q < nq; ++q) {
-    const InvE iv = tab.inv2[q0 + q + top];
-    if (iv.cnt > 0) { oyA = min(oyA, (int)iv.lo); oyB = max(oyB, (int)iv.lo + iv.cnt - 1); }
-  }
-  const int nu = oyA <= oyB ? oyB - oyA + 1 : 0;
-  if (nu == 0) oyA = 0;
+  // y1 rows feeding this band of source rows and the gout rows feeding those: scanned once on the host (band table)
+  const short4 bd = tab.band[blockIdx.x];
+  const int q0 = bd.x, nq = bd.y, oyA = bd.z, nu = bd.w;
+  const bool any = nq > 0;
+  const int q1 = q0 + nq - 1;
 
   if (TMA_STAGE) {
     if (tid == 0) {
@@ -366,6 +368,7 @@ int dim_bwd_direct(const float* gout, float* gin, int planes, int S, int rnd, in
   int g_rows = 1, u_rows = 1;
   for (int sy0 = 0; sy0 < S; sy0 += RB) {
     const int sy1 = (sy0 + RB < S ? sy0 + RB : S) - 1;
+    tab.band[sy0 / RB] = make_short4(0, 0, 0, 0);
     int q0 = 0x7fffffff, q1 = -1;
     for (int sy = sy0; sy <= sy1; ++sy)
       if (tab.inv1[sy].cnt > 0) {
@@ -380,6 +383,7 @@ int dim_bwd_direct(const float* gout, float* gin, int planes, int S, int rnd, in
       if (iv.cnt > 0) { if (iv.lo < a) a = iv.lo; if (iv.lo + iv.cnt - 1 > b) b = iv.lo + iv.cnt - 1; }
     }
     if (a <= b && b - a + 1 > u_rows) u_rows = b - a + 1;
+    tab.band[sy0 / RB] = make_short4((short)q0, (short)(q1 - q0 + 1), (short)(a <= b ? a : 0), (short)(a <= b ? b - a + 1 : 0));
   }
   Geo gm{S, rnd, R, top, left, u_rows, g_rows};
   const size_t smem = ((sizeof(float) * ((size_t)u_rows * S + (size_t)g_rows * rnd) + 15) & ~(size_t)15) + 16 * (size_t)(u_rows + g_rows);

@@ -9,6 +9,8 @@ namespace ta {
 constexpr int kDimMaxS = 512;     // image side the tables are sized for
 constexpr int kDimMaxR = 576;     // >= int(kDimMaxS * 1.1) + a margin: padded size / intermediate size
 
+constexpr int kDimRB = 16;        // destination rows per CTA (band height)
+
 struct TapE { float l1; int i01; };          // 1-D bilinear tap of one destination index: i0 | i1 << 16, l0 = 1 - l1
 struct InvE { short lo; short cnt; };        // destination indices [lo, lo + cnt) read this source index
 
@@ -21,6 +23,7 @@ struct DimTabB {                              // adjoint: 13 KB
   TapE t1[kDimMaxR];
   InvE inv2[kDimMaxR];                        //   y2 index p is read by outputs [lo, lo + cnt)
   InvE inv1[kDimMaxS];                        //   source index s is read by y1 indices [lo, lo + cnt)
+  short4 band[kDimMaxS / kDimRB];             //   per band of source rows: {q0, nq, oyA, nu} (y1 rows / gout rows it needs)
 };
 
 bool dim_direct_ok(int S, int rnd, int R);

@@ -354,6 +354,139 @@ __global__ void __launch_bounds__(128) dwconv_sep_rs_kernel(const float* __restr
   }
 }
 
+// packed fp32x2 FMA (sm_100: SASS FFMA2, two IEEE fmas per issued instruction; same lanes per clock as FFMA — measured,
+// tools/microbench/ffma_rate.cu — but half the issue slots and half the code bytes)
+typedef unsigned long long f32x2_t;
+__device__ __forceinline__ f32x2_t pack2(float a, float b) { f32x2_t r; asm("mov.b64 %0, {%1,%2};" : "=l"(r) : "f"(a), "f"(b)); return r; }
+__device__ __forceinline__ void unpack2(f32x2_t p, float& a, float& b) { asm("mov.b64 {%0,%1}, %2;" : "=f"(a), "=f"(b) : "l"(p)); }
+__device__ __forceinline__ f32x2_t ffma2(f32x2_t w, f32x2_t a, f32x2_t c) {
+  f32x2_t d; asm("fma.rn.f32x2 %0, %1, %2, %3;" : "=l"(d) : "l"(w), "l"(a), "l"(c)); return d;
+}
+
+// ---- register-sliding variant fed straight from global memory (no shared memory, no barriers) ------------------------------
+// Same per-thread walk as dwconv_sep_rs_kernel, but the 4-output window of each input row comes from NV predicated 128-bit
+// loads (L1-resident: neighbouring threads overlap in KS-1 of their KS+3 columns; out-of-image rows / columns are the
+// predicate, i.e. the zero padding) and the next row's loads are issued before the current row's 8*KS FMAs. ncu on the
+// staged kernel (profiles/ncu_tim_dim_r1b.md) showed 2.2 warps per scheduler (44 KB of staging per 2-warp CTA) and 77 % SM
+// active time (1.8 waves); this form is limited by registers only and its grid is a flat list of (plane, band, column
+// group) items, 128 per CTA, so that at B = 64 all of it is resident in one wave.
+template <int KS, int BHR, bool PW, bool F2>
+__global__ void __launch_bounds__(128, 4) dwconv_sep_rg_kernel(const float* __restrict__ g, const float* __restrict__ kcol,
+                                                            const float* __restrict__ krow,
+                                                            const __grid_constant__ SepWeights<KS> wp, float* __restrict__ out,
+                                                            int C, int H, int W, int nbands, int64_t items) {
+  using G = RsGeom<KS>;
+  constexpr int R = G::R, PADX = G::PADX, OFF = G::OFF, NV = G::NV;
+  constexpr int ROWS = BHR + KS - 1;
+  const int64_t item = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (item >= items) return;
+  const int Q = W >> 2;
+  const int q = (int)(item % Q);
+  const int64_t pb = item / Q;
+  const int band = (int)(pb % nbands);
+  const int plane = (int)(pb / nbands);
+  const int y0 = band * BHR;
+
+  float wr[PW ? 1 : KS], wc[PW ? 1 : KS];
+  if (!PW) {
+    const int c = plane % C;
+#pragma unroll
+    for (int j = 0; j < KS; ++j) { wr[j] = __ldg(krow + c * KS + j); wc[j] = __ldg(kcol + c * KS + j); }
+  }
+  bool cv[NV];                                                     // float4 k of the window lies inside the row
+#pragma unroll
+  for (int k = 0; k < NV; ++k) { const int col = 4 * q - PADX + 4 * k; cv[k] = col >= 0 && col < W; }
+
+  float acc[KS][4];
+#pragma unroll
+  for (int s = 0; s < KS; ++s) { acc[s][0] = 0.f; acc[s][1] = 0.f; acc[s][2] = 0.f; acc[s][3] = 0.f; }
+
+  int yy = y0 - R;                                                 // image row of band row r
+  const float4* ip = reinterpret_cast<const float4*>(g + (int64_t)plane * H * W + (int64_t)yy * W + 4 * q - PADX);
+  const int pitch4 = W >> 2;
+  int yl = -(KS - 1);
+  const unsigned ylim = (unsigned)min(BHR, H - y0);
+  float* op = out + (int64_t)plane * H * W + (int64_t)(y0 + yl) * W + 4 * q;
+
+  float4 nxt[NV];
+  {
+    const bool rv = (unsigned)yy < (unsigned)H;
+#pragma unroll
+    for (int k = 0; k < NV; ++k) nxt[k] = (rv && cv[k]) ? __ldg(ip + k) : make_float4(0.f, 0.f, 0.f, 0.f);
+  }
+  constexpr int NG = (ROWS + KS - 1) / KS;
+#pragma unroll 1
+  for (int gi = 0; gi < NG; ++gi) {
+#pragma unroll
+    for (int rr = 0; rr < KS; ++rr) {
+      if (gi * KS + rr < ROWS) {
+        float v[4 * NV];
+#pragma unroll
+        for (int t = 0; t < NV; ++t) { v[4 * t] = nxt[t].x; v[4 * t + 1] = nxt[t].y; v[4 * t + 2] = nxt[t].z; v[4 * t + 3] = nxt[t].w; }
+        ++yy; ip += pitch4;
+        {                                                          // prefetch band row r + 1 (predicate false past the band)
+          const bool rv = (unsigned)yy < (unsigned)H && gi * KS + rr + 1 < ROWS;
+#pragma unroll
+          for (int k = 0; k < NV; ++k) nxt[k] = (rv && cv[k]) ? __ldg(ip + k) : make_float4(0.f, 0.f, 0.f, 0.f);
+        }
+        float t0 = 0.f, t1 = 0.f, t2 = 0.f, t3 = 0.f;
+        if (F2) {
+          // pairs along x: (t0,t1) += w_j * (v[j], v[j+1]), (t2,t3) += w_j * (v[j+2], v[j+3]); per lane the same fma chain
+          f32x2_t p0 = pack2(0.f, 0.f), p1 = pack2(0.f, 0.f);
+#pragma unroll
+          for (int j = 0; j < KS; ++j) {
+            const float w = PW ? wp.kr[j] : wr[j];
+            const f32x2_t ww = pack2(w, w);
+            p0 = ffma2(ww, pack2(v[OFF + j], v[OFF + j + 1]), p0);
+            p1 = ffma2(ww, pack2(v[OFF + j + 2], v[OFF + j + 3]), p1);
+          }
+          const f32x2_t tp0 = p0, tp1 = p1;
+#pragma unroll
+          for (int i = 0; i < KS; ++i) {
+            const int s = ((rr - i) % KS + KS) % KS;
+            const float w = PW ? wp.kc[i] : wc[i];
+            const f32x2_t ww = pack2(w, w);
+            f32x2_t a0 = pack2(acc[s][0], acc[s][1]), a1 = pack2(acc[s][2], acc[s][3]);
+            a0 = ffma2(ww, tp0, a0); a1 = ffma2(ww, tp1, a1);
+            unpack2(a0, acc[s][0], acc[s][1]); unpack2(a1, acc[s][2], acc[s][3]);
+          }
+        } else {
+#pragma unroll
+          for (int j = 0; j < KS; ++j) {
+            const float w = PW ? wp.kr[j] : wr[j];
+            t0 = fmaf(w, v[OFF + j], t0); t1 = fmaf(w, v[OFF + j + 1], t1);
+            t2 = fmaf(w, v[OFF + j + 2], t2); t3 = fmaf(w, v[OFF + j + 3], t3);
+          }
+#pragma unroll
+          for (int i = 0; i < KS; ++i) {
+            const int s = ((rr - i) % KS + KS) % KS;
+            const float w = PW ? wp.kc[i] : wc[i];
+            acc[s][0] = fmaf(w, t0, acc[s][0]); acc[s][1] = fmaf(w, t1, acc[s][1]);
+            acc[s][2] = fmaf(w, t2, acc[s][2]); acc[s][3] = fmaf(w, t3, acc[s][3]);
+          }
+        }
+        const int sc = (rr + 1) % KS;
+        if ((unsigned)yl < ylim)
+          *reinterpret_cast<float4*>(op) = make_float4(acc[sc][0], acc[sc][1], acc[sc][2], acc[sc][3]);
+        acc[sc][0] = 0.f; acc[sc][1] = 0.f; acc[sc][2] = 0.f; acc[sc][3] = 0.f;
+        op += W; ++yl;
+      }
+    }
+  }
+}
+
+template <int KS, int BHR, bool PW, bool F2>
+int launch_rg(const float* g, const float* kcol, const float* krow, const SepWeights<KS>& wp, float* out, int B, int C, int H,
+              int W, cudaStream_t s) {
+  const int nbands = (H + BHR - 1) / BHR;
+  const int64_t items = (int64_t)B * C * nbands * (W / 4);
+  const int64_t blocks = (items + 127) / 128;
+  TA_REQUIRE(blocks <= 0x7fffffff, "ta_dwconv2d_sep: too many work items");
+  dwconv_sep_rg_kernel<KS, BHR, PW, F2><<<(unsigned)blocks, 128, 0, s>>>(g, kcol, krow, wp, out, C, H, W, nbands, items);
+  count_launch();
+  return check_launch("ta_dwconv2d_sep[rg]");
+}
+
 template <int KS, int BHR, bool PW>
 int launch_rs(const float* g, const float* kcol, const float* krow, const SepWeights<KS>& wp, float* out, int B, int C, int H,
               int W, cudaStream_t s) {
@@ -373,7 +506,16 @@ int launch_rs(const float* g, const float* kcol, const float* krow, const SepWei
 template <int KS, bool PW>
 int launch_rs_bh(const float* g, const float* kcol, const float* krow, const SepWeights<KS>& wp, float* out, int B, int C,
                  int H, int W, cudaStream_t s) {
-  if (tune_get("tim.bh", 32) == 56) return launch_rs<KS, 56, PW>(g, kcol, krow, wp, out, B, C, H, W, s);
+  const int bh = tune_get("tim.bh", 32);
+  if (tune_get("tim.band", 3) == 3) {       // straight from global memory; tim.f2: packed fp32x2 FMAs
+    if (tune_get("tim.f2", 1) != 0) {
+      if (bh == 56) return launch_rg<KS, 56, PW, true>(g, kcol, krow, wp, out, B, C, H, W, s);
+      return launch_rg<KS, 32, PW, true>(g, kcol, krow, wp, out, B, C, H, W, s);
+    }
+    if (bh == 56) return launch_rg<KS, 56, PW, false>(g, kcol, krow, wp, out, B, C, H, W, s);
+    return launch_rg<KS, 32, PW, false>(g, kcol, krow, wp, out, B, C, H, W, s);
+  }
+  if (bh == 56) return launch_rs<KS, 56, PW>(g, kcol, krow, wp, out, B, C, H, W, s);
   return launch_rs<KS, 32, PW>(g, kcol, krow, wp, out, B, C, H, W, s);
 }
 
@@ -454,10 +596,10 @@ int ta_dwconv2d_sep(const float* g, const float* kcol, const float* krow, int ks
   int rc = check_conv("ta_dwconv2d_sep", g, kcol, out, ks, B, C, H, W);
   if (rc != TA_OK) return rc;
   TA_REQUIRE(krow, "ta_dwconv2d_sep: null krow");
-  // hot case (TIM on 224-class images): full-width bands staged by bulk-TMA; tim.band: 2 = register-sliding kernel
-  // (default), 1 = two-pass band kernel, 0 = 32x32 tiles
-  const int mode = tune_get("tim.band", 2);
-  if (mode == 2 && rs_ok(g, out, ks, W)) {
+  // hot case (TIM on 224-class images), tim.band: 3 = register-sliding kernel fed from global memory (default), 2 = the
+  // same fed from bulk-TMA-staged shared memory, 1 = two-pass band kernel, 0 = 32x32 tiles
+  const int mode = tune_get("tim.band", 3);
+  if (mode >= 2 && rs_ok(g, out, ks, W)) {
     cudaStream_t bs = (cudaStream_t)stream;
     switch (ks) {
       case 3: return launch_rs_bh<3, false>(g, kcol, krow, SepWeights<3>{}, out, B, C, H, W, bs);
