@@ -478,6 +478,11 @@ def run_kernels(args):
         add("dwconv2d_sep k=15 [%s, parameters, band 56]" % tag, 8, lambda: be.dwconv2d_sep(g, kc3, kr3, host=(hc, hr)))
         _lib.tune_set("tim.bh", 32)
         add("dwconv2d_sep k=15 [%s, factors from device arrays]" % tag, 8, lambda: be.dwconv2d_sep(g, kc3, kr3))
+    _lib.tune_set("tim.band", 3); _lib.tune_set("tim.f2", 1)
+    for pf in (1, 0):
+        _lib.tune_set("tim.prefetch", pf)
+        add("dwconv2d_sep k=15 [from global memory, FFMA2, parameters, prefetch mode %d]" % pf, 8, lambda: be.dwconv2d_sep(g, kc3, kr3, host=(hc, hr)))
+    _lib.tune_set("tim.prefetch", 2)
     _lib.tune_set("tim.band", 1)
     add("dwconv2d_sep k=15 [two-pass band kernel]", 8, lambda: be.dwconv2d_sep(g, kc3, kr3))
     _lib.tune_set("tim.band", 3); _lib.tune_set("tim.f2", 1)

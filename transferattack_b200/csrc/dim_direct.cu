@@ -179,27 +179,48 @@ __device__ __forceinline__ float tap_w(const TapE& t, int i) {
 // with l0 / l1. emit(row, value) is called exactly once for every destination row in [emit_lo, emit_hi], ascending.
 struct __align__(16) RowT { int i0, i1; float l1; int pad; };
 
-template <class Emit>
+// Sinks: where completed destination rows go. `at(row)` positions the cursor (once), `put(v)` stores at the cursor,
+// `next()` moves it one destination row down — a running address, no per-row multiply.
+struct SmemSink {                                    // g1 band in shared memory
+  uint32_t base, pitch, cur; int row0;
+  __device__ __forceinline__ void at(int row) { cur = base + (uint32_t)(row - row0) * pitch; }
+  __device__ __forceinline__ void put(float v) const { sts_f32(cur, v); }
+  __device__ __forceinline__ void next() { cur += pitch; }
+};
+struct GlobalSink {                                  // gin rows in global memory (coalesced across the CTA's columns)
+  float* base; int64_t pitch; float* cur;
+  __device__ __forceinline__ void at(int row) { cur = base + (int64_t)row * pitch; }
+  __device__ __forceinline__ void put(float v) const { *cur = v; }
+  __device__ __forceinline__ void next() { cur += pitch; }
+};
+
+template <class Sink>
 __device__ __forceinline__ void gather_scatter(uint32_t src, uint32_t pitch_bytes, int nrows, const RowT* __restrict__ desc,
                                                const TapE* __restrict__ th_tab, int lo, int cnt, int col,
-                                               const float (&w)[kMaxW], int emit_lo, int emit_hi, Emit emit) {
+                                               const float (&w)[kMaxW], int emit_lo, int emit_hi, Sink sink) {
   asm volatile("" : "+r"(pitch_bytes));                  // keep the pitch in a register (else re-read from the constant bank per row)
+  const unsigned span = (unsigned)(emit_hi - emit_lo);
   int pcur = nrows > 0 ? desc[0].i0 : emit_hi + 1;
-  for (int p = emit_lo; p < pcur && p <= emit_hi; ++p) emit(p, 0.0f);
+  sink.at(emit_lo);
+  int p = emit_lo;
+#pragma unroll 1
+  for (; p < pcur && p <= emit_hi; ++p) { sink.put(0.0f); sink.next(); }     // rows before the first tap: nothing reads them
+  sink.at(pcur);
   float accA = 0.0f, accB = 0.0f;
   uint32_t sp = src + (uint32_t)lo * 4;
-  const unsigned span = (unsigned)(emit_hi - emit_lo);
   // software pipeline: the taps of row r + 1 and its descriptor are requested before row r is consumed
   float nx[kMaxW];
   int4 ne = make_int4(0, 0, 0, 0);
 #pragma unroll
   for (int k = 0; k < kMaxW; ++k) nx[k] = (nrows > 0 && k < cnt) ? lds_f32(sp + 4 * k) : 0.0f;
   if (nrows > 0) ne = *reinterpret_cast<const int4*>(desc);
+#pragma unroll 1
   for (int r = 0; r < nrows; ++r) {
     const int4 e = ne;
     float h = 0.0f;
 #pragma unroll
     for (int k = 0; k < kMaxW; ++k) if (k < cnt) h = fmaf(w[k], nx[k], h);
+#pragma unroll 1
     for (int k = kMaxW; k < cnt; ++k) h = fmaf(tap_w(th_tab[lo + k], col), lds_f32(sp + 4 * k), h);
     sp += pitch_bytes;
     if (r + 1 < nrows) {
@@ -207,8 +228,10 @@ __device__ __forceinline__ void gather_scatter(uint32_t src, uint32_t pitch_byte
       for (int k = 0; k < kMaxW; ++k) if (k < cnt) nx[k] = lds_f32(sp + 4 * k);
       ne = *reinterpret_cast<const int4*>(desc + r + 1);
     }
+#pragma unroll 1
     while (pcur < e.x) {                             // rows the monotone tap index has moved past are complete
-      if ((unsigned)(pcur - emit_lo) <= span) emit(pcur, accA);
+      if ((unsigned)(pcur - emit_lo) <= span) sink.put(accA);
+      sink.next();
       accA = accB; accB = 0.0f; ++pcur;
     }
     const float l1 = __int_as_float(e.z), l0 = sub_rn(1.0f, l1);
@@ -216,9 +239,13 @@ __device__ __forceinline__ void gather_scatter(uint32_t src, uint32_t pitch_byte
     if (e.y == e.x) accA = fmaf(l1, h, accA); else accB = fmaf(l1, h, accB);
   }
   if (nrows > 0) {
-    if ((unsigned)(pcur - emit_lo) <= span) emit(pcur, accA);
-    if ((unsigned)(pcur + 1 - emit_lo) <= span) emit(pcur + 1, accB);
-    for (int p = max(pcur + 2, emit_lo); p <= emit_hi; ++p) emit(p, 0.0f);
+    if ((unsigned)(pcur - emit_lo) <= span) sink.put(accA);
+    sink.next();
+    if ((unsigned)(pcur + 1 - emit_lo) <= span) sink.put(accB);
+    p = max(pcur + 2, emit_lo);
+    sink.at(p);
+#pragma unroll 1
+    for (; p <= emit_hi; ++p) { sink.put(0.0f); sink.next(); }
   }
 }
 
@@ -273,10 +300,8 @@ __global__ void __launch_bounds__(kThreads) dim_bwd_direct_kernel(const float* _
     float w[kMaxW];
 #pragma unroll
     for (int k = 0; k < kMaxW; ++k) w[k] = (k < iv.cnt) ? tap_w(tab.t2[iv.lo + k], px) : 0.0f;
-    const uint32_t g1 = smem_u32(bufG + col);
-    const int base = top + q0;
-    gather_scatter(smem_u32(bufU), (uint32_t)S * 4, nu, descU, tab.t2, iv.lo, iv.cnt, px, w, q0 + top, q1 + top,
-                   [&](int p, float v) { sts_f32(g1 + (uint32_t)((p - base) * rnd) * 4, v); });
+    SmemSink sink{smem_u32(bufG + col), (uint32_t)rnd * 4, 0u, top + q0};
+    gather_scatter(smem_u32(bufU), (uint32_t)S * 4, nu, descU, tab.t2, iv.lo, iv.cnt, px, w, q0 + top, q1 + top, sink);
   }
   __syncthreads();
   // phase A^T: gin[sy][sx], sy in [sy0, sy1]: gather over y1 columns, scatter over source rows (coalesced stores)
@@ -285,9 +310,8 @@ __global__ void __launch_bounds__(kThreads) dim_bwd_direct_kernel(const float* _
     float w[kMaxW];
 #pragma unroll
     for (int k = 0; k < kMaxW; ++k) w[k] = (k < iv.cnt) ? tap_w(tab.t1[iv.lo + k], col) : 0.0f;
-    float* o = ip + col;
-    gather_scatter(smem_u32(bufG), (uint32_t)rnd * 4, nq, descQ, tab.t1, iv.lo, iv.cnt, col, w, sy0, sy1,
-                   [&](int s, float v) { o[(int64_t)s * S] = v; });
+    GlobalSink sink{ip + col, (int64_t)S, nullptr};
+    gather_scatter(smem_u32(bufG), (uint32_t)rnd * 4, nq, descQ, tab.t1, iv.lo, iv.cnt, col, w, sy0, sy1, sink);
   }
 }
 
