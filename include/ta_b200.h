@@ -117,6 +117,20 @@ int ta_fused_update_linf(const float* g, const float* m, float* m_out,
                          float decay, float alpha, float eps, float lo, float hi,
                          int B, int64_t n, ta_stream_t stream);
 
+/* ---- Normalize folded into the fused tail (reference utils.py:72-79 PreprocessingModel) ------------------
+ *   Same as ta_fused_update_linf, but the emitted next model input is the NORMALISED image
+ *       xn = ((data + delta') - mean[c]) / std[c]        (torchvision Normalize: sub_ then div_, two roundings)
+ *   with c = (element index inside the sample) / plane, so the surrogate is entered after its PreprocessingModel; with
+ *   grad_wrt_xn != 0, `g` is the gradient w.r.t. xn and is first divided by std[c] (Normalize's adjoint) — then neither
+ *   direction of the normalisation costs a launch. mean_host / std_host: HOST arrays [C] read during the call, C <= 4,
+ *   plane % 4 == 0, C * plane == n, 16-byte aligned buffers; otherwise TA_EUNSUPPORTED (keep the separate kernels).      */
+int ta_fused_update_linf_nf(const float* g, const float* m, float* m_out,
+                            const float* delta, float* delta_out, const float* data, float* xn_out,
+                            const float* scale, float* scale_out, int mean_mode,
+                            float decay, float alpha, float eps, float lo, float hi, int B, int64_t n,
+                            const float* mean_host, const float* std_host, int C, int64_t plane,
+                            int grad_wrt_xn, ta_stream_t stream);
+
 /* ---- ENS with one surrogate per GPU (ensemble/ens.py:31-36 + utils.py:94-100, new multi-GPU functionality) -----------
  *   The gradient reduce-scatter, the fused update and the all-gather of the next model input as ONE kernel over NVLink
  *   peer memory. Rank r owns samples [b0, b0+Bown). g_peers[k] / xadv_peers[k] (HOST arrays of K device pointers valid in

@@ -115,6 +115,19 @@ def fused_update_linf(g, m, delta, data, scale, decay, alpha, eps, lo=0.0, hi=1.
     return m_out, d_out, x_out
 
 
+def fused_update_linf_nf(g, m, delta, data, scale, decay, alpha, eps, mean, std, grad_wrt_xn, lo=0.0, hi=1.0):
+    """Normalize folded into the fused tail restated as the chain of reference ops it replaces
+    (utils.py:72-79 around attack.py:88,124-153): Normalize's adjoint g / std (when the gradient is w.r.t. the normalised
+    input), the per-sample mean of |g| (when `scale` is None), the unfused tail, then Normalize's forward on data + delta'."""
+    g = _c(g)
+    if grad_wrt_xn:
+        g = normalize_bwd(g, std)
+    if scale is None:
+        scale = abs_mean_per_sample(g)
+    m_out, d_out, x_out = fused_update_linf(g, m, delta, data, scale, decay, alpha, eps, lo, hi, want_xadv=True)
+    return m_out, d_out, normalize_fwd(x_out, mean, std), _c(scale)
+
+
 def stage_add(data, delta, look=None, coef=0.0):
     data = _c(data); delta = _c(delta); look = _c(look)
     out = np.empty_like(data)

@@ -70,6 +70,19 @@ class OracleBackend:
             if scale_out is not None:
                 scale_out.copy_(_t(sc))
 
+    def fused_update_linf_nf(self, g, m, m_out, delta, delta_out, data, xn_out, scale, scale_out, decay, alpha, eps, lo, hi,
+                             mean, std, grad_wrt_xn, mean_mode=0):
+        self._log("fused_update_linf_nf")
+        sc = _np(scale).reshape(-1) if scale is not None else None
+        mo, do, xo, sc = oracle.fused_update_linf_nf(_np(g), _np(m), _np(delta), _np(data), sc, float(decay), float(alpha),
+                                                     float(eps), np.asarray(mean, np.float32), np.asarray(std, np.float32),
+                                                     bool(grad_wrt_xn), float(lo), float(hi))
+        with torch.no_grad():
+            m_out.copy_(_t(mo)); delta_out.copy_(_t(do)); xn_out.copy_(_t(xo))
+            if scale_out is not None:
+                scale_out.copy_(_t(sc))
+        return True
+
     def stage_add(self, data, delta, look=None, coef=0.0, out=None):
         self._log("stage_add")
         d = _np(data)

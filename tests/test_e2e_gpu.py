@@ -179,6 +179,7 @@ def test_cuda_graph_replay_is_bit_identical(name, kw):
     x, y = _data()
     lab = torch.stack([y, (y + 1) % 1000]) if kw.get("targeted") else y
     plain = make_attack(tab, name, net, **kw)
+    plain.use_cuda_graph = False
     seed_all(2); torch.cuda.manual_seed_all(2)
     d_plain = plain(x, lab)
     graphed = make_attack(tab, name, net, **kw)
@@ -195,6 +196,34 @@ def test_cuda_graph_replay_is_bit_identical(name, kw):
     d2_graph = graphed(x2, lab2)
     assert torch.equal(d2_plain, d2_graph) and len(graphed._graphs) == 1
     REPORT["graph/" + name + ("_" + "_".join(kw) if kw else "")] = {"bit_identical": True}
+
+
+@pytest.mark.parametrize("graph", [False, True], ids=["eager", "graph"])
+@pytest.mark.parametrize("mean_mode", ["torch", "exact"])
+@pytest.mark.parametrize("name", ["mifgsm", "ifgsm", "tim"])
+def test_normalize_fold_is_bit_identical(name, mean_mode, graph):
+    """SURVEY §8 f1 on the GPU: fused tail emitting the normalised model input (+ Normalize's adjoint in 'exact' mode with
+    the base get_grad) ≡ separate ta_normalize_* kernels, eager launches and CUDA-graph replay; strict mode ≡ the reference."""
+    from transferattack_b200 import _lib
+    net = _net()
+    x, y = _data()
+    res = {}
+    for fold in (False, True):
+        atk = make_attack(tab, name, net, epoch=4)
+        atk.mean_mode = mean_mode; atk.fold_normalize = fold; atk.use_cuda_graph = graph
+        assert (atk._fold_plan(x.cuda()) is not None) == fold
+        before = _lib.launch_count()
+        res[fold] = atk(x, y)
+        res[fold, "launches"] = _lib.launch_count() - before
+        assert bool(getattr(atk, "_graphs", None)) == graph
+    assert torch.equal(res[False], res[True])
+    if not graph:       # launches of OUR kernels per attack: the fold removes the Normalize forward (and adjoint when deferred)
+        deferred = mean_mode == "exact" and name != "tim"
+        assert res[False, "launches"] - res[True, "launches"] == 4 * (2 if deferred else 1) - 1      # one extra Normalize forward up front
+    if mean_mode == "torch":
+        ref = torch_ref.REF_ZOO[name](torch_ref.ref_wrap_model(net), epoch=4)(x, y)
+        assert torch.equal(res[True], ref)
+    REPORT["fold/%s_%s_%s" % (name, mean_mode, "graph" if graph else "eager")] = {"bit_identical": True}
 
 
 def test_cuda_graph_is_refused_for_host_rng_transforms():

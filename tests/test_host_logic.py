@@ -87,6 +87,49 @@ def test_fused_and_unfused_loops_agree(E, key, oracle_backend):
     assert bits_equal(d_fused.numpy(), d_hooks.numpy())
 
 
+@pytest.mark.parametrize("mean_mode", ["torch", "exact"])
+@pytest.mark.parametrize("name", ["mifgsm", "nifgsm", "tim"])
+def test_normalize_fold_is_bit_identical(oracle_backend, name, mean_mode):
+    """at the surrogate's native size the fused tail emits the normalised model input itself (and, in
+    'exact' mean mode with the base get_grad, applies Normalize's adjoint too). Same ops in the same order → the same
+    perturbation bit for bit as with the separate Normalize kernels and as the reference restatement."""
+    gen = torch.Generator().manual_seed(11)
+    x = torch.rand(2, 3, 224, 224, generator=gen); y = torch.randint(0, 10, (2,), generator=gen)
+    epoch = 3
+    atk = make_attack(tab, name, tiny_net(0), epoch=epoch)
+    atk.mean_mode = mean_mode
+    atk.fold_normalize = False
+    oracle_backend.calls.clear()
+    d_sep = atk(x, y)
+    assert "fused_update_linf_nf" not in oracle_backend.calls
+    n_sep = oracle_backend.calls.count("normalize")
+    atk.fold_normalize = True
+    oracle_backend.calls.clear()
+    d_fold = atk(x, y)
+    deferred = mean_mode == "exact" and name != "tim"          # TIM overrides get_grad: it needs the true gradient
+    if name == "nifgsm":                                        # NI-FGSM overrides transform (look-ahead) → nothing to fold into
+        assert "fused_update_linf_nf" not in oracle_backend.calls
+    else:
+        assert oracle_backend.calls.count("fused_update_linf_nf") == epoch and "fused_update_linf" not in oracle_backend.calls
+        assert n_sep == 2 * epoch and oracle_backend.calls.count("normalize") == 1 + (0 if deferred else epoch)
+    assert bits_equal(d_fold.numpy(), d_sep.numpy()), n_diff_bits(d_fold.numpy(), d_sep.numpy())
+    if mean_mode == "torch":
+        ref = torch_ref.REF_ZOO[name](torch_ref.ref_wrap_model(tiny_net(0)), epoch=epoch)(x, y)
+        assert bits_equal(d_fold.numpy(), ref.numpy())
+
+
+def test_normalize_fold_declines_what_it_cannot_fold(oracle_backend):
+    x = torch.rand(2, 3, 32, 32); y = torch.tensor([1, 2])
+    atk = make_attack(tab, "mifgsm", tiny_net(0), epoch=2)
+    assert atk._fold_plan(x) is None                                         # Resize(224) is not a no-op at 32x32
+    assert atk._fold_plan(torch.rand(1, 3, 224, 226)) is not None            # short side 224: Resize keeps the tensor
+    assert atk._fold_plan(torch.rand(1, 3, 230, 226)) is None
+    ens = make_attack(tab, "ens", [tiny_net(0), tiny_net(3)], epoch=2)
+    assert ens._fold_plan(torch.rand(2, 3, 224, 224)) is None                # members normalise individually
+    atk(x, y)
+    assert "fused_update_linf_nf" not in oracle_backend.calls
+
+
 @pytest.mark.parametrize("key", sorted(MINE) + ["ens"])
 def test_against_reference_golden(E, key):
     if not _host_matches_golden_host(E):

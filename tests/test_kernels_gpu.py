@@ -346,6 +346,55 @@ def test_fused_update_exact_mean(be, tune):
             _lib.tune_set(k, defaults[k])
 
 
+@pytest.mark.parametrize("tune", [dict(), {"fused.variant": 1}, {"fused.cluster": 2}], ids=["default", "variant1", "cluster2"])
+def test_fused_update_with_normalize_folded(be, tune):
+    """ta_fused_update_linf_nf against the chain of reference ops it replaces (oracle.fused_update_linf_nf):
+    strict (scale given) and exact (in-kernel mean) modes, gradient w.r.t. delta or w.r.t. the normalised input, first
+    iteration (no momentum) and later ones, in place on momentum and delta."""
+    from transferattack_b200 import _lib
+    for k, v in {"fused.variant": 0, "fused.cluster": 0, **tune}.items():
+        _lib.tune_set(k, v)
+    try:
+        for B, shape in [(5, (3, 224, 224)), (2, (3, 64, 64)), (3, (1, 32, 32)), (2, (4, 16, 16)), (2, (3, 226, 224))]:
+            rng = np.random.default_rng(B + shape[0])
+            full = (B,) + shape
+            C = shape[0]
+            mean = rng.random(C, dtype=np.float32); std = (0.2 + rng.random(C, dtype=np.float32)).astype(np.float32)
+            g = (rng.standard_normal(full) * 1e-3).astype(np.float32)
+            m = rng.standard_normal(full).astype(np.float32)
+            x = rng.random(full, dtype=np.float32)
+            d = ((rng.random(full, dtype=np.float32) * 2 - 1) * EPS).astype(np.float32)
+            for wrt_xn in (False, True):
+                for strict in (True, False):
+                    for has_m in (True, False):
+                        g_eff = oracle.normalize_bwd(g, std) if wrt_xn else g
+                        gm, dd = cu(m), cu(d)
+                        m_out, xn = torch.empty_like(gm), torch.empty_like(gm)
+                        so = torch.empty(B, device="cuda")
+                        sc = cu(oracle.abs_mean_per_sample(g_eff)) if strict else None
+                        ok = be.fused_update_linf_nf(cu(g), gm if has_m else None, gm if has_m else m_out, dd, dd, cu(x), xn, sc, so,
+                                                     0.9, ALPHA, EPS, 0, 1.0, mean, std, wrt_xn)
+                        assert ok
+                        scale = npy(so)
+                        assert ulp_diff(scale, oracle.abs_mean_per_sample(g_eff)).max() <= (0 if strict else 1)
+                        mo, do, xo, _ = oracle.fused_update_linf_nf(g, m if has_m else None, d, x, scale, 0.9, ALPHA, EPS, mean, std, wrt_xn)
+                        tag = (B, shape, wrt_xn, strict, has_m)
+                        assert bits_equal(npy(gm if has_m else m_out), mo), tag
+                        assert bits_equal(npy(dd), do), tag
+                        assert bits_equal(npy(xn), xo), tag
+    finally:
+        _lib.tune_set("fused.variant", 0); _lib.tune_set("fused.cluster", 0)
+
+
+def test_fused_update_nf_declines_unfoldable_shapes(be):
+    for full in [(2, 3, 5, 5), (2, 5, 8, 8)]:          # plane % 4 != 0; more than 4 channels
+        t = torch.zeros(full, device="cuda")
+        so = torch.empty(full[0], device="cuda")
+        C = full[1]
+        assert be.fused_update_linf_nf(t, None, t.clone(), t.clone(), t.clone(), t, t.clone(), None, so, 1.0, ALPHA, EPS, 0, 1.0,
+                                       [0.5] * C, [0.5] * C, False) is False
+
+
 def test_fused_all_zero_gradient_sample(be):
     rng = np.random.default_rng(0)
     full = (3, 3, 32, 32)

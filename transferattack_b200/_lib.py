@@ -34,6 +34,7 @@ SIGNATURES = {
     "ta_clamp_box": (_i, [_p, _p, _f, _f, _p, _l, _p]),
     "ta_init_l2_scale": (_i, [_p, _p, _p, _f, _f, _f, _p, _i, _l, _p, _p]),
     "ta_fused_update_linf": (_i, [_p, _p, _p, _p, _p, _p, _p, _p, _p, _i, _f, _f, _f, _f, _f, _i, _l, _p]),
+    "ta_fused_update_linf_nf": (_i, [_p, _p, _p, _p, _p, _p, _p, _p, _p, _i, _f, _f, _f, _f, _f, _i, _l, _p, _p, _i, _l, _i, _p]),
     "ta_fused_allreduce_update_linf": (_i, [ctypes.POINTER(_p), ctypes.POINTER(_p), _i, _p, _p, _p, _p, _p, _p, _p, _i,
                                             _f, _f, _f, _f, _f, _i, _i, _l, _p]),
     "ta_stage_add": (_i, [_p, _p, _p, _f, _p, _l, _p]),

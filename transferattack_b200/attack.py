@@ -31,7 +31,7 @@ import torch.nn as nn
 
 from . import _lib, ops
 from .utils import *  # noqa: F401,F403  (plugins expect the reference's star-exports through this module too)
-from .utils import EnsembleModel, clamp, img_max, img_min, models, timm, wrap_model
+from .utils import EnsembleModel, PreprocessingModel, clamp, img_max, img_min, models, timm, wrap_model
 
 _ZERO_TYPES = (int, float)
 
@@ -60,6 +60,13 @@ class Attack(object):
     graph_safe = True
     #: captured graphs kept per attacker (one per batch shape); the oldest is dropped beyond this
     max_cached_graphs = 4
+    #: SURVEY §8 f1: when the surrogate is ``Sequential(PreprocessingModel, net)`` (what ``wrap_model`` builds), its Resize is a
+    #: no-op at the input size and neither ``transform`` nor ``get_logits`` is overridden, the fused tail writes the NORMALISED
+    #: next input ((data + delta') - mean) / std itself (``ta_fused_update_linf_nf``) and ``net`` is entered directly: the
+    #: Normalize forward kernel disappears from every iteration. Its adjoint g / std stays a ``ta_normalize_bwd`` launch in
+    #: strict mean mode (torch's own mean op needs the gradient w.r.t. delta in memory) and moves into the fused kernel too
+    #: in 'exact' mode with the base ``get_grad``. Same arithmetic in the same order → same bits. Env TA_B200_FOLD=0 disables.
+    fold_normalize = os.environ.get("TA_B200_FOLD", "1") == "1"
 
     def __init__(self, attack, model_name, epsilon, targeted, random_start, norm, loss, device=None):
         """attack.py:12-38 — same arguments, same attributes, same ``Unsupported norm`` exception."""
@@ -122,6 +129,37 @@ class Attack(object):
                 and cls.init_delta is Attack.init_delta
                 and isinstance(self.alpha, (int, float)) and isinstance(self.decay, (int, float)))
 
+    def _fold_plan(self, data):
+        """(pre, net, mean, std, defer) when Normalize can be folded into the fused tail for this batch, else None."""
+        cls = type(self)
+        if not self.fold_normalize or cls.get_logits is not Attack.get_logits or cls.transform is not Attack.transform:
+            return None
+        m = self.model
+        if not (isinstance(m, nn.Sequential) and len(m) == 2 and isinstance(m[0], PreprocessingModel)) or data.dim() != 4:
+            return None
+        pre = m[0]
+        B, C, H, W = data.shape
+        size = pre.resize.size
+        size = size[0] if isinstance(size, (list, tuple)) and len(size) == 1 else size
+        if not isinstance(size, int) or min(H, W) != size:           # Resize(int) keeps the tensor only when the short side matches
+            return None
+        if pre.mean.numel() != C or C > 4 or (H * W) % 4 != 0 or data.data_ptr() % 16 != 0:
+            return None
+        defer = self.mean_mode != 'torch' and cls.get_grad is Attack.get_grad
+        return pre, m[1], [float(v) for v in pre.mean.tolist()], [float(v) for v in pre.std.tolist()], defer
+
+    @staticmethod
+    def _first_normalized(pre, data, delta, out=None):
+        """xn of the first iteration: the two separate kernels, once per batch"""
+        be = ops.backend()
+        with torch.no_grad():
+            pre._buffers_on(data.device)
+            xn = be.normalize(be.stage_add(data, delta.detach()), pre.mean, pre.std, True)
+            if out is not None:
+                out.copy_(xn)
+                return out
+        return xn
+
     def forward(self, data, label, **kwargs):
         """The general attack procedure (attack.py:67-102).
 
@@ -159,12 +197,20 @@ class Attack(object):
         iteration. delta / momentum / x_adv live in buffers this loop owns and are updated in place."""
         be = ops.backend()
         m_buf = torch.empty_like(data)
-        xadv = torch.empty_like(data)
         scale_out = torch.empty(data.shape[0], device=data.device, dtype=torch.float32)
-        momentum, pre = None, None
+        fold = self._fold_plan(data)
+        if fold is not None:
+            pre, net, mean, std, defer = fold
+            xadv = self._first_normalized(pre, data, delta)          # holds the NORMALISED model input from here on
+        else:
+            xadv = torch.empty_like(data)
+        momentum, pre_x = None, None
         for _ in range(self.epoch):
-            x = ops.stage_add(data, delta, precomputed=pre)
-            logits = self.get_logits(self.transform(x, momentum=0 if momentum is None else momentum))
+            if fold is not None:
+                logits = net(ops.stage_normalized(delta, xadv, pre.std, defer))
+            else:
+                x = ops.stage_add(data, delta, precomputed=pre_x)
+                logits = self.get_logits(self.transform(x, momentum=0 if momentum is None else momentum))
             loss = self.get_loss(logits, label)
             grad = self.get_grad(loss, delta)
             scale = self._torch_abs_mean(grad) if self.mean_mode == 'torch' else None
@@ -173,26 +219,42 @@ class Attack(object):
                 e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
                 e0.record()
             with torch.no_grad():
-                be.fused_update_linf(grad, momentum, m_buf, delta, delta, data, xadv, scale, scale_out,
-                                     self.decay, self.alpha, self.epsilon, img_min, img_max, _lib.TA_MEAN_EXACT)
+                if fold is not None:
+                    if not be.fused_update_linf_nf(grad, momentum, m_buf, delta, delta, data, xadv, scale, scale_out, self.decay,
+                                                   self.alpha, self.epsilon, img_min, img_max, mean, std, defer, _lib.TA_MEAN_EXACT):
+                        raise RuntimeError("ta_fused_update_linf_nf refused a shape _fold_plan accepted")
+                else:
+                    be.fused_update_linf(grad, momentum, m_buf, delta, delta, data, xadv, scale, scale_out,
+                                         self.decay, self.alpha, self.epsilon, img_min, img_max, _lib.TA_MEAN_EXACT)
             if ev is not None:
                 e1.record()
                 ev.append((e0, e1))
-            momentum, pre = m_buf, xadv
+            momentum, pre_x = m_buf, xadv
         return delta.detach()
 
     # ---- CUDA-graph replay of the fused loop -------------------------------------------------------------
     def _graph_iteration(self, st):
         """One iteration on the static buffers `st` (this body is what gets captured)."""
-        x = ops.stage_add(st["data"], st["delta"], precomputed=st["xadv"])
-        logits = self.get_logits(self.transform(x, momentum=st["m"]))
+        fold = st.get("fold")
+        if fold is not None:
+            pre, net, mean, std, defer = fold
+            logits = net(ops.stage_normalized(st["delta"], st["xadv"], pre.std, defer))
+        else:
+            x = ops.stage_add(st["data"], st["delta"], precomputed=st["xadv"])
+            logits = self.get_logits(self.transform(x, momentum=st["m"]))
         loss = self.get_loss(logits, st["label"])
         grad = self.get_grad(loss, st["delta"])
         scale = self._torch_abs_mean(grad) if self.mean_mode == 'torch' else None
         with torch.no_grad():
-            ops.backend().fused_update_linf(grad, st["m"], st["m"], st["delta"], st["delta"], st["data"], st["xadv"], scale,
-                                            st["scale_out"], self.decay, self.alpha, self.epsilon, img_min, img_max,
-                                            _lib.TA_MEAN_EXACT)
+            if fold is not None:
+                if not ops.backend().fused_update_linf_nf(grad, st["m"], st["m"], st["delta"], st["delta"], st["data"], st["xadv"],
+                                                          scale, st["scale_out"], self.decay, self.alpha, self.epsilon, img_min,
+                                                          img_max, mean, std, defer, _lib.TA_MEAN_EXACT):
+                    raise RuntimeError("ta_fused_update_linf_nf refused a shape _fold_plan accepted")
+            else:
+                ops.backend().fused_update_linf(grad, st["m"], st["m"], st["delta"], st["delta"], st["data"], st["xadv"], scale,
+                                                st["scale_out"], self.decay, self.alpha, self.epsilon, img_min, img_max,
+                                                _lib.TA_MEAN_EXACT)
 
     def _graph_reset(self, st, data, label, delta0):
         with torch.no_grad():
@@ -200,11 +262,15 @@ class Attack(object):
             st["label"].copy_(label)
             st["delta"].copy_(delta0)
             st["m"].zero_()          # momentum * decay with momentum = +0 is the reference's first-iteration `0 * decay`
-            ops.backend().stage_add(st["data"], st["delta"], out=st["xadv"])
+            if st.get("fold") is not None:
+                self._first_normalized(st["fold"][0], st["data"], st["delta"], out=st["xadv"])
+            else:
+                ops.backend().stage_add(st["data"], st["delta"], out=st["xadv"])
 
     def _graph_for(self, data, label, delta0):
+        fold = self._fold_plan(data)
         key = (tuple(data.shape), str(data.device), tuple(label.shape), self.mean_mode, float(self.alpha), float(self.decay),
-               float(self.epsilon), bool(self.targeted), id(self.model))
+               float(self.epsilon), bool(self.targeted), id(self.model), fold is not None, bool(fold[4]) if fold else False)
         cache = self.__dict__.setdefault("_graphs", {})
         st = cache.get(key)
         if st is not None:
@@ -213,7 +279,8 @@ class Attack(object):
             cache.pop(next(iter(cache)))
         st = {"data": torch.empty_like(data), "label": torch.empty_like(label),
               "delta": torch.zeros_like(data).requires_grad_(True), "m": torch.zeros_like(data),
-              "xadv": torch.empty_like(data), "scale_out": torch.empty(data.shape[0], device=data.device, dtype=torch.float32)}
+              "xadv": torch.empty_like(data), "scale_out": torch.empty(data.shape[0], device=data.device, dtype=torch.float32),
+              "fold": fold}
         self._graph_reset(st, data, label, delta0)
         cur = torch.cuda.current_stream(data.device)
         side = torch.cuda.Stream(device=data.device)

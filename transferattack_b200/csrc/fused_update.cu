@@ -26,12 +26,30 @@ using namespace ta;
 
 namespace {
 
+// Normalize folding (reference utils.py:72-79): the model input the kernel emits is the NORMALISED image
+// (x + delta' - mean_c) / std_c (torchvision's sub_ then div_: two roundings), and — when `bwd` — the incoming gradient is
+// the one w.r.t. that normalised input, turned into the gradient w.r.t. delta by Normalize's adjoint g / std_c first.
+struct NormFold {
+  float mean[4], std[4];
+  int64_t plane_vec;      // vectors (of the launch's width) per channel plane
+  int C, fwd, bwd;
+};
+
 struct FusedParams {
   const float* g; const float* m; float* m_out; const float* delta; float* delta_out; const float* data;
   float* xadv; const float* scale; float* scale_out;
   float decay, alpha, eps, lo, hi;
   int64_t n;
+  NormFold nf;
 };
+
+// channel of vector j (index inside one sample); C <= 4
+__device__ __forceinline__ int nf_channel(const NormFold& nf, int64_t j) {
+  int c = 0;
+#pragma unroll
+  for (int k = 1; k < 4; ++k) c += (k < nf.C && j >= k * nf.plane_vec) ? 1 : 0;
+  return c;
+}
 
 // one element of the fused tail; all roundings as in the reference's eager ops
 __device__ __forceinline__ void fused_elem(float g, float m, bool has_m, float d, float x, float mu, const FusedParams& p,
@@ -41,10 +59,18 @@ __device__ __forceinline__ void fused_elem(float g, float m, bool has_m, float d
   d_new = project_linf(d, mul_rn(p.alpha, sign_t(m_new)), x, p.eps, p.lo, p.hi);
   xa = add_rn(x, d_new);
 }
+template <bool NF>
+__device__ __forceinline__ void fused_elem_nf(float g, float m, bool has_m, float d, float x, float mu, const FusedParams& p,
+                                              float mean_c, float std_c, float& m_new, float& d_new, float& xa) {
+  if (NF && p.nf.bwd) g = div_rn(g, std_c);
+  fused_elem(g, m, has_m, d, x, mu, p, m_new, d_new, xa);
+  if (NF && p.nf.fwd) xa = div_rn(sub_rn(xa, mean_c), std_c);
+}
 
 // ---- strict / fallback path: scale[b] given, flat streaming ---------------------------------------------------
 template <int V> struct FusedIn { Vec<V> g, x, d, m; float mu; };
-struct FusedStreamOp {
+template <bool NF>
+struct FusedStreamOpT {
   FusedParams p; int64_t nvec;     // vectors per sample
   template <int V> __device__ __forceinline__ FusedIn<V> load(int row, int64_t j) const {
     FusedIn<V> r;
@@ -57,21 +83,28 @@ struct FusedStreamOp {
   template <int V> __device__ __forceinline__ void apply(int row, int64_t j, const FusedIn<V>& r) const {
     const int64_t i = (int64_t)row * nvec + j;
     Vec<V> mo, dn, xa;
+    float mean_c = 0.0f, std_c = 1.0f;
+    if (NF) { const int c = nf_channel(p.nf, j); mean_c = p.nf.mean[c]; std_c = p.nf.std[c]; }
 #pragma unroll
     for (int k = 0; k < V; ++k)
-      fused_elem(r.g.v[k], p.m ? r.m.v[k] : 0.0f, p.m != nullptr, r.d.v[k], r.x.v[k], r.mu, p, mo.v[k], dn.v[k], xa.v[k]);
+      fused_elem_nf<NF>(r.g.v[k], p.m ? r.m.v[k] : 0.0f, p.m != nullptr, r.d.v[k], r.x.v[k], r.mu, p, mean_c, std_c, mo.v[k],
+                        dn.v[k], xa.v[k]);
     stv<V>(p.m_out, i, mo);
     stv<V>(p.delta_out, i, dn);
     if (p.xadv) stv<V>(p.xadv, i, xa);
   }
 };
+using FusedStreamOp = FusedStreamOpT<false>;
 
 // ---- cluster kernel ----------------------------------------------------------------------------------------------
 constexpr int kChunks = 4;
 
 // STAGE = true : g slice resident in shared memory (bulk-TMA), read from HBM once
 // STAGE = false: g re-read through L2 in phase B
-template <int THREADS, int U, bool STAGE>
+__device__ __forceinline__ double abs4(const float4& v) {
+  double a = (double)fabsf(v.x); a += (double)fabsf(v.y); a += (double)fabsf(v.z); a += (double)fabsf(v.w); return a;
+}
+template <int THREADS, int U, bool STAGE, bool NF>
 __global__ void __launch_bounds__(THREADS) fused_cluster_kernel(FusedParams p) {
   extern __shared__ __align__(128) unsigned char smem_raw[];
   __shared__ double s_scratch[32];
@@ -116,14 +149,16 @@ __global__ void __launch_bounds__(THREADS) fused_cluster_kernel(FusedParams p) {
       if (c1 > c0) {
         mbar_wait(&s_bar[c], 0);
         for (int64_t i = c0 + tid; i < c1; i += THREADS) {
-          const float4 v = sg4[i];
+          float4 v = sg4[i];
+          if (NF && p.nf.bwd) { const float sc = p.nf.std[nf_channel(p.nf, begin + i)]; v.x = div_rn(v.x, sc); v.y = div_rn(v.y, sc); v.z = div_rn(v.z, sc); v.w = div_rn(v.w, sc); }
           acc += (double)fabsf(v.x); acc += (double)fabsf(v.y); acc += (double)fabsf(v.z); acc += (double)fabsf(v.w);
         }
       }
     }
   } else {
     for (int64_t i = tid; i < cnt; i += THREADS) {
-      const float4 v = __ldg(g4 + i);
+      float4 v = __ldg(g4 + i);
+      if (NF && p.nf.bwd) { const float sc = p.nf.std[nf_channel(p.nf, begin + i)]; v.x = div_rn(v.x, sc); v.y = div_rn(v.y, sc); v.z = div_rn(v.z, sc); v.w = div_rn(v.w, sc); }
       acc += (double)fabsf(v.x); acc += (double)fabsf(v.y); acc += (double)fabsf(v.z); acc += (double)fabsf(v.w);
     }
   }
@@ -161,10 +196,12 @@ __global__ void __launch_bounds__(THREADS) fused_cluster_kernel(FusedParams p) {
       const int64_t i = i0 + (int64_t)u * THREADS;
       if (i < cnt) {
         float4 mo, dn, xa;
-        fused_elem(gv[u].x, mv[u].x, has_m, dv[u].x, xv[u].x, mu, p, mo.x, dn.x, xa.x);
-        fused_elem(gv[u].y, mv[u].y, has_m, dv[u].y, xv[u].y, mu, p, mo.y, dn.y, xa.y);
-        fused_elem(gv[u].z, mv[u].z, has_m, dv[u].z, xv[u].z, mu, p, mo.z, dn.z, xa.z);
-        fused_elem(gv[u].w, mv[u].w, has_m, dv[u].w, xv[u].w, mu, p, mo.w, dn.w, xa.w);
+        float mean_c = 0.0f, std_c = 1.0f;
+        if (NF) { const int c = nf_channel(p.nf, begin + i); mean_c = p.nf.mean[c]; std_c = p.nf.std[c]; }
+        fused_elem_nf<NF>(gv[u].x, mv[u].x, has_m, dv[u].x, xv[u].x, mu, p, mean_c, std_c, mo.x, dn.x, xa.x);
+        fused_elem_nf<NF>(gv[u].y, mv[u].y, has_m, dv[u].y, xv[u].y, mu, p, mean_c, std_c, mo.y, dn.y, xa.y);
+        fused_elem_nf<NF>(gv[u].z, mv[u].z, has_m, dv[u].z, xv[u].z, mu, p, mean_c, std_c, mo.z, dn.z, xa.z);
+        fused_elem_nf<NF>(gv[u].w, mv[u].w, has_m, dv[u].w, xv[u].w, mu, p, mean_c, std_c, mo.w, dn.w, xa.w);
         mo4[i] = mo;
         do4[i] = dn;
         if (p.xadv) xa4[i] = xa;
@@ -174,9 +211,9 @@ __global__ void __launch_bounds__(THREADS) fused_cluster_kernel(FusedParams p) {
   cluster_wait();                         // keep s_part alive until every rank has read it
 }
 
-template <int THREADS, int U, bool STAGE>
+template <int THREADS, int U, bool STAGE, bool NF = false>
 int launch_fused(const FusedParams& p, int B, int cl, size_t smem, cudaStream_t s) {
-  auto k = fused_cluster_kernel<THREADS, U, STAGE>;
+  auto k = fused_cluster_kernel<THREADS, U, STAGE, NF>;
   static SmemOptIn optin = {};
   static bool nonportable[64] = {};
   int rc = ensure_dyn_smem("ta_fused_update_linf", k, smem, optin);
@@ -308,23 +345,30 @@ constexpr size_t kMaxStageBytes = 200 * 1024;   // per-CTA g slice bound (227 KB
 
 }  // namespace
 
-extern "C" int ta_fused_update_linf(const float* g, const float* m, float* m_out, const float* delta, float* delta_out,
-                                    const float* data, float* xadv_out, const float* scale, float* scale_out, int mean_mode,
-                                    float decay, float alpha, float eps, float lo, float hi, int B, int64_t n,
-                                    ta_stream_t stream) {
-  TA_REQUIRE(g && m_out && delta && delta_out && data && B > 0 && n > 0,
-             "ta_fused_update_linf: null pointer or empty shape (B=%d n=%lld)", B, (long long)n);
-  TA_REQUIRE(B <= 65535, "ta_fused_update_linf: B=%d exceeds 65535", B);
+namespace {
+
+int fused_update_impl(const float* g, const float* m, float* m_out, const float* delta, float* delta_out, const float* data,
+                      float* xadv_out, const float* scale, float* scale_out, int mean_mode, float decay, float alpha, float eps,
+                      float lo, float hi, int B, int64_t n, const NormFold* nf, ta_stream_t stream) {
+  const char* who = nf ? "ta_fused_update_linf_nf" : "ta_fused_update_linf";
+  TA_REQUIRE(g && m_out && delta && delta_out && data && B > 0 && n > 0, "%s: null pointer or empty shape (B=%d n=%lld)", who, B,
+             (long long)n);
+  TA_REQUIRE(B <= 65535, "%s: B=%d exceeds 65535", who, B);
   cudaStream_t s = (cudaStream_t)stream;
   FusedParams p{g, m, m_out, delta, delta_out, data, xadv_out, scale, scale_out, decay, alpha, eps, lo, hi, n};
   const bool v4 = (n % 4 == 0) && aligned16(g) && aligned16(m) && aligned16(m_out) && aligned16(delta) &&
                   aligned16(delta_out) && aligned16(data) && aligned16(xadv_out);
+  if (nf) {
+    if (!v4) { set_error("%s: needs n %% 4 == 0 and 16-byte aligned buffers", who); return TA_EUNSUPPORTED; }
+    p.nf = *nf;          // plane_vec already in 128-bit vectors
+  }
 
   if (scale) {   // strict: no reduction, flat streaming
     if (scale_out && scale_out != scale) {
       const cudaError_t e = cudaMemcpyAsync(scale_out, scale, sizeof(float) * (size_t)B, cudaMemcpyDeviceToDevice, s);
-      if (e != cudaSuccess) { set_error("ta_fused_update_linf: scale copy failed: %s", cudaGetErrorString(e)); return TA_ECUDA; }
+      if (e != cudaSuccess) { set_error("%s: scale copy failed: %s", who, cudaGetErrorString(e)); return TA_ECUDA; }
     }
+    if (nf) return launch_ew_rows2<1>("ta_fused_update_linf_nf[stream]", B, n, true, FusedStreamOpT<true>{p, n / 4}, s, 0);
     const FusedStreamOp op{p, v4 ? n / 4 : n};
     const int cap = tune_get("stream.cap", 0);          // resident CTAs per SM (0 = one batch per thread, no loop)
     switch (tune_get("stream.unroll", 1)) {
@@ -335,7 +379,7 @@ extern "C" int ta_fused_update_linf(const float* g, const float* m, float* m_out
   }
 
   if (mean_mode != TA_MEAN_EXACT) {
-    set_error("ta_fused_update_linf: mean_mode %d not available in this build", mean_mode);
+    set_error("%s: mean_mode %d not available in this build", who, mean_mode);
     return TA_EUNSUPPORTED;
   }
 
@@ -362,6 +406,8 @@ extern "C" int ta_fused_update_linf(const float* g, const float* m, float* m_out
 
   const bool stage = (variant == 0) && slice_bytes <= kMaxStageBytes;
   const size_t smem = stage ? slice_bytes : 0;
+  if (nf)   // one tuning point (the default) for the folded form
+    return stage ? launch_fused<512, 2, true, true>(p, B, cl, smem, s) : launch_fused<512, 2, false, true>(p, B, cl, 0, s);
 #define TA_FUSED_CASE(T, U_)                                                        \
   if (threads == T && unroll == U_)                                                 \
     return stage ? launch_fused<T, U_, true>(p, B, cl, smem, s) : launch_fused<T, U_, false>(p, B, cl, 0, s);
@@ -376,6 +422,40 @@ extern "C" int ta_fused_update_linf(const float* g, const float* m, float* m_out
 #undef TA_FUSED_CASE
   set_error("ta_fused_update_linf: unsupported tuning threads=%d unroll=%d", threads, unroll);
   return TA_EUNSUPPORTED;
+}
+
+}  // namespace
+
+extern "C" int ta_fused_update_linf(const float* g, const float* m, float* m_out, const float* delta, float* delta_out,
+                                    const float* data, float* xadv_out, const float* scale, float* scale_out, int mean_mode,
+                                    float decay, float alpha, float eps, float lo, float hi, int B, int64_t n,
+                                    ta_stream_t stream) {
+  return fused_update_impl(g, m, m_out, delta, delta_out, data, xadv_out, scale, scale_out, mean_mode, decay, alpha, eps, lo, hi,
+                           B, n, nullptr, stream);
+}
+
+// Normalize folded in: `xn_out` receives the NORMALISED next model input ((data + delta') - mean_c) / std_c,
+// channel c = (element index inside the sample) / plane; with grad_wrt_xn != 0, `g` is the gradient w.r.t. that normalised
+// input and is divided by std_c (Normalize's adjoint) before anything else. mean_host / std_host: HOST arrays [C], C <= 4.
+extern "C" int ta_fused_update_linf_nf(const float* g, const float* m, float* m_out, const float* delta, float* delta_out,
+                                       const float* data, float* xn_out, const float* scale, float* scale_out, int mean_mode,
+                                       float decay, float alpha, float eps, float lo, float hi, int B, int64_t n,
+                                       const float* mean_host, const float* std_host, int C, int64_t plane, int grad_wrt_xn,
+                                       ta_stream_t stream) {
+  TA_REQUIRE(mean_host && std_host && xn_out, "ta_fused_update_linf_nf: null pointer");
+  if (C < 1 || C > 4 || plane <= 0 || plane % 4 != 0 || (int64_t)C * plane != n) {
+    set_error("ta_fused_update_linf_nf: needs 1 <= C <= 4, plane %% 4 == 0 and C * plane == n (C=%d plane=%lld n=%lld)", C,
+              (long long)plane, (long long)n);
+    return TA_EUNSUPPORTED;
+  }
+  NormFold nf = {};
+  for (int c = 0; c < C; ++c) {
+    TA_REQUIRE(std_host[c] != 0.0f, "ta_fused_update_linf_nf: std[%d] == 0", c);
+    nf.mean[c] = mean_host[c]; nf.std[c] = std_host[c];
+  }
+  nf.C = C; nf.fwd = 1; nf.bwd = grad_wrt_xn ? 1 : 0; nf.plane_vec = plane / 4;
+  return fused_update_impl(g, m, m_out, delta, delta_out, data, xn_out, scale, scale_out, mean_mode, decay, alpha, eps, lo, hi, B,
+                           n, &nf, stream);
 }
 
 extern "C" int ta_fused_allreduce_update_linf(const float* const* g_peers, float* const* xadv_peers, int K, const float* m,

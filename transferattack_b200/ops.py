@@ -128,6 +128,24 @@ class CudaBackend:
                                                      float(alpha), float(eps), float(lo), float(hi), B, n, _stream()),
                        "ta_fused_update_linf")
 
+    def fused_update_linf_nf(self, g, m, m_out, delta, delta_out, data, xn_out, scale, scale_out, decay, alpha, eps, lo, hi,
+                             mean, std, grad_wrt_xn, mean_mode=_lib.TA_MEAN_EXACT):
+        """ta_fused_update_linf_nf: the fused tail emitting the NORMALISED next model input; mean/std: host sequences [C].
+        Returns False (nothing launched) when the library cannot fold this shape — the caller keeps the separate kernels."""
+        g = _f32c(g, "grad"); B, C = g.shape[0], g.shape[1]; n = g.numel() // B
+        hm = np.ascontiguousarray(mean, np.float32); hs = np.ascontiguousarray(std, np.float32)
+        if hm.size != C or hs.size != C:
+            return False
+        with _DeviceOf(g):
+            rc = self.lib.ta_fused_update_linf_nf(_ptr(g), _ptr(m), _ptr(m_out), _ptr(delta), _ptr(delta_out), _ptr(data),
+                                                  _ptr(xn_out), _ptr(scale), _ptr(scale_out), mean_mode, float(decay), float(alpha),
+                                                  float(eps), float(lo), float(hi), B, n, hm.ctypes.data, hs.ctypes.data, C, n // C,
+                                                  1 if grad_wrt_xn else 0, _stream())
+        if rc == _lib.TA_EUNSUPPORTED:
+            return False
+        _lib.check(rc, "ta_fused_update_linf_nf")
+        return True
+
     # ---- staging ----------------------------------------------------------------------------------
     def stage_add(self, data, delta, look=None, coef=0.0, out=None):
         data = _f32c(data, "data"); delta = _f32c(delta, "delta"); look = _f32c(look, "momentum")
@@ -288,6 +306,25 @@ class StageAdd(torch.autograd.Function):
         return None, gout, None, None, None
 
 
+class StageNormalized(torch.autograd.Function):
+    """The surrogate's NORMALISED input ((data + delta) - mean) / std as a function of delta, when the fused tail already
+    wrote it into `xn`: forward hands `xn` out, backward is Normalize's adjoint g / std (``ta_normalize_bwd``)
+    — or the identity when the fused kernel will apply that division itself (`defer`)."""
+
+    @staticmethod
+    def forward(ctx, delta, xn, std, defer):
+        ctx.defer = defer
+        ctx.save_for_backward(std)
+        return xn.view_as(delta)
+
+    @staticmethod
+    def backward(ctx, gout):
+        if ctx.defer:
+            return gout, None, None, None
+        (std,) = ctx.saved_tensors
+        return backend().normalize(gout, None, std, False), None, None, None
+
+
 class LookAhead(torch.autograd.Function):
     """NI-FGSM's x + (alpha*decay) * momentum on an already formed x (nifgsm.py:39); identity backward."""
 
@@ -372,6 +409,10 @@ class LinSample(torch.autograd.Function):
 
 def stage_add(data, delta, look=None, coef=0.0, precomputed=None):
     return StageAdd.apply(data, delta, look, coef, precomputed)
+
+
+def stage_normalized(delta, xn, std, defer=False):
+    return StageNormalized.apply(delta, xn, std, defer)
 
 
 def look_ahead(x, momentum, coef):
