@@ -213,6 +213,16 @@ int ta_lin_sample_bwd(const float* gout, float* gin, int K, int64_t N, ta_stream
  *   finalize:        v = acc / num_neighbor - cur_grad                                                  */
 int ta_neighbor_stage(const float* data, const float* delta, const float* noise, const float* look,
                       float coef, float* out, int64_t N, ta_stream_t stream);
+/* The same staging with the noise generated in the kernel: noise[i] is bit for bit what torch's CUDA
+ * `zeros_like(delta).uniform_(from, to)` (vmifgsm.py:50) would have written at element i for the device generator state
+ * (seed, offset) — Philox4_32_10, torch's thread/element mapping (ATen DistributionTemplates.h) — so the attack consumes the
+ * same random stream; the caller then advances the generator's offset by *offset_increment of ta_uniform_fill_policy(N).
+ * One launch and 12 B/elem instead of 4 launches and 32 B/elem. noise_out (optional) receives the noise itself.
+ * offset % 4 == 0, N < 2^31.                                                                                               */
+int ta_uniform_fill_policy(int64_t numel, int64_t* threads_total, int64_t* offset_increment);
+int ta_neighbor_stage_philox(const float* data, const float* delta, const float* look, float coef,
+                             float from, float to, uint64_t seed, uint64_t offset,
+                             float* out, float* noise_out, int64_t N, ta_stream_t stream);
 int ta_accumulate(float* acc, const float* g, int first, int64_t N, ta_stream_t stream);
 int ta_variance_finalize(const float* acc, const float* cur, int num_neighbor, float* out,
                          int64_t N, ta_stream_t stream);

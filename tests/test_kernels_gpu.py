@@ -411,6 +411,44 @@ def test_fused_all_zero_gradient_sample(be):
     assert bits_equal(npy(gm), mo) and bits_equal(npy(dd), do)
 
 
+# ---------------------------------------------------------------------------------------------- VMI noise in the kernel
+@pytest.mark.parametrize("shape", [(64, 3, 224, 224), (4, 3, 224, 224), (2, 3, 299, 299), (1, 3, 17, 19), (1000,), (3, 5, 7)])
+def test_neighbor_stage_philox_reproduces_torch_uniform(be, shape):
+    """ta_neighbor_stage_philox must put exactly the numbers of `zeros_like(delta).uniform_(-r, r)` (vmifgsm.py:50) at exactly
+    the same elements, leave torch's device generator where that call would have left it, and equal the numpy restatement."""
+    from oracle import philox as P
+    r = 1.5 * EPS
+    gen = torch.cuda.default_generators[0]
+    data = torch.rand(shape, device="cuda"); delta = (torch.rand(shape, device="cuda") * 2 - 1) * EPS
+    look = torch.randn(shape, device="cuda")
+    for seed in (0, 1234567, 2 ** 40 + 17):
+        for warm in (0, 3):
+            torch.cuda.manual_seed(seed)
+            for _ in range(warm):
+                torch.rand(1000, device="cuda")                          # move the offset off zero
+            state = gen.get_state()
+            off0 = gen.get_offset()
+            want_noise = torch.zeros_like(delta).uniform_(-r, r)
+            off_torch = gen.get_offset()
+            follow_torch = torch.rand(5, device="cuda")
+            gen.set_state(state)
+            noise = torch.empty_like(delta)
+            out = be.neighbor_stage_philox(data, delta, -r, r, noise_out=noise)
+            assert gen.get_offset() == off_torch                         # generator advanced identically
+            assert torch.equal(torch.rand(5, device="cuda"), follow_torch)
+            assert torch.equal(noise, want_noise), (shape, seed, warm, int((noise != want_noise).sum()))
+            assert torch.equal(out, (data + delta) + want_noise)
+            T, inc = be.torch_uniform_policy(delta.numel())
+            assert inc == off_torch - off0
+            if delta.numel() <= 1_000_000:
+                ref = P.torch_uniform(delta.numel(), seed, off0, -r, r, T).reshape(shape)
+                assert bits_equal(npy(noise), ref), (shape, seed)
+    # with the Nesterov look-ahead term of VNI-FGSM
+    gen.set_state(state)
+    out = be.neighbor_stage_philox(data, delta, -r, r, look=look, coef=0.01)
+    assert torch.equal(out, ((data + delta) + want_noise) + 0.01 * look)
+
+
 # ---------------------------------------------------------------------------------------------- BASELINE-size properties
 def test_full_size_fused_equals_unfused_and_bounds(be):
     torch.manual_seed(0)

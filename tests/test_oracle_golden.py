@@ -176,3 +176,21 @@ def test_tim_conv_separable_matches_2d():
         x = T[key + "_a_in"]
         out = oracle.dwconv2d_sep(x, np.stack([kcol] * 3), np.stack([krow] * 3))
         np.testing.assert_allclose(out, T[key + "_a_out"], rtol=0, atol=1e-6, err_msg=key)
+
+
+def test_philox_restatement_known_answers():
+    """oracle/philox.py: Philox4x32-10 against the Random123 known-answer vectors (Salmon et al., SC'11, kat_vectors), and
+    the execution policy / element mapping of the uniform fill on a B200-shaped device (148 SMs x 2048 threads)."""
+    from oracle import philox as P
+
+    def kat(c, k):
+        o = P.philox4x32_10(*[np.array([v], np.uint64) for v in c], k[0], k[1])
+        return tuple(int(v[0]) for v in o)
+    assert kat((0, 0, 0, 0), (0, 0)) == (0x6627e8d5, 0xe169c58d, 0xbc57ac4c, 0x9b00dbd8)
+    assert kat((0xffffffff,) * 4, (0xffffffff, 0xffffffff)) == (0x408f276d, 0x41c83b0e, 0xa20bc7c6, 0x6d5451fd)
+    assert kat((0x243f6a88, 0x85a308d3, 0x13198a2e, 0x03707344), (0xa4093822, 0x299f31d0)) == (0xd16cfe09, 0x94fdcceb, 0x5001e420, 0x24126ea1)
+    assert P.torch_uniform_policy(64 * 3 * 224 * 224, 148, 2048) == (303104, 32)
+    assert P.torch_uniform_policy(1000, 148, 2048) == (1024, 4)
+    v = P.torch_uniform(5000, seed=1234, offset=8, frm=-0.094, to=0.094, T=1024)
+    assert v.dtype == np.float32 and v.min() >= np.float32(-0.094) and v.max() < np.float32(0.094)
+    assert abs(float(v.mean())) < 0.01 and len(np.unique(v)) > 4900

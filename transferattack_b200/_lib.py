@@ -52,6 +52,8 @@ SIGNATURES = {
     "ta_lin_sample_fwd": (_i, [_p, _p, ctypes.POINTER(_f), _i, _p, _l, _p]),
     "ta_lin_sample_bwd": (_i, [_p, _p, _i, _l, _p]),
     "ta_neighbor_stage": (_i, [_p, _p, _p, _p, _f, _p, _l, _p]),
+    "ta_uniform_fill_policy": (_i, [_l, ctypes.POINTER(_l), ctypes.POINTER(_l)]),
+    "ta_neighbor_stage_philox": (_i, [_p, _p, _p, _f, _f, _f, ctypes.c_uint64, ctypes.c_uint64, _p, _p, _l, _p]),
     "ta_accumulate": (_i, [_p, _p, _i, _l, _p]),
     "ta_variance_finalize": (_i, [_p, _p, _i, _p, _l, _p]),
     "ta_add": (_i, [_p, _p, _p, _l, _p]),

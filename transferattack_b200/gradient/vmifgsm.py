@@ -11,6 +11,10 @@ from ..attack import Attack
 
 
 class VMIFGSM(Attack):
+    #: draw the neighbour noise inside the staging kernel (``ta_neighbor_stage_philox``: torch's own Philox stream reproduced
+    #: bit for bit, generator advanced as ``uniform_`` would) instead of ``zeros_like().uniform_()`` + a read of it
+    philox_noise = os.environ.get("TA_B200_PHILOX", "1") == "1"
+
     def __init__(self, model_name, epsilon=16/255, alpha=1.6/255, beta=1.5, num_neighbor=20, epoch=10, decay=1., targeted=False,
                  random_start=False, norm='linfty', loss='crossentropy', device=None, attack='VMI-FGSM', **kwargs):
         super().__init__(attack, model_name, epsilon, targeted, random_start, norm, loss, device)
@@ -22,8 +26,11 @@ class VMIFGSM(Attack):
         be = ops.backend()
         acc = None
         for k in range(self.num_neighbor):
-            noise = torch.zeros_like(delta).uniform_(-self.radius, self.radius).to(self.device)
-            x_near = ops.neighbor_stage(data, delta, noise)
+            if self.philox_noise and ops.philox_noise_available(delta):
+                x_near = ops.neighbor_stage_philox(data, delta, -self.radius, self.radius)
+            else:
+                noise = torch.zeros_like(delta).uniform_(-self.radius, self.radius).to(self.device)
+                x_near = ops.neighbor_stage(data, delta, noise)
             loss = self.get_loss(self.get_logits(self.transform(x_near, momentum=momentum)), label)
             acc = be.accumulate(acc, self.get_grad(loss, delta), first=(k == 0))
         return be.variance_finalize(acc, cur_grad, self.num_neighbor)

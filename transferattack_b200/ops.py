@@ -162,6 +162,29 @@ class CudaBackend:
                                                   data.numel(), _stream()), "ta_neighbor_stage")
         return out
 
+    def torch_uniform_policy(self, numel):
+        """(threads, philox offset increment) torch's CUDA uniform_ uses for a contiguous tensor of `numel` elements"""
+        T, inc = ctypes.c_int64(), ctypes.c_int64()
+        _lib.check(self.lib.ta_uniform_fill_policy(int(numel), ctypes.byref(T), ctypes.byref(inc)), "ta_uniform_fill_policy")
+        return T.value, inc.value
+
+    def neighbor_stage_philox(self, data, delta, frm, to, look=None, coef=0.0, generator=None, noise_out=None):
+        """(data + delta) + U(frm, to) [+ coef * look] with the noise drawn in the kernel from torch's device generator state:
+        the same numbers, in the same places, as `torch.zeros_like(delta).uniform_(frm, to)`; the generator is advanced as
+        that call would have advanced it."""
+        data = _f32c(data, "data"); delta = _f32c(delta, "delta"); look = _f32c(look, "momentum")
+        gen = generator if generator is not None else torch.cuda.default_generators[data.device.index]
+        seed, offset = int(gen.initial_seed()), int(gen.get_offset())
+        out = torch.empty_like(data)
+        with _DeviceOf(data):
+            _, inc = self.torch_uniform_policy(data.numel())
+            _lib.check(self.lib.ta_neighbor_stage_philox(_ptr(data), _ptr(delta), _ptr(look), float(coef),
+                                                         float(np.float32(frm)), float(np.float32(to)), seed & (2 ** 64 - 1), offset,
+                                                         _ptr(out), _ptr(noise_out), data.numel(), _stream()),
+                       "ta_neighbor_stage_philox")
+        gen.set_offset(offset + inc)
+        return out
+
     def normalize(self, x, mean, std, forward=True):
         x = _f32c(x, "x"); B, C = x.shape[0], x.shape[1]; plane = x.numel() // (B * C)
         out = torch.empty_like(x)
@@ -349,6 +372,18 @@ class NeighborStage(torch.autograd.Function):
         return None, gout, None, None, None
 
 
+class NeighborStagePhilox(torch.autograd.Function):
+    """NeighborStage with the uniform noise drawn inside the kernel (torch's own random stream, see ta_neighbor_stage_philox)."""
+
+    @staticmethod
+    def forward(ctx, data, delta, frm, to, look, coef):
+        return backend().neighbor_stage_philox(data, delta, frm, to, look, coef)
+
+    @staticmethod
+    def backward(ctx, gout):
+        return None, gout, None, None, None, None
+
+
 class Normalize(torch.autograd.Function):
     @staticmethod
     def forward(ctx, x, mean, std):
@@ -421,6 +456,16 @@ def look_ahead(x, momentum, coef):
 
 def neighbor_stage(data, delta, noise, look=None, coef=0.0):
     return NeighborStage.apply(data, delta, noise, look, coef)
+
+
+def neighbor_stage_philox(data, delta, frm, to, look=None, coef=0.0):
+    return NeighborStagePhilox.apply(data, delta, frm, to, look, coef)
+
+
+def philox_noise_available(t):
+    """in-kernel noise needs the real library, a CUDA tensor, torch's eager generator (no graph capture) and 32-bit indexing"""
+    return (_test_backend is None and torch.is_tensor(t) and t.is_cuda and t.numel() < 2 ** 31
+            and not torch.cuda.is_current_stream_capturing())
 
 
 def normalize(x, mean, std):
