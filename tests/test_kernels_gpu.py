@@ -158,13 +158,14 @@ def _dim_cases():
     return D, sorted({k.rsplit("_", 1)[0] for k in D.files})
 
 
-@pytest.fixture(params=[1, 0], ids=["direct", "fourpass"])
+@pytest.fixture(params=[(1, 1), (1, 0), (0, 0)], ids=["direct-gather", "direct-scatter", "fourpass"])
 def dim_impl(request):
-    """Both generations of the DIM kernels (csrc/dim_direct.cu = default, csrc/dim.cu) must meet the same parity bar."""
+    """All generations of the DIM kernels (csrc/dim_direct.cu: forward + two adjoint forms = default; csrc/dim.cu) must meet the
+    same parity bar."""
     from transferattack_b200 import _lib
-    _lib.tune_set("dim.impl", request.param)
+    _lib.tune_set("dim.impl", request.param[0]); _lib.tune_set("dim.bwd", request.param[1])
     yield request.param
-    _lib.tune_set("dim.impl", 1)
+    _lib.tune_set("dim.impl", 1); _lib.tune_set("dim.bwd", 1)
 
 
 @pytest.mark.parametrize("tma", [1, 0])
@@ -418,9 +419,9 @@ def test_neighbor_stage_philox_reproduces_torch_uniform(be, shape):
     the same elements, leave torch's device generator where that call would have left it, and equal the numpy restatement."""
     from oracle import philox as P
     r = 1.5 * EPS
-    gen = torch.cuda.default_generators[0]
     data = torch.rand(shape, device="cuda"); delta = (torch.rand(shape, device="cuda") * 2 - 1) * EPS
     look = torch.randn(shape, device="cuda")
+    gen = torch.cuda.default_generators[0]                               # (populated once CUDA is initialised)
     for seed in (0, 1234567, 2 ** 40 + 17):
         for warm in (0, 3):
             torch.cuda.manual_seed(seed)

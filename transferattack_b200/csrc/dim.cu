@@ -315,9 +315,12 @@ int ta_dim_bwd(const float* gout, float* gin, int planes, int S, int rnd, int R,
   TA_REQUIRE(gout && gin, "ta_dim_bwd: null pointer");
   int rc = check_geom("ta_dim_bwd", planes, S, rnd, R, pad_top, pad_left);
   if (rc != TA_OK) return rc;
+  // dim.impl: 1 (default) = direct kernels of dim_direct.cu (dim.bwd: 1 = independent separable gather per element (default),
+  // 0 = gather + scatter into rotating accumulators), 0 = four-pass kernel below
   if (tune_get("dim.impl", 1) != 0 && dim_direct_ok(S, rnd, R))
     return dim_bwd_direct(gout, gin, planes, S, rnd, R, pad_top, pad_left,
-                          (S % 4 == 0) && aligned16(gout) && tune_get("dim.tma", 1) != 0, (cudaStream_t)stream);
+                          (S % 4 == 0) && aligned16(gout) && tune_get("dim.tma", 1) != 0, tune_get("dim.bwd", 1) != 0,
+                          (cudaStream_t)stream);
   DimGeom gm{S, rnd, R, pad_top, pad_left, 0, 0, 0, 0};
   // y1 rows reading RB consecutive source rows of the S -> rnd resize
   gm.y1_rows_max = (int)((double)(RB + 1) * (double)rnd / (double)S) + 3;

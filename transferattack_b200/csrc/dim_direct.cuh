@@ -29,7 +29,7 @@ struct DimTabB {                              // adjoint: 13 KB
 bool dim_direct_ok(int S, int rnd, int R);
 int dim_fwd_direct(const float* x, float* out, int planes, int S, int rnd, int R, int top, int left, int blend, bool tma,
                    cudaStream_t stream);
-int dim_bwd_direct(const float* gout, float* gin, int planes, int S, int rnd, int R, int top, int left, bool tma,
+int dim_bwd_direct(const float* gout, float* gin, int planes, int S, int rnd, int R, int top, int left, bool tma, bool gather,
                    cudaStream_t stream);
 
 }  // namespace ta
