@@ -183,6 +183,14 @@ int ta_dim_fwd(const float* x, float* out, int planes, int S, int rnd, int R, in
                ta_stream_t stream);
 int ta_dim_bwd(const float* gout, float* gin, int planes, int S, int rnd, int R, int pad_top, int pad_left,
                ta_stream_t stream);
+/* The same two operations through the second-generation kernels, which keep their per-call tap / inverse-range tables in a
+ * caller-provided DEVICE workspace of ta_dim_ws_bytes() bytes (16-byte aligned, alive until the stream has passed the call;
+ * NULL falls back to the functions above). Forward: bit-identical to ta_dim_fwd; adjoint: same sums, other association.    */
+int64_t ta_dim_ws_bytes(void);
+int ta_dim_fwd_ws(const float* x, float* out, int planes, int S, int rnd, int R, int pad_top, int pad_left,
+                  void* ws, ta_stream_t stream);
+int ta_dim_bwd_ws(const float* gout, float* gin, int planes, int S, int rnd, int R, int pad_top, int pad_left,
+                  void* ws, ta_stream_t stream);
 
 /* ---- TIM (input_transformation/tim.py:68-73) ------------------------------------------------------
  *   out = conv2d(g, K[C,1,ks,ks], stride 1, zero padding 'same', groups=C)  (cross-correlation)

@@ -46,6 +46,9 @@ SIGNATURES = {
     "ta_admix_bwd": (_i, [_p, _p, _i, _i, _i, _l, _p]),
     "ta_dim_fwd": (_i, [_p, _p, _i, _i, _i, _i, _i, _i, _p]),
     "ta_dim_bwd": (_i, [_p, _p, _i, _i, _i, _i, _i, _i, _p]),
+    "ta_dim_ws_bytes": (_l, []),
+    "ta_dim_fwd_ws": (_i, [_p, _p, _i, _i, _i, _i, _i, _i, _p, _p]),
+    "ta_dim_bwd_ws": (_i, [_p, _p, _i, _i, _i, _i, _i, _i, _p, _p]),
     "ta_dwconv2d": (_i, [_p, _p, _i, _p, _i, _i, _i, _i, _p]),
     "ta_dwconv2d_sep": (_i, [_p, _p, _p, _i, _p, _i, _i, _i, _i, _p]),
     "ta_dwconv2d_sep_hw": (_i, [_p, _p, _p, _i, _p, _i, _i, _i, _i, _p]),

@@ -286,10 +286,6 @@ int ta_dim_fwd(const float* x, float* out, int planes, int S, int rnd, int R, in
   TA_REQUIRE(x && out, "ta_dim_fwd: null pointer");
   int rc = check_geom("ta_dim_fwd", planes, S, rnd, R, pad_top, pad_left);
   if (rc != TA_OK) return rc;
-  // dim.impl: 1 (default) = direct two-phase kernels with host-built tap tables (dim_direct.cu), 0 = four-pass kernels below
-  if (tune_get("dim.impl", 1) != 0 && dim_direct_ok(S, rnd, R))
-    return dim_fwd_direct(x, out, planes, S, rnd, R, pad_top, pad_left, tune_get("dim.blend", 1),
-                          (S % 4 == 0) && aligned16(x) && tune_get("dim.tma", 1) != 0, (cudaStream_t)stream);
   DimGeom gm{S, rnd, R, pad_top, pad_left, 0, 0, 0, tune_get("dim.blend", 1)};
   gm.t2_rows_max = band_rows(RB, R, S);
   if (gm.t2_rows_max > R) gm.t2_rows_max = R;
@@ -315,12 +311,6 @@ int ta_dim_bwd(const float* gout, float* gin, int planes, int S, int rnd, int R,
   TA_REQUIRE(gout && gin, "ta_dim_bwd: null pointer");
   int rc = check_geom("ta_dim_bwd", planes, S, rnd, R, pad_top, pad_left);
   if (rc != TA_OK) return rc;
-  // dim.impl: 1 (default) = direct kernels of dim_direct.cu (dim.bwd: 1 = independent separable gather per element (default),
-  // 0 = gather + scatter into rotating accumulators), 0 = four-pass kernel below
-  if (tune_get("dim.impl", 1) != 0 && dim_direct_ok(S, rnd, R))
-    return dim_bwd_direct(gout, gin, planes, S, rnd, R, pad_top, pad_left,
-                          (S % 4 == 0) && aligned16(gout) && tune_get("dim.tma", 1) != 0, tune_get("dim.bwd", 1) != 0,
-                          (cudaStream_t)stream);
   DimGeom gm{S, rnd, R, pad_top, pad_left, 0, 0, 0, 0};
   // y1 rows reading RB consecutive source rows of the S -> rnd resize
   gm.y1_rows_max = (int)((double)(RB + 1) * (double)rnd / (double)S) + 3;
@@ -336,6 +326,36 @@ int ta_dim_bwd(const float* gout, float* gin, int planes, int S, int rnd, int R,
   dim_bwd_kernel<<<grid, kThreads, smem, (cudaStream_t)stream>>>(gout, gin, gm);
   count_launch();
   return check_launch("ta_dim_bwd");
+}
+
+// ---- with a caller-provided device workspace: the direct kernels of dim_direct.cu ---------------------------------------------
+// ws: ta_dim_ws_bytes() bytes of DEVICE memory, 16-byte aligned, owned by the caller until the stream has passed the call
+// (the per-call tap / inverse-range tables are uploaded into it in stream order). dim.impl: 1 (default) = direct kernels
+// (dim.bwd: 1 = independent separable gather per element, 0 = gather + scatter into rotating accumulators), 0 = the four-pass
+// kernels above. Same results as ta_dim_fwd (bit-identical) / ta_dim_bwd (same sums, different association).
+int64_t ta_dim_ws_bytes(void) { return (int64_t)dim_direct_ws_bytes(); }
+
+int ta_dim_fwd_ws(const float* x, float* out, int planes, int S, int rnd, int R, int pad_top, int pad_left, void* ws,
+                  ta_stream_t stream) {
+  TA_REQUIRE(x && out, "ta_dim_fwd_ws: null pointer");
+  int rc = check_geom("ta_dim_fwd_ws", planes, S, rnd, R, pad_top, pad_left);
+  if (rc != TA_OK) return rc;
+  if (ws && aligned16(ws) && tune_get("dim.impl", 1) != 0 && dim_direct_ok(S, rnd, R))
+    return dim_fwd_direct(x, out, planes, S, rnd, R, pad_top, pad_left, tune_get("dim.blend", 1),
+                          (S % 4 == 0) && aligned16(x) && tune_get("dim.tma", 1) != 0, ws, (cudaStream_t)stream);
+  return ta_dim_fwd(x, out, planes, S, rnd, R, pad_top, pad_left, stream);
+}
+
+int ta_dim_bwd_ws(const float* gout, float* gin, int planes, int S, int rnd, int R, int pad_top, int pad_left, void* ws,
+                  ta_stream_t stream) {
+  TA_REQUIRE(gout && gin, "ta_dim_bwd_ws: null pointer");
+  int rc = check_geom("ta_dim_bwd_ws", planes, S, rnd, R, pad_top, pad_left);
+  if (rc != TA_OK) return rc;
+  if (ws && aligned16(ws) && tune_get("dim.impl", 1) != 0 && dim_direct_ok(S, rnd, R))
+    return dim_bwd_direct(gout, gin, planes, S, rnd, R, pad_top, pad_left,
+                          (S % 4 == 0) && aligned16(gout) && tune_get("dim.tma", 1) != 0, tune_get("dim.bwd", 1) != 0, ws,
+                          (cudaStream_t)stream);
+  return ta_dim_bwd(gout, gin, planes, S, rnd, R, pad_top, pad_left, stream);
 }
 
 }  // extern "C"

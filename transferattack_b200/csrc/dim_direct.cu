@@ -69,7 +69,8 @@ __device__ __forceinline__ void sts_f32(uint32_t addr, float v) {
 // row nq and column rnd are zero | descA [c_rows] | descB [RB]
 template <int MODE, bool TMA_STAGE>
 __global__ void __launch_bounds__(kThreads) dim_fwd_direct_kernel(const float* __restrict__ x, float* __restrict__ out,
-                                                                  const __grid_constant__ DimTabF tab, const Geo gm) {
+                                                                  const DimTabF* __restrict__ tabp, const Geo gm) {
+  const DimTabF& tab = *tabp;
   extern __shared__ __align__(128) unsigned char smem_raw[];
   __shared__ __align__(8) uint64_t s_bar;
   const int S = gm.S, rnd = gm.rnd, top = gm.top, left = gm.left;
@@ -253,7 +254,8 @@ __device__ __forceinline__ void gather_scatter(uint32_t src, uint32_t pitch_byte
 // descQ [g_rows]
 template <bool TMA_STAGE>
 __global__ void __launch_bounds__(kThreads) dim_bwd_direct_kernel(const float* __restrict__ gout, float* __restrict__ gin,
-                                                                  const __grid_constant__ DimTabB tab, const Geo gm) {
+                                                                  const DimTabB* __restrict__ tabp, const Geo gm) {
+  const DimTabB& tab = *tabp;
   extern __shared__ __align__(128) unsigned char smem_raw[];
   __shared__ __align__(8) uint64_t s_bar;
   const int S = gm.S, rnd = gm.rnd, top = gm.top, left = gm.left;
@@ -358,7 +360,8 @@ __device__ __forceinline__ float gather_rows(const RowG* __restrict__ d, const f
 // smem: bufU [u_rows * S] | bufG [g_rows * rnd] | descQ [g_rows] | descS [RB] | wextQ [g_rows * wext] | wextS [RB * wext]
 template <bool TMA_STAGE>
 __global__ void __launch_bounds__(kThreads) dim_bwd_gather_kernel(const float* __restrict__ gout, float* __restrict__ gin,
-                                                                  const __grid_constant__ DimTabB tab, const Geo gm, const int wext) {
+                                                                  const DimTabB* __restrict__ tabp, const Geo gm, const int wext) {
+  const DimTabB& tab = *tabp;
   extern __shared__ __align__(128) unsigned char smem_raw[];
   __shared__ __align__(8) uint64_t s_bar;
   const int S = gm.S, rnd = gm.rnd, top = gm.top, left = gm.left;
@@ -443,6 +446,25 @@ __global__ void __launch_bounds__(kThreads) dim_bwd_gather_kernel(const float* _
   }
 }
 
+// ---- table upload -------------------------------------------------------------------------------------------------------
+// The tables are built on the host per call and must reach GLOBAL memory in stream order without a host-side staging buffer
+// whose lifetime the library would have to manage: they travel as the parameter of this one-wave copy kernel (128-bit
+// constant-bank reads, one per thread) into the caller's workspace. (Reading 9-13 KB of tables straight from the parameter
+// space inside the main kernels was measured slow: indexed constant loads of 32 different addresses per warp serialise and
+// evict the small constant cache, so that even uniform parameter reads miss — ncu: LDC consumers top the stall samples.)
+template <class T>
+__global__ void __launch_bounds__(256) upload_tab_kernel(const __grid_constant__ T tab, T* __restrict__ dst) {
+  static_assert(sizeof(T) % 16 == 0, "table size must be a multiple of 16 bytes");
+  const int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i < (int)(sizeof(T) / 16)) reinterpret_cast<uint4*>(dst)[i] = reinterpret_cast<const uint4*>(&tab)[i];
+}
+template <class T>
+int upload_tab(const T& tab, void* ws, cudaStream_t s) {
+  upload_tab_kernel<T><<<(unsigned)((sizeof(T) / 16 + 255) / 256), 256, 0, s>>>(tab, reinterpret_cast<T*>(ws));
+  count_launch();
+  return check_launch("ta_dim[table upload]");
+}
+
 // ---- host: tables ------------------------------------------------------------------------------------------------------
 void host_taps(int in, int out, TapE* t) {           // ATen area_pixel_compute_source_index, align_corners=False
   const float scale = (float)in / (float)out;
@@ -475,7 +497,9 @@ namespace ta {
 
 bool dim_direct_ok(int S, int rnd, int R) { return S <= kDimMaxS && R <= kDimMaxR && rnd <= kDimMaxR && S >= 1; }
 
-int dim_fwd_direct(const float* x, float* out, int planes, int S, int rnd, int R, int top, int left, int blend, bool tma,
+size_t dim_direct_ws_bytes() { return sizeof(DimTabB) > sizeof(DimTabF) ? sizeof(DimTabB) : sizeof(DimTabF); }
+
+int dim_fwd_direct(const float* x, float* out, int planes, int S, int rnd, int R, int top, int left, int blend, bool tma, void* ws,
                    cudaStream_t stream) {
   static thread_local DimTabF tab;
   host_taps(R, S, tab.t2);
@@ -494,7 +518,7 @@ int dim_fwd_direct(const float* x, float* out, int planes, int S, int rnd, int R
   Geo gm{S, rnd, R, top, left, a_rows, c_rows};
   const size_t smem = ((sizeof(float) * ((size_t)a_rows * S + (size_t)(c_rows + 1) * (rnd + 1)) + 15) & ~(size_t)15) + 16 * (size_t)(c_rows + RB);
   TA_REQUIRE(smem <= 200 * 1024, "ta_dim_fwd: image size S=%d needs %zu B of shared memory per CTA", S, smem);
-  void (*k)(const float*, float*, const DimTabF, const Geo);
+  void (*k)(const float*, float*, const DimTabF*, const Geo);
   int slot;
   if (blend == 1) { k = tma ? dim_fwd_direct_kernel<1, true> : dim_fwd_direct_kernel<1, false>; slot = tma ? 0 : 1; }
   else if (blend == 0) { k = tma ? dim_fwd_direct_kernel<0, true> : dim_fwd_direct_kernel<0, false>; slot = tma ? 2 : 3; }
@@ -504,14 +528,16 @@ int dim_fwd_direct(const float* x, float* out, int planes, int S, int rnd, int R
   static SmemOptIn optin[10] = {};
   const int rc = ensure_dyn_smem("ta_dim_fwd", k, smem, optin[slot]);
   if (rc != TA_OK) return rc;
+  const int ru = upload_tab(tab, ws, stream);
+  if (ru != TA_OK) return ru;
   dim3 grid((unsigned)((S + RB - 1) / RB), (unsigned)planes);
-  k<<<grid, kThreads, smem, stream>>>(x, out, tab, gm);
+  k<<<grid, kThreads, smem, stream>>>(x, out, reinterpret_cast<const DimTabF*>(ws), gm);
   count_launch();
   return check_launch("ta_dim_fwd[direct]");
 }
 
 int dim_bwd_direct(const float* gout, float* gin, int planes, int S, int rnd, int R, int top, int left, bool tma, bool gather,
-                   cudaStream_t stream) {
+                   void* ws, cudaStream_t stream) {
   static thread_local DimTabB tab;
   host_taps(R, S, tab.t2);
   host_taps(S, rnd, tab.t1);
@@ -538,6 +564,9 @@ int dim_bwd_direct(const float* gout, float* gin, int planes, int S, int rnd, in
     tab.band[sy0 / RB] = make_short4((short)q0, (short)(q1 - q0 + 1), (short)(a <= b ? a : 0), (short)(a <= b ? b - a + 1 : 0));
   }
   Geo gm{S, rnd, R, top, left, u_rows, g_rows};
+  const int ru = upload_tab(tab, ws, stream);
+  if (ru != TA_OK) return ru;
+  const DimTabB* dtab = reinterpret_cast<const DimTabB*>(ws);
   if (gather) {
     int cmax = 2;
     for (int i = 0; i < R; ++i) if (tab.inv2[i].cnt > cmax) cmax = tab.inv2[i].cnt;
@@ -551,7 +580,7 @@ int dim_bwd_direct(const float* gout, float* gin, int planes, int S, int rnd, in
     const int rcg = ensure_dyn_smem("ta_dim_bwd", kg, smem_g, optin_g[tma ? 0 : 1]);
     if (rcg != TA_OK) return rcg;
     dim3 grid_g((unsigned)((S + RB - 1) / RB), (unsigned)planes);
-    kg<<<grid_g, kThreads, smem_g, stream>>>(gout, gin, tab, gm, wext);
+    kg<<<grid_g, kThreads, smem_g, stream>>>(gout, gin, dtab, gm, wext);
     count_launch();
     return check_launch("ta_dim_bwd[gather]");
   }
@@ -562,7 +591,7 @@ int dim_bwd_direct(const float* gout, float* gin, int planes, int S, int rnd, in
   const int rc = ensure_dyn_smem("ta_dim_bwd", k, smem, optin[tma ? 0 : 1]);
   if (rc != TA_OK) return rc;
   dim3 grid((unsigned)((S + RB - 1) / RB), (unsigned)planes);
-  k<<<grid, kThreads, smem, stream>>>(gout, gin, tab, gm);
+  k<<<grid, kThreads, smem, stream>>>(gout, gin, dtab, gm);
   count_launch();
   return check_launch("ta_dim_bwd[direct]");
 }

@@ -14,7 +14,7 @@ constexpr int kDimRB = 16;        // destination rows per CTA (band height)
 struct TapE { float l1; int i01; };          // 1-D bilinear tap of one destination index: i0 | i1 << 16, l0 = 1 - l1
 struct InvE { short lo; short cnt; };        // destination indices [lo, lo + cnt) read this source index
 
-struct DimTabF {                              // forward: 8.7 KB of kernel parameters
+struct DimTabF {                              // forward: 8.7 KB
   TapE t2[kDimMaxS];                          //   R -> S resize: output index o reads y2 indices
   TapE t1[kDimMaxR];                          //   S -> rnd resize: y1 index q reads source indices
 };
@@ -27,9 +27,10 @@ struct DimTabB {                              // adjoint: 13 KB
 };
 
 bool dim_direct_ok(int S, int rnd, int R);
-int dim_fwd_direct(const float* x, float* out, int planes, int S, int rnd, int R, int top, int left, int blend, bool tma,
+size_t dim_direct_ws_bytes();              // device workspace the direct kernels need for their tables (16-byte aligned)
+int dim_fwd_direct(const float* x, float* out, int planes, int S, int rnd, int R, int top, int left, int blend, bool tma, void* ws,
                    cudaStream_t stream);
 int dim_bwd_direct(const float* gout, float* gin, int planes, int S, int rnd, int R, int top, int left, bool tma, bool gather,
-                   cudaStream_t stream);
+                   void* ws, cudaStream_t stream);
 
 }  // namespace ta

@@ -225,9 +225,12 @@ class CudaBackend:
             raise ValueError("DIM kernels need square images (the reference resizes with x.shape[-1] only)")
         planes = x.numel() // (S * S)
         out = torch.empty_like(x)
-        fn = self.lib.ta_dim_fwd if forward else self.lib.ta_dim_bwd
+        fn = self.lib.ta_dim_fwd_ws if forward else self.lib.ta_dim_bwd_ws
         with _DeviceOf(x):
-            _lib.check(fn(_ptr(x), _ptr(out), planes, S, int(rnd), int(R), int(top), int(left), _stream()), "ta_dim")
+            # per-call table workspace from torch's stream-ordered caching allocator (freed back to it on return: the next user
+            # of the block is ordered behind this launch on the same stream)
+            ws = torch.empty(int(self.lib.ta_dim_ws_bytes()), dtype=torch.uint8, device=x.device)
+            _lib.check(fn(_ptr(x), _ptr(out), planes, S, int(rnd), int(R), int(top), int(left), _ptr(ws), _stream()), "ta_dim")
         return out
 
     def dwconv2d(self, g, k):
