@@ -464,13 +464,12 @@ def run_kernels(args):
     add("stage_add", 12, lambda: be.stage_add(x, d, out=xa))
     add("sim_fwd S=5", 24, lambda: be.sim(x, 5, True))
     add("sim_bwd S=5", 24, lambda: be.sim(g5, 5, False))
-    for impl, bwd, tag in ((1, 1, "direct 2-phase, host tap tables; adjoint = independent gather"), (1, 0, "direct; adjoint = gather + scatter"),
-                           (0, 0, "4-pass")):
-        _lib.tune_set("dim.impl", impl); _lib.tune_set("dim.bwd", bwd)
-        if not (impl == 1 and bwd == 0):
-            add("dim_fwd [%s]" % tag, 8, lambda: be.dim(x, 235, 246, 5, 6, True))
+    for impl, bwd, fwdtab, tag in ((1, 0, 0, "direct; fwd tables = kernel parameters; adjoint = gather + scatter, tables in workspace"),
+                                   (1, 1, 1, "direct; fwd tables in workspace; adjoint = independent gather"), (0, 0, 0, "4-pass")):
+        _lib.tune_set("dim.impl", impl); _lib.tune_set("dim.bwd", bwd); _lib.tune_set("dim.fwdtab", fwdtab)
+        add("dim_fwd [%s]" % tag, 8, lambda: be.dim(x, 235, 246, 5, 6, True))
         add("dim_bwd [%s]" % tag, 8, lambda: be.dim(g, 235, 246, 5, 6, False))
-    _lib.tune_set("dim.impl", 1); _lib.tune_set("dim.bwd", 1)
+    _lib.tune_set("dim.impl", 1); _lib.tune_set("dim.bwd", 0); _lib.tune_set("dim.fwdtab", 0)
     hc, hr = kc3.cpu().numpy(), kr3.cpu().numpy()
     for band, f2, tag in ((3, 1, "register-sliding from global memory, FFMA2"), (3, 0, "register-sliding from global memory, FFMA"),
                           (2, 0, "register-sliding from TMA-staged smem")):

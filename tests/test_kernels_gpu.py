@@ -158,14 +158,15 @@ def _dim_cases():
     return D, sorted({k.rsplit("_", 1)[0] for k in D.files})
 
 
-@pytest.fixture(params=[(1, 1), (1, 0), (0, 0)], ids=["direct-gather", "direct-scatter", "fourpass"])
+@pytest.fixture(params=[(1, 0, 0), (1, 1, 1), (0, 0, 0)], ids=["direct", "direct-gather-wstab", "fourpass"])
 def dim_impl(request):
-    """All generations of the DIM kernels (csrc/dim_direct.cu: forward + two adjoint forms = default; csrc/dim.cu) must meet the
-    same parity bar."""
+    """All generations of the DIM kernels must meet the same parity bar: csrc/dim_direct.cu (default: forward with its tables as
+    kernel parameters, adjoint = gather + scatter with the tables in the workspace; alternative: forward tables in the workspace,
+    adjoint = independent gather) and the four-pass kernels of csrc/dim.cu."""
     from transferattack_b200 import _lib
-    _lib.tune_set("dim.impl", request.param[0]); _lib.tune_set("dim.bwd", request.param[1])
+    _lib.tune_set("dim.impl", request.param[0]); _lib.tune_set("dim.bwd", request.param[1]); _lib.tune_set("dim.fwdtab", request.param[2])
     yield request.param
-    _lib.tune_set("dim.impl", 1); _lib.tune_set("dim.bwd", 1)
+    _lib.tune_set("dim.impl", 1); _lib.tune_set("dim.bwd", 0); _lib.tune_set("dim.fwdtab", 0)
 
 
 @pytest.mark.parametrize("tma", [1, 0])

@@ -331,7 +331,8 @@ int ta_dim_bwd(const float* gout, float* gin, int planes, int S, int rnd, int R,
 // ---- with a caller-provided device workspace: the direct kernels of dim_direct.cu ---------------------------------------------
 // ws: ta_dim_ws_bytes() bytes of DEVICE memory, 16-byte aligned, owned by the caller until the stream has passed the call
 // (the per-call tap / inverse-range tables are uploaded into it in stream order). dim.impl: 1 (default) = direct kernels
-// (dim.bwd: 1 = independent separable gather per element, 0 = gather + scatter into rotating accumulators), 0 = the four-pass
+// (dim.bwd: 0 (default) = gather + scatter into rotating accumulators, 1 = independent separable gather per element;
+// dim.fwdtab: 0 (default) = forward tables as kernel parameters, 1 = in the workspace), 0 = the four-pass
 // kernels above. Same results as ta_dim_fwd (bit-identical) / ta_dim_bwd (same sums, different association).
 int64_t ta_dim_ws_bytes(void) { return (int64_t)dim_direct_ws_bytes(); }
 
@@ -342,7 +343,9 @@ int ta_dim_fwd_ws(const float* x, float* out, int planes, int S, int rnd, int R,
   if (rc != TA_OK) return rc;
   if (ws && aligned16(ws) && tune_get("dim.impl", 1) != 0 && dim_direct_ok(S, rnd, R))
     return dim_fwd_direct(x, out, planes, S, rnd, R, pad_top, pad_left, tune_get("dim.blend", 1),
-                          (S % 4 == 0) && aligned16(x) && tune_get("dim.tma", 1) != 0, ws, (cudaStream_t)stream);
+                          (S % 4 == 0) && aligned16(x) && tune_get("dim.tma", 1) != 0,
+                          tune_get("dim.fwdtab", 0) != 0 ? ws : nullptr,      // forward: tables as kernel parameters by default
+                          (cudaStream_t)stream);
   return ta_dim_fwd(x, out, planes, S, rnd, R, pad_top, pad_left, stream);
 }
 
@@ -353,7 +356,7 @@ int ta_dim_bwd_ws(const float* gout, float* gin, int planes, int S, int rnd, int
   if (rc != TA_OK) return rc;
   if (ws && aligned16(ws) && tune_get("dim.impl", 1) != 0 && dim_direct_ok(S, rnd, R))
     return dim_bwd_direct(gout, gin, planes, S, rnd, R, pad_top, pad_left,
-                          (S % 4 == 0) && aligned16(gout) && tune_get("dim.tma", 1) != 0, tune_get("dim.bwd", 1) != 0, ws,
+                          (S % 4 == 0) && aligned16(gout) && tune_get("dim.tma", 1) != 0, tune_get("dim.bwd", 0) != 0, ws,
                           (cudaStream_t)stream);
   return ta_dim_bwd(gout, gin, planes, S, rnd, R, pad_top, pad_left, stream);
 }

@@ -67,10 +67,15 @@ __device__ __forceinline__ void sts_f32(uint32_t addr, float v) {
 
 // smem: bufA [a_rows * S] source band (offset 0: the bulk-TMA destination) | bufC [(c_rows + 1) * (rnd + 1)] y1 band,
 // row nq and column rnd are zero | descA [c_rows] | descB [RB]
-template <int MODE, bool TMA_STAGE>
+// table source of the forward kernel: the 8.7 KB struct itself as a kernel parameter (default: the forward reads 2 column
+// taps per thread and phase, measured 34 us against 38 us with the extra upload launch) or a pointer into the workspace
+struct FwdTabParam { DimTabF t; __device__ __forceinline__ const DimTabF& get() const { return t; } };
+struct FwdTabPtr { const DimTabF* p; __device__ __forceinline__ const DimTabF& get() const { return *p; } };
+
+template <int MODE, bool TMA_STAGE, class TR>
 __global__ void __launch_bounds__(kThreads) dim_fwd_direct_kernel(const float* __restrict__ x, float* __restrict__ out,
-                                                                  const DimTabF* __restrict__ tabp, const Geo gm) {
-  const DimTabF& tab = *tabp;
+                                                                  const __grid_constant__ TR tr, const Geo gm) {
+  const DimTabF& tab = tr.get();
   extern __shared__ __align__(128) unsigned char smem_raw[];
   __shared__ __align__(8) uint64_t s_bar;
   const int S = gm.S, rnd = gm.rnd, top = gm.top, left = gm.left;
@@ -518,20 +523,32 @@ int dim_fwd_direct(const float* x, float* out, int planes, int S, int rnd, int R
   Geo gm{S, rnd, R, top, left, a_rows, c_rows};
   const size_t smem = ((sizeof(float) * ((size_t)a_rows * S + (size_t)(c_rows + 1) * (rnd + 1)) + 15) & ~(size_t)15) + 16 * (size_t)(c_rows + RB);
   TA_REQUIRE(smem <= 200 * 1024, "ta_dim_fwd: image size S=%d needs %zu B of shared memory per CTA", S, smem);
-  void (*k)(const float*, float*, const DimTabF*, const Geo);
-  int slot;
-  if (blend == 1) { k = tma ? dim_fwd_direct_kernel<1, true> : dim_fwd_direct_kernel<1, false>; slot = tma ? 0 : 1; }
-  else if (blend == 0) { k = tma ? dim_fwd_direct_kernel<0, true> : dim_fwd_direct_kernel<0, false>; slot = tma ? 2 : 3; }
-  else if (blend == 2) { k = tma ? dim_fwd_direct_kernel<2, true> : dim_fwd_direct_kernel<2, false>; slot = tma ? 4 : 5; }
-  else if (blend == 3) { k = tma ? dim_fwd_direct_kernel<3, true> : dim_fwd_direct_kernel<3, false>; slot = tma ? 6 : 7; }
-  else { k = tma ? dim_fwd_direct_kernel<4, true> : dim_fwd_direct_kernel<4, false>; slot = tma ? 8 : 9; }
-  static SmemOptIn optin[10] = {};
-  const int rc = ensure_dyn_smem("ta_dim_fwd", k, smem, optin[slot]);
-  if (rc != TA_OK) return rc;
-  const int ru = upload_tab(tab, ws, stream);
-  if (ru != TA_OK) return ru;
   dim3 grid((unsigned)((S + RB - 1) / RB), (unsigned)planes);
-  k<<<grid, kThreads, smem, stream>>>(x, out, reinterpret_cast<const DimTabF*>(ws), gm);
+  static SmemOptIn optin[20] = {};
+#define TA_DIM_FWD_LAUNCH(MODE_, SLOT_)                                                                             \
+  do {                                                                                                              \
+    if (ws) {                                                                                                       \
+      auto k = tma ? dim_fwd_direct_kernel<MODE_, true, FwdTabPtr> : dim_fwd_direct_kernel<MODE_, false, FwdTabPtr>; \
+      const int rc = ensure_dyn_smem("ta_dim_fwd", k, smem, optin[2 * SLOT_ + (tma ? 0 : 1)]);                      \
+      if (rc != TA_OK) return rc;                                                                                   \
+      const int ru = upload_tab(tab, ws, stream);                                                                   \
+      if (ru != TA_OK) return ru;                                                                                   \
+      k<<<grid, kThreads, smem, stream>>>(x, out, FwdTabPtr{reinterpret_cast<const DimTabF*>(ws)}, gm);             \
+    } else {                                                                                                        \
+      auto k = tma ? dim_fwd_direct_kernel<MODE_, true, FwdTabParam> : dim_fwd_direct_kernel<MODE_, false, FwdTabParam>; \
+      const int rc = ensure_dyn_smem("ta_dim_fwd", k, smem, optin[10 + 2 * SLOT_ + (tma ? 0 : 1)]);                 \
+      if (rc != TA_OK) return rc;                                                                                   \
+      k<<<grid, kThreads, smem, stream>>>(x, out, *reinterpret_cast<const FwdTabParam*>(&tab), gm);                 \
+    }                                                                                                               \
+  } while (0)
+  switch (blend) {
+    case 1: TA_DIM_FWD_LAUNCH(1, 0); break;
+    case 0: TA_DIM_FWD_LAUNCH(0, 1); break;
+    case 2: TA_DIM_FWD_LAUNCH(2, 2); break;
+    case 3: TA_DIM_FWD_LAUNCH(3, 3); break;
+    default: TA_DIM_FWD_LAUNCH(4, 4); break;
+  }
+#undef TA_DIM_FWD_LAUNCH
   count_launch();
   return check_launch("ta_dim_fwd[direct]");
 }
