@@ -292,9 +292,10 @@ def run_ours(args, rank, local_rank, world, dist):
     launches = _lib.launch_count() - launches0
     clocks = clk.summary()
     value = world * B * args.steps / (ms / 1e3)
-    if args.graph:        # launches replayed from the captured graph: count the graph's kernels, not the host calls
-        g = sum(1 for st in getattr(atk, "_graphs", {}).values())
-        launches = (1 + args.epoch * 3) * args.steps if g else launches      # stage_add + (fused + 2 normalize) per iteration
+    if args.graph:        # kernels replayed from the captured graph are not host launches: add the graph's own count per replay
+        sts = list(getattr(atk, "_graphs", {}).values())
+        if sts:
+            launches += sts[-1].get("kernels_per_replay", 0) * args.epoch * args.steps
 
     # roofline of the dominant kernel: CUDA events around every ta_fused_update_linf launch, on its stream, live inside a
     # run of the same attack (eager launches of the same kernels: a graph replay cannot host per-launch events)
@@ -379,7 +380,10 @@ def run_ours(args, rank, local_rank, world, dist):
             "metric": METRIC, "value": value, "unit": "images/s", "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
             "ms_per_step": ms / args.steps, "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32",
             "data": "synthetic",
-            "config": {"workload": "MI-FGSM, ResNet-50, batch 64, 10 iters, eps=16/255 (BASELINE configs[1])", "attack": args.attack,
+            "config": {"workload": ("MI-FGSM, ResNet-50, batch 64, 10 iters, eps=16/255 (BASELINE configs[1])"
+                                    if (args.attack, args.arch, B, args.epoch) == ("mifgsm", "resnet50", 64, 10)
+                                    else "%s, %s, batch %d, %d iters, eps=16/255" % (args.attack, args.arch, B, args.epoch)),
+                       "attack": args.attack, "normalize_folded": bool(getattr(atk, "fold_normalize", False) and atk._fold_plan(x_dev) is not None),
                        "arch": args.arch, "batch_per_gpu": B, "global_batch": B * world, "epoch": args.epoch,
                        "parallelism": "batch-sharded x%d, no collective" % world, "mean_mode": args.mean_mode,
                        "surrogate": "torch autograd, fp32 (cuDNN TF32 convs as torch defaults), random-init weights",
