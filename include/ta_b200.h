@@ -207,6 +207,18 @@ int ta_dwconv2d_sep(const float* g, const float* kcol, const float* krow, int ks
 int ta_dwconv2d_sep_hw(const float* g, const float* kcol_host, const float* krow_host, int ks,
                        float* out, int B, int C, int H, int W, ta_stream_t stream);
 
+/* ---- PI-FGSM (gradient/pifgsm.py:55-68, 94-102) --------------------------------------------------------
+ *   ta_pi_cut_noise:   amp' = amp + coef * sign(momentum)   (amp == NULL: the first iteration's python 0.0)
+ *                      cut  = clamp(|amp'| - eps, 0, 10000) * sign(amp')
+ *   project_noise (pifgsm.py:55-58) is ta_dwconv2d(cut, K) with K = ones/(k*k-1), centre 0.
+ *   ta_pi_update_linf: proj = gamma * sign(conv);  amp'' = amp' + proj;
+ *                      delta' = box(clamp((delta + alpha * sign(g)) + proj, -eps, eps))   (amp_out / delta_out may alias)   */
+int ta_pi_cut_noise(const float* amp, const float* momentum, float coef, float eps, float* amp_out,
+                    float* cut_out, int64_t N, ta_stream_t stream);
+int ta_pi_update_linf(const float* delta, const float* data, const float* g, const float* conv,
+                      const float* amp, float alpha, float gamma, float eps, float lo, float hi,
+                      float* amp_out, float* delta_out, int64_t N, ta_stream_t stream);
+
 /* ---- EMI (gradient/emifgsm.py:53-58, 86-103) ---------------------------------------------------------
  *   out[k*N + i] = x[i] + coef[k] * gbar[i]  (coef[k] = (float)(factor_k * alpha), host array, K <= 32)
  *   gbar == NULL is the first iteration (`bar_grad = 0`): out[k*N+i] = x[i] + 0.

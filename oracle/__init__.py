@@ -261,3 +261,19 @@ def quantize_u8(data, delta, to_nhwc=True):
     lib().orc_quantize_u8(_fp(data), _fp(delta), out.ctypes.data_as(ctypes.POINTER(ctypes.c_uint8)), B, C,
                           ctypes.c_int64(plane), int(bool(to_nhwc)))
     return out
+
+
+def pi_cut_noise(amp, m, coef, eps):
+    m = _c(m); amp = _c(amp)
+    amp_out = np.empty_like(m); cut = np.empty_like(m)
+    lib().orc_pi_cut_noise(_fp(amp), _fp(m), ctypes.c_float(coef), ctypes.c_float(eps), _fp(amp_out), _fp(cut), ctypes.c_int64(m.size))
+    return amp_out, cut
+
+
+def pi_update_linf(delta, data, g, conv, amp, alpha, gamma, eps, lo=0.0, hi=1.0):
+    delta = _c(delta); data = _c(data); g = _c(g); conv = _c(conv); amp = _c(amp)
+    amp_out = np.empty_like(delta); d_out = np.empty_like(delta)
+    lib().orc_pi_update_linf(_fp(delta), _fp(data), _fp(g), _fp(conv), _fp(amp), ctypes.c_float(alpha), ctypes.c_float(gamma),
+                             ctypes.c_float(eps), ctypes.c_float(lo), ctypes.c_float(hi), _fp(amp_out), _fp(d_out),
+                             ctypes.c_int64(delta.size))
+    return amp_out, d_out

@@ -449,3 +449,31 @@ ORC_API void orc_quantize_u8(const float* data, const float* delta, uint8_t* out
         out[o] = (uint8_t)q;
       }
 }
+
+/* ---- gradient/pifgsm.py:94-102, 61-68 (PI-FGSM; project_noise itself is orc_dwconv2d) -------------------------------- */
+ORC_API void orc_pi_cut_noise(const float* amp, const float* m, float coef, float eps, float* amp_out, float* cut_out, int64_t N) {
+  for (int64_t j = 0; j < N; ++j) {
+    const float st = coef * sgnf(m[j]);
+    const float a1 = (amp ? amp[j] : 0.0f) + st;
+    const float t = fabsf(a1) - eps;
+    const float c = min_nan(max_nan(t, 0.0f), 10000.0f);
+    amp_out[j] = a1;
+    cut_out[j] = c * sgnf(a1);
+  }
+}
+ORC_API void orc_pi_update_linf(const float* delta, const float* data, const float* g, const float* conv, const float* amp,
+                                float alpha, float gamma, float eps, float lo, float hi, float* amp_out, float* delta_out,
+                                int64_t N) {
+  const float neg_eps = -eps;
+  for (int64_t j = 0; j < N; ++j) {
+    const float proj = gamma * sgnf(conv[j]);
+    const float a2 = amp[j] + proj;
+    const float st = alpha * sgnf(g[j]);
+    const float d0 = delta[j] + st;
+    const float d1 = d0 + proj;
+    const float d2 = min_nan(max_nan(d1, neg_eps), eps);
+    const float l = lo - data[j], h = hi - data[j];
+    amp_out[j] = a2;
+    delta_out[j] = min_nan(max_nan(d2, l), h);
+  }
+}

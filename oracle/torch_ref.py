@@ -323,10 +323,52 @@ class RefEMIFGSM(RefAttack):          # gradient/emifgsm.py:53-105
         return delta.detach()
 
 
+class RefPIFGSM(RefAttack):           # gradient/pifgsm.py:33-102 (device-agnostic: the reference hard-codes .cuda())
+    def __init__(self, model, epsilon=16.0 / 255, alpha=1.6 / 255, epoch=10, decay=0., kern_size=3, gamma=16.0, beta=10.0, **kw):
+        super().__init__(model, epsilon=epsilon, alpha=alpha, epoch=epoch, decay=decay, **kw)
+        self.kern_size, self.gamma, self.beta = kern_size, gamma / 255.0, beta
+
+    def project_kern(self, kern_size):
+        kern = np.ones((kern_size, kern_size), dtype=np.float32) / (kern_size ** 2 - 1)
+        kern[kern_size // 2, kern_size // 2] = 0.0
+        kern = kern.astype(np.float32)
+        stack_kern = np.expand_dims(np.stack([kern, kern, kern]), 1)
+        return torch.tensor(stack_kern).to(self.device), kern_size // 2
+
+    def project_noise(self, x, stack_kern, padding_size):
+        return F.conv2d(x, stack_kern, padding=(padding_size, padding_size), groups=3)
+
+    def update_delta(self, delta, data, grad, alpha, projection, **kw):
+        if self.norm == "linfty":
+            delta = torch.clamp(delta + alpha * grad.sign() + projection, -self.epsilon, self.epsilon)
+        else:
+            gnorm = torch.norm(grad.view(grad.size(0), -1), dim=1).view(-1, 1, 1, 1)
+            delta = (delta + grad / (gnorm + 1e-20) * alpha + projection).view(delta.size(0), -1).renorm(p=2, dim=0, maxnorm=self.epsilon).view_as(delta)
+        return _box(delta, 0 - data, 1.0 - data)
+
+    def forward(self, data, label, **kw):
+        data, label = self._prep(data, label)
+        delta = self.init_delta(data)
+        delta.requires_grad = True
+        stack_kern, padding_size = self.project_kern(self.kern_size)
+        momentum, amplification = 0.0, 0.0
+        for _ in range(self.epoch):
+            logits = self.get_logits(self.transform(data + delta))
+            loss = self.get_loss(logits, label)
+            grad = self.get_grad(loss, delta)
+            momentum = self.get_momentum(grad, momentum)
+            amplification += self.beta * self.alpha * momentum.sign()
+            cut_noise = torch.clamp(abs(amplification) - self.epsilon, 0, 10000.0) * torch.sign(amplification)
+            projection = self.gamma * torch.sign(self.project_noise(cut_noise, stack_kern, padding_size))
+            amplification += projection
+            delta = self.update_delta(delta, data, momentum, self.beta * self.alpha, projection)
+        return delta.detach()
+
+
 REF_ZOO = {
     "fgsm": ref_fgsm, "ifgsm": ref_ifgsm, "mifgsm": ref_mifgsm, "nifgsm": RefNIFGSM, "dim": RefDIM,
     "tim": RefTIM, "sim": RefSIM, "admix": RefAdmix, "ditimi": RefDITIMI, "vmifgsm": RefVMIFGSM,
-    "vnifgsm": RefVNIFGSM, "emifgsm": RefEMIFGSM, "ens": ref_mifgsm,
+    "vnifgsm": RefVNIFGSM, "emifgsm": RefEMIFGSM, "ens": ref_mifgsm, "pifgsm": RefPIFGSM,
 }
 
 

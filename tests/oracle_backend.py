@@ -125,6 +125,17 @@ class OracleBackend:
         self._log("dwconv2d_sep")
         return _t(oracle.dwconv2d_sep(_np(g), _np(kcol), _np(krow)))
 
+    def pi_cut_noise(self, amp, momentum, coef, eps):
+        self._log("pi_cut_noise")
+        a, c = oracle.pi_cut_noise(_np(amp), _np(momentum), float(coef), float(eps))
+        return _t(a), _t(c)
+
+    def pi_update_linf(self, delta, data, g, conv, amp, alpha, gamma, eps, lo, hi):
+        self._log("pi_update_linf")
+        a, d = oracle.pi_update_linf(_np(delta), _np(data), _np(g), _np(conv), _np(amp), float(alpha), float(gamma), float(eps),
+                                     float(lo), float(hi))
+        return _t(a), _t(d)
+
     def lin_sample(self, x, gbar, coefs, forward=True):
         self._log("lin_sample")
         if forward:

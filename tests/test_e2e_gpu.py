@@ -226,6 +226,21 @@ def test_normalize_fold_is_bit_identical(name, mean_mode, graph):
     REPORT["fold/%s_%s_%s" % (name, mean_mode, "graph" if graph else "eager")] = {"bit_identical": True}
 
 
+def test_pifgsm_native_matches_restatement_on_gpu():
+    """PI-FGSM on the kernels against the eager restatement of gradient/pifgsm.py on the same GPU (the
+    restatement is pinned to the live reference in tests/test_reference_live.py). Only the 3x3 projection convolution's
+    summation order is free (cuDNN vs ours) and it only enters through sign(): a handful of elements per million at most."""
+    net = _net()
+    x, y = _data()
+    for kw in ({}, {"decay": 1.0, "epoch": 4}):
+        ref = torch_ref.RefPIFGSM(torch_ref.ref_wrap_model(net), **kw)(x, y)
+        d = make_attack(tab, "pifgsm", net, **kw)(x, y)
+        st = _stats(d, ref, x)
+        REPORT["pifgsm" + ("_mpi" if kw else "")] = st
+        assert int((d != ref).sum()) <= 1e-5 * d.numel(), st
+        assert float(d.abs().max()) <= 16 / 255 + 1e-7
+
+
 def test_cuda_graph_is_refused_for_host_rng_transforms():
     net = _net()
     x, y = _data(2)

@@ -118,6 +118,25 @@ def test_normalize_fold_is_bit_identical(oracle_backend, name, mean_mode):
         assert bits_equal(d_fold.numpy(), ref.numpy())
 
 
+def test_pifgsm_native_matches_restatement(E, oracle_backend):
+    """PI-FGSM on the kernels (ta_pi_cut_noise → ta_dwconv2d → ta_pi_update_linf) against the eager restatement
+    of gradient/pifgsm.py. Every op is bit-exact except the 3x3 projection convolution, whose 8-term sums torch may add in
+    another order; the result only enters through sign(), so a difference needs a sum that is exactly zero in one order and
+    a rounding residue in the other — none on these inputs, and at most a handful per million is tolerated."""
+    x, y = _inputs(E)
+    for kw in ({}, {"decay": 1.0, "epoch": 4}, {"kern_size": 5, "epoch": 3}):
+        ref = torch_ref.RefPIFGSM(torch_ref.ref_wrap_model(tiny_net(0)), **kw)(x, y)
+        oracle_backend.calls.clear()
+        atk = make_attack(tab, "pifgsm", tiny_net(0), **kw)
+        d = atk(x, y)
+        n = kw.get("epoch", 10)
+        assert oracle_backend.calls.count("pi_cut_noise") == n and oracle_backend.calls.count("pi_update_linf") == n
+        assert oracle_backend.calls.count("dwconv2d") == n
+        bad = int((d != ref).sum())
+        assert bad <= 1e-5 * d.numel(), (kw, bad)
+        assert float(d.abs().max()) <= atk.epsilon + 1e-8
+
+
 def test_normalize_fold_declines_what_it_cannot_fold(oracle_backend):
     x = torch.rand(2, 3, 32, 32); y = torch.tensor([1, 2])
     atk = make_attack(tab, "mifgsm", tiny_net(0), epoch=2)

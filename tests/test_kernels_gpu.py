@@ -413,6 +413,28 @@ def test_fused_all_zero_gradient_sample(be):
     assert bits_equal(npy(gm), mo) and bits_equal(npy(dd), do)
 
 
+# ---------------------------------------------------------------------------------------------- PI-FGSM
+@pytest.mark.parametrize("shape", [(4, 3, 224, 224), (2, 3, 17, 19), (1, 3, 8, 8)])
+def test_pifgsm_kernels_match_oracle(be, shape):
+    rng = np.random.default_rng(sum(shape))
+    coef, gamma = 10.0 * ALPHA, 16.0 / 255
+    m = rng.standard_normal(shape).astype(np.float32); m.reshape(-1)[:5] = 0.0; m.reshape(-1)[5] = np.nan
+    amp = (rng.standard_normal(shape) * 0.2).astype(np.float32)
+    x = rng.random(shape, dtype=np.float32)
+    d = ((rng.random(shape, dtype=np.float32) * 2 - 1) * EPS).astype(np.float32)
+    for a0 in (None, amp):
+        a1, cut = be.pi_cut_noise(cu(a0), cu(m), coef, EPS)
+        oa, oc = oracle.pi_cut_noise(a0, m, coef, EPS)
+        assert bits_equal(npy(a1), oa) and bits_equal(npy(cut), oc), (shape, a0 is None)
+        k = np.ones((3, 3, 3), np.float32) / 8; k[:, 1, 1] = 0
+        conv = be.dwconv2d(cut, cu(k))
+        assert bits_equal(npy(conv), oracle.dwconv2d(oc, k.reshape(3, 1, 3, 3)))
+        a2, dn = be.pi_update_linf(cu(d), cu(x), cu(m), conv, a1, coef, gamma, EPS, 0, 1.0)
+        oa2, od = oracle.pi_update_linf(d, x, m, npy(conv), oa, coef, gamma, EPS)
+        assert bits_equal(npy(a2), oa2) and bits_equal(npy(dn), od), (shape, a0 is None)
+        assert np.nanmax(np.abs(npy(dn))) <= EPS + 1e-8
+
+
 # ---------------------------------------------------------------------------------------------- VMI noise in the kernel
 @pytest.mark.parametrize("shape", [(64, 3, 224, 224), (4, 3, 224, 224), (2, 3, 299, 299), (1, 3, 17, 19), (1000,), (3, 5, 7)])
 def test_neighbor_stage_philox_reproduces_torch_uniform(be, shape):

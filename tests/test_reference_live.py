@@ -64,6 +64,19 @@ def test_torch_ref_equals_live_reference(ref, name):
     assert bits_equal(d.numpy(), d_ref.numpy()), n_diff_bits(d.numpy(), d_ref.numpy())
 
 
+def test_torch_ref_pifgsm_equals_live_reference(ref, monkeypatch):
+    """gradient/pifgsm.py hard-codes .cuda() (pifgsm.py:52); with Tensor.cuda shimmed to the identity the UNMODIFIED file runs
+    on this GPU-less box and pins the device-agnostic restatement bit for bit (two configurations)."""
+    from oracle import torch_ref
+    monkeypatch.setattr(torch.Tensor, "cuda", lambda self, *a, **k: self)
+    x, y = _data()
+    for kw in ({"epoch": 4}, {"epoch": 3, "decay": 1.0, "kern_size": 5}):
+        net = _net()
+        d_ref = make_attack(ref, "pifgsm", net, **kw)(x, y)
+        d = torch_ref.RefPIFGSM(torch_ref.ref_wrap_model(net), **kw)(x, y)
+        assert bits_equal(d.numpy(), d_ref.numpy()), (kw, n_diff_bits(d.numpy(), d_ref.numpy()))
+
+
 def test_torch_ref_ens_and_composite(ref):
     from oracle import torch_ref
     x, y = _data()

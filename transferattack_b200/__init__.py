@@ -12,7 +12,7 @@ def _zoo():
     """name → (relative module, class); same keys and classes as the reference registry for the accelerated attacks."""
     table = {
         "gradient": ["fgsm:FGSM", "ifgsm:IFGSM", "mifgsm:MIFGSM", "nifgsm:NIFGSM", "vmifgsm:VMIFGSM", "vnifgsm:VNIFGSM",
-                     "emifgsm:EMIFGSM"],
+                     "emifgsm:EMIFGSM", "pifgsm:PIFGSM"],
         "input_transformation": ["dim:DIM", "tim:TIM", "sim:SIM", "admix:Admix", "di_ti_mi:DITIMI=ditimi"],
         "ensemble": ["ens:ENS"],
     }

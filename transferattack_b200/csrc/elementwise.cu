@@ -71,6 +71,47 @@ struct ClampBoxOp {
   }
 };
 
+// ---- gradient/pifgsm.py:94-98 (PI-FGSM) ------------------------------------------------------------------------
+//   amplification += (beta*alpha) * sign(momentum)
+//   cut_noise      = clamp(|amplification| - eps, 0, 10000) * sign(amplification)
+struct PiCutOp {
+  const float* amp; const float* m; float* amp_out; float* cut_out; float coef, eps;
+  template <int V> __device__ void run(int64_t i) const {
+    const Vec<V> mv = ldv<V>(m, i);
+    Vec<V> av, ao, co;
+    if (amp) av = ldv_rw<V>(amp, i);
+#pragma unroll
+    for (int k = 0; k < V; ++k) {
+      const float a1 = add_rn(amp ? av.v[k] : 0.0f, mul_rn(coef, sign_t(mv.v[k])));
+      const float c = min_nan(max_nan(sub_rn(fabsf(a1), eps), 0.0f), 10000.0f);
+      ao.v[k] = a1;
+      co.v[k] = mul_rn(c, sign_t(a1));
+    }
+    stv<V>(amp_out, i, ao);
+    stv<V>(cut_out, i, co);
+  }
+};
+//   projection     = gamma * sign(conv3x3(cut_noise));  amplification += projection                       (pifgsm.py:99-100)
+//   delta          = clamp(delta + alpha*sign(g) + projection, -eps, eps), then the box clamp              (pifgsm.py:61-68)
+struct PiUpdateOp {
+  const float* delta; const float* data; const float* g; const float* conv; const float* amp; float* amp_out; float* delta_out;
+  float alpha, gamma, eps, lo, hi;
+  template <int V> __device__ void run(int64_t i) const {
+    const Vec<V> dv = ldv_rw<V>(delta, i), xv = ldv<V>(data, i), gv = ldv<V>(g, i), cv = ldv<V>(conv, i), av = ldv_rw<V>(amp, i);
+    Vec<V> ao, dn;
+#pragma unroll
+    for (int k = 0; k < V; ++k) {
+      const float proj = mul_rn(gamma, sign_t(cv.v[k]));
+      ao.v[k] = add_rn(av.v[k], proj);
+      const float d1 = add_rn(add_rn(dv.v[k], mul_rn(alpha, sign_t(gv.v[k]))), proj);
+      const float d2 = min_nan(max_nan(d1, -eps), eps);
+      dn.v[k] = min_nan(max_nan(d2, sub_rn(lo, xv.v[k])), sub_rn(hi, xv.v[k]));
+    }
+    stv<V>(amp_out, i, ao);
+    stv<V>(delta_out, i, dn);
+  }
+};
+
 // ---- attack.py:88 / nifgsm.py:39 / vmifgsm.py:50 ------------------------------------------------------------------
 template <int V> struct StageIn { Vec<V> x, d, n, l; };
 struct StageOp {
@@ -343,6 +384,22 @@ int ta_stage_add(const float* data, const float* delta, const float* look, float
   TA_REQUIRE(data && out && N > 0, "ta_stage_add: null pointer or N=%lld", (long long)N);
   const bool v4 = (N % 4 == 0) && all_aligned(data, delta, look, out);
   return launch_ew2<1>("ta_stage_add", N, v4, StageOp{data, delta, nullptr, look, out, coef}, (cudaStream_t)stream);
+}
+
+int ta_pi_cut_noise(const float* amp, const float* momentum, float coef, float eps, float* amp_out, float* cut_out, int64_t N,
+                    ta_stream_t stream) {
+  TA_REQUIRE(momentum && amp_out && cut_out && N > 0, "ta_pi_cut_noise: null pointer or N=%lld", (long long)N);
+  const bool v4 = (N % 4 == 0) && all_aligned(amp, momentum, amp_out, cut_out);
+  return launch_ew("ta_pi_cut_noise", N, v4, PiCutOp{amp, momentum, amp_out, cut_out, coef, eps}, (cudaStream_t)stream);
+}
+
+int ta_pi_update_linf(const float* delta, const float* data, const float* g, const float* conv, const float* amp, float alpha,
+                      float gamma, float eps, float lo, float hi, float* amp_out, float* delta_out, int64_t N, ta_stream_t stream) {
+  TA_REQUIRE(delta && data && g && conv && amp && amp_out && delta_out && N > 0, "ta_pi_update_linf: null pointer or N=%lld",
+             (long long)N);
+  const bool v4 = (N % 4 == 0) && all_aligned(delta, data, g, conv, amp, amp_out, delta_out);
+  return launch_ew("ta_pi_update_linf", N, v4, PiUpdateOp{delta, data, g, conv, amp, amp_out, delta_out, alpha, gamma, eps, lo, hi},
+                   (cudaStream_t)stream);
 }
 
 int ta_neighbor_stage(const float* data, const float* delta, const float* noise, const float* look, float coef, float* out,

@@ -257,6 +257,25 @@ class CudaBackend:
             _lib.check(self.lib.ta_dwconv2d_sep(_ptr(g), _ptr(kcol), _ptr(krow), ks, _ptr(out), B, C, H, W, _stream()), "ta_dwconv2d_sep")
         return out
 
+    def pi_cut_noise(self, amp, momentum, coef, eps):
+        """PI-FGSM (pifgsm.py:94-96): returns (amplification + coef*sign(momentum), its cut noise); amp None = first iteration"""
+        m = _f32c(momentum, "momentum"); amp = _f32c(amp, "amplification")
+        amp_out, cut = torch.empty_like(m), torch.empty_like(m)
+        with _DeviceOf(m):
+            _lib.check(self.lib.ta_pi_cut_noise(_ptr(amp), _ptr(m), float(coef), float(eps), _ptr(amp_out), _ptr(cut), m.numel(),
+                                                _stream()), "ta_pi_cut_noise")
+        return amp_out, cut
+
+    def pi_update_linf(self, delta, data, g, conv, amp, alpha, gamma, eps, lo, hi):
+        """PI-FGSM (pifgsm.py:97-102, 61-68): returns (amplification + projection, delta')"""
+        delta = _f32c(delta, "delta"); data = _f32c(data, "data"); g = _f32c(g, "grad"); conv = _f32c(conv, "conv"); amp = _f32c(amp, "amp")
+        amp_out, d_out = torch.empty_like(delta), torch.empty_like(delta)
+        with _DeviceOf(delta):
+            _lib.check(self.lib.ta_pi_update_linf(_ptr(delta), _ptr(data), _ptr(g), _ptr(conv), _ptr(amp), float(alpha), float(gamma),
+                                                  float(eps), float(lo), float(hi), _ptr(amp_out), _ptr(d_out), delta.numel(),
+                                                  _stream()), "ta_pi_update_linf")
+        return amp_out, d_out
+
     def lin_sample(self, x, gbar, coefs, forward=True):
         x = _f32c(x, "x"); K = len(coefs)
         with _DeviceOf(x):
