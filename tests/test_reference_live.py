@@ -116,6 +116,20 @@ def _try_make(pkg, name, nets, extra):
         return make_attack(pkg, name, nets, **kw)
 
 
+# reference plugin files that hard-code `.cuda()` (pifgsm.py:52, ssm.py:50-52, …): runnable on this GPU-less box once
+# Tensor.cuda / Module.cuda are shimmed to the identity — the plugin FILES stay unmodified
+CUDA_HARDCODED = ["pifgsm", "ssm"]          # (su / lpm / everywhere / stm need a feature-hook model, scikit-opt, a target or checkpoints)
+
+
+@pytest.mark.parametrize("name", CUDA_HARDCODED)
+def test_reference_plugin_with_cuda_shim_runs_unchanged_on_this_base(ref, adopted, name, monkeypatch):
+    monkeypatch.setattr(torch.Tensor, "cuda", lambda self, *a, **k: self)
+    monkeypatch.setattr(torch.nn.Module, "cuda", lambda self, *a, **k: self)
+    if name not in ref.attack_zoo:
+        pytest.skip("not in the reference registry")
+    test_reference_plugin_runs_unchanged_on_this_base(ref, adopted, name)
+
+
 @pytest.mark.parametrize("name", GRADIENT + INPUT_T + ENSEMBLE)
 def test_reference_plugin_runs_unchanged_on_this_base(ref, adopted, name):
     x, y = _data(2, 224)
