@@ -262,6 +262,22 @@ class RefDITIMI(RefDIM):
     get_grad = RefTIM.get_grad
 
 
+class RefSIDITIMI(RefDITIMI):
+    """Config 3's "+SIM" variant composed from the reference's hooks: DIM.transform(SIM.transform(x)) (sim.py:36-46 then
+    dim.py:42-68, one DIM draw for the S*B batch), SIM's get_loss, TIM's get_grad."""
+
+    def __init__(self, model, num_scale=5, **kw):
+        super().__init__(model, **kw)
+        self.num_scale = num_scale
+
+    def transform(self, x, **kw):
+        return RefDIM.transform(self, torch.cat([x / (2 ** i) for i in range(self.num_scale)]))
+
+    def get_loss(self, logits, label):
+        v = self.loss(logits, label.repeat(self.num_scale))
+        return -v if self.targeted else v
+
+
 class RefVMIFGSM(RefAttack):          # gradient/vmifgsm.py:42-97
     def __init__(self, model, beta=1.5, num_neighbor=20, **kw):
         super().__init__(model, **kw)
@@ -368,7 +384,7 @@ class RefPIFGSM(RefAttack):           # gradient/pifgsm.py:33-102 (device-agnost
 REF_ZOO = {
     "fgsm": ref_fgsm, "ifgsm": ref_ifgsm, "mifgsm": ref_mifgsm, "nifgsm": RefNIFGSM, "dim": RefDIM,
     "tim": RefTIM, "sim": RefSIM, "admix": RefAdmix, "ditimi": RefDITIMI, "vmifgsm": RefVMIFGSM,
-    "vnifgsm": RefVNIFGSM, "emifgsm": RefEMIFGSM, "ens": ref_mifgsm, "pifgsm": RefPIFGSM,
+    "vnifgsm": RefVNIFGSM, "emifgsm": RefEMIFGSM, "ens": ref_mifgsm, "pifgsm": RefPIFGSM, "siditimi": RefSIDITIMI,
 }
 
 

@@ -205,7 +205,7 @@ def test_trace_from_reference_replays_through_hooks(E):
         assert d.requires_grad and d.is_leaf
 
 
-@pytest.mark.parametrize("name", ["dim", "tim", "ditimi"])
+@pytest.mark.parametrize("name", ["dim", "tim", "ditimi", "siditimi"])
 def test_dim_tim_single_step(E, name):
     """DIM's blend and TIM's conv are tolerance-level vs ATen (FMA contraction / summation order), so after sign() a few
     near-zero elements may flip: one iteration, <= 0.2 % of elements may differ, and only by 2*alpha."""
@@ -299,7 +299,7 @@ def test_graph_capture_is_opt_in_per_hook_owner():
     be captured. Every class defining a loop hook has to declare graph_safe itself — inheriting the flag is not enough."""
     ok = {n: make_attack(tab, n, [tiny_net(0), tiny_net(1)] if n == "ens" else tiny_net(0))._graph_ok() for n in tab.attack_zoo}
     assert ok == {"fgsm": True, "ifgsm": True, "mifgsm": True, "nifgsm": True, "tim": True, "sim": True, "ens": True,
-                  "dim": False, "admix": False, "ditimi": False, "vmifgsm": False, "vnifgsm": False, "emifgsm": False, "pifgsm": False}
+                  "dim": False, "admix": False, "ditimi": False, "vmifgsm": False, "vnifgsm": False, "emifgsm": False, "pifgsm": False, "siditimi": False}
     base = tab.load_attack_class("mifgsm")
 
     class Custom(base):                          # a user plugin overriding a hook without declaring anything

@@ -96,6 +96,18 @@ def test_torch_ref_ens_and_composite(ref):
     seed_all(4); d_ref = make_attack(ref, Composite, net, epoch=3)(x, y)
     seed_all(4); d = torch_ref.RefDITIMI(torch_ref.ref_wrap_model(net), epoch=3)(x, y)
     assert bits_equal(d.numpy(), d_ref.numpy())
+    # … and with SIM's scale copies in front (config 3's "+SIM S=5" variant), again composed from the reference's own hooks
+    SIM = ref.load_attack_class("sim")
+
+    class Composite5(Composite):
+        num_scale = 5
+
+        def transform(self, x, **kw):
+            return DIM.transform(self, SIM.transform(self, x))
+        get_loss = SIM.get_loss
+    seed_all(4); d_ref = make_attack(ref, Composite5, net, epoch=2)(x, y)
+    seed_all(4); d = torch_ref.RefSIDITIMI(torch_ref.ref_wrap_model(net), epoch=2)(x, y)
+    assert bits_equal(d.numpy(), d_ref.numpy())
 
 
 # ---- drop-in matrix: reference plugin files on OUR base class ------------------------------------------------------------
