@@ -130,7 +130,8 @@ def host_cores():
 def build_attack(pkg, name, net, **kw):
     cls = pkg.load_attack_class(name)
     wrap = pkg.utils.wrap_model
-    P = type("Bench" + cls.__name__, (cls,), {"load_model": lambda self, _n: wrap(net)})   # documented override point (attack.py:40-65)
+    # load_model is the documented override point (attack.py:40-65); the class supplying the surrogate declares it capturable
+    P = type("Bench" + cls.__name__, (cls,), {"load_model": lambda self, _n: wrap(net), "graph_safe": True})
     return P(model_name="synthetic", **kw)
 
 

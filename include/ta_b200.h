@@ -40,8 +40,12 @@ enum {
 
 /* how ta_abs_mean_per_sample / ta_fused_update_linf form mean|g| */
 enum {
-  TA_MEAN_EXACT = 0     /* fp64 accumulation, mean = (float)(sum / n): order-independent up to the final rounding.
-                           (Strict parity with torch's fp32 tree sum is obtained by passing torch's own result as `scale`.) */
+  TA_MEAN_EXACT = 0,    /* fp64 accumulation, mean = (float)(sum / n): order-independent up to the final rounding. */
+  TA_MEAN_TORCH = 1     /* the fp32 summation tree of torch's own CUDA kernel for `x.abs().mean(dim=(1,2,3))` (attack.py:128):
+                           ATen's launch policy for the device (block shape, CTAs per output), 4 accumulators per thread,
+                           shared-memory / shuffle trees, sum * (float)(B / numel) — the reference's bits without an ATen
+                           launch. TA_EUNSUPPORTED outside the replayed launch family (B == 1, tiny samples): pass torch's own
+                           result as `scale` there. */
 };
 
 /* direction modes of ta_update_linf */
@@ -72,6 +76,11 @@ int ta_tune_set(const char* key, int value);
 int64_t ta_abs_mean_ws_bytes(int B, int64_t n);
 int ta_abs_mean_per_sample(const float* g, float* mean_out, int B, int64_t n, int mode,
                            void* ws, ta_stream_t stream);
+/* The launch policy TA_MEAN_TORCH replays (PyTorch ATen/native/cuda/Reduce.cuh setReduceConfig, fp32, vt0 = 4) for a device
+ * with `sm_count` SMs and `max_threads_per_sm` resident threads per SM: block (block_w, block_h), ctas_per_output.
+ * Host-only (no CUDA call). TA_EUNSUPPORTED when (B, n) is outside the replayed family.                                     */
+int ta_aten_mean_policy(int B, int64_t n, int sm_count, int max_threads_per_sm, int* block_w, int* block_h,
+                        int* ctas_per_output);
 
 /* m_out = m * decay + g / scale[b]      (m == NULL means the reference's `momentum = 0` first call)
  * scale: [B] per-sample mean|g| (from torch or from ta_abs_mean_per_sample). m_out may alias m. */
@@ -116,6 +125,27 @@ int ta_fused_update_linf(const float* g, const float* m, float* m_out,
                          float* xadv_out, const float* scale, float* scale_out, int mean_mode,
                          float decay, float alpha, float eps, float lo, float hi,
                          int B, int64_t n, ta_stream_t stream);
+
+/* The same tail with every option, as one argument block (zero-initialise, then fill what applies):
+ *   addend   (nullable) g' = g + addend before everything else — VMI/VNI's `grad + variance` (gradient/vmifgsm.py:87);
+ *   gbar_out (nullable) receives g' / mu_b — EMI's bar_grad (gradient/emifgsm.py:97);
+ *   emit_normalized / grad_wrt_xn + mean_host, std_host, C, plane: the Normalize fold of ta_fused_update_linf_nf below;
+ *   delta_out != delta keeps the old delta intact (VMI evaluates its neighbours at the old point after the momentum update).
+ * addend and grad_wrt_xn need n % 4 == 0, 16-byte aligned buffers and a sample that fits the cluster's shared memory
+ * (TA_EUNSUPPORTED otherwise: keep the separate kernels).                                                                  */
+typedef struct ta_fused_tail_args {
+  const float* g; const float* addend;
+  const float* m; float* m_out;
+  const float* delta; float* delta_out;
+  const float* data;
+  float* xadv_out; float* gbar_out;
+  const float* scale; float* scale_out;
+  int mean_mode;
+  float decay, alpha, eps, lo, hi;
+  int B; int64_t n;
+  const float* mean_host; const float* std_host; int C; int64_t plane; int emit_normalized; int grad_wrt_xn;
+} ta_fused_tail_args;
+int ta_fused_tail(const ta_fused_tail_args* args, ta_stream_t stream);
 
 /* ---- Normalize folded into the fused tail (reference utils.py:72-79 PreprocessingModel) ------------------
  *   Same as ta_fused_update_linf, but the emitted next model input is the NORMALISED image

@@ -58,7 +58,8 @@ def _build_attacker(args):
         def load_model(self, names):
             one = lambda n: wrap_model(models.__dict__[n](weights=None).eval().cuda())
             return EnsembleModel([one(n) for n in names]) if isinstance(names, list) else one(names)
-        cls = type(cls.__name__, (cls,), {"load_model": load_model})
+        # plain torchvision nets: the class supplying the surrogate declares it capturable (attack.py: _GRAPH_HOOKS)
+        cls = type(cls.__name__, (cls,), {"load_model": load_model, "graph_safe": True})
     return cls(model_name=model_name, targeted=args.targeted, **_attack_kwargs(args))
 
 

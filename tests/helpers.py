@@ -41,7 +41,9 @@ def make_attack(pkg, name, net_or_list, wrap=None, ens=None, **kw):
             return ens([wrap(m) for m in net_or_list])
         return wrap(net_or_list)
 
-    P = type("P_" + cls.__name__, (cls,), {"load_model": load_model})
+    # graph_safe: this loader returns plain seeded torchvision / tiny nets (no host randomness in their forward), so the class
+    # that supplies the surrogate opts in to CUDA-graph capture itself (attack.py: _GRAPH_HOOKS includes load_model)
+    P = type("P_" + cls.__name__, (cls,), {"load_model": load_model, "graph_safe": True})
     return P(model_name="tiny", **kw)
 
 

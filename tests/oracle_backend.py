@@ -27,6 +27,11 @@ class OracleBackend:
 
     def abs_mean(self, g, mode=0):
         self._log("abs_mean")
+        if mode == 1:
+            from oracle import aten_reduce
+            gn = _np(g)
+            r = aten_reduce.emulate_numpy(np.abs(gn).reshape(gn.shape[0], -1))
+            return None if r is None else _t(r)
         return _t(oracle.abs_mean_per_sample(_np(g)))
 
     def momentum(self, g, m, scale, decay, out=None):
@@ -56,32 +61,48 @@ class OracleBackend:
         self._log("init_l2_scale")
         return _t(oracle.init_l2_scale(_np(delta), _np(r), _np(data), float(eps), float(lo), float(hi)))
 
-    def fused_update_linf(self, g, m, m_out, delta, delta_out, data, xadv_out, scale, scale_out, decay, alpha, eps, lo, hi,
-                          mean_mode=0):
-        self._log("fused_update_linf")
+    def fused_tail(self, g, m, m_out, delta, delta_out, data, xadv_out, scale, scale_out, decay, alpha, eps, lo, hi,
+                   mean_mode=0, addend=None, gbar_out=None, mean=None, std=None, emit_normalized=False, grad_wrt_xn=False):
+        """ta_fused_tail composed from the oracle's single ops, in the kernel's order: g / std, + addend, mean, momentum,
+        update, x + delta', Normalize."""
+        self._log("fused_tail_nf" if emit_normalized else "fused_tail")
         gn = _np(g)
-        sc = _np(scale).reshape(-1) if scale is not None else oracle.abs_mean_per_sample(gn)
+        if grad_wrt_xn:
+            gn = oracle.normalize_bwd(gn, np.asarray(std, np.float32))
+        if addend is not None:
+            gn = oracle.add(gn, _np(addend))
+        if scale is not None:
+            sc = _np(scale).reshape(-1)
+        elif mean_mode == 1:        # TA_MEAN_TORCH: the summation tree of torch's CUDA kernel on a 148-SM device
+            from oracle import aten_reduce
+            sc = aten_reduce.emulate_numpy(np.abs(gn).reshape(gn.shape[0], -1))
+            if sc is None:
+                return False
+        else:
+            sc = oracle.abs_mean_per_sample(gn)
         mo, do, xo = oracle.fused_update_linf(gn, _np(m), _np(delta), _np(data), sc, float(decay), float(alpha), float(eps),
                                               float(lo), float(hi), want_xadv=xadv_out is not None)
+        if emit_normalized:
+            xo = oracle.normalize_fwd(xo, np.asarray(mean, np.float32), np.asarray(std, np.float32))
         with torch.no_grad():
             m_out.copy_(_t(mo)); delta_out.copy_(_t(do))
             if xadv_out is not None:
                 xadv_out.copy_(_t(xo))
             if scale_out is not None:
                 scale_out.copy_(_t(sc))
+            if gbar_out is not None:
+                B = gn.shape[0]
+                gbar_out.copy_(_t((gn.reshape(B, -1) / sc.reshape(B, 1).astype(np.float32)).astype(np.float32).reshape(gn.shape)))
+        return True
+
+    def fused_update_linf(self, g, m, m_out, delta, delta_out, data, xadv_out, scale, scale_out, decay, alpha, eps, lo, hi,
+                          mean_mode=0):
+        self.fused_tail(g, m, m_out, delta, delta_out, data, xadv_out, scale, scale_out, decay, alpha, eps, lo, hi, mean_mode)
 
     def fused_update_linf_nf(self, g, m, m_out, delta, delta_out, data, xn_out, scale, scale_out, decay, alpha, eps, lo, hi,
                              mean, std, grad_wrt_xn, mean_mode=0):
-        self._log("fused_update_linf_nf")
-        sc = _np(scale).reshape(-1) if scale is not None else None
-        mo, do, xo, sc = oracle.fused_update_linf_nf(_np(g), _np(m), _np(delta), _np(data), sc, float(decay), float(alpha),
-                                                     float(eps), np.asarray(mean, np.float32), np.asarray(std, np.float32),
-                                                     bool(grad_wrt_xn), float(lo), float(hi))
-        with torch.no_grad():
-            m_out.copy_(_t(mo)); delta_out.copy_(_t(do)); xn_out.copy_(_t(xo))
-            if scale_out is not None:
-                scale_out.copy_(_t(sc))
-        return True
+        return self.fused_tail(g, m, m_out, delta, delta_out, data, xn_out, scale, scale_out, decay, alpha, eps, lo, hi, mean_mode,
+                               mean=mean, std=std, emit_normalized=True, grad_wrt_xn=grad_wrt_xn)
 
     def stage_add(self, data, delta, look=None, coef=0.0, out=None):
         self._log("stage_add")

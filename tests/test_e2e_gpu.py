@@ -74,12 +74,15 @@ def _pair(key, net, mean_mode="torch", **over):
     return d, dr, x
 
 
+@pytest.mark.parametrize("mean_mode", ["torch", "aten"])
 @pytest.mark.parametrize("key", sorted(CASES))
-def test_strict_mode_is_bit_identical(key):
+def test_strict_mode_is_bit_identical(key, mean_mode):
+    """'torch': mean|g| formed inside the fused kernel in torch's own summation order (TA_MEAN_TORCH) — no ATen kernel in the
+    tail; 'aten': the scale from torch's own op. Both must reproduce the reference bit for bit."""
     net = _net()
-    d, dr, x = _pair(key, net)
+    d, dr, x = _pair(key, net, mean_mode=mean_mode)
     st = _stats(d, dr, x)
-    REPORT["strict/" + key] = st
+    REPORT["strict_%s/%s" % (mean_mode, key)] = st
     assert d.is_cuda and not d.requires_grad
     assert st["bit_identical"], st
 
@@ -96,7 +99,9 @@ def test_reference_noise_floor_and_exact_mean_mode():
     st = _stats(d, dr, x)
     REPORT["exact/mifgsm"] = st
     assert st["max_abs"] <= 2 * 16 / 255 + 1e-6
-    assert st["n_gt_1e-5"] <= 0.02 * st["numel"], st
+    # measured floor on B200: 0 differing elements; the fp64-exact mean can differ from torch's fp32 tree in the last bit, which
+    # only matters for momentum entries that are zero to rounding → at most a handful per million (was 2 % in round 1)
+    assert st["n_gt_1e-5"] <= 1e-5 * st["numel"], st
 
 
 def test_ens_two_members_bit_identical():
@@ -199,7 +204,7 @@ def test_cuda_graph_replay_is_bit_identical(name, kw):
 
 
 @pytest.mark.parametrize("graph", [False, True], ids=["eager", "graph"])
-@pytest.mark.parametrize("mean_mode", ["torch", "exact"])
+@pytest.mark.parametrize("mean_mode", ["torch", "aten", "exact"])
 @pytest.mark.parametrize("name", ["mifgsm", "ifgsm", "tim"])
 def test_normalize_fold_is_bit_identical(name, mean_mode, graph):
     """SURVEY §8 f1 on the GPU: fused tail emitting the normalised model input (+ Normalize's adjoint in 'exact' mode with
@@ -218,9 +223,9 @@ def test_normalize_fold_is_bit_identical(name, mean_mode, graph):
         assert bool(getattr(atk, "_graphs", None)) == graph
     assert torch.equal(res[False], res[True])
     if not graph:       # launches of OUR kernels per attack: the fold removes the Normalize forward (and adjoint when deferred)
-        deferred = mean_mode == "exact" and name != "tim"
+        deferred = mean_mode != "aten" and name != "tim"       # in-kernel mean + base get_grad → Normalize's adjoint in the kernel too
         assert res[False, "launches"] - res[True, "launches"] == 4 * (2 if deferred else 1) - 1      # one extra Normalize forward up front
-    if mean_mode == "torch":
+    if mean_mode in ("torch", "aten"):
         ref = torch_ref.REF_ZOO[name](torch_ref.ref_wrap_model(net), epoch=4)(x, y)
         assert torch.equal(res[True], ref)
     REPORT["fold/%s_%s_%s" % (name, mean_mode, "graph" if graph else "eager")] = {"bit_identical": True}

@@ -80,10 +80,10 @@ def test_plugin_matches_torch_ref_bitwise(E, key):
 def test_fused_and_unfused_loops_agree(E, key, oracle_backend):
     x, y = _inputs(E)
     d_fused, _ = _run_mine(key, x, y, fuse=True)
-    assert "fused_update_linf" in oracle_backend.calls
+    assert "fused_tail" in oracle_backend.calls
     oracle_backend.calls.clear()
     d_hooks, _ = _run_mine(key, x, y, fuse=False)
-    assert "fused_update_linf" not in oracle_backend.calls and "momentum" in oracle_backend.calls
+    assert "fused_tail" not in oracle_backend.calls and "momentum" in oracle_backend.calls
     assert bits_equal(d_fused.numpy(), d_hooks.numpy())
 
 
@@ -101,16 +101,16 @@ def test_normalize_fold_is_bit_identical(oracle_backend, name, mean_mode):
     atk.fold_normalize = False
     oracle_backend.calls.clear()
     d_sep = atk(x, y)
-    assert "fused_update_linf_nf" not in oracle_backend.calls
+    assert "fused_tail_nf" not in oracle_backend.calls
     n_sep = oracle_backend.calls.count("normalize")
     atk.fold_normalize = True
     oracle_backend.calls.clear()
     d_fold = atk(x, y)
     deferred = mean_mode == "exact" and name != "tim"          # TIM overrides get_grad: it needs the true gradient
     if name == "nifgsm":                                        # NI-FGSM overrides transform (look-ahead) → nothing to fold into
-        assert "fused_update_linf_nf" not in oracle_backend.calls
+        assert "fused_tail_nf" not in oracle_backend.calls
     else:
-        assert oracle_backend.calls.count("fused_update_linf_nf") == epoch and "fused_update_linf" not in oracle_backend.calls
+        assert oracle_backend.calls.count("fused_tail_nf") == epoch and "fused_tail" not in oracle_backend.calls
         assert n_sep == 2 * epoch and oracle_backend.calls.count("normalize") == 1 + (0 if deferred else epoch)
     assert bits_equal(d_fold.numpy(), d_sep.numpy()), n_diff_bits(d_fold.numpy(), d_sep.numpy())
     if mean_mode == "torch":
@@ -146,7 +146,7 @@ def test_normalize_fold_declines_what_it_cannot_fold(oracle_backend):
     ens = make_attack(tab, "ens", [tiny_net(0), tiny_net(3)], epoch=2)
     assert ens._fold_plan(torch.rand(2, 3, 224, 224)) is None                # members normalise individually
     atk(x, y)
-    assert "fused_update_linf_nf" not in oracle_backend.calls
+    assert "fused_tail_nf" not in oracle_backend.calls
 
 
 @pytest.mark.parametrize("key", sorted(MINE) + ["ens"])

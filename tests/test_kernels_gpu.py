@@ -309,18 +309,56 @@ def test_abs_mean_exact(be, B, shape):
 
 
 FUSED_SHAPES = [(5, (3, 224, 224)), (3, (3, 20, 20)), (2, (3, 299, 299)), (2, (37,)), (9, (3, 64, 64)), (1, (3, 512, 512))]
-FUSED_TUNES = [dict(), {"fused.variant": 1}, {"fused.threads": 256, "fused.unroll": 4}, {"fused.threads": 1024, "fused.unroll": 1},
-               {"fused.cluster": 4}, {"fused.cluster": 16, "fused.threads": 256, "fused.unroll": 2},
-               {"fused.cluster": 1, "fused.variant": 1}, {"fused.variant": 1, "fused.threads": 256, "fused.unroll": 2}]
+FUSED_TUNES = [dict(), {"fused.unroll": 1}, {"fused.unroll": 4}, {"fused.cluster": 4}, {"fused.cluster": 16, "fused.unroll": 1},
+               {"fused.cluster": 1}, {"fused.cluster": 2, "fused.unroll": 4}]
+FUSED_KEYS = {"fused.unroll": 2, "fused.cluster": 0}
 
 
-@pytest.mark.parametrize("tune", FUSED_TUNES, ids=lambda t: ",".join("%s=%s" % kv for kv in t.items()) or "default")
-def test_fused_update_exact_mean(be, tune):
+def _torch_mean(g):
+    """the reference's own op (attack.py:128) on the GPU: the bits TA_MEAN_TORCH must reproduce"""
+    t = cu(g)
+    return npy(t.abs().mean(dim=tuple(range(1, t.dim()))))
+
+
+@pytest.mark.parametrize("B,shape", [(5, (3, 224, 224)), (64, (3, 224, 224)), (256, (3, 224, 224)), (2, (3, 299, 299)), (3, (3, 299, 299)),
+                                     (4, (3, 32, 32)), (16, (3, 64, 64)), (31, (3, 224, 224)), (600, (3, 224, 224)), (8, (3, 384, 384)),
+                                     (128, (1, 224, 224))])
+def test_abs_mean_torch_order_is_bit_identical_to_torch(be, B, shape):
+    """TA_MEAN_TORCH replays the launch policy and summation tree of torch's CUDA mean kernel (csrc/aten_mean.cuh): the result
+    must equal `g.abs().mean(dim=(1,2,3))` of the installed torch BIT FOR BIT, and the numpy restatement (oracle/aten_reduce.py)."""
     from transferattack_b200 import _lib
-    keys = ["fused.variant", "fused.threads", "fused.unroll", "fused.cluster"]
-    defaults = {"fused.variant": 0, "fused.threads": 512, "fused.unroll": 2, "fused.cluster": 0}
-    for k in keys:
-        _lib.tune_set(k, tune.get(k, defaults[k]))
+    from oracle import aten_reduce
+    prop = torch.cuda.get_device_properties(0)
+    for seed, scale in ((0, 1.0), (1, 1e-4), (2, 3e3)):
+        rng = np.random.default_rng(B + seed)
+        g = (rng.standard_normal((B,) + shape) * scale).astype(np.float32)
+        got = be.abs_mean(cu(g), _lib.TA_MEAN_TORCH)
+        assert got is not None, (B, shape)
+        ref = _torch_mean(g)
+        assert bits_equal(npy(got), ref), (B, shape, seed, ulp_diff(npy(got), ref).max())
+        if g.size <= 40 * 150528:
+            em = aten_reduce.emulate_numpy(np.abs(g).reshape(B, -1), prop.multi_processor_count, prop.max_threads_per_multi_processor)
+            assert bits_equal(em, ref), (B, shape, seed)
+
+
+def test_abs_mean_torch_order_declines_what_it_does_not_replay(be):
+    from transferattack_b200 import _lib
+    for B, shape in [(1, (3, 224, 224)), (2, (37,)), (4, (8,))]:        # 1-D vectorised ATen path; per-warp-row outputs
+        assert be.abs_mean(torch.zeros((B,) + shape, device="cuda"), _lib.TA_MEAN_TORCH) is None
+    from transferattack_b200 import ops
+    assert ops.aten_mean_replay_ok(torch.zeros(1, 3, 224, 224, device="cuda")) is False
+    assert ops.aten_mean_replay_ok(torch.zeros(6, 3, 224, 224, device="cuda")) is True
+
+
+@pytest.mark.parametrize("mean_mode", ["exact", "torch"])
+@pytest.mark.parametrize("tune", FUSED_TUNES, ids=lambda t: ",".join("%s=%s" % kv for kv in t.items()) or "default")
+def test_fused_update_in_kernel_mean(be, tune, mean_mode):
+    """the cluster kernel for every tuning point, odd sizes (generic two-launch form), in place on momentum and delta.
+    'exact': fp64 mean within 1 ulp of the correctly rounded one; 'torch': the mean is torch's own, bit for bit."""
+    from transferattack_b200 import _lib
+    mode = _lib.TA_MEAN_TORCH if mean_mode == "torch" else _lib.TA_MEAN_EXACT
+    for k in FUSED_KEYS:
+        _lib.tune_set(k, tune.get(k, FUSED_KEYS[k]))
     try:
         for B, shape in FUSED_SHAPES:
             rng = np.random.default_rng(B * 7 + len(shape))
@@ -335,26 +373,77 @@ def test_fused_update_exact_mean(be, tune):
                 m_out, xa = torch.empty_like(gm), torch.empty_like(gm)
                 so = torch.empty(B, device="cuda")
                 # in place on momentum and delta, as the base loop uses it
-                be.fused_update_linf(cu(g), gm if has_m else None, gm if has_m else m_out, dd, dd, cu(x), xa, None, so, 0.9, ALPHA, EPS, 0, 1.0)
+                ok = be.fused_tail(cu(g), gm if has_m else None, gm if has_m else m_out, dd, dd, cu(x), xa, None, so, 0.9, ALPHA, EPS, 0, 1.0,
+                                   mean_mode=mode)
+                if not ok:                      # outside the replayed ATen launch family (or more columns per CTA than the forced
+                    from oracle import aten_reduce        # cluster size holds): the caller passes torch's scale instead
+                    prop = torch.cuda.get_device_properties(0)
+                    cfg = aten_reduce.config(B, int(np.prod(shape)), prop.multi_processor_count, prop.max_threads_per_multi_processor)
+                    cl = tune.get("fused.cluster", 0)
+                    assert mean_mode == "torch" and (cfg is None or (cl in (1, 2) and cfg["stride"] // cl > 2560)), (B, shape, tune, cfg)
+                    continue
                 scale = npy(so)
-                assert ulp_diff(scale, oracle.abs_mean_per_sample(g)).max() <= 1
+                if mean_mode == "torch":
+                    assert bits_equal(scale, _torch_mean(g)), (B, shape, tune)
+                else:
+                    assert ulp_diff(scale, oracle.abs_mean_per_sample(g)).max() <= 1
                 mo, do, xo = oracle.fused_update_linf(g, m if has_m else None, d, x, scale, 0.9, ALPHA, EPS)
                 got_m = npy(gm if has_m else m_out)
                 assert bits_equal(got_m, mo), (B, shape, has_m, n_diff_bits(got_m, mo))
                 assert bits_equal(npy(dd), do), (B, shape, has_m, n_diff_bits(npy(dd), do))
                 assert bits_equal(npy(xa), xo), (B, shape, has_m)
     finally:
-        for k in keys:
-            _lib.tune_set(k, defaults[k])
+        for k in FUSED_KEYS:
+            _lib.tune_set(k, FUSED_KEYS[k])
 
 
-@pytest.mark.parametrize("tune", [dict(), {"fused.variant": 1}, {"fused.cluster": 2}], ids=["default", "variant1", "cluster2"])
+@pytest.mark.parametrize("mean_mode", ["scale", "exact", "torch"])
+def test_fused_tail_addend_and_gbar(be, mean_mode):
+    """ta_fused_tail's VMI / EMI options against the chain of reference ops (vmifgsm.py:87 `grad + variance`, emifgsm.py:97
+    `grad / mean|grad|`): g' = g + v (one rounding), mean|g'|, momentum, update into a SECOND delta buffer (the old delta must
+    survive for VMI's neighbours), next model input, and g'/mean as an extra output."""
+    from transferattack_b200 import _lib
+    for B, shape in [(5, (3, 224, 224)), (16, (3, 64, 64)), (3, (3, 20, 20))]:
+        rng = np.random.default_rng(B)
+        full = (B,) + shape
+        g = (rng.standard_normal(full) * 1e-3).astype(np.float32)
+        v = (rng.standard_normal(full) * 3e-4).astype(np.float32)
+        m = rng.standard_normal(full).astype(np.float32)
+        x = rng.random(full, dtype=np.float32)
+        d = ((rng.random(full, dtype=np.float32) * 2 - 1) * EPS).astype(np.float32)
+        for addend in (None, v):
+            gsum = g if addend is None else oracle.add(g, addend)
+            gm, dd = cu(m), cu(d)
+            d_next, xa, gb = torch.empty_like(dd), torch.empty_like(dd), torch.empty_like(dd)
+            so = torch.empty(B, device="cuda")
+            if mean_mode == "scale":
+                sc, mode = cu(_torch_mean(gsum)), _lib.TA_MEAN_EXACT
+            else:
+                sc, mode = None, (_lib.TA_MEAN_TORCH if mean_mode == "torch" else _lib.TA_MEAN_EXACT)
+            ok = be.fused_tail(cu(g), gm, gm, dd, d_next, cu(x), xa, sc, so, 0.9, ALPHA, EPS, 0, 1.0, mean_mode=mode,
+                               addend=cu(addend), gbar_out=gb)
+            assert ok, (B, shape, _lib.last_error())
+            scale = npy(so)
+            if mean_mode == "exact":
+                assert ulp_diff(scale, oracle.abs_mean_per_sample(gsum)).max() <= 1
+            else:
+                assert bits_equal(scale, _torch_mean(gsum)), (B, shape)
+            mo, do, xo = oracle.fused_update_linf(gsum, m, d, x, scale, 0.9, ALPHA, EPS)
+            tag = (B, shape, addend is not None)
+            assert bits_equal(npy(gm), mo), tag
+            assert bits_equal(npy(d_next), do) and bits_equal(npy(dd), d), tag          # old delta untouched
+            assert bits_equal(npy(xa), xo), tag
+            ref_gb = (gsum.reshape(B, -1) / scale.reshape(B, 1)).astype(np.float32).reshape(full)
+            assert bits_equal(npy(gb), ref_gb), tag
+
+
+@pytest.mark.parametrize("tune", [dict(), {"fused.unroll": 1}, {"fused.cluster": 2}], ids=["default", "unroll1", "cluster2"])
 def test_fused_update_with_normalize_folded(be, tune):
     """ta_fused_update_linf_nf against the chain of reference ops it replaces (oracle.fused_update_linf_nf):
     strict (scale given) and exact (in-kernel mean) modes, gradient w.r.t. delta or w.r.t. the normalised input, first
     iteration (no momentum) and later ones, in place on momentum and delta."""
     from transferattack_b200 import _lib
-    for k, v in {"fused.variant": 0, "fused.cluster": 0, **tune}.items():
+    for k, v in {**FUSED_KEYS, **tune}.items():
         _lib.tune_set(k, v)
     try:
         for B, shape in [(5, (3, 224, 224)), (2, (3, 64, 64)), (3, (1, 32, 32)), (2, (4, 16, 16)), (2, (3, 226, 224))]:
@@ -367,7 +456,8 @@ def test_fused_update_with_normalize_folded(be, tune):
             x = rng.random(full, dtype=np.float32)
             d = ((rng.random(full, dtype=np.float32) * 2 - 1) * EPS).astype(np.float32)
             for wrt_xn in (False, True):
-                for strict in (True, False):
+                for mmode in ("scale", "exact", "torch"):
+                    strict = mmode == "scale"
                     for has_m in (True, False):
                         g_eff = oracle.normalize_bwd(g, std) if wrt_xn else g
                         gm, dd = cu(m), cu(d)
@@ -375,17 +465,25 @@ def test_fused_update_with_normalize_folded(be, tune):
                         so = torch.empty(B, device="cuda")
                         sc = cu(oracle.abs_mean_per_sample(g_eff)) if strict else None
                         ok = be.fused_update_linf_nf(cu(g), gm if has_m else None, gm if has_m else m_out, dd, dd, cu(x), xn, sc, so,
-                                                     0.9, ALPHA, EPS, 0, 1.0, mean, std, wrt_xn)
+                                                     0.9, ALPHA, EPS, 0, 1.0, mean, std, wrt_xn,
+                                                     _lib.TA_MEAN_TORCH if mmode == "torch" else _lib.TA_MEAN_EXACT)
+                        if mmode == "torch" and not ok:
+                            assert be.abs_mean(cu(g_eff), _lib.TA_MEAN_TORCH) is None or tune.get("fused.cluster", 0) == 2, (B, shape)
+                            continue
                         assert ok
                         scale = npy(so)
-                        assert ulp_diff(scale, oracle.abs_mean_per_sample(g_eff)).max() <= (0 if strict else 1)
+                        if mmode == "torch":
+                            assert bits_equal(scale, _torch_mean(g_eff)), (B, shape, wrt_xn)
+                        else:
+                            assert ulp_diff(scale, oracle.abs_mean_per_sample(g_eff)).max() <= (0 if strict else 1)
                         mo, do, xo, _ = oracle.fused_update_linf_nf(g, m if has_m else None, d, x, scale, 0.9, ALPHA, EPS, mean, std, wrt_xn)
                         tag = (B, shape, wrt_xn, strict, has_m)
                         assert bits_equal(npy(gm if has_m else m_out), mo), tag
                         assert bits_equal(npy(dd), do), tag
                         assert bits_equal(npy(xn), xo), tag
     finally:
-        _lib.tune_set("fused.variant", 0); _lib.tune_set("fused.cluster", 0)
+        for k, v in FUSED_KEYS.items():
+            _lib.tune_set(k, v)
 
 
 def test_fused_update_nf_declines_unfoldable_shapes(be):

@@ -10,13 +10,23 @@ _HERE = os.path.dirname(os.path.abspath(__file__))
 SO_PATH = os.path.join(_HERE, "libta_b200.so")
 
 TA_OK, TA_EINVAL, TA_ECUDA, TA_EUNSUPPORTED = 0, -1, -2, -3
-TA_MEAN_EXACT = 0
+TA_MEAN_EXACT, TA_MEAN_TORCH = 0, 1
 TA_DIR_SIGN, TA_DIR_RAW = 0, 1
 
 _p = ctypes.c_void_p
 _f = ctypes.c_float
 _i = ctypes.c_int
 _l = ctypes.c_int64
+
+
+
+class FusedTailArgs(ctypes.Structure):
+    """``ta_fused_tail_args`` of include/ta_b200.h, field for field."""
+    _fields_ = [("g", _p), ("addend", _p), ("m", _p), ("m_out", _p), ("delta", _p), ("delta_out", _p), ("data", _p),
+                ("xadv_out", _p), ("gbar_out", _p), ("scale", _p), ("scale_out", _p), ("mean_mode", _i),
+                ("decay", _f), ("alpha", _f), ("eps", _f), ("lo", _f), ("hi", _f), ("B", _i), ("n", _l),
+                ("mean_host", _p), ("std_host", _p), ("C", _i), ("plane", _l), ("emit_normalized", _i), ("grad_wrt_xn", _i)]
+
 
 # name -> (restype, argtypes); mirrors include/ta_b200.h one to one
 SIGNATURES = {
@@ -27,6 +37,7 @@ SIGNATURES = {
     "ta_tune_set": (_i, [ctypes.c_char_p, _i]),
     "ta_abs_mean_ws_bytes": (_l, [_i, _l]),
     "ta_abs_mean_per_sample": (_i, [_p, _p, _i, _l, _i, _p, _p]),
+    "ta_aten_mean_policy": (_i, [_i, _l, _i, _i, ctypes.POINTER(_i), ctypes.POINTER(_i), ctypes.POINTER(_i)]),
     "ta_momentum": (_i, [_p, _p, _p, _f, _p, _i, _l, _p]),
     "ta_update_linf": (_i, [_p, _p, _p, _p, _f, _f, _f, _f, _i, _p, _l, _p]),
     "ta_update_l2_ws_bytes": (_l, [_i]),
@@ -34,6 +45,7 @@ SIGNATURES = {
     "ta_clamp_box": (_i, [_p, _p, _f, _f, _p, _l, _p]),
     "ta_init_l2_scale": (_i, [_p, _p, _p, _f, _f, _f, _p, _i, _l, _p, _p]),
     "ta_fused_update_linf": (_i, [_p, _p, _p, _p, _p, _p, _p, _p, _p, _i, _f, _f, _f, _f, _f, _i, _l, _p]),
+    "ta_fused_tail": (_i, [ctypes.POINTER(FusedTailArgs), _p]),
     "ta_fused_update_linf_nf": (_i, [_p, _p, _p, _p, _p, _p, _p, _p, _p, _i, _f, _f, _f, _f, _f, _i, _l, _p, _p, _i, _l, _i, _p]),
     "ta_fused_allreduce_update_linf": (_i, [ctypes.POINTER(_p), ctypes.POINTER(_p), _i, _p, _p, _p, _p, _p, _p, _p, _i,
                                             _f, _f, _f, _f, _f, _i, _i, _l, _p]),

@@ -19,11 +19,17 @@ The surrogate forward and ``torch.autograd.grad`` backward stay PyTorch. There i
 raise on CPU tensors (``ops``), exactly like a missing ``libta_b200.so`` does.
 
 ``mean_mode`` selects how ``mean(|grad|)`` per sample is formed:
-  'torch' (default) — the reference's own ``grad.abs().mean(dim=(1,2,3))`` ATen reduction, so that momentum
-                      and perturbation are bit-identical to the reference given the same gradient;
-  'exact'           — reduced inside the kernels in fp64 (``TA_MEAN_EXACT``): one launch for the whole tail,
-                      correctly rounded mean, may differ from torch's fp32 tree sum in the last bit.
+  'torch' (default) — the bits of the reference's own ``grad.abs().mean(dim=(1,2,3))``: formed INSIDE the fused kernel by
+                      replaying the launch policy and fp32 summation tree of torch's CUDA mean kernel (``TA_MEAN_TORCH``,
+                      csrc/aten_mean.cuh), so the whole tail is one launch and momentum / perturbation stay bit-identical
+                      to the reference given the same gradient. The replay is self-checked against torch once per
+                      (device, shape) (``ops.aten_mean_replay_ok``); where it does not apply, torch's own op supplies the scale;
+  'aten'            — always torch's own ATen reduction for the scale (two more launches, +12 B/elem);
+  'exact'           — reduced inside the kernels in fp64 (``TA_MEAN_EXACT``): correctly rounded mean, may differ from torch's
+                      fp32 tree sum in the last bit.
 """
+import warnings
+
 import os
 
 import torch
@@ -43,7 +49,7 @@ def _is_zero_scalar(v):
 class Attack(object):
     """Base class of every attack plugin (reference attack.py:8-169)."""
 
-    #: 'torch' | 'exact' — see module docstring. Env override: TA_B200_MEAN.
+    #: 'torch' | 'aten' | 'exact' — see module docstring. Env override: TA_B200_MEAN.
     mean_mode = os.environ.get("TA_B200_MEAN", "torch")
     #: use the single-launch fused tail in the base loop when the hooks are not overridden
     fuse_update = os.environ.get("TA_B200_FUSE", "1") != "0"
@@ -112,15 +118,33 @@ class Attack(object):
             return t
         return t.to(self.device, non_blocking=t.is_pinned() if not t.is_cuda else False)
 
-    _GRAPH_HOOKS = ("forward", "transform", "get_logits", "get_loss", "get_grad", "get_momentum", "update_delta", "init_delta")
+    #: hooks whose OWNER class must itself declare graph_safe = True for the loop to be captured. ``load_model`` is one of
+    #: them: it is the reference's documented override point for customised surrogates (sapr, ghost, sgm, ... override only
+    #: it), and a surrogate with host-side randomness or Python control flow in its forward must never be frozen into a graph.
+    _GRAPH_HOOKS = ("forward", "transform", "get_logits", "get_loss", "get_grad", "get_momentum", "update_delta", "init_delta",
+                    "load_model")
 
     def _graph_ok(self):
-        """every loop hook in effect is defined by a class that itself declares graph_safe = True"""
+        """every loop hook in effect (and the surrogate's loader) is defined by a class that itself declares graph_safe = True,
+        and the surrogate carries no forward / backward module hooks (registered by code that did not opt in)"""
         for hook in self._GRAPH_HOOKS:
             owner = next(c for c in type(self).__mro__ if hook in c.__dict__)
             if not owner.__dict__.get("graph_safe", False):
                 return False
+        if not getattr(self, "graph_safe_module_hooks", False) and isinstance(self.model, nn.Module):
+            for mod in self.model.modules():
+                if (mod._forward_hooks or mod._forward_pre_hooks or mod._backward_hooks
+                        or getattr(mod, "_backward_pre_hooks", None)):
+                    return False
         return True
+
+    def _mean_kernel_mode(self, like):
+        """the in-kernel mean mode for gradients shaped like `like`, or None = take the scale from torch's own op"""
+        if self.mean_mode == 'exact':
+            return _lib.TA_MEAN_EXACT
+        if self.mean_mode == 'torch' and ops.aten_mean_replay_ok(like):
+            return _lib.TA_MEAN_TORCH
+        return None
 
     def _fusable(self):
         cls = type(self)
@@ -129,8 +153,9 @@ class Attack(object):
                 and cls.init_delta is Attack.init_delta
                 and isinstance(self.alpha, (int, float)) and isinstance(self.decay, (int, float)))
 
-    def _fold_plan(self, data):
-        """(pre, net, mean, std, defer) when Normalize can be folded into the fused tail for this batch, else None."""
+    def _fold_plan(self, data, kmode=None):
+        """(pre, net, mean, std, defer) when Normalize can be folded into the fused tail for this batch, else None.
+        `kmode`: the in-kernel mean mode (``_mean_kernel_mode``); with one, Normalize's adjoint moves into the kernel too."""
         cls = type(self)
         if not self.fold_normalize or cls.get_logits is not Attack.get_logits or cls.transform is not Attack.transform:
             return None
@@ -145,7 +170,8 @@ class Attack(object):
             return None
         if pre.mean.numel() != C or C > 4 or (H * W) % 4 != 0 or data.data_ptr() % 16 != 0:
             return None
-        defer = self.mean_mode != 'torch' and cls.get_grad is Attack.get_grad
+        # Normalize's adjoint inside the kernel needs the staged (cluster) form: the sample must fit 8 CTAs' shared memory
+        defer = kmode is not None and cls.get_grad is Attack.get_grad and C * H * W <= 384 * 1024
         return pre, m[1], [float(v) for v in pre.mean.tolist()], [float(v) for v in pre.std.tolist()], defer
 
     @staticmethod
@@ -175,11 +201,20 @@ class Attack(object):
         if self._fusable():
             if (self.use_cuda_graph and self._graph_ok() and data.is_cuda and ops._test_backend is None
                     and getattr(self, "_kernel_events", None) is None and not self.__dict__.get("_graph_failed", False)):
+                self._mean_kernel_mode(data)     # the one-time self-check synchronises: never inside the capture
                 try:
                     return self._loop_graph(data, label, delta)
-                except RuntimeError as e:        # capture refused (e.g. the surrogate synchronises): eager launches from now on
+                except RuntimeError as e:
+                    # only a REFUSED CAPTURE (the surrogate synchronises, allocates through an uncapturable path, ...) turns
+                    # the loop eager; out-of-memory, kernel failures and bugs in hooks are raised as they are
+                    msg = str(e)
+                    if isinstance(e, torch.OutOfMemoryError) or "libta_b200" in msg or not any(
+                            k in msg.lower() for k in ("captur", "cudagraph", "cuda graph", "graph")):
+                        raise
                     self._graph_failed = True
-                    self._graph_error = str(e)
+                    self._graph_error = msg
+                    warnings.warn("transferattack_b200: CUDA-graph capture of the attack iteration was refused (%s); "
+                                  "launching the same kernels eagerly from now on" % msg.splitlines()[0][:200])
                     torch.cuda.synchronize(data.device)
             return self._loop_fused(data, label, delta)
 
@@ -192,13 +227,32 @@ class Attack(object):
             delta = self.update_delta(delta, data, momentum, self.alpha)
         return delta.detach()
 
+    def _tail(self, be, grad, momentum, m_out, delta, delta_out, data, xadv, scale_out, kmode, fold, addend=None, gbar_out=None):
+        """get_momentum + update_delta + the next model input as ONE ``ta_fused_tail`` launch. `kmode` None (or a shape the
+        in-kernel reduction does not serve): the scale comes from torch's own ``abs().mean`` op and the streaming form runs."""
+        norm = {}
+        if fold is not None:
+            norm = dict(mean=fold[2], std=fold[3], emit_normalized=True, grad_wrt_xn=fold[4])
+        with torch.no_grad():
+            if kmode is not None and be.fused_tail(grad, momentum, m_out, delta, delta_out, data, xadv, None, scale_out, self.decay,
+                                                   self.alpha, self.epsilon, img_min, img_max, mean_mode=kmode, addend=addend,
+                                                   gbar_out=gbar_out, **norm):
+                return
+            if fold is not None and fold[4]:
+                raise RuntimeError("ta_fused_tail refused a folded shape _fold_plan accepted")
+            g = grad if addend is None else be.add(grad, addend)
+            if not be.fused_tail(g, momentum, m_out, delta, delta_out, data, xadv, self._torch_abs_mean(g), scale_out, self.decay,
+                                 self.alpha, self.epsilon, img_min, img_max, gbar_out=gbar_out, **norm):
+                raise RuntimeError("ta_fused_tail refused the streaming form: %s" % _lib.last_error())
+
     def _loop_fused(self, data, label, delta):
         """attack.py:86-100 with get_momentum + update_delta + the next `data + delta` in one launch per
         iteration. delta / momentum / x_adv live in buffers this loop owns and are updated in place."""
         be = ops.backend()
         m_buf = torch.empty_like(data)
         scale_out = torch.empty(data.shape[0], device=data.device, dtype=torch.float32)
-        fold = self._fold_plan(data)
+        kmode = self._mean_kernel_mode(data)
+        fold = self._fold_plan(data, kmode)
         if fold is not None:
             pre, net, mean, std, defer = fold
             xadv = self._first_normalized(pre, data, delta)          # holds the NORMALISED model input from here on
@@ -213,19 +267,11 @@ class Attack(object):
                 logits = self.get_logits(self.transform(x, momentum=0 if momentum is None else momentum))
             loss = self.get_loss(logits, label)
             grad = self.get_grad(loss, delta)
-            scale = self._torch_abs_mean(grad) if self.mean_mode == 'torch' else None
-            ev = getattr(self, "_kernel_events", None)      # bench.py: CUDA events around the launch, on its stream
-            if ev is not None:
+            ev = getattr(self, "_kernel_events", None)      # bench.py: CUDA events around the WHOLE tail (everything between
+            if ev is not None:                               # autograd.grad and the next forward), on its stream
                 e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
                 e0.record()
-            with torch.no_grad():
-                if fold is not None:
-                    if not be.fused_update_linf_nf(grad, momentum, m_buf, delta, delta, data, xadv, scale, scale_out, self.decay,
-                                                   self.alpha, self.epsilon, img_min, img_max, mean, std, defer, _lib.TA_MEAN_EXACT):
-                        raise RuntimeError("ta_fused_update_linf_nf refused a shape _fold_plan accepted")
-                else:
-                    be.fused_update_linf(grad, momentum, m_buf, delta, delta, data, xadv, scale, scale_out,
-                                         self.decay, self.alpha, self.epsilon, img_min, img_max, _lib.TA_MEAN_EXACT)
+            self._tail(be, grad, momentum, m_buf, delta, delta, data, xadv, scale_out, kmode, fold)
             if ev is not None:
                 e1.record()
                 ev.append((e0, e1))
@@ -244,17 +290,8 @@ class Attack(object):
             logits = self.get_logits(self.transform(x, momentum=st["m"]))
         loss = self.get_loss(logits, st["label"])
         grad = self.get_grad(loss, st["delta"])
-        scale = self._torch_abs_mean(grad) if self.mean_mode == 'torch' else None
-        with torch.no_grad():
-            if fold is not None:
-                if not ops.backend().fused_update_linf_nf(grad, st["m"], st["m"], st["delta"], st["delta"], st["data"], st["xadv"],
-                                                          scale, st["scale_out"], self.decay, self.alpha, self.epsilon, img_min,
-                                                          img_max, mean, std, defer, _lib.TA_MEAN_EXACT):
-                    raise RuntimeError("ta_fused_update_linf_nf refused a shape _fold_plan accepted")
-            else:
-                ops.backend().fused_update_linf(grad, st["m"], st["m"], st["delta"], st["delta"], st["data"], st["xadv"], scale,
-                                                st["scale_out"], self.decay, self.alpha, self.epsilon, img_min, img_max,
-                                                _lib.TA_MEAN_EXACT)
+        self._tail(ops.backend(), grad, st["m"], st["m"], st["delta"], st["delta"], st["data"], st["xadv"], st["scale_out"],
+                   st["kmode"], fold)
 
     def _graph_reset(self, st, data, label, delta0):
         with torch.no_grad():
@@ -268,8 +305,9 @@ class Attack(object):
                 ops.backend().stage_add(st["data"], st["delta"], out=st["xadv"])
 
     def _graph_for(self, data, label, delta0):
-        fold = self._fold_plan(data)
-        key = (tuple(data.shape), str(data.device), tuple(label.shape), self.mean_mode, float(self.alpha), float(self.decay),
+        kmode = self._mean_kernel_mode(data)
+        fold = self._fold_plan(data, kmode)
+        key = (tuple(data.shape), str(data.device), tuple(label.shape), self.mean_mode, kmode, float(self.alpha), float(self.decay),
                float(self.epsilon), bool(self.targeted), id(self.model), fold is not None, bool(fold[4]) if fold else False)
         cache = self.__dict__.setdefault("_graphs", {})
         st = cache.get(key)
@@ -280,7 +318,7 @@ class Attack(object):
         st = {"data": torch.empty_like(data), "label": torch.empty_like(label),
               "delta": torch.zeros_like(data).requires_grad_(True), "m": torch.zeros_like(data),
               "xadv": torch.empty_like(data), "scale_out": torch.empty(data.shape[0], device=data.device, dtype=torch.float32),
-              "fold": fold}
+              "fold": fold, "kmode": kmode}
         self._graph_reset(st, data, label, delta0)
         cur = torch.cuda.current_stream(data.device)
         side = torch.cuda.Stream(device=data.device)
@@ -325,9 +363,14 @@ class Attack(object):
         return grad.abs().mean(dim=(1, 2, 3))
 
     def _abs_mean(self, grad):
-        if self.mean_mode == 'torch':
-            return self._torch_abs_mean(grad)
-        return ops.backend().abs_mean(grad, _lib.TA_MEAN_EXACT)
+        """mean|grad| per sample for the public hooks: one ``ta_abs_mean_per_sample`` launch in the attack's mean mode, or
+        torch's own op where the in-kernel replay does not apply"""
+        kmode = self._mean_kernel_mode(grad) if grad.dim() >= 2 else None
+        if kmode is not None:
+            out = ops.backend().abs_mean(grad, kmode)
+            if out is not None:
+                return out
+        return self._torch_abs_mean(grad)
 
     def get_momentum(self, grad, momentum, **kwargs):
         """attack.py:124-128: momentum * decay + grad / mean(|grad|) per sample. ``momentum`` may be the

@@ -1,0 +1,117 @@
+// aten_mean.cu — host policy of the TA_MEAN_TORCH reduction (see aten_mean.cuh) and the standalone kernel behind
+// ta_abs_mean_per_sample(mode = TA_MEAN_TORCH): mean|g| per sample with the bits of torch's CUDA
+// `grad.abs().mean(dim=(1,2,3))` (transferattack/attack.py:128), for the public get_momentum hook.
+#include "aten_mean.cuh"
+
+namespace ta {
+
+static int last_pow2(int64_t n) { int p = 1; while ((int64_t)p * 2 <= n) p *= 2; return p; }
+static int64_t div_up(int64_t a, int64_t b) { return (a + b - 1) / b; }
+
+// PyTorch ATen/native/cuda/Reduce.cuh setReduceConfig<float, float, vt0 = 4> for a [B, n] fp32 iterator reduced over the
+// stride-1 dimension with B >= 2 outputs (restated; validated against torch on the GPU, oracle/aten_reduce.py).
+bool aten_mean_policy(int B, int64_t n, int sm_count, int max_threads_per_sm, int* bw_, int* bh_, int* cpo_) {
+  const int kMax = 512;
+  if (B < 2 || n < 32 || sm_count <= 0 || max_threads_per_sm < kMax) return false;
+  const int d0p = n < kMax ? last_pow2(n) : kMax;
+  const int d1p = B < kMax ? last_pow2(B) : kMax;
+  int bw = d0p < 32 ? d0p : 32;
+  int bh = d1p < kMax / bw ? d1p : kMax / bw;
+  bw = d0p < kMax / bh ? d0p : kMax / bh;
+  if (bw * bh != kMax || bh > 16 || bw < 32) return false;      // the replay kernels assume ATen's full 512-thread block
+  int64_t step = bw;
+  int64_t vpt = div_up(n, step);
+  if (!(vpt >= (int64_t)bh * 16 || vpt >= 256)) return false;   // warp rows own separate outputs: not restated
+  step *= bh;
+  vpt = div_up(n, step);
+  const int64_t target = (int64_t)sm_count * (max_threads_per_sm / kMax);
+  int64_t cpo = 1;
+  if (vpt >= 256 && B <= target) {
+    const int64_t c1 = div_up(target, B), c2 = div_up(vpt, 16), c3 = div_up(vpt, 256);
+    const int64_t mn = c1 < c2 ? c1 : c2;
+    cpo = mn > c3 ? mn : c3;
+  }
+  if (cpo > 32) return false;                                      // final tree here: one partial per lane of one warp
+  *bw_ = bw; *bh_ = bh; *cpo_ = (int)cpo;
+  return true;
+}
+
+static int g_max_threads_per_sm[64];
+
+int aten_mean_plan(const char* who, int B, int64_t n, int cl, AtenMeanCfg* cfg) {
+  int dev = 0;
+  if (cudaGetDevice(&dev) != cudaSuccess || dev < 0 || dev >= 64) dev = 0;
+  if (g_max_threads_per_sm[dev] == 0) {
+    int v = 0;
+    if (cudaDeviceGetAttribute(&v, cudaDevAttrMaxThreadsPerMultiProcessor, dev) != cudaSuccess || v <= 0) v = 2048;
+    g_max_threads_per_sm[dev] = v;
+  }
+  int bw, bh, cpo;
+  if (!aten_mean_policy(B, n, sm_count(), g_max_threads_per_sm[dev], &bw, &bh, &cpo)) {
+    set_error("%s: TA_MEAN_TORCH does not cover B=%d n=%lld (outside the replayed ATen launch family)", who, B, (long long)n);
+    return TA_EUNSUPPORTED;
+  }
+  const int S = kAtenThreads * cpo;
+  if (cl < 1 || S % cl != 0 || (S / cl) % 4 != 0 || S / cl > kAtenMaxW) {
+    set_error("%s: TA_MEAN_TORCH: cluster %d does not divide the %d virtual threads into <= %d columns", who, cl, S, kAtenMaxW);
+    return TA_EUNSUPPORTED;
+  }
+  cfg->bw = bw; cfg->bh = bh; cfg->cpo = cpo; cfg->S = S; cfg->W = S / cl;
+  cfg->factor = (float)B / (float)((int64_t)B * n);
+  return TA_OK;
+}
+
+namespace {
+
+// grid = (cluster, B); dynamic smem = cpo*bw floats
+__global__ void __launch_bounds__(kAtenThreads) aten_abs_mean_kernel(const float* __restrict__ g, float* __restrict__ mean_out,
+                                                                     int64_t n, AtenMeanCfg c) {
+  extern __shared__ __align__(16) float s_tree[];
+  __shared__ float s_val[kAtenMaxW];
+  __shared__ float s_blk[32];
+  const float* gp = g + (int64_t)blockIdx.y * n;
+  const int64_t col0 = (int64_t)cluster_ctarank() * c.W;
+  for (int col = threadIdx.x; col < c.W; col += kAtenThreads) {
+    const int64_t e0 = col0 + col;
+    const int rows = e0 < n ? (int)((n - e0 + c.S - 1) / c.S) : 0;
+    const float* p = gp + e0;
+    const int64_t S = c.S;
+    ColAcc A;
+    aten_column_rows(A, 0, rows, [p, S](int j) { return fabsf(__ldg(p + (int64_t)j * S)); });
+    s_val[col] = aten_column_value(A);
+  }
+  cluster_sync_all();
+  const float mu = aten_tree_mean(c, s_val, s_tree, s_blk);
+  if (cluster_ctarank() == 0 && threadIdx.x == 0) mean_out[blockIdx.y] = mu;
+  cluster_sync_all();                         // s_val must outlive every remote read
+}
+
+}  // namespace
+
+int aten_abs_mean_launch(const float* g, float* mean_out, int B, int64_t n, cudaStream_t s) {
+  int cl = tune_get("reduce.cluster", 0);
+  if (cl <= 0) cl = 8;
+  AtenMeanCfg c;
+  int rc = aten_mean_plan("ta_abs_mean_per_sample", B, n, cl, &c);
+  while (rc != TA_OK && cl > 1) { cl >>= 1; rc = aten_mean_plan("ta_abs_mean_per_sample", B, n, cl, &c); }   // W must fit s_val
+  if (rc != TA_OK) return rc;
+  return launch_cluster("ta_abs_mean_per_sample[torch order]", aten_abs_mean_kernel, cl, B, kAtenThreads,
+                        sizeof(float) * (size_t)aten_mean_tree_floats(c), s, g, mean_out, n, c);
+}
+
+}  // namespace ta
+
+// ATen's launch policy for x.mean over the last dimension of a contiguous [B, n] fp32 tensor on a device with `sm_count` SMs and
+// `max_threads_per_sm` resident threads per SM (host-only: callable without a GPU; tests compare it with oracle/aten_reduce.py).
+extern "C" int ta_aten_mean_policy(int B, int64_t n, int sm_count, int max_threads_per_sm, int* block_w, int* block_h,
+                                   int* ctas_per_output) {
+  int bw = 0, bh = 0, cpo = 0;
+  if (!ta::aten_mean_policy(B, n, sm_count, max_threads_per_sm, &bw, &bh, &cpo)) {
+    ta::set_error("ta_aten_mean_policy: B=%d n=%lld is outside the replayed launch family", B, (long long)n);
+    return TA_EUNSUPPORTED;
+  }
+  if (block_w) *block_w = bw;
+  if (block_h) *block_h = bh;
+  if (ctas_per_output) *ctas_per_output = cpo;
+  return TA_OK;
+}

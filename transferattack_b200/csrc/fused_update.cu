@@ -1,28 +1,32 @@
-// fused_update.cu — ta_fused_update_linf: the whole tail of one attack iteration in ONE launch
+// fused_update.cu — the whole tail of one attack iteration in ONE launch
 //   (attack.py:124-128 get_momentum, :145-153 update_delta, and the next iteration's :88 `data + delta`).
 //
-//   mu_b   = mean|g_b|                               per sample b
-//   m'     = m * decay + g / mu_b
+//   g'     = g [/ std_c] [+ addend]                  (Normalize's adjoint when folded; VMI's `grad + variance`, vmifgsm.py:87)
+//   mu_b   = mean|g'_b|                              per sample b
+//   m'     = m * decay + g' / mu_b
 //   delta' = clamp(clamp(delta + alpha*sign(m'), -eps, eps), lo - x, hi - x)
-//   xadv   = x + delta'
+//   xadv   = x + delta'   [then (xadv - mean_c) / std_c when Normalize is folded]
+//   gbar   = g' / mu_b                               (optional output: EMI's bar_grad, emifgsm.py:97)
 //
 // HBM roofline: 16 B/elem read (g, m, delta, x) + 12 B/elem written (m', delta', xadv) = 28 B/elem
 // (24 without xadv). The per-sample mean needs all of g_b before the first output can be formed, so the
 // kernel runs one thread-block CLUSTER per sample:
-//   phase A: every CTA pulls its slice of g_b into shared memory with bulk-TMA (cp.async.bulk, chunked on
-//            mbarriers so the |g| reduction of chunk c overlaps the transfer of chunk c+1), reduces it in
-//            fp64, and the cluster combines the partials through DSMEM in rank order;
-//   phase B: streams m, delta, x with 128-bit loads, takes g from shared memory (so g crosses HBM once),
+//   phase A: every CTA pulls its part of g_b into shared memory with bulk-TMA (cp.async.bulk, row groups on mbarriers so the
+//            |g| reduction of group q overlaps the transfer of group q+1), reduces it, and the cluster combines through DSMEM:
+//              TA_MEAN_EXACT — fp64 partial sums, combined in rank order;
+//              TA_MEAN_TORCH — the fp32 summation tree of torch's own CUDA mean kernel (aten_mean.cuh), bit for bit;
+//   phase B: streams m, delta, x with 128-bit loads, takes g' from shared memory (so g crosses HBM once),
 //            and writes m', delta', xadv with 128-bit stores.
-// Variant 1 keeps nothing in shared memory and re-reads g in phase B (an L2 hit: the cluster touched it
-// microseconds earlier); it trades L2 bandwidth for occupancy. Both are exposed through ta_tune_set for the
-// sweep in bench/; the default is chosen from measurements.
+// Layout: the sample is viewed as rows of S elements; CTA r owns columns [r*W, (r+1)*W) of every row (TORCH: S = ATen's
+// 512*ctas_per_output virtual threads, so a column is one virtual thread's elements; EXACT: S chosen for 16 rows).
 //
-// With `scale` given (strict mode: torch computed mean|g| with the reference's own op) there is no phase A
-// and the work is a flat 128-bit streaming kernel.
-#include "common.cuh"
+// With `scale` given (torch computed mean|g| with the reference's own op) there is no phase A and the work is a flat 128-bit
+// streaming kernel.
+#include "aten_mean.cuh"
 
 using namespace ta;
+
+namespace ta { int aten_abs_mean_launch(const float* g, float* mean_out, int B, int64_t n, cudaStream_t s); }
 
 namespace {
 
@@ -31,44 +35,41 @@ namespace {
 // the one w.r.t. that normalised input, turned into the gradient w.r.t. delta by Normalize's adjoint g / std_c first.
 struct NormFold {
   float mean[4], std[4];
-  int64_t plane_vec;      // vectors (of the launch's width) per channel plane
+  int64_t plane_vec;      // 128-bit vectors per channel plane
   int C, fwd, bwd;
 };
 
 struct FusedParams {
-  const float* g; const float* m; float* m_out; const float* delta; float* delta_out; const float* data;
-  float* xadv; const float* scale; float* scale_out;
+  const float* g; const float* addend; const float* m; float* m_out; const float* delta; float* delta_out; const float* data;
+  float* xadv; float* gbar; const float* scale; float* scale_out;
   float decay, alpha, eps, lo, hi;
   int64_t n;
   NormFold nf;
 };
 
-// channel of vector j (index inside one sample); C <= 4
+// channel of vector j (128-bit vector index inside one sample, j < C * plane_vec): three compares, no table
 __device__ __forceinline__ int nf_channel(const NormFold& nf, int64_t j) {
-  int c = 0;
-#pragma unroll
-  for (int k = 1; k < 4; ++k) c += (k < nf.C && j >= k * nf.plane_vec) ? 1 : 0;
-  return c;
+  return (j >= nf.plane_vec ? 1 : 0) + (j >= 2 * nf.plane_vec ? 1 : 0) + (j >= 3 * nf.plane_vec ? 1 : 0);
 }
+__device__ __forceinline__ float pick4(const float (&a)[4], int c) { return c == 0 ? a[0] : (c == 1 ? a[1] : (c == 2 ? a[2] : a[3])); }
 
 // one element of the fused tail; all roundings as in the reference's eager ops
 __device__ __forceinline__ void fused_elem(float g, float m, bool has_m, float d, float x, float mu, const FusedParams& p,
-                                           float& m_new, float& d_new, float& xa) {
+                                           float& m_new, float& d_new, float& xa, float& gb) {
+  gb = div_rn(g, mu);
   const float t1 = has_m ? mul_rn(m, p.decay) : 0.0f;
-  m_new = add_rn(t1, div_rn(g, mu));
+  m_new = add_rn(t1, gb);
   d_new = project_linf(d, mul_rn(p.alpha, sign_t(m_new)), x, p.eps, p.lo, p.hi);
   xa = add_rn(x, d_new);
 }
-template <bool NF>
-__device__ __forceinline__ void fused_elem_nf(float g, float m, bool has_m, float d, float x, float mu, const FusedParams& p,
-                                              float mean_c, float std_c, float& m_new, float& d_new, float& xa) {
-  if (NF && p.nf.bwd) g = div_rn(g, std_c);
-  fused_elem(g, m, has_m, d, x, mu, p, m_new, d_new, xa);
-  if (NF && p.nf.fwd) xa = div_rn(sub_rn(xa, mean_c), std_c);
+__device__ __forceinline__ void fused_elem(float g, float m, bool has_m, float d, float x, float mu, const FusedParams& p,
+                                           float& m_new, float& d_new, float& xa) {
+  float gb;
+  fused_elem(g, m, has_m, d, x, mu, p, m_new, d_new, xa, gb);
 }
 
 // ---- strict / fallback path: scale[b] given, flat streaming ---------------------------------------------------
-template <int V> struct FusedIn { Vec<V> g, x, d, m; float mu; };
+template <int V> struct FusedIn { Vec<V> g, a, x, d, m; float mu; };
 template <bool NF>
 struct FusedStreamOpT {
   FusedParams p; int64_t nvec;     // vectors per sample
@@ -77,146 +78,235 @@ struct FusedStreamOpT {
     const int64_t i = (int64_t)row * nvec + j;
     r.mu = __ldg(p.scale + row);
     r.g = ldv<V>(p.g, i); r.x = ldv<V>(p.data, i); r.d = ldv_rw<V>(p.delta, i);
+    if (p.addend) r.a = ldv<V>(p.addend, i);
     if (p.m) r.m = ldv_rw<V>(p.m, i);
     return r;
   }
   template <int V> __device__ __forceinline__ void apply(int row, int64_t j, const FusedIn<V>& r) const {
     const int64_t i = (int64_t)row * nvec + j;
-    Vec<V> mo, dn, xa;
+    Vec<V> mo, dn, xa, gb;
     float mean_c = 0.0f, std_c = 1.0f;
-    if (NF) { const int c = nf_channel(p.nf, j); mean_c = p.nf.mean[c]; std_c = p.nf.std[c]; }
+    if (NF) { const int c = nf_channel(p.nf, j); mean_c = pick4(p.nf.mean, c); std_c = pick4(p.nf.std, c); }
 #pragma unroll
-    for (int k = 0; k < V; ++k)
-      fused_elem_nf<NF>(r.g.v[k], p.m ? r.m.v[k] : 0.0f, p.m != nullptr, r.d.v[k], r.x.v[k], r.mu, p, mean_c, std_c, mo.v[k],
-                        dn.v[k], xa.v[k]);
+    for (int k = 0; k < V; ++k) {
+      float g = r.g.v[k];
+      if (NF && p.nf.bwd) g = div_rn(g, std_c);
+      if (p.addend) g = add_rn(g, r.a.v[k]);
+      fused_elem(g, p.m ? r.m.v[k] : 0.0f, p.m != nullptr, r.d.v[k], r.x.v[k], r.mu, p, mo.v[k], dn.v[k], xa.v[k], gb.v[k]);
+      if (NF && p.nf.fwd) xa.v[k] = div_rn(sub_rn(xa.v[k], mean_c), std_c);
+    }
     stv<V>(p.m_out, i, mo);
     stv<V>(p.delta_out, i, dn);
     if (p.xadv) stv<V>(p.xadv, i, xa);
+    if (p.gbar) stv<V>(p.gbar, i, gb);
   }
 };
 using FusedStreamOp = FusedStreamOpT<false>;
 
 // ---- cluster kernel ----------------------------------------------------------------------------------------------
-constexpr int kChunks = 4;
+constexpr int kChunks = 4;             // mbarrier-tracked row groups of the g transfer
+constexpr int kThreads = kAtenThreads; // 512: ATen's block size (the TORCH tree maps one thread per block position)
 
-// STAGE = true : g slice resident in shared memory (bulk-TMA), read from HBM once
-// STAGE = false: g re-read through L2 in phase B
-__device__ __forceinline__ double abs4(const float4& v) {
-  double a = (double)fabsf(v.x); a += (double)fabsf(v.y); a += (double)fabsf(v.z); a += (double)fabsf(v.w); return a;
-}
-template <int THREADS, int U, bool STAGE, bool NF>
-__global__ void __launch_bounds__(THREADS) fused_cluster_kernel(FusedParams p) {
+struct TailLayout {
+  int S4, W4;              // 128-bit vectors per row of the sample / per row of one CTA
+  int rows_per_group;      // rows per mbarrier group (multiple of 4)
+  unsigned long long w4_magic;   // floor(2^32 / W4) + 1: i / W4 == (i * magic) >> 32 for the i that occur
+};
+
+__device__ __forceinline__ float4 div4(float4 v, float s) { v.x = div_rn(v.x, s); v.y = div_rn(v.y, s); v.z = div_rn(v.z, s); v.w = div_rn(v.w, s); return v; }
+__device__ __forceinline__ float4 add4(float4 a, const float4& b) { a.x = add_rn(a.x, b.x); a.y = add_rn(a.y, b.y); a.z = add_rn(a.z, b.z); a.w = add_rn(a.w, b.w); return a; }
+
+// MEAN: 0 = TA_MEAN_EXACT, 1 = TA_MEAN_TORCH.  grid = (cluster, B), 512 threads.
+// dynamic smem: [g' part of this CTA: rows x W4 float4][TORCH: cpo*bw floats for the tree]
+template <int U, int MEAN, bool NF>
+__global__ void __launch_bounds__(kThreads, (U <= 2 ? 2 : 1)) fused_cluster_kernel(FusedParams p, TailLayout L, AtenMeanCfg c, int tree_off4) {
   extern __shared__ __align__(128) unsigned char smem_raw[];
   __shared__ double s_scratch[32];
   __shared__ double s_part;
+  __shared__ float s_val[MEAN == 1 ? kAtenMaxW : 1];
+  __shared__ float s_blk[32];
   __shared__ __align__(8) uint64_t s_bar[kChunks];
 
   const int tid = threadIdx.x;
   const int64_t nvec = p.n >> 2;
-  const int64_t nr = cluster_nctarank(), rank = cluster_ctarank();
-  const int64_t per = (nvec + nr - 1) / nr;
-  const int64_t begin = rank * per < nvec ? rank * per : nvec;
-  const int64_t end = (rank + 1) * per < nvec ? (rank + 1) * per : nvec;
-  const int64_t cnt = end - begin;                                   // 128-bit vectors in this CTA's slice
-  const int64_t off = (int64_t)blockIdx.y * nvec + begin;            // slice start, in vectors, in the batch
-  const float4* g4 = reinterpret_cast<const float4*>(p.g) + off;
+  const int rank = (int)cluster_ctarank();
+  const int64_t col0 = (int64_t)rank * L.W4;                         // first vector column of this CTA
+  // row j of this CTA = vectors [j*S4 + col0, +W4) of the sample, clipped to nvec: Jf full rows, then `last` vectors
+  int Jf = 0;
+  if (nvec >= col0 + L.W4) Jf = (int)((nvec - col0 - L.W4) / L.S4) + 1;
+  const int64_t rem = nvec - ((int64_t)Jf * L.S4 + col0);
+  const int last = rem > 0 ? (int)rem : 0;                            // < W4 by construction of Jf
+  const int Jtot = Jf + (last > 0 ? 1 : 0);
+  const int cnt = Jf * L.W4 + last;                                   // vectors of this CTA, contiguous in shared memory
+  const int RG = L.rows_per_group;
+  const int64_t sbase = (int64_t)blockIdx.y * nvec;                   // sample start, in vectors
+  const float4* g4 = reinterpret_cast<const float4*>(p.g) + sbase;
   float4* sg4 = reinterpret_cast<float4*>(smem_raw);
-  const int64_t per_chunk = (cnt + kChunks - 1) / kChunks;
+  const bool fill = p.addend != nullptr;                              // g' built by the threads instead of bulk-TMA
+  const bool nfb = NF && p.nf.bwd;
 
-  // ---------------- phase A: sum |g| over the slice ----------------
-  double acc = 0.0;
-  if (STAGE) {
+  // ---------------- phase A.1: g' of this CTA into shared memory ----------------
+  if (!fill) {
     if (tid == 0) {
 #pragma unroll
-      for (int c = 0; c < kChunks; ++c) mbar_init(&s_bar[c], 1);
+      for (int q = 0; q < kChunks; ++q) mbar_init(&s_bar[q], 1);
       mbar_fence_init();
     }
     __syncthreads();
-    if (tid == 0) {
+    if (tid < 32) {
+      if (tid == 0) {
 #pragma unroll
-      for (int c = 0; c < kChunks; ++c) {
-        const int64_t c0 = c * per_chunk, c1 = (c0 + per_chunk < cnt) ? c0 + per_chunk : cnt;
-        if (c1 > c0) {
-          const uint32_t bytes = (uint32_t)((c1 - c0) * 16);
-          mbar_expect_tx(&s_bar[c], bytes);
-          tma_bulk_g2s(sg4 + c0, g4 + c0, bytes, &s_bar[c]);
+        for (int q = 0; q < kChunks; ++q) {
+          const int a = q * RG, b = (a + RG < Jtot) ? a + RG : Jtot;
+          if (b > a) {
+            const int full = ((b < Jf ? b : Jf) - a) > 0 ? (b < Jf ? b : Jf) - a : 0;
+            const int part = (last > 0 && Jf >= a && Jf < b) ? last : 0;
+            mbar_expect_tx(&s_bar[q], (uint32_t)(full * L.W4 + part) * 16u);
+          }
         }
       }
+      __syncwarp();
+      for (int j = tid; j < Jtot; j += 32) {
+        const int w = j < Jf ? L.W4 : last;
+        tma_bulk_g2s(sg4 + (int64_t)j * L.W4, g4 + (int64_t)j * L.S4 + col0, (uint32_t)w * 16u, &s_bar[j / RG]);
+      }
     }
+  } else {
+    const float4* a4 = reinterpret_cast<const float4*>(p.addend) + sbase;
+    for (int i = tid; i < cnt; i += kThreads) {
+      const int row = (int)(((unsigned long long)i * L.w4_magic) >> 32);
+      const int64_t gi = (int64_t)row * L.S4 + col0 + (i - row * L.W4);
+      float4 v = __ldg(g4 + gi);
+      if (nfb) v = div4(v, pick4(p.nf.std, nf_channel(p.nf, gi)));
+      sg4[i] = add4(v, __ldg(a4 + gi));
+    }
+    __syncthreads();
+  }
+  const bool nfb_pass = nfb && !fill;                                 // Normalize's adjoint still to be applied (in place) below
+
+  // ---------------- phase A.2: mean|g'| ----------------
+  float mu;
+  if (MEAN == 1) {
+    float* sg = reinterpret_cast<float*>(smem_raw);
+    const int W = L.W4 * 4;
+    for (int col = tid; col < W; col += kThreads) {
+      const int rows = Jf + (col < 4 * last ? 1 : 0);
+      float* sp = sg + col;
+      const int64_t gi0 = col0 + (col >> 2);
+      ColAcc A;
 #pragma unroll
-    for (int c = 0; c < kChunks; ++c) {
-      const int64_t c0 = c * per_chunk, c1 = (c0 + per_chunk < cnt) ? c0 + per_chunk : cnt;
-      if (c1 > c0) {
-        mbar_wait(&s_bar[c], 0);
-        for (int64_t i = c0 + tid; i < c1; i += THREADS) {
+      for (int q = 0; q < kChunks; ++q) {
+        const int a = q * RG, b = (a + RG < rows) ? a + RG : rows;
+        if (b > a) {
+          if (!fill) mbar_wait(&s_bar[q], 0);
+          if (nfb_pass)
+            aten_column_rows(A, a, b, [&](int j) {
+              const float v = div_rn(sp[j * W], pick4(p.nf.std, nf_channel(p.nf, (int64_t)j * L.S4 + gi0)));
+              sp[j * W] = v;
+              return fabsf(v);
+            });
+          else
+            aten_column_rows(A, a, b, [sp, W](int j) { return fabsf(sp[j * W]); });
+        }
+      }
+      s_val[col] = aten_column_value(A);
+    }
+    if (!fill) {                          // every thread reads rows of every group in phase B
+#pragma unroll
+      for (int q = 0; q < kChunks; ++q) if (q * RG < Jtot) mbar_wait(&s_bar[q], 0);
+    }
+    cluster_sync_all();
+    mu = aten_tree_mean(c, s_val, reinterpret_cast<float*>(sg4 + tree_off4), s_blk);
+    cluster_arrive();                     // "done reading remote shared memory"; matched by cluster_wait() at exit
+  } else {
+    double acc = 0.0;
+#pragma unroll
+    for (int q = 0; q < kChunks; ++q) {
+      const int a = q * RG, b = (a + RG < Jtot) ? a + RG : Jtot;
+      if (b > a) {
+        if (!fill) mbar_wait(&s_bar[q], 0);
+        const int i1 = (b * L.W4 < cnt) ? b * L.W4 : cnt;
+        for (int i = a * L.W4 + tid; i < i1; i += kThreads) {
           float4 v = sg4[i];
-          if (NF && p.nf.bwd) { const float sc = p.nf.std[nf_channel(p.nf, begin + i)]; v.x = div_rn(v.x, sc); v.y = div_rn(v.y, sc); v.z = div_rn(v.z, sc); v.w = div_rn(v.w, sc); }
+          if (nfb_pass) {
+            const int row = (int)(((unsigned long long)i * L.w4_magic) >> 32);
+            v = div4(v, pick4(p.nf.std, nf_channel(p.nf, (int64_t)row * L.S4 + col0 + (i - row * L.W4))));
+            sg4[i] = v;
+          }
           acc += (double)fabsf(v.x); acc += (double)fabsf(v.y); acc += (double)fabsf(v.z); acc += (double)fabsf(v.w);
         }
       }
     }
-  } else {
-    for (int64_t i = tid; i < cnt; i += THREADS) {
-      float4 v = __ldg(g4 + i);
-      if (NF && p.nf.bwd) { const float sc = p.nf.std[nf_channel(p.nf, begin + i)]; v.x = div_rn(v.x, sc); v.y = div_rn(v.y, sc); v.z = div_rn(v.z, sc); v.w = div_rn(v.w, sc); }
-      acc += (double)fabsf(v.x); acc += (double)fabsf(v.y); acc += (double)fabsf(v.z); acc += (double)fabsf(v.w);
-    }
+    const double part = block_sum(acc, s_scratch);
+    if (tid == 0) s_part = part;
+    cluster_sync_all();
+    double tot = 0.0;
+    const uint32_t nr = cluster_nctarank();
+    for (uint32_t r = 0; r < nr; ++r) tot += dsmem_ld_f64(&s_part, r);
+    cluster_arrive();
+    mu = (float)(tot / (double)p.n);
   }
-  const double part = block_sum(acc, s_scratch);
-  if (tid == 0) s_part = part;
-  cluster_sync_all();
-  double tot = 0.0;
-  for (uint32_t r = 0; r < (uint32_t)nr; ++r) tot += dsmem_ld_f64(&s_part, r);
-  cluster_arrive();                       // "done reading remote shared memory"; matched by cluster_wait() at exit
-  const float mu = (float)(tot / (double)p.n);
   if (rank == 0 && tid == 0 && p.scale_out) p.scale_out[blockIdx.y] = mu;
+  if (nfb_pass) __syncthreads();          // in-place g / std written by other threads of this CTA (TORCH: other columns)
 
   // ---------------- phase B: stream the update ----------------
   const bool has_m = p.m != nullptr;
-  const float4* m4 = reinterpret_cast<const float4*>(p.m) + off;
-  const float4* d4 = reinterpret_cast<const float4*>(p.delta) + off;
-  const float4* x4 = reinterpret_cast<const float4*>(p.data) + off;
-  float4* mo4 = reinterpret_cast<float4*>(p.m_out) + off;
-  float4* do4 = reinterpret_cast<float4*>(p.delta_out) + off;
-  float4* xa4 = reinterpret_cast<float4*>(p.xadv) + off;
-  for (int64_t i0 = tid; i0 < cnt; i0 += (int64_t)THREADS * U) {
-    float4 gv[U], mv[U], dv[U], xv[U];
+  const float4* m4 = reinterpret_cast<const float4*>(p.m) + sbase;
+  const float4* d4 = reinterpret_cast<const float4*>(p.delta) + sbase;
+  const float4* x4 = reinterpret_cast<const float4*>(p.data) + sbase;
+  float4* mo4 = reinterpret_cast<float4*>(p.m_out) + sbase;
+  float4* do4 = reinterpret_cast<float4*>(p.delta_out) + sbase;
+  float4* xa4 = reinterpret_cast<float4*>(p.xadv) + sbase;
+  float4* gb4 = reinterpret_cast<float4*>(p.gbar) + sbase;
+  for (int i0 = tid; i0 < cnt; i0 += kThreads * U) {
+    float4 mv[U], dv[U], xv[U];
+    int gi[U];
 #pragma unroll
     for (int u = 0; u < U; ++u) {
-      const int64_t i = i0 + (int64_t)u * THREADS;
+      const int i = i0 + u * kThreads;
       if (i < cnt) {
-        gv[u] = STAGE ? sg4[i] : __ldg(g4 + i);
-        xv[u] = __ldg(x4 + i);
-        dv[u] = d4[i];
-        mv[u] = has_m ? m4[i] : make_float4(0.f, 0.f, 0.f, 0.f);
+        const int row = (int)(((unsigned long long)i * L.w4_magic) >> 32);
+        gi[u] = row * L.S4 + (int)col0 + (i - row * L.W4);
+        xv[u] = __ldg(x4 + gi[u]);
+        dv[u] = d4[gi[u]];
+        mv[u] = has_m ? m4[gi[u]] : make_float4(0.f, 0.f, 0.f, 0.f);
       }
     }
 #pragma unroll
     for (int u = 0; u < U; ++u) {
-      const int64_t i = i0 + (int64_t)u * THREADS;
+      const int i = i0 + u * kThreads;
       if (i < cnt) {
-        float4 mo, dn, xa;
-        float mean_c = 0.0f, std_c = 1.0f;
-        if (NF) { const int c = nf_channel(p.nf, begin + i); mean_c = p.nf.mean[c]; std_c = p.nf.std[c]; }
-        fused_elem_nf<NF>(gv[u].x, mv[u].x, has_m, dv[u].x, xv[u].x, mu, p, mean_c, std_c, mo.x, dn.x, xa.x);
-        fused_elem_nf<NF>(gv[u].y, mv[u].y, has_m, dv[u].y, xv[u].y, mu, p, mean_c, std_c, mo.y, dn.y, xa.y);
-        fused_elem_nf<NF>(gv[u].z, mv[u].z, has_m, dv[u].z, xv[u].z, mu, p, mean_c, std_c, mo.z, dn.z, xa.z);
-        fused_elem_nf<NF>(gv[u].w, mv[u].w, has_m, dv[u].w, xv[u].w, mu, p, mean_c, std_c, mo.w, dn.w, xa.w);
-        mo4[i] = mo;
-        do4[i] = dn;
-        if (p.xadv) xa4[i] = xa;
+        const float4 gv = sg4[i];
+        float4 mo, dn, xa, gb;
+        fused_elem(gv.x, mv[u].x, has_m, dv[u].x, xv[u].x, mu, p, mo.x, dn.x, xa.x, gb.x);
+        fused_elem(gv.y, mv[u].y, has_m, dv[u].y, xv[u].y, mu, p, mo.y, dn.y, xa.y, gb.y);
+        fused_elem(gv.z, mv[u].z, has_m, dv[u].z, xv[u].z, mu, p, mo.z, dn.z, xa.z, gb.z);
+        fused_elem(gv.w, mv[u].w, has_m, dv[u].w, xv[u].w, mu, p, mo.w, dn.w, xa.w, gb.w);
+        if (NF && p.nf.fwd) {
+          const int ch = nf_channel(p.nf, gi[u]);
+          const float mean_c = pick4(p.nf.mean, ch), std_c = pick4(p.nf.std, ch);
+          xa.x = div_rn(sub_rn(xa.x, mean_c), std_c); xa.y = div_rn(sub_rn(xa.y, mean_c), std_c);
+          xa.z = div_rn(sub_rn(xa.z, mean_c), std_c); xa.w = div_rn(sub_rn(xa.w, mean_c), std_c);
+        }
+        mo4[gi[u]] = mo;
+        do4[gi[u]] = dn;
+        if (p.xadv) xa4[gi[u]] = xa;
+        if (p.gbar) gb4[gi[u]] = gb;
       }
     }
   }
-  cluster_wait();                         // keep s_part alive until every rank has read it
+  cluster_wait();                         // keep s_part / s_val alive until every rank has read them
 }
 
-template <int THREADS, int U, bool STAGE, bool NF = false>
-int launch_fused(const FusedParams& p, int B, int cl, size_t smem, cudaStream_t s) {
-  auto k = fused_cluster_kernel<THREADS, U, STAGE, NF>;
+constexpr size_t kMaxStageBytes = 200 * 1024;   // per-CTA dynamic shared memory bound (227 KB/SM minus static + system use)
+
+template <int U, int MEAN, bool NF>
+int launch_fused(const char* who, const FusedParams& p, const TailLayout& L, const AtenMeanCfg& c, int tree_off4, int B, int cl,
+                 size_t smem, cudaStream_t s) {
+  auto k = fused_cluster_kernel<U, MEAN, NF>;
   static SmemOptIn optin = {};
   static bool nonportable[64] = {};
-  int rc = ensure_dyn_smem("ta_fused_update_linf", k, smem, optin);
+  int rc = ensure_dyn_smem(who, k, smem, optin);
   if (rc != TA_OK) return rc;
   if (cl > 8) {
     int dev = 0;
@@ -224,16 +314,15 @@ int launch_fused(const FusedParams& p, int B, int cl, size_t smem, cudaStream_t 
     if (!nonportable[dev]) {
       const cudaError_t e = cudaFuncSetAttribute(k, cudaFuncAttributeNonPortableClusterSizeAllowed, 1);
       if (e != cudaSuccess) {
-        set_error("ta_fused_update_linf: cluster size %d not allowed: %s", cl, cudaGetErrorString(e));
+        set_error("%s: cluster size %d not allowed: %s", who, cl, cudaGetErrorString(e));
         cudaGetLastError();
         return TA_ECUDA;
       }
       nonportable[dev] = true;
     }
   }
-  return launch_cluster("ta_fused_update_linf", k, cl, B, THREADS, smem, s, p);
+  return launch_cluster(who, k, cl, B, kThreads, smem, s, p, L, c, tree_off4);
 }
-
 
 // ---- ENS, one surrogate per GPU: reduce-scatter + fused update + all-gather in ONE kernel over NVLink peer memory ------------
 // Rank r owns the samples [b0, b0 + Bown). For those samples the kernel
@@ -341,47 +430,48 @@ __global__ void __launch_bounds__(THREADS) fused_p2p_kernel(FusedParams p, PeerP
   cluster_wait();
 }
 
-constexpr size_t kMaxStageBytes = 200 * 1024;   // per-CTA g slice bound (227 KB/SM minus static + system use)
-
 }  // namespace
 
 namespace {
 
-int fused_update_impl(const float* g, const float* m, float* m_out, const float* delta, float* delta_out, const float* data,
-                      float* xadv_out, const float* scale, float* scale_out, int mean_mode, float decay, float alpha, float eps,
-                      float lo, float hi, int B, int64_t n, const NormFold* nf, ta_stream_t stream) {
-  const char* who = nf ? "ta_fused_update_linf_nf" : "ta_fused_update_linf";
-  TA_REQUIRE(g && m_out && delta && delta_out && data && B > 0 && n > 0, "%s: null pointer or empty shape (B=%d n=%lld)", who, B,
+int fused_tail_impl(const ta_fused_tail_args& a, const NormFold* nf, ta_stream_t stream) {
+  const char* who = nf ? "ta_fused_tail[nf]" : "ta_fused_tail";
+  const int B = a.B; const int64_t n = a.n;
+  TA_REQUIRE(a.g && a.m_out && a.delta && a.delta_out && a.data && B > 0 && n > 0, "%s: null pointer or empty shape (B=%d n=%lld)", who, B,
              (long long)n);
   TA_REQUIRE(B <= 65535, "%s: B=%d exceeds 65535", who, B);
   cudaStream_t s = (cudaStream_t)stream;
-  FusedParams p{g, m, m_out, delta, delta_out, data, xadv_out, scale, scale_out, decay, alpha, eps, lo, hi, n};
-  const bool v4 = (n % 4 == 0) && aligned16(g) && aligned16(m) && aligned16(m_out) && aligned16(delta) &&
-                  aligned16(delta_out) && aligned16(data) && aligned16(xadv_out);
+  FusedParams p = {};
+  p.g = a.g; p.addend = a.addend; p.m = a.m; p.m_out = a.m_out; p.delta = a.delta; p.delta_out = a.delta_out; p.data = a.data;
+  p.xadv = a.xadv_out; p.gbar = a.gbar_out; p.scale = a.scale; p.scale_out = a.scale_out;
+  p.decay = a.decay; p.alpha = a.alpha; p.eps = a.eps; p.lo = a.lo; p.hi = a.hi; p.n = n;
+  const bool v4 = (n % 4 == 0) && aligned16(a.g) && aligned16(a.addend) && aligned16(a.m) && aligned16(a.m_out) && aligned16(a.delta) &&
+                  aligned16(a.delta_out) && aligned16(a.data) && aligned16(a.xadv_out) && aligned16(a.gbar_out);
   if (nf) {
     if (!v4) { set_error("%s: needs n %% 4 == 0 and 16-byte aligned buffers", who); return TA_EUNSUPPORTED; }
     p.nf = *nf;          // plane_vec already in 128-bit vectors
   }
 
-  if (scale) {   // strict: no reduction, flat streaming
-    if (scale_out && scale_out != scale) {
-      const cudaError_t e = cudaMemcpyAsync(scale_out, scale, sizeof(float) * (size_t)B, cudaMemcpyDeviceToDevice, s);
+  if (a.scale) {   // scale given: no reduction, flat streaming
+    if (a.scale_out && a.scale_out != a.scale) {
+      const cudaError_t e = cudaMemcpyAsync(a.scale_out, a.scale, sizeof(float) * (size_t)B, cudaMemcpyDeviceToDevice, s);
       if (e != cudaSuccess) { set_error("%s: scale copy failed: %s", who, cudaGetErrorString(e)); return TA_ECUDA; }
     }
-    if (nf) return launch_ew_rows2<1>("ta_fused_update_linf_nf[stream]", B, n, true, FusedStreamOpT<true>{p, n / 4}, s, 0);
+    if (nf) return launch_ew_rows2<1>("ta_fused_tail[stream,nf]", B, n, true, FusedStreamOpT<true>{p, n / 4}, s, 0);
     const FusedStreamOp op{p, v4 ? n / 4 : n};
     const int cap = tune_get("stream.cap", 0);          // resident CTAs per SM (0 = one batch per thread, no loop)
     switch (tune_get("stream.unroll", 1)) {
-      case 4: return launch_ew_rows2<4>("ta_fused_update_linf[stream]", B, n, v4, op, s, cap);
-      case 2: return launch_ew_rows2<2>("ta_fused_update_linf[stream]", B, n, v4, op, s, cap);
-      default: return launch_ew_rows2<1>("ta_fused_update_linf[stream]", B, n, v4, op, s, cap);
+      case 4: return launch_ew_rows2<4>("ta_fused_tail[stream]", B, n, v4, op, s, cap);
+      case 2: return launch_ew_rows2<2>("ta_fused_tail[stream]", B, n, v4, op, s, cap);
+      default: return launch_ew_rows2<1>("ta_fused_tail[stream]", B, n, v4, op, s, cap);
     }
   }
 
-  if (mean_mode != TA_MEAN_EXACT) {
-    set_error("%s: mean_mode %d not available in this build", who, mean_mode);
+  if (a.mean_mode != TA_MEAN_EXACT && a.mean_mode != TA_MEAN_TORCH) {
+    set_error("%s: mean_mode %d not available in this build", who, a.mean_mode);
     return TA_EUNSUPPORTED;
   }
+  const bool torch_order = a.mean_mode == TA_MEAN_TORCH;
 
   // cluster geometry
   int cl = tune_get("fused.cluster", 0);
@@ -389,49 +479,100 @@ int fused_update_impl(const float* g, const float* m, float* m_out, const float*
     cl = 1;
     while (cl < 8 && n / (cl * 2) >= 2048) cl *= 2;          // >= 2K elements per CTA before splitting further
   }
-  const int variant = tune_get("fused.variant", 0);          // 0 = g staged in smem by bulk-TMA, 1 = re-read via L2
-  const int threads = tune_get("fused.threads", 512);
   const int unroll = tune_get("fused.unroll", 2);
   const int64_t nvec = n / 4;
-  const size_t slice_bytes = (size_t)((nvec + cl - 1) / cl) * 16;
-
-  if (!v4) {
-    // generic fallback: exact mean into scale_out, then the streaming kernel (two launches)
-    TA_REQUIRE(scale_out, "ta_fused_update_linf: n %% 4 != 0 or misaligned pointers need scale_out as scratch");
-    const int rc = ta_abs_mean_per_sample(g, scale_out, B, n, TA_MEAN_EXACT, nullptr, stream);
-    if (rc != TA_OK) return rc;
-    p.scale = scale_out;
-    return launch_ew_rows2<2>("ta_fused_update_linf[stream]", B, n, false, FusedStreamOp{p, n}, s);
+  AtenMeanCfg c = {};
+  TailLayout L = {};
+  size_t smem = 0;
+  int tree_off4 = 0;
+  bool staged = v4 && nvec < (int64_t)1 << 28;
+  if (staged) {
+    int64_t rows;
+    if (torch_order) {
+      const int rc = aten_mean_plan(who, B, n, cl, &c);
+      if (rc != TA_OK) return rc;
+      L.S4 = c.S / 4; L.W4 = c.W / 4;
+    } else {
+      int64_t w4 = (nvec + (int64_t)cl * 16 - 1) / ((int64_t)cl * 16);     // ~16 rows: 4 transfer groups of 4 rows
+      if (w4 < 1) w4 = 1;
+      L.W4 = (int)w4; L.S4 = (int)(w4 * cl);
+    }
+    rows = (nvec + L.S4 - 1) / L.S4;
+    L.rows_per_group = (int)(4 * ((rows + 15) / 16));
+    L.w4_magic = (1ull << 32) / (unsigned long long)L.W4 + 1ull;
+    const size_t slice = (size_t)rows * (size_t)L.W4 * 16;
+    tree_off4 = (int)(rows * L.W4);
+    smem = slice + (torch_order ? sizeof(float) * (size_t)aten_mean_tree_floats(c) : 0);
+    if (smem > kMaxStageBytes || rows > 0x3fffffff / (L.W4 > 0 ? L.W4 : 1)) staged = false;
   }
 
-  const bool stage = (variant == 0) && slice_bytes <= kMaxStageBytes;
-  const size_t smem = stage ? slice_bytes : 0;
-  if (nf)   // one tuning point (the default) for the folded form
-    return stage ? launch_fused<512, 2, true, true>(p, B, cl, smem, s) : launch_fused<512, 2, false, true>(p, B, cl, 0, s);
-#define TA_FUSED_CASE(T, U_)                                                        \
-  if (threads == T && unroll == U_)                                                 \
-    return stage ? launch_fused<T, U_, true>(p, B, cl, smem, s) : launch_fused<T, U_, false>(p, B, cl, 0, s);
-  TA_FUSED_CASE(256, 1)
-  TA_FUSED_CASE(256, 2)
-  TA_FUSED_CASE(256, 4)
-  TA_FUSED_CASE(512, 1)
-  TA_FUSED_CASE(512, 2)
-  TA_FUSED_CASE(512, 4)
-  TA_FUSED_CASE(1024, 1)
-  TA_FUSED_CASE(1024, 2)
+  if (!staged) {
+    // generic fallback (odd n, misaligned pointers, sample too large for the cluster's shared memory):
+    // the mean into scale_out, then the streaming kernel (two launches)
+    if (a.addend) { set_error("%s: the addend form needs n %% 4 == 0, aligned buffers and a sample that fits the cluster", who); return TA_EUNSUPPORTED; }
+    if (nf && nf->bwd) { set_error("%s: grad_wrt_xn needs the staged form", who); return TA_EUNSUPPORTED; }
+    TA_REQUIRE(a.scale_out, "%s: n %% 4 != 0, misaligned pointers or oversized samples need scale_out as scratch", who);
+    const int rc = ta_abs_mean_per_sample(a.g, a.scale_out, B, n, a.mean_mode, nullptr, stream);
+    if (rc != TA_OK) return rc;
+    p.scale = a.scale_out;
+    if (nf) return launch_ew_rows2<1>("ta_fused_tail[stream,nf]", B, n, true, FusedStreamOpT<true>{p, n / 4}, s, 0);
+    return launch_ew_rows2<2>("ta_fused_tail[stream]", B, n, v4, FusedStreamOp{p, v4 ? n / 4 : n}, s);
+  }
+
+#define TA_FUSED_CASE(U_)                                                                                        \
+  if (unroll == U_) {                                                                                            \
+    if (torch_order) return nf ? launch_fused<U_, 1, true>(who, p, L, c, tree_off4, B, cl, smem, s)              \
+                               : launch_fused<U_, 1, false>(who, p, L, c, tree_off4, B, cl, smem, s);            \
+    return nf ? launch_fused<U_, 0, true>(who, p, L, c, tree_off4, B, cl, smem, s)                               \
+              : launch_fused<U_, 0, false>(who, p, L, c, tree_off4, B, cl, smem, s);                             \
+  }
+  TA_FUSED_CASE(1)
+  TA_FUSED_CASE(2)
+  TA_FUSED_CASE(4)
 #undef TA_FUSED_CASE
-  set_error("ta_fused_update_linf: unsupported tuning threads=%d unroll=%d", threads, unroll);
+  set_error("%s: unsupported tuning unroll=%d", who, unroll);
   return TA_EUNSUPPORTED;
 }
 
+int make_normfold(const char* who, const float* mean_host, const float* std_host, int C, int64_t plane, int64_t n, int emit, int bwd,
+                  NormFold* nf) {
+  TA_REQUIRE(mean_host && std_host, "%s: null mean/std", who);
+  if (C < 1 || C > 4 || plane <= 0 || plane % 4 != 0 || (int64_t)C * plane != n) {
+    set_error("%s: needs 1 <= C <= 4, plane %% 4 == 0 and C * plane == n (C=%d plane=%lld n=%lld)", who, C, (long long)plane, (long long)n);
+    return TA_EUNSUPPORTED;
+  }
+  *nf = NormFold{};
+  for (int c = 0; c < C; ++c) {
+    TA_REQUIRE(std_host[c] != 0.0f, "%s: std[%d] == 0", who, c);
+    nf->mean[c] = mean_host[c]; nf->std[c] = std_host[c];
+  }
+  nf->C = C; nf->fwd = emit ? 1 : 0; nf->bwd = bwd ? 1 : 0; nf->plane_vec = plane / 4;
+  return TA_OK;
+}
+
 }  // namespace
+
+extern "C" int ta_fused_tail(const ta_fused_tail_args* a, ta_stream_t stream) {
+  TA_REQUIRE(a != nullptr, "ta_fused_tail: null argument block");
+  if (a->emit_normalized || a->grad_wrt_xn) {
+    TA_REQUIRE(a->xadv_out || !a->emit_normalized, "ta_fused_tail: emit_normalized needs xadv_out");
+    NormFold nf;
+    const int rc = make_normfold("ta_fused_tail", a->mean_host, a->std_host, a->C, a->plane, a->n, a->emit_normalized, a->grad_wrt_xn, &nf);
+    if (rc != TA_OK) return rc;
+    return fused_tail_impl(*a, &nf, stream);
+  }
+  return fused_tail_impl(*a, nullptr, stream);
+}
 
 extern "C" int ta_fused_update_linf(const float* g, const float* m, float* m_out, const float* delta, float* delta_out,
                                     const float* data, float* xadv_out, const float* scale, float* scale_out, int mean_mode,
                                     float decay, float alpha, float eps, float lo, float hi, int B, int64_t n,
                                     ta_stream_t stream) {
-  return fused_update_impl(g, m, m_out, delta, delta_out, data, xadv_out, scale, scale_out, mean_mode, decay, alpha, eps, lo, hi,
-                           B, n, nullptr, stream);
+  ta_fused_tail_args a = {};
+  a.g = g; a.m = m; a.m_out = m_out; a.delta = delta; a.delta_out = delta_out; a.data = data; a.xadv_out = xadv_out;
+  a.scale = scale; a.scale_out = scale_out; a.mean_mode = mean_mode; a.decay = decay; a.alpha = alpha; a.eps = eps; a.lo = lo; a.hi = hi;
+  a.B = B; a.n = n;
+  return fused_tail_impl(a, nullptr, stream);
 }
 
 // Normalize folded in: `xn_out` receives the NORMALISED next model input ((data + delta') - mean_c) / std_c,
@@ -443,19 +584,14 @@ extern "C" int ta_fused_update_linf_nf(const float* g, const float* m, float* m_
                                        const float* mean_host, const float* std_host, int C, int64_t plane, int grad_wrt_xn,
                                        ta_stream_t stream) {
   TA_REQUIRE(mean_host && std_host && xn_out, "ta_fused_update_linf_nf: null pointer");
-  if (C < 1 || C > 4 || plane <= 0 || plane % 4 != 0 || (int64_t)C * plane != n) {
-    set_error("ta_fused_update_linf_nf: needs 1 <= C <= 4, plane %% 4 == 0 and C * plane == n (C=%d plane=%lld n=%lld)", C,
-              (long long)plane, (long long)n);
-    return TA_EUNSUPPORTED;
-  }
-  NormFold nf = {};
-  for (int c = 0; c < C; ++c) {
-    TA_REQUIRE(std_host[c] != 0.0f, "ta_fused_update_linf_nf: std[%d] == 0", c);
-    nf.mean[c] = mean_host[c]; nf.std[c] = std_host[c];
-  }
-  nf.C = C; nf.fwd = 1; nf.bwd = grad_wrt_xn ? 1 : 0; nf.plane_vec = plane / 4;
-  return fused_update_impl(g, m, m_out, delta, delta_out, data, xn_out, scale, scale_out, mean_mode, decay, alpha, eps, lo, hi, B,
-                           n, &nf, stream);
+  NormFold nf;
+  const int rc = make_normfold("ta_fused_update_linf_nf", mean_host, std_host, C, plane, n, 1, grad_wrt_xn, &nf);
+  if (rc != TA_OK) return rc;
+  ta_fused_tail_args a = {};
+  a.g = g; a.m = m; a.m_out = m_out; a.delta = delta; a.delta_out = delta_out; a.data = data; a.xadv_out = xn_out;
+  a.scale = scale; a.scale_out = scale_out; a.mean_mode = mean_mode; a.decay = decay; a.alpha = alpha; a.eps = eps; a.lo = lo; a.hi = hi;
+  a.B = B; a.n = n;
+  return fused_tail_impl(a, &nf, stream);
 }
 
 extern "C" int ta_fused_allreduce_update_linf(const float* const* g_peers, float* const* xadv_peers, int K, const float* m,
@@ -476,7 +612,9 @@ extern "C" int ta_fused_allreduce_update_linf(const float* const* g_peers, float
     if (k < K) { TA_REQUIRE(pp.g[k] && pp.x[k], "ta_fused_allreduce_update_linf: null peer pointer %d", k); ok = ok && aligned16(pp.g[k]) && aligned16(pp.x[k]); }
   }
   TA_REQUIRE(ok, "ta_fused_allreduce_update_linf: needs n %% 4 == 0 and 16-byte aligned buffers");
-  FusedParams p{nullptr, m, m_out, delta, delta_out, data, nullptr, scale, scale_out, decay, alpha, eps, lo, hi, n};
+  FusedParams p = {};
+  p.m = m; p.m_out = m_out; p.delta = delta; p.delta_out = delta_out; p.data = data; p.scale = scale; p.scale_out = scale_out;
+  p.decay = decay; p.alpha = alpha; p.eps = eps; p.lo = lo; p.hi = hi; p.n = n;
   const int64_t nvec = n / 4;
   int cl = tune_get("fused.cluster", 0);
   if (cl <= 0) { cl = 1; while (cl < 8 && n / (cl * 2) >= 2048) cl *= 2; }

@@ -3,7 +3,9 @@ iteration's L1-normalised gradient, x + c_k * alpha * g_bar with c = linspace(-r
 Reference: transferattack/gradient/emifgsm.py:33-105 (same constructor, factors, label repetition, loop order).
 
 The K-way replication is one ``ta_lin_sample_fwd`` launch (reads x and g_bar once, writes K copies) and its adjoint
-one ``ta_lin_sample_bwd`` (sums the K gradient slices in autograd's accumulation order)."""
+one ``ta_lin_sample_bwd`` (sums the K gradient slices in autograd's accumulation order). With the base ``get_momentum`` /
+``update_delta`` the tail of an iteration — bar_grad = g / mean|g|, momentum, update_delta, next `data + delta`
+(emifgsm.py:97-103) — is ONE ``ta_fused_tail`` launch that also emits bar_grad."""
 from ..utils import *
 from .. import ops
 from .mifgsm import MIFGSM
@@ -41,10 +43,22 @@ class EMIFGSM(MIFGSM):
         if self.targeted:
             assert len(label) == 2
             label = label[1]
-        data = self._to_device(data)
+        data = self._to_device(data).contiguous()
         label = self._to_device(label)
         be = ops.backend()
         delta = self.init_delta(data)
+        if self._fusable():
+            kmode = self._mean_kernel_mode(data)
+            m_buf, xadv, bar_buf = torch.empty_like(data), torch.empty_like(data), torch.empty_like(data)
+            scale_out = torch.empty(data.shape[0], device=data.device, dtype=torch.float32)
+            momentum, bar_grad, pre_x = None, 0, None
+            for _ in range(self.epoch):
+                x = ops.stage_add(data, delta, precomputed=pre_x)
+                loss = self.get_loss(self.get_logits(self.transform(x, grad=bar_grad)), label)
+                grad = self.get_grad(loss, delta)
+                self._tail(be, grad, momentum, m_buf, delta, delta, data, xadv, scale_out, kmode, None, gbar_out=bar_buf)
+                momentum, bar_grad, pre_x = m_buf, bar_buf, xadv
+            return delta.detach()
         momentum, bar_grad = 0, 0
         for _ in range(self.epoch):
             loss = self.get_loss(self.get_logits(self.transform(ops.stage_add(data, delta), grad=bar_grad)), label)

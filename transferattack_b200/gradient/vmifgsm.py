@@ -4,7 +4,10 @@ Reference: transferattack/gradient/vmifgsm.py:33-97 (same constructor, ``get_var
 neighbour noise is drawn with the same torch call so the device generator is consumed identically).
 
 Kernels per neighbour: ``ta_neighbor_stage`` ((data+delta)+noise, identity backward) and ``ta_accumulate``;
-once per iteration ``ta_variance_finalize`` (acc/N - g), ``ta_add`` (g + v), then the base hooks."""
+once per iteration ``ta_variance_finalize`` (acc/N - g) and ONE ``ta_fused_tail`` launch for `grad + variance` → mean →
+momentum → update_delta → next `data + delta` (vmifgsm.py:86-97) when ``get_momentum`` / ``update_delta`` are the base
+hooks: the kernel takes the variance as its addend and writes delta' into a second buffer, because the reference evaluates
+the neighbours at the OLD delta after the momentum update (vmifgsm.py:90-94). Otherwise ``ta_add`` and the public hooks."""
 from ..utils import *
 from .. import ops
 from ..attack import Attack
@@ -39,10 +42,12 @@ class VMIFGSM(Attack):
         if self.targeted:
             assert len(label) == 2
             label = label[1]
-        data = self._to_device(data)
+        data = self._to_device(data).contiguous()
         label = self._to_device(label)
         be = ops.backend()
         delta = self.init_delta(data)
+        if self._fusable():
+            return self._forward_fused(be, data, label, delta)
         momentum, variance = 0, None
         for _ in range(self.epoch):
             loss = self.get_loss(self.get_logits(self.transform(ops.stage_add(data, delta), momentum=momentum)), label)
@@ -50,4 +55,23 @@ class VMIFGSM(Attack):
             momentum = self.get_momentum(grad if variance is None else be.add(grad, variance), momentum)
             variance = self.get_variance(data, delta, label, grad, momentum)
             delta = self.update_delta(delta, data, momentum, self.alpha)
+        return delta.detach()
+
+    def _forward_fused(self, be, data, label, delta):
+        """The same loop with the tail of every iteration as one launch. momentum is updated in place; delta ping-pongs between
+        two leaves so that get_variance still sees the point the gradient was taken at."""
+        kmode = self._mean_kernel_mode(data)
+        m_buf = torch.empty_like(data)
+        xadv = torch.empty_like(data)
+        scale_out = torch.empty(data.shape[0], device=data.device, dtype=torch.float32)
+        nxt = torch.empty_like(data).requires_grad_(True)
+        momentum, variance, pre_x = None, None, None
+        for _ in range(self.epoch):
+            x = ops.stage_add(data, delta, precomputed=pre_x)
+            loss = self.get_loss(self.get_logits(self.transform(x, momentum=0 if momentum is None else momentum)), label)
+            grad = self.get_grad(loss, delta)
+            self._tail(be, grad, momentum, m_buf, delta, nxt, data, xadv, scale_out, kmode, None, addend=variance)
+            momentum, pre_x = m_buf, xadv
+            variance = self.get_variance(data, delta, label, grad, momentum)
+            delta, nxt = nxt, delta
         return delta.detach()

@@ -145,8 +145,20 @@ def make_ens_attack(attack_cls, member, group=None, **kwargs):
     reference's documented override point, attack.py:40-65). The base ``Attack`` treats ``ShardedEnsembleModel`` like any
     module; ``device`` is taken from the member."""
     model = ShardedEnsembleModel(member, group)
+
+    def init_delta(self, data, **kw):
+        # every rank must start from the SAME delta (the replicated update assumes it): a random start is drawn from each
+        # rank's own device generator (attack.py:131-141), so rank 0's draw is broadcast
+        delta = attack_cls.init_delta(self, data, **kw)
+        if self.random_start and _world(group)[1] > 1:
+            with torch.no_grad():
+                grp = group if group is not None else dist.group.WORLD
+                dist.broadcast(delta, src=dist.get_global_rank(grp, 0), group=group)
+        return delta
+
     # collectives inside forward/backward: keep the loop eager (NCCL inside a captured graph is not exercised here)
-    P = type("Sharded" + attack_cls.__name__, (attack_cls,), {"load_model": lambda self, _n: model, "use_cuda_graph": False})
+    P = type("Sharded" + attack_cls.__name__, (attack_cls,),
+             {"load_model": lambda self, _n: model, "use_cuda_graph": False, "init_delta": init_delta})
     return P(model_name="sharded-ensemble", device=model.device, **kwargs)
 
 

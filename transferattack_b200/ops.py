@@ -71,10 +71,15 @@ class CudaBackend:
 
     # ---- reductions -------------------------------------------------------------------------------
     def abs_mean(self, g, mode=_lib.TA_MEAN_EXACT):
+        """mean|g| per sample. mode TA_MEAN_EXACT (fp64) or TA_MEAN_TORCH (the summation tree of torch's CUDA mean kernel);
+        returns None when TA_MEAN_TORCH does not cover the shape (the caller then uses torch's own op)."""
         g = _f32c(g, "grad"); B = g.shape[0]; n = g.numel() // B
         out = torch.empty(B, device=g.device, dtype=torch.float32)
         with _DeviceOf(g):
-            _lib.check(self.lib.ta_abs_mean_per_sample(_ptr(g), _ptr(out), B, n, mode, None, _stream()), "ta_abs_mean_per_sample")
+            rc = self.lib.ta_abs_mean_per_sample(_ptr(g), _ptr(out), B, n, mode, None, _stream())
+        if rc == _lib.TA_EUNSUPPORTED and mode == _lib.TA_MEAN_TORCH:
+            return None
+        _lib.check(rc, "ta_abs_mean_per_sample")
         return out
 
     # ---- hooks ------------------------------------------------------------------------------------
@@ -118,6 +123,43 @@ class CudaBackend:
             _lib.check(self.lib.ta_init_l2_scale(_ptr(delta), _ptr(r), _ptr(data), float(eps), float(lo), float(hi), _ptr(out), B, n,
                                                  None, _stream()), "ta_init_l2_scale")
         return out
+
+    def fused_tail(self, g, m, m_out, delta, delta_out, data, xadv_out, scale, scale_out, decay, alpha, eps, lo, hi,
+                   mean_mode=_lib.TA_MEAN_EXACT, addend=None, gbar_out=None, mean=None, std=None, emit_normalized=False,
+                   grad_wrt_xn=False):
+        """ta_fused_tail: momentum + L-inf update + next model input in one launch (include/ta_b200.h). Options: `addend`
+        (g' = g + addend: VMI's grad + variance), `gbar_out` (g'/mean|g'|: EMI's bar_grad), Normalize fold (`mean`/`std` host
+        sequences [C], `emit_normalized`, `grad_wrt_xn`). Returns False (nothing launched) for a request the library cannot
+        serve in one launch — the caller keeps the separate kernels."""
+        g = _f32c(g, "grad"); B = g.shape[0]; n = g.numel() // B
+        addend = _f32c(addend, "addend")
+        a = _lib.FusedTailArgs()
+        a.g, a.addend, a.m, a.m_out = g.data_ptr(), (addend.data_ptr() if addend is not None else None), \
+            (m.data_ptr() if m is not None else None), m_out.data_ptr()
+        a.delta, a.delta_out, a.data = delta.data_ptr(), delta_out.data_ptr(), data.data_ptr()
+        a.xadv_out = xadv_out.data_ptr() if xadv_out is not None else None
+        a.gbar_out = gbar_out.data_ptr() if gbar_out is not None else None
+        a.scale = scale.data_ptr() if scale is not None else None
+        a.scale_out = scale_out.data_ptr() if scale_out is not None else None
+        a.mean_mode = int(mean_mode)
+        a.decay, a.alpha, a.eps, a.lo, a.hi = float(decay), float(alpha), float(eps), float(lo), float(hi)
+        a.B, a.n = B, n
+        keep = None
+        if emit_normalized or grad_wrt_xn:
+            C = g.shape[1]
+            hm = np.ascontiguousarray(mean, np.float32); hs = np.ascontiguousarray(std, np.float32)
+            if hm.size != C or hs.size != C:
+                return False
+            keep = (hm, hs)
+            a.mean_host, a.std_host, a.C, a.plane = hm.ctypes.data, hs.ctypes.data, C, n // C
+            a.emit_normalized, a.grad_wrt_xn = (1 if emit_normalized else 0), (1 if grad_wrt_xn else 0)
+        with _DeviceOf(g):
+            rc = self.lib.ta_fused_tail(ctypes.byref(a), _stream())
+        del keep
+        if rc == _lib.TA_EUNSUPPORTED:
+            return False
+        _lib.check(rc, "ta_fused_tail")
+        return True
 
     def fused_update_linf(self, g, m, m_out, delta, delta_out, data, xadv_out, scale, scale_out, decay, alpha, eps, lo, hi,
                           mean_mode=_lib.TA_MEAN_EXACT):
@@ -333,6 +375,47 @@ def backend():
     return _cuda_backend
 
 
+_aten_replay_ok = {}
+
+
+def aten_mean_replay_ok(t):
+    """May TA_MEAN_TORCH stand in for ``t.abs().mean(dim=(1,2,3))`` on this device for tensors shaped like `t`?
+
+    TA_MEAN_TORCH replays the launch policy and summation tree of torch's CUDA mean kernel (csrc/aten_mean.cuh), i.e. an
+    implementation detail of the installed torch build. So it is never trusted blindly: the first time a (device, shape) is
+    seen, the kernel is run against torch's own op on random gradients of that shape and must agree BIT FOR BIT; otherwise
+    (or when the library does not cover the shape) the answer is False and the callers keep torch's op for the scale. The
+    verdict is cached per (device, shape). The check synchronises, so it is made outside CUDA-graph capture only."""
+    if _test_backend is not None or not torch.is_tensor(t) or not t.is_cuda or t.dim() < 2 or t.dtype != torch.float32:
+        return False
+    key = (t.device.index, tuple(t.shape))
+    ok = _aten_replay_ok.get(key)
+    if ok is not None:
+        return ok
+    if torch.cuda.is_current_stream_capturing():
+        return False
+    be = backend()
+    ok, covered = True, True
+    with torch.no_grad():
+        gen = torch.Generator(device=t.device).manual_seed(0x7A)
+        for scale in (1.0, 1e-4):
+            g = torch.randn(t.shape, device=t.device, dtype=torch.float32, generator=gen) * scale
+            ours = be.abs_mean(g, _lib.TA_MEAN_TORCH)
+            if ours is None:
+                ok = covered = False
+                break
+            if not torch.equal(ours, g.abs().mean(dim=tuple(range(1, g.dim())))):
+                ok = False
+                break
+    if not ok and covered:
+        import warnings
+        warnings.warn("transferattack_b200: TA_MEAN_TORCH does not reproduce this torch build's mean kernel for shape %s on %s; "
+                      "keeping torch's own op for mean|grad| (results stay bit-identical, one more launch per iteration)"
+                      % (tuple(t.shape), t.device))
+    _aten_replay_ok[key] = ok
+    return ok
+
+
 # =====================================================================================================
 # autograd wrappers for the ops that sit between delta and the surrogate (SURVEY.md H3)
 # =====================================================================================================
@@ -484,10 +567,44 @@ def neighbor_stage_philox(data, delta, frm, to, look=None, coef=0.0):
     return NeighborStagePhilox.apply(data, delta, frm, to, look, coef)
 
 
+_philox_ok = {}
+
+
+def _philox_self_check(device):
+    """ta_neighbor_stage_philox re-implements the launch policy of this torch build's CUDA ``uniform_`` (threads, draws per
+    thread, generator offset increment). Checked once per device against torch itself on a private generator: the noise must
+    be bit-equal and the generator must end at the same offset; otherwise the in-kernel noise is not used."""
+    ok = _philox_ok.get(device.index)
+    if ok is not None:
+        return ok
+    be = backend()
+    ok = True
+    with torch.no_grad():
+        for numel in (4096 + 12, 3 * 224 * 224 * 2):
+            g1 = torch.Generator(device=device).manual_seed(1234)
+            g2 = torch.Generator(device=device).manual_seed(1234)
+            ref = torch.zeros(numel, device=device).uniform_(-0.25, 0.25, generator=g1)
+            z = torch.zeros(numel, device=device)
+            noise = torch.empty(numel, device=device)
+            be.neighbor_stage_philox(z, z, -0.25, 0.25, generator=g2, noise_out=noise)
+            if not torch.equal(noise, ref) or g1.get_offset() != g2.get_offset():
+                ok = False
+                break
+    if not ok:
+        import warnings
+        warnings.warn("transferattack_b200: in-kernel Philox noise does not reproduce this torch build's uniform_; VMI/VNI draw "
+                      "their neighbour noise with torch (same results, three more launches per neighbour)")
+    _philox_ok[device.index] = ok
+    return ok
+
+
 def philox_noise_available(t):
-    """in-kernel noise needs the real library, a CUDA tensor, torch's eager generator (no graph capture) and 32-bit indexing"""
-    return (_test_backend is None and torch.is_tensor(t) and t.is_cuda and t.numel() < 2 ** 31
-            and not torch.cuda.is_current_stream_capturing())
+    """in-kernel noise needs the real library, a CUDA tensor, torch's eager generator (no graph capture), 32-bit indexing and
+    a torch build whose uniform_ the kernel reproduces (self-checked once per device)"""
+    if not (_test_backend is None and torch.is_tensor(t) and t.is_cuda and t.numel() < 2 ** 31
+            and not torch.cuda.is_current_stream_capturing()):
+        return False
+    return _philox_self_check(t.device)
 
 
 def normalize(x, mean, std):
