@@ -39,12 +39,13 @@ def parse():
     p.add_argument("--arch", default="resnet50")
     p.add_argument("--attack", default="mifgsm")
     p.add_argument("--epoch", type=int, default=10)
-    p.add_argument("--mean-mode", default="torch", choices=["torch", "exact"])
+    p.add_argument("--mean-mode", default="torch", choices=["torch", "aten", "exact"])
+    p.add_argument("--no-extras", action="store_true", help="skip the time-boxed rows for BASELINE configs 1 / 3 / 4 and the ensemble block")
     p.add_argument("--graph", type=int, default=int(os.environ.get("TA_B200_GRAPH", "1")))
     p.add_argument("--kernels", action="store_true")
     p.add_argument("--sweep", action="store_true")
     p.add_argument("--no-cpu-baseline", action="store_true")
-    p.add_argument("--cpu-worker", default="", help="internal: 'budget_seconds,steps,warmup,max_b' → JSON on stdout")
+    p.add_argument("--cpu-worker", default="", help="internal: 'sample_b,steps,warmup' → JSON on stdout")
     p.add_argument("--no-eager-gpu", action="store_true")
     return p.parse_args()
 
@@ -135,10 +136,46 @@ def build_attack(pkg, name, net, **kw):
     return P(model_name="synthetic", **kw)
 
 
-def make_net(arch, device):
+def make_net(arch, device, seed=0):
     import torchvision
-    torch.manual_seed(0)
-    return getattr(torchvision.models, arch)(weights=None).eval().to(device)
+    torch.manual_seed(seed)
+    kw = {"aux_logits": True, "init_weights": False} if arch == "inception_v3" else {}
+    return getattr(torchvision.models, arch)(weights=None, **kw).eval().to(device)
+
+
+def seed_host(s):
+    import random
+    torch.manual_seed(s); np.random.seed(s); random.seed(s)
+
+
+def parity_stats(d, dr, x):
+    """north_star's acceptance: perturbation within 1e-5 abs fp32, bit-identical after uint8 quantisation (utils.py:63-66)"""
+    from oracle import torch_ref
+    d, dr, x = d.float().cpu(), dr.float().cpu(), x.float().cpu()
+    diff = (d - dr).abs()
+    q, qr = torch_ref.save_images_u8(x, d), torch_ref.save_images_u8(x, dr)
+    return {"bit_identical": bool(torch.equal(d, dr)), "n_gt_1e-5": int((diff > 1e-5).sum()), "u8_mismatch": int((q != qr).sum()),
+            "max_abs": float(diff.max()), "numel": int(d.numel())}
+
+
+def parity_block(atk, net, x_dev, y_dev, args, last):
+    """the perturbation of the LAST TIMED step against the eager restatement of the reference (oracle/torch_ref.py — the checker,
+    outside every timed region) on the same GPU, surrogate and inputs; plus the reference against itself (its own floor)."""
+    from oracle import torch_ref
+    kw = {"epoch": args.epoch}
+    ref = torch_ref.REF_ZOO[args.attack](torch_ref.ref_wrap_model(net), **kw)
+    seed_host(7); torch.cuda.manual_seed_all(7)
+    dr = ref(x_dev, y_dev)
+    seed_host(7); torch.cuda.manual_seed_all(7)
+    dr2 = ref(x_dev, y_dev)
+    seed_host(7); torch.cuda.manual_seed_all(7)
+    d = atk(x_dev, y_dev)
+    out = parity_stats(d, dr, x_dev)
+    out["timed_output_equals_checked_output"] = bool(last is not None and torch.equal(last, d)) if args.attack in (
+        "mifgsm", "ifgsm", "nifgsm", "fgsm", "tim", "sim", "emifgsm") else None      # host-RNG attacks draw per call
+    out["reference_vs_itself"] = parity_stats(dr, dr2, x_dev)
+    out["against"] = "oracle/torch_ref.py (eager restatement of attack.py:67-153) on the same GPU, surrogate and inputs"
+    return out
 
 
 def synth(B, seed=1):
@@ -186,31 +223,16 @@ def cpu_reference_run(args, sample_b, steps, warmup):
     return sample_b * steps / dt, dt / steps
 
 
-def cpu_probe(args):
-    """seconds per image for one full attack on the host, from a short probe (epoch=2 on 2 images)."""
-    from oracle import torch_ref
-    torch.set_num_threads(host_cores())
-    net = make_net(args.arch, "cpu")
-    atk = torch_ref.REF_ZOO[args.attack](torch_ref.ref_wrap_model(net), epoch=2)
-    x, y = synth(4)
-    atk(x, y)
-    t0 = time.perf_counter(); atk(x, y); dt = time.perf_counter() - t0
-    return dt / 4 / 2 * args.epoch
-
-
 def cpu_worker(args):
-    """child process: size a bounded sample from a probe, time it, print JSON"""
-    budget, steps, warmup, max_b = [float(v) for v in args.cpu_worker.split(",")]
-    steps, warmup, max_b = int(steps), int(warmup), int(max_b)
-    per_img = cpu_probe(args)
-    sample_b = int(max(1, min(max_b, budget / max(per_img * (steps + warmup), 1e-9))))
+    """child process: time `steps` attacks (after `warmup`) on `sample_b` images on the host cores, print JSON"""
+    sample_b, steps, warmup = [int(float(v)) for v in args.cpu_worker.split(",")]
     val, per_step = cpu_reference_run(args, sample_b, steps, warmup)
-    print(json.dumps({"value": val, "per_step_s": per_step, "sample_b": sample_b, "cores": host_cores(), "probe_s_per_img": per_img}), flush=True)
+    print(json.dumps({"value": val, "per_step_s": per_step, "sample_b": sample_b, "cores": host_cores()}), flush=True)
 
 
-def cpu_leg(args, budget, steps, warmup, max_b, hard_timeout):
+def cpu_leg(args, sample_b, steps, warmup, hard_timeout):
     """run the CPU leg in a child with a hard wall-clock bound (killed by PID on overrun)"""
-    cmd = [sys.executable, os.path.abspath(__file__), "--cpu-worker", "%g,%d,%d,%d" % (budget, steps, warmup, max_b),
+    cmd = [sys.executable, os.path.abspath(__file__), "--cpu-worker", "%d,%d,%d" % (sample_b, steps, warmup),
            "--arch", args.arch, "--attack", args.attack, "--epoch", str(args.epoch)]
     env = dict(os.environ, CUDA_VISIBLE_DEVICES="")
     try:
@@ -224,24 +246,30 @@ def cpu_leg(args, budget, steps, warmup, max_b, hard_timeout):
 
 
 def run_reference_arm(args, rank):
+    """the reference's own CPU path (oracle/torch_ref.py: the port; the Python reference cannot travel to this box) on all host
+    threads; every step = one full 10-iteration attack on a bounded sample of CPU_SAMPLE_B of the batch's images."""
     if rank != 0:
         return
-    r = cpu_leg(args, 120.0, args.steps, args.warmup, args.batch, 420)
+    sample_b = min(CPU_SAMPLE_B, args.batch)
+    # bound the whole run: ~0.35 s per image and attack on 16 threads → 25 steps of 16 images ≈ 2.5 min
+    r = cpu_leg(args, sample_b, args.steps, args.warmup, 900)
     if "error" in r:   # the oracle always exists; report the failure loudly but keep the line parseable
         r = {"value": float("nan"), "per_step_s": float("nan"), "sample_b": 0, "cores": host_cores(), "error": r["error"]}
     val, per_step, sample_b = r["value"], r["per_step_s"], r["sample_b"]
     cores = r["cores"]
-    sample = "%d of %d images per step, %d iterations each" % (sample_b, args.batch, args.epoch)
+    sample = "%d of %d images per step, %d iterations each, oracle/torch_ref.py on %d host threads" % (sample_b, args.batch, args.epoch, cores)
+    cfg = workload_config(args, 1)
+    cfg.update({"device": "cpu", "parallelism": "host threads x%d" % cores, "sample": sample})
     line = {
         "impl": "reference", "metric": METRIC, "value": val, "unit": "images/s", "n_gpus": args.gpus, "steps": args.steps,
         "warmup": args.warmup, "ms_per_step": per_step * 1e3, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
-        "dtype": "f32", "data": "synthetic",
-        "config": {"workload": "MI-FGSM, ResNet-50, batch 64, 10 iters, eps=16/255 (BASELINE configs[1])", "attack": args.attack,
-                   "arch": args.arch, "batch_per_gpu": args.batch, "epoch": args.epoch, "device": "cpu"},
+        "dtype": "f32", "data": "synthetic", "config": cfg,
         "cpu_baseline": {"value": val, "unit": "images/s", "cores": cores, "kind": "port", "sample": sample},
         "e2e": {"value": val, "unit": "images/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
         "gpu_launches": 0,
     }
+    if "error" in r:
+        line["error"] = r["error"]
     print(json.dumps(line), flush=True)
 
 
@@ -264,6 +292,39 @@ def timed_steps(fn, steps, dist, device):
     return float(ms.item())
 
 
+def tail_kernel_name(atk, x_dev):
+    """which form of the fused tail this attacker launches for inputs like x_dev (also the key into profiles/traffic.json)"""
+    from transferattack_b200 import _lib
+    kmode = atk._mean_kernel_mode(x_dev)
+    fold = atk._fold_plan(x_dev, kmode)
+    nf = "" if fold is None else (",nf+adjoint" if fold[4] else ",nf")
+    if kmode is None:
+        return "ta_fused_tail[stream%s] after ATen abs+mean" % nf, 3
+    return "ta_fused_tail[cluster,%s%s]" % ("torch-order mean" if kmode == _lib.TA_MEAN_TORCH else "fp64 mean", nf), 1
+
+
+def graph_status(atk, requested):
+    return {"requested": bool(requested), "captured": bool(getattr(atk, "_graphs", None)),
+            "failed": bool(atk.__dict__.get("_graph_failed", False)), "error": atk.__dict__.get("_graph_error")}
+
+
+def time_attack(atk, x_dev, y_dev, steps, warmup, dist, device):
+    for _ in range(warmup):
+        atk(x_dev, y_dev)
+    torch.cuda.synchronize(device)
+    return timed_steps(lambda: atk(x_dev, y_dev), steps, dist, device)
+
+
+def tail_events(atk, x_dev, y_dev, steps, dist, device):
+    """CUDA events around the WHOLE tail of every iteration (everything between autograd.grad and the next forward), on its
+    stream, live inside a run of the same attack (eager launches of the same kernels: a graph replay cannot host events)"""
+    ev = []
+    atk._kernel_events = ev
+    ms = timed_steps(lambda: atk(x_dev, y_dev), steps, dist, device)
+    atk._kernel_events = None
+    return [a.elapsed_time(b) for a, b in ev], ms
+
+
 def run_ours(args, rank, local_rank, world, dist):
     import transferattack_b200 as tab
     from transferattack_b200 import _lib
@@ -281,30 +342,31 @@ def run_ours(args, rank, local_rank, world, dist):
     out_pin = torch.empty_like(x_pin).pin_memory()
     n_elem = B * IMG_ELEMS
 
-    # -- warm-up (also triggers cuDNN heuristics / graph capture) ---------------------------------------------
+    # -- warm-up (also triggers cuDNN heuristics / graph capture / the one-time TA_MEAN_TORCH self-check) ----------
     for _ in range(max(args.warmup, 3)):
         atk(x_dev, y_dev)
     torch.cuda.synchronize(device)
 
     # -- value: inputs resident in HBM ---------------------------------------------------------------------------
+    keep = {}
+
+    def step_resident():
+        keep["d"] = atk(x_dev, y_dev)
     launches0 = _lib.launch_count()
     with ClockSampler(local_rank) as clk:
-        ms = timed_steps(lambda: atk(x_dev, y_dev), args.steps, dist, device)
+        ms = timed_steps(step_resident, args.steps, dist, device)
     launches = _lib.launch_count() - launches0
     clocks = clk.summary()
     value = world * B * args.steps / (ms / 1e3)
-    if args.graph:        # kernels replayed from the captured graph are not host launches: add the graph's own count per replay
-        sts = list(getattr(atk, "_graphs", {}).values())
-        if sts:
-            launches += sts[-1].get("kernels_per_replay", 0) * args.epoch * args.steps
+    gstat = graph_status(atk, args.graph)
+    if gstat["captured"]:  # kernels replayed from the captured graph are not host launches: add the graph's own count per replay
+        sts = list(atk._graphs.values())
+        launches += sts[-1].get("kernels_per_replay", 0) * args.epoch * args.steps
+    last_timed = keep.get("d")
 
-    # roofline of the dominant kernel: CUDA events around every ta_fused_update_linf launch, on its stream, live inside a
-    # run of the same attack (eager launches of the same kernels: a graph replay cannot host per-launch events)
-    kernel_events = []
-    atk._kernel_events = kernel_events          # the base loop brackets its fused launch with CUDA events when set
-    ms_ev = timed_steps(lambda: atk(x_dev, y_dev), max(2, args.steps // 2), dist, device)
-    atk._kernel_events = None
-    k_ms = [a.elapsed_time(b) for a, b in kernel_events]
+    # -- roofline of the tail -----------------------------------------------------------------------------------------
+    k_ms, ms_ev = tail_events(atk, x_dev, y_dev, max(2, args.steps // 2), dist, device)
+    kname, tail_launches = tail_kernel_name(atk, x_dev)
 
     # -- e2e: host buffers through the plugin call, H2D of the batch and D2H of the perturbation inside the timed region
     def e2e_step():
@@ -320,35 +382,36 @@ def run_ours(args, rank, local_rank, world, dist):
     if k_ms:
         avg_ms = float(np.mean(k_ms))
         achieved = FUSED_BYTES_PER_ELEM * n_elem / (avg_ms * 1e-3) / 1e9
-        traffic = None
+        traffic, traffic_src = None, None
         tf = os.path.join(ROOT, "profiles", "traffic.json")
         if os.path.exists(tf):
-            traffic = json.load(open(tf)).get("fused_update_%s_B%d" % (args.mean_mode, B))
-        roof = {"bound": "hbm", "kernel": "ta_fused_update_linf (%s)" % ("streaming, scale from torch" if args.mean_mode == "torch"
-                                                                       else "cluster, in-kernel mean|g|"),
+            ent = json.load(open(tf)).get("%s B=%d" % (kname, B))       # keyed by the kernel form that was timed: never another variant's
+            if isinstance(ent, dict):
+                traffic, traffic_src = ent.get("dram_bytes"), ent.get("source")
+        roof = {"bound": "hbm", "kernel": kname, "bracket": "the whole tail of an iteration: everything between autograd.grad and the "
+                "next forward (%d launch%s)" % (tail_launches, "" if tail_launches == 1 else "es"),
                 "achieved": achieved, "peak": hbm_peak, "unit": "GB/s", "frac": achieved / hbm_peak, "traffic": traffic,
-                "peak_source": peak_src, "avg_launch_us": avg_ms * 1e3, "launches_timed": len(k_ms),
-                "algorithmic_bytes_per_launch": FUSED_BYTES_PER_ELEM * n_elem,
-                "share_of_step": float(np.sum(k_ms)) / ms_ev}
+                "traffic_source": traffic_src, "peak_source": peak_src, "avg_launch_us": avg_ms * 1e3, "launches_timed": len(k_ms),
+                "algorithmic_bytes_per_launch": FUSED_BYTES_PER_ELEM * n_elem, "share_of_step": float(np.sum(k_ms)) / ms_ev}
+
+    parity = None
+    if rank == 0:
+        parity = parity_block(atk, net, x_dev, y_dev, args, last_timed)
 
     extra = {}
     if rank == 0 and world == 1:
-        # the other mean mode, for the record (same timed procedure)
-        other = "exact" if args.mean_mode == "torch" else "torch"
-        atk.mean_mode = other
-        for _ in range(2):
-            atk(x_dev, y_dev)
-        ms2 = timed_steps(lambda: atk(x_dev, y_dev), args.steps, None, device)
-        ev2 = []
-        atk._kernel_events = ev2
-        timed_steps(lambda: atk(x_dev, y_dev), max(2, args.steps // 2), None, device)
-        atk._kernel_events = None
-        k2 = [a.elapsed_time(b) for a, b in ev2]
-        ach2 = FUSED_BYTES_PER_ELEM * n_elem / (float(np.mean(k2)) * 1e-3) / 1e9 if k2 else None
-        extra["alt_mean_mode"] = {"mode": other, "value": B * args.steps / (ms2 / 1e3), "ms_per_step": ms2 / args.steps,
-                                  "roofline": {"achieved": ach2, "frac": ach2 / hbm_peak if ach2 else None,
-                                               "avg_launch_us": float(np.mean(k2)) * 1e3 if k2 else None}}
+        # the other mean modes, for the record (same timed procedure)
+        alts = {}
+        for other in [m for m in ("torch", "aten", "exact") if m != args.mean_mode]:
+            atk.mean_mode = other
+            ms2 = time_attack(atk, x_dev, y_dev, max(3, args.steps // 2), 2, None, device)
+            k2, _ = tail_events(atk, x_dev, y_dev, 3, None, device)
+            ach2 = FUSED_BYTES_PER_ELEM * n_elem / (float(np.mean(k2)) * 1e-3) / 1e9 if k2 else None
+            alts[other] = {"value": B * max(3, args.steps // 2) / (ms2 / 1e3), "kernel": tail_kernel_name(atk, x_dev)[0],
+                           "roofline": {"achieved": ach2, "frac": ach2 / hbm_peak if ach2 else None,
+                                        "avg_tail_us": float(np.mean(k2)) * 1e3 if k2 else None}}
         atk.mean_mode = args.mean_mode
+        extra["alt_mean_modes"] = alts
         if not args.no_eager_gpu:
             # the reference's eager hook chain on this GPU (same surrogate, torchvision normalise incl. its host sync)
             from oracle import torch_ref  # comparator only
@@ -365,15 +428,22 @@ def run_ours(args, rank, local_rank, world, dist):
             extra["reference_gpu_eager"] = {"value": B * args.steps / (ms3 / 1e3), "ms_per_step": ms3 / args.steps,
                                             "e2e_value": B * max(2, args.steps // 2) / (ms4 / 1e3),
                                             "note": "eager PyTorch hooks of attack.py on the same GPU/surrogate; informational"}
+        if not args.no_extras:
+            extra["other_configs"] = other_config_rows(args, device, hbm_peak)
+
+    if world > 1 and not args.no_extras:
+        ens = ens_block(args, rank, local_rank, world, dist, device)
+        if rank == 0:
+            extra["ens"] = ens
 
     cpu_base = None
     if rank == 0 and world == 1 and not args.no_cpu_baseline:
-        r = cpu_leg(args, 20.0, 1, 0, 16, 240)
+        r = cpu_leg(args, CPU_SAMPLE_B, 2, 1, 300)
         if "error" in r:
             cpu_base = {"value": None, "unit": "images/s", "cores": host_cores(), "kind": "port", "sample": "failed: " + r["error"]}
         else:
             cpu_base = {"value": r["value"], "unit": "images/s", "cores": r["cores"], "kind": "port",
-                        "sample": "1 step of %d images (of %d), %d iterations, oracle/torch_ref.py on %d host threads"
+                        "sample": "%d of %d images per step, %d iterations each, 1 warm-up + 2 timed steps, oracle/torch_ref.py on %d host threads"
                                   % (r["sample_b"], B, args.epoch, r["cores"])}
 
     if rank == 0:
@@ -381,24 +451,198 @@ def run_ours(args, rank, local_rank, world, dist):
             "metric": METRIC, "value": value, "unit": "images/s", "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
             "ms_per_step": ms / args.steps, "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32",
             "data": "synthetic",
-            "config": {"workload": ("MI-FGSM, ResNet-50, batch 64, 10 iters, eps=16/255 (BASELINE configs[1])"
-                                    if (args.attack, args.arch, B, args.epoch) == ("mifgsm", "resnet50", 64, 10)
-                                    else "%s, %s, batch %d, %d iters, eps=16/255" % (args.attack, args.arch, B, args.epoch)),
-                       "attack": args.attack, "normalize_folded": bool(getattr(atk, "fold_normalize", False) and atk._fold_plan(x_dev) is not None),
-                       "arch": args.arch, "batch_per_gpu": B, "global_batch": B * world, "epoch": args.epoch,
-                       "parallelism": "batch-sharded x%d, no collective" % world, "mean_mode": args.mean_mode,
-                       "surrogate": "torch autograd, fp32 (cuDNN TF32 convs as torch defaults), random-init weights",
-                       "l2": "working set per step (activations of %d images) exceeds the 126 MB L2; no explicit flush" % B,
-                       "cuda_graph": bool(args.graph)},
+            "config": workload_config(args, world, atk, x_dev),
             "clocks": clocks,
             "e2e": {"value": e2e_value, "unit": "images/s", "h2d_bytes_per_step": B * IMG_ELEMS * 4 + B * 8,
                     "d2h_bytes_per_step": B * IMG_ELEMS * 4, "ms_per_step": ms_e2e / args.steps},
             "gpu_launches": int(launches),
             "roofline": roof,
+            "parity": parity,
+            "graph": gstat,
             "cpu_baseline": cpu_base,
         }
         line.update(extra)
         print(json.dumps(line), flush=True)
+
+
+def workload_config(args, world, atk=None, x_dev=None):
+    B = args.batch
+    cfg = {"workload": ("MI-FGSM, ResNet-50, batch 64, 10 iters, eps=16/255 (BASELINE configs[1])"
+                        if (args.attack, args.arch, B, args.epoch) == ("mifgsm", "resnet50", 64, 10)
+                        else "%s, %s, batch %d, %d iters, eps=16/255" % (args.attack, args.arch, B, args.epoch)),
+           "attack": args.attack, "arch": args.arch, "batch_per_gpu": B, "global_batch": B * world, "epoch": args.epoch,
+           "parallelism": "batch-sharded x%d, no collective" % world,
+           "surrogate": "torch autograd, fp32 (cuDNN TF32 convs as torch defaults), random-init weights"}
+    if atk is not None:
+        kmode = atk._mean_kernel_mode(x_dev)
+        cfg.update({"normalize_folded": bool(atk._fold_plan(x_dev, kmode) is not None), "mean_mode": args.mean_mode,
+                    "l2": "working set per step (activations of %d images) exceeds the 126 MB L2; no explicit flush" % B,
+                    "cuda_graph": bool(getattr(atk, "_graphs", None))})
+    return cfg
+
+
+# ------------------------------------------------------------------------------------------------------------------
+def kernel_fracs(B, hbm_peak, names):
+    """standalone fraction-of-peak of the dominant kernels of a configuration at ITS batch size (clean L2 before every launch)"""
+    from transferattack_b200 import ops, _lib
+    import transferattack_b200.input_transformation.tim as tim
+    be = ops.backend()
+    dev = "cuda"
+    N = B * IMG_ELEMS
+    flush = torch.empty(512 * 1024 * 1024 // 4, device=dev)
+    g = torch.randn(B, 3, 224, 224, device=dev) * 1e-4
+    m = torch.randn_like(g); x = torch.rand_like(g); d = (torch.rand_like(g) * 2 - 1) * (16 / 255)
+    m2, d2, xa, v = torch.empty_like(g), torch.empty_like(g), torch.empty_like(g), torch.randn_like(g) * 1e-5
+    so = torch.empty(B, device=dev)
+    k2d, kcol, krow = tim.make_kernel("gaussian", 15)
+    kc3 = torch.from_numpy(np.stack([kcol] * 3)).to(dev); kr3 = torch.from_numpy(np.stack([krow] * 3)).to(dev)
+    hc, hr = kc3.cpu().numpy(), kr3.cpu().numpy()
+    a, al = 1.6 / 255, 16 / 255
+    table = {
+        "dim_fwd": (8, lambda: be.dim(x, 235, 246, 5, 6, True)),
+        "dim_bwd": (8, lambda: be.dim(g, 235, 246, 5, 6, False)),
+        "tim_dwconv2d_sep_k15": (8, lambda: be.dwconv2d_sep(g, kc3, kr3, host=(hc, hr))),
+        "fused_tail_torch_order": (28, lambda: be.fused_tail(g, m, m2, d, d2, x, xa, None, so, 1.0, a, al, 0, 1.0, mean_mode=_lib.TA_MEAN_TORCH)),
+        "fused_tail_addend_torch_order": (32, lambda: be.fused_tail(g, m, m2, d, d2, x, xa, None, so, 1.0, a, al, 0, 1.0,
+                                                                    mean_mode=_lib.TA_MEAN_TORCH, addend=v)),
+        "neighbor_stage_philox": (12, lambda: be.neighbor_stage_philox(x, d, -0.09, 0.09)),
+        "accumulate": (12, lambda: be.accumulate(m2, g, False)),
+    }
+    out = {}
+    for nme in names:
+        bpe, fn = table[nme]
+        med, _ = time_kernel(fn, iters=10, flush=flush)
+        gbs = bpe * N / (med * 1e-3) / 1e9
+        out[nme] = {"us": med * 1e3, "bytes_per_elem": bpe, "GBps": gbs, "frac": gbs / hbm_peak}
+    return out
+
+
+CPU_SAMPLE_B = 16        # images per step of every CPU leg (a bounded sample of the batch-64 workload; stated in the line)
+
+
+def other_config_rows(args, device, hbm_peak):
+    """time-boxed rows for BASELINE configs 1 / 3 / 4: images/s through the plugin API + the dominant kernels'
+    fraction of the measured HBM peak at that configuration's batch size. Informational; the headline stays configs[1]."""
+    import transferattack_b200 as tab
+    rows = {}
+    # configs[0]: I-FGSM / ResNet-18 / B=4 on the host cores (the reference's own CPU-runnable case), oracle port
+    import copy
+    a1 = copy.copy(args); a1.attack, a1.arch, a1.epoch = "ifgsm", "resnet18", 10
+    r = cpu_leg(a1, 4, 5, 1, 120)
+    rows["config1_ifgsm_resnet18_b4_cpu"] = ({"error": r["error"]} if "error" in r else
+                                              {"images_per_s": r["value"], "s_per_attack": r["per_step_s"], "cores": r["cores"], "device": "cpu",
+                                               "impl": "oracle/torch_ref.py (port of the reference), 1 warm-up + 5 timed attacks"})
+    for key, attack, arch, B, kw, steps, knames in (
+            ("config3_ditimi_resnet50_b32_per_gpu_share", "ditimi", "resnet50", 32, {}, 5, ["dim_fwd", "dim_bwd", "tim_dwconv2d_sep_k15", "fused_tail_torch_order"]),
+            ("config4_vmifgsm_n20_vit_b16_b16", "vmifgsm", "vit_b_16", 16, {"num_neighbor": 20}, 1,
+             ["neighbor_stage_philox", "accumulate", "fused_tail_addend_torch_order"])):
+        try:
+            net = make_net(arch, device)
+            atk = build_attack(tab, attack, net, epoch=10, **kw)
+            x, y = synth(B, seed=3)
+            x, y = x.to(device), y.to(device)
+            seed_host(11)
+            ms = time_attack(atk, x, y, steps, 1, None, device)
+            rows[key] = {"images_per_s": B * steps / (ms / 1e3), "ms_per_attack": ms / steps, "batch": B, "steps": steps,
+                         "cuda_graph": bool(getattr(atk, "_graphs", None)), "kernels": kernel_fracs(B, hbm_peak, knames)}
+            del atk, net
+            torch.cuda.empty_cache()
+        except Exception as e:       # an informational row must never cost the headline line
+            rows[key] = {"error": repr(e)[:300]}
+    return rows
+
+
+ENS_MEMBERS = ["resnet50", "resnet152", "inception_v3", "vit_b_16"]
+
+
+def ens_block(args, rank, local_rank, K, dist, device):
+    """BASELINE configs[4] — ensemble MI-FGSM, ONE surrogate per GPU (K = world size, members cycled) — beside the headline:
+      p2p    ta_fused_allreduce_update_linf: gradient reduce-scatter + update + all-gather of the next input in ONE kernel over
+             NVLink peer memory (logits by all_gather + the reference's own mean);
+      nccl   NCCL all-reduce of logits (forward) and input gradient (backward) + replicated fused update;
+      single the reference's layout: all K members sequentially on ONE GPU (rank 0), same kernels.
+    Times are CUDA events, max over ranks; the three perturbations are compared (reference semantics: utils.py:82-105,
+    ensemble/ens.py:31-36)."""
+    import transferattack_b200 as tab
+    from transferattack_b200 import multigpu, _lib, ops
+    B, steps = args.batch, 2
+    g = torch.Generator().manual_seed(1)
+    x = torch.rand(B, 3, 224, 224, generator=g).to(device)
+    y = torch.randint(0, 1000, (B,), generator=g).to(device)
+    names = [ENS_MEMBERS[k % len(ENS_MEMBERS)] for k in range(K)]
+    member = tab.utils.wrap_model(make_net(names[rank], device, seed=rank))
+    ens_cls = tab.load_attack_class("ens")
+    out = {"K": K, "batch": B, "epoch": args.epoch, "members": names, "mean_mode": "exact"}
+
+    def timed(fn):
+        return timed_steps(fn, steps, dist, device) / steps
+
+    a_nccl = multigpu.make_ens_attack(ens_cls, member, epoch=args.epoch)
+    a_nccl.mean_mode = "exact"
+    d_nccl = a_nccl(x, y); a_nccl(x, y)
+    ms = timed(lambda: a_nccl(x, y))
+    out["nccl"] = {"ms_per_attack": ms, "images_per_s": B / ms * 1e3}
+
+    a_p2p = multigpu.make_fused_p2p_ens(ens_cls, member, epoch=args.epoch)
+    d_p2p = a_p2p(x, y); a_p2p(x, y)
+    ms = timed(lambda: a_p2p(x, y))
+    out["p2p"] = {"ms_per_attack": ms, "images_per_s": B / ms * 1e3}
+    out["p2p_vs_nccl_mismatch"] = int((d_p2p != d_nccl).sum())
+
+    # the exchange + update step in isolation (same gradient tensor on every rank; median of 20 after 5 warm-ups)
+    be = ops.backend(); lib = _lib.load()
+    gfull = torch.randn_like(x) * 1e-4
+    m = torch.zeros_like(x); d = torch.zeros_like(x); xa = torch.empty_like(x); so = torch.empty(B, device=device)
+    st = a_p2p._buffers(x)
+    lo, hi = multigpu.shard_bounds(B, rank, K)
+    n = x[0].numel()
+    stream = torch.cuda.current_stream(device)
+
+    def step_nccl():
+        gg = gfull.clone()
+        dist.all_reduce(gg)
+        be.fused_update_linf(gg, m, m, d, d, x, xa, None, so, 1.0, 1.6 / 255, 16 / 255, 0, 1.0)
+
+    def step_p2p():
+        st["G"].copy_(gfull)
+        st["hg"].barrier(channel=0)
+        _lib.check(lib.ta_fused_allreduce_update_linf(st["g_ptrs"], st["x_ptrs"], K, m.data_ptr(), m.data_ptr(), d.data_ptr(), d.data_ptr(),
+                                                      x.data_ptr(), None, so.data_ptr(), 0, 1.0, 1.6 / 255, 16 / 255, 0.0, 1.0, lo, hi - lo, n,
+                                                      stream.cuda_stream), "p2p")
+        st["hx"].barrier(channel=0)
+
+    for name, fn in (("nccl_allreduce_plus_update_us", step_nccl), ("p2p_fused_exchange_update_us", step_p2p)):
+        for _ in range(5):
+            fn()
+        ts = sorted(timed_steps(fn, 1, dist, device) * 1e3 for _ in range(20))
+        out[name] = ts[len(ts) // 2]
+    # NVLink volume of the fused step per GPU: (K-1)/K of the gradient in + (K-1)/K of the next input out
+    wire = 2 * (K - 1) / K * B * IMG_ELEMS * 4
+    out["p2p_nvlink_bytes_per_gpu"] = wire
+    out["p2p_nvlink_GBps_per_direction"] = (wire / 2) / (out["p2p_fused_exchange_update_us"] * 1e-6) / 1e9
+    out["nvlink_peak_GBps_per_direction"] = 770.0
+
+    # the reference's layout: every member on one device, sequentially (rank 0 measures, the others wait at the barrier)
+    single = None
+    if rank == 0:
+        nets = [tab.utils.wrap_model(make_net(names[k], device, seed=k)) for k in range(K)]
+        P = type("SingleENS", (ens_cls,), {"load_model": lambda self, _n: tab.utils.EnsembleModel(nets), "graph_safe": True})
+        a_one = P(model_name="all-on-one", epoch=args.epoch)
+        a_one.mean_mode = "exact"
+        d_one = a_one(x, y); a_one(x, y)
+        ms1 = timed_steps(lambda: a_one(x, y), steps, None, device) / steps
+        single = {"ms_per_attack": ms1, "images_per_s": B / ms1 * 1e3}
+        out["single_gpu_all_members"] = single
+        out["p2p_vs_single_mismatch"] = int((d_p2p != d_one).sum())
+        out["nccl_vs_single_mismatch"] = int((d_nccl != d_one).sum())
+        out["bit_identical"] = out["p2p_vs_single_mismatch"] == 0 and out["nccl_vs_single_mismatch"] == 0 and out["p2p_vs_nccl_mismatch"] == 0
+        per_iter_ms = out["p2p"]["ms_per_attack"] / args.epoch
+        out["bound"] = ("the slowest member's forward/backward bounds the step: the fused exchange+update is %.0f us of a %.1f ms iteration"
+                        % (out["p2p_fused_exchange_update_us"], per_iter_ms))
+        del nets, a_one
+    dist.barrier()
+    torch.cuda.empty_cache()
+    return out
 
 
 # ------------------------------------------------------------------------------------------------------------------
@@ -455,8 +699,28 @@ def run_kernels(args):
 
     add("ATen reference: torch.add(x, d, out=) (same harness)", 12, lambda: torch.add(x, d, out=xa))
     add("ATen reference: tensor.copy_ (same harness)", 8, lambda: xa.copy_(x))
-    add("fused_update_linf[cluster, in-kernel mean]", 28, lambda: be.fused_update_linf(g, m, m2, d, d2, x, xa, None, so, 1.0, a, al, 0, 1.0))
-    add("fused_update_linf[stream, scale given]", 28, lambda: be.fused_update_linf(g, m, m2, d, d2, x, xa, scale, None, 1.0, a, al, 0, 1.0))
+    MEAN, STD = [0.485, 0.456, 0.406], [0.229, 0.224, 0.225]
+    vadd = torch.randn_like(g) * 1e-5; gb = torch.empty_like(g)
+    add("fused_tail[cluster, fp64 mean]", 28, lambda: be.fused_tail(g, m, m2, d, d2, x, xa, None, so, 1.0, a, al, 0, 1.0, mean_mode=_lib.TA_MEAN_EXACT))
+    add("fused_tail[cluster, torch-order mean]", 28, lambda: be.fused_tail(g, m, m2, d, d2, x, xa, None, so, 1.0, a, al, 0, 1.0, mean_mode=_lib.TA_MEAN_TORCH))
+    add("fused_tail[cluster, torch-order mean, nf]", 28, lambda: be.fused_tail(g, m, m2, d, d2, x, xa, None, so, 1.0, a, al, 0, 1.0, mean_mode=_lib.TA_MEAN_TORCH,
+                                                                              mean=MEAN, std=STD, emit_normalized=True))
+    add("fused_tail[cluster, torch-order mean, nf+adjoint] (the default base loop)", 28,
+        lambda: be.fused_tail(g, m, m2, d, d2, x, xa, None, so, 1.0, a, al, 0, 1.0, mean_mode=_lib.TA_MEAN_TORCH, mean=MEAN, std=STD,
+                              emit_normalized=True, grad_wrt_xn=True))
+    for un in (1, 4):
+        _lib.tune_set("fused.unroll", un)
+        add("  fused_tail[cluster, torch-order mean, nf+adjoint] unroll=%d" % un, 28,
+            lambda: be.fused_tail(g, m, m2, d, d2, x, xa, None, so, 1.0, a, al, 0, 1.0, mean_mode=_lib.TA_MEAN_TORCH, mean=MEAN, std=STD,
+                                  emit_normalized=True, grad_wrt_xn=True))
+    _lib.tune_set("fused.unroll", 2)
+    add("fused_tail[cluster, torch-order mean, addend] (VMI)", 32, lambda: be.fused_tail(g, m, m2, d, d2, x, xa, None, so, 1.0, a, al, 0, 1.0,
+                                                                                        mean_mode=_lib.TA_MEAN_TORCH, addend=vadd))
+    add("fused_tail[cluster, torch-order mean, gbar] (EMI)", 32, lambda: be.fused_tail(g, m, m2, d, d2, x, xa, None, so, 1.0, a, al, 0, 1.0,
+                                                                                      mean_mode=_lib.TA_MEAN_TORCH, gbar_out=gb))
+    add("fused_tail[stream, scale given]", 28, lambda: be.fused_update_linf(g, m, m2, d, d2, x, xa, scale, None, 1.0, a, al, 0, 1.0))
+    add("abs_mean_per_sample [torch order]", 4, lambda: be.abs_mean(g, _lib.TA_MEAN_TORCH))
+    add("ATen reference: g.abs().mean(dim=(1,2,3)) (2 launches)", 12, lambda: g.abs().mean(dim=(1, 2, 3)))
     for cap in (0, 4, 8, 16):
         for un in (1, 2, 4):
             _lib.tune_set("stream.cap", cap); _lib.tune_set("stream.unroll", un)
@@ -525,22 +789,22 @@ def run_sweep(args):
         m = torch.randn_like(g); x = torch.rand_like(g); d = (torch.rand_like(g) * 2 - 1) * (16 / 255)
         m2, d2, xa = torch.empty_like(g), torch.empty_like(g), torch.empty_like(g)
         so = torch.empty(B, device=dev)
-        for variant in (0, 1):
+        for mode_name, mode in (("exact", _lib.TA_MEAN_EXACT), ("torch", _lib.TA_MEAN_TORCH)):
             for cl in (2, 4, 8, 16):
-                for threads, unroll in ((256, 1), (256, 2), (512, 1), (512, 2), (1024, 1)):
-                    for k, v in (("fused.variant", variant), ("fused.cluster", cl), ("fused.threads", threads), ("fused.unroll", unroll)):
+                for unroll in (1, 2, 4):
+                    for k, v in (("fused.cluster", cl), ("fused.unroll", unroll)):
                         _lib.tune_set(k, v)
-                    try:
-                        med, mn = time_kernel(lambda: be.fused_update_linf(g, m, m2, d, d2, x, xa, None, so, 1.0, 1.6 / 255, 16 / 255, 0, 1.0),
-                                              iters=10, flush=flush)
-                    except RuntimeError as e:
-                        res.append({"B": B, "variant": variant, "cluster": cl, "threads": threads, "unroll": unroll, "error": str(e)[:120]})
+                    ok = be.fused_tail(g, m, m2, d, d2, x, xa, None, so, 1.0, 1.6 / 255, 16 / 255, 0, 1.0, mean_mode=mode)
+                    if not ok:
+                        res.append({"B": B, "mean": mode_name, "cluster": cl, "unroll": unroll, "error": _lib.last_error()[:120]})
                         continue
+                    med, mn = time_kernel(lambda: be.fused_tail(g, m, m2, d, d2, x, xa, None, so, 1.0, 1.6 / 255, 16 / 255, 0, 1.0, mean_mode=mode),
+                                          iters=10, flush=flush)
                     gbs = 28 * N / (med * 1e-3) / 1e9
-                    res.append({"B": B, "variant": variant, "cluster": cl, "threads": threads, "unroll": unroll,
+                    res.append({"B": B, "mean": mode_name, "cluster": cl, "unroll": unroll,
                                 "median_us": med * 1e3, "GBps": gbs, "frac": gbs / hbm_peak})
         del g, m, x, d, m2, d2, xa
-    for k, v in (("fused.variant", 0), ("fused.cluster", 0), ("fused.threads", 512), ("fused.unroll", 2)):
+    for k, v in (("fused.cluster", 0), ("fused.unroll", 2)):
         _lib.tune_set(k, v)
     os.makedirs(os.path.join(ROOT, "gpurun_out"), exist_ok=True)
     json.dump(res, open(os.path.join(ROOT, "gpurun_out", "sweep.json"), "w"), indent=1)

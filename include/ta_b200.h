@@ -249,6 +249,23 @@ int ta_pi_update_linf(const float* delta, const float* data, const float* g, con
                       const float* amp, float alpha, float gamma, float eps, float lo, float hi,
                       float* amp_out, float* delta_out, int64_t N, ta_stream_t stream);
 
+/* ---- GRA / FGSRA decay indicator (gradient/gra.py:74-93, 148-149) -----------------------------------------
+ *   eq = float(sign(last) == sign(cur));  M' = M * (eq + (1 - eq) * eta)         (last == NULL: the first iteration's python 0)
+ *   delta' = L-inf update_delta(delta, data, cur, alpha_t = M' * alpha)           (attack.py:145-153 with a tensor step)
+ *   One launch for the reference's 17 elementwise launches. M_out / delta_out may alias M / delta.                        */
+int ta_gra_update(const float* M, const float* last, const float* cur, float eta, float alpha,
+                  const float* delta, const float* data, float eps, float lo, float hi,
+                  float* M_out, float* delta_out, int64_t N, ta_stream_t stream);
+
+/* ---- AdaEA disparity-reduced filter (ensemble/adaea.py:115-136, 74-76, 82) ------------------------------------
+ *   grads: HOST array of K (2..8) device pointers to the members' input gradients [B, C, plane], C in {1, 3}.
+ *   Per pixel: u_k = normalize_C(g_k, eps 1e-12); cos(i,j) = cosine_similarity_C(u_i, u_j, eps 1e-8);
+ *   r_i = (sum_{j != i} cos(i,j)) / (K-1) for i < K-1 (the reference's loop leaves the last member's row zero); map = mean_i r_i;
+ *   mask = map >= threshold ? 1 : 0;  out = grad * mask.  map_out ([B, plane], nullable) receives the un-thresholded map;
+ *   grad/out (nullable together) the filtered ensemble gradient. One launch for the reference's ~10 K^2 launches.        */
+int ta_adaea_drf(const float* const* grads, int K, float threshold, const float* grad, float* out,
+                 float* map_out, int B, int C, int64_t plane, ta_stream_t stream);
+
 /* ---- EMI (gradient/emifgsm.py:53-58, 86-103) ---------------------------------------------------------
  *   out[k*N + i] = x[i] + coef[k] * gbar[i]  (coef[k] = (float)(factor_k * alpha), host array, K <= 32)
  *   gbar == NULL is the first iteration (`bar_grad = 0`): out[k*N+i] = x[i] + 0.

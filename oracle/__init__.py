@@ -277,3 +277,24 @@ def pi_update_linf(delta, data, g, conv, amp, alpha, gamma, eps, lo=0.0, hi=1.0)
                              ctypes.c_float(eps), ctypes.c_float(lo), ctypes.c_float(hi), _fp(amp_out), _fp(d_out),
                              ctypes.c_int64(delta.size))
     return amp_out, d_out
+
+
+def gra_update(M, last, cur, eta, alpha, delta, data, eps, lo=0.0, hi=1.0):
+    """gradient/gra.py:74-93 + :149 — returns (M', delta')"""
+    M = _c(M); last = _c(last); cur = _c(cur); delta = _c(delta); data = _c(data)
+    M_out = np.empty_like(M); d_out = np.empty_like(M)
+    lib().orc_gra_update(_fp(M), _fp(last), _fp(cur), ctypes.c_float(eta), ctypes.c_float(alpha), _fp(delta), _fp(data),
+                         ctypes.c_float(eps), ctypes.c_float(lo), ctypes.c_float(hi), _fp(M_out), _fp(d_out), ctypes.c_int64(M.size))
+    return M_out, d_out
+
+
+def adaea_drf(grads, threshold, grad=None):
+    """ensemble/adaea.py:115-136, 74-76, 82 — returns (map [B,1,H,W], grad * mask or None)"""
+    grads = [_c(g) for g in grads]; grad = _c(grad)
+    B, C = grads[0].shape[0], grads[0].shape[1]
+    plane = grads[0].size // (B * C)
+    arr = (_F * len(grads))(*[_fp(g) for g in grads])
+    mp = np.empty((B, 1) + grads[0].shape[2:], np.float32)
+    out = np.empty_like(grad) if grad is not None else None
+    lib().orc_adaea_drf(arr, len(grads), ctypes.c_float(threshold), _fp(grad), _fp(out), _fp(mp), B, C, ctypes.c_int64(plane))
+    return mp, out

@@ -477,3 +477,60 @@ ORC_API void orc_pi_update_linf(const float* delta, const float* data, const flo
     delta_out[j] = min_nan(max_nan(d2, l), h);
   }
 }
+
+/* ---- gradient/gra.py:74-93 + :149 (GRA decay indicator + tensor-step update_delta) ------------------------------------- */
+ORC_API void orc_gra_update(const float* M, const float* last, const float* cur, float eta, float alpha, const float* delta,
+                            const float* data, float eps, float lo, float hi, float* M_out, float* delta_out, int64_t N) {
+  const float neg_eps = -eps;
+  for (int64_t j = 0; j < N; ++j) {
+    const float sl = last ? sgnf(last[j]) : 0.0f, sc = sgnf(cur[j]);
+    const float eq = (sl == sc) ? 1.0f : 0.0f;
+    const float di = 1.0f - eq;
+    const float t = di * eta;
+    const float f = eq + t;
+    const float m = M[j] * f;
+    const float a = m * alpha;
+    const float st = a * sc;
+    const float d1 = delta[j] + st;
+    const float d2 = min_nan(max_nan(d1, neg_eps), eps);
+    const float l = lo - data[j], h = hi - data[j];
+    M_out[j] = m;
+    delta_out[j] = min_nan(max_nan(d2, l), h);
+  }
+}
+
+/* ---- ensemble/adaea.py:115-136 (disparity-reduced filter) + :74-76 (threshold) + :82 (grad * mask) ------------------------
+ * grads: K pointers to [B, C, plane]; map_out [B, plane] (nullable); out = grad * mask (both nullable together).           */
+ORC_API void orc_adaea_drf(const float* const* grads, int K, float threshold, const float* grad, float* out, float* map_out,
+                           int B, int C, int64_t plane) {
+  float u[8][4];
+  for (int b = 0; b < B; ++b)
+    for (int64_t q = 0; q < plane; ++q) {
+      for (int k = 0; k < K; ++k) {
+        float s = 0.0f, w[4], s2 = 0.0f;
+        for (int c = 0; c < C; ++c) { const float v = grads[k][((int64_t)b * C + c) * plane + q]; const float vv = v * v; s = s + vv; }
+        const float nrm = sqrtf(s);
+        const float den = nrm > 1e-12f ? nrm : 1e-12f;
+        for (int c = 0; c < C; ++c) { w[c] = grads[k][((int64_t)b * C + c) * plane + q] / den; const float ww = w[c] * w[c]; s2 = s2 + ww; }
+        const float n2 = sqrtf(s2);
+        const float den2 = n2 > 1e-8f ? n2 : 1e-8f;
+        for (int c = 0; c < C; ++c) u[k][c] = w[c] / den2;
+      }
+      float tot = 0.0f;
+      for (int a = 0; a < K - 1; ++a) {
+        float row = 0.0f;
+        for (int j = 0; j < K; ++j) {
+          if (j == a) continue;
+          float d = 0.0f;
+          for (int c = 0; c < C; ++c) { const float pr = u[a][c] * u[j][c]; d = d + pr; }
+          row = row + d;
+        }
+        tot = tot + row / (float)(K - 1);
+      }
+      const float m = tot / (float)K;
+      const float mask = (m >= threshold) ? 1.0f : ((m < threshold) ? 0.0f : m);
+      if (map_out) map_out[(int64_t)b * plane + q] = m;
+      if (grad)
+        for (int c = 0; c < C; ++c) { const int64_t i = ((int64_t)b * C + c) * plane + q; out[i] = grad[i] * mask; }
+    }
+}

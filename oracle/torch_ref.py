@@ -381,10 +381,90 @@ class RefPIFGSM(RefAttack):           # gradient/pifgsm.py:33-102 (device-agnost
         return delta.detach()
 
 
+class RefGRA(RefAttack):              # gradient/gra.py:33-153
+    def __init__(self, model, beta=3.5, num_neighbor=20, **kw):
+        super().__init__(model, **kw)
+        self.radius, self.num_neighbor = beta * self.epsilon, num_neighbor
+
+    def forward(self, data, label, **kw):
+        data, label = self._prep(data, label)
+        delta = self.init_delta(data)
+        eta = 0.94
+        M = torch.full_like(delta, 1 / eta)
+        momentum = 0
+        for _ in range(self.epoch):
+            grad = self.get_grad(self.get_loss(self.get_logits(self.transform(data + delta, momentum=momentum)), label), delta)
+            sam = 0
+            for _k in range(self.num_neighbor):                                                           # gra.py:42-58
+                noise = torch.zeros_like(delta).uniform_(-self.radius, self.radius).to(self.device)
+                sam += self.get_grad(self.get_loss(self.get_logits(self.transform(data + delta + noise, momentum=momentum)), label), delta)
+            sam = sam / self.num_neighbor
+            a, b = grad.view(grad.size(0), -1), sam.view(sam.size(0), -1)                                 # gra.py:60-72
+            s = (torch.sum(a * b, dim=1) / (torch.sqrt(torch.sum(a ** 2, dim=1)) * torch.sqrt(torch.sum(b ** 2, dim=1)))).view(-1, 1, 1, 1)
+            cur = s * grad + (1 - s) * sam
+            last = momentum
+            momentum = self.get_momentum(cur, momentum)
+            last_t = torch.full(momentum.shape, last).to(momentum.device) if isinstance(last, int) else last   # gra.py:79-85
+            eq = (last_t.sign() == momentum.sign()).float()                                              # gra.py:87-91
+            M = M * (eq + (torch.ones_like(delta) - eq) * eta)
+            delta = self.update_delta(delta, data, momentum, M * self.alpha)
+        return delta.detach()
+
+
+class RefAdaEA(RefAttack):            # ensemble/adaea.py:10-150 (model: RefEnsemble)
+    def __init__(self, model, beta=10, threshold=-0.3, random_start=True, **kw):
+        super().__init__(model, random_start=random_start, **kw)
+        self.beta, self.threshold, self.K = beta, threshold, model.num_models
+
+    def _one_step(self, x0, xa, g):                                                                     # adaea.py:138-148
+        d = torch.clamp(xa.detach() + g.sign() * self.alpha - x0.detach(), -self.epsilon, self.epsilon)
+        return torch.clamp(x0.detach() + d, max=1.0, min=0.0)
+
+    def drf_map(self, grads, shape):                                                                    # adaea.py:115-136
+        K, (B, _, H, W) = self.K, shape
+        pair = torch.zeros(K, K, B, H, W, dtype=torch.float, device=self.device)
+        rows = torch.zeros(K, B, H, W, dtype=torch.float, device=self.device)
+        cos = nn.CosineSimilarity(dim=1, eps=1e-8)
+        for i in range(K):
+            for j in range(i + 1, K):
+                pair[i][j] = cos(F.normalize(grads[i], dim=1), F.normalize(grads[j], dim=1))
+            if i < K - 1:                       # the reference tests the inner loop's leaked j (= K-1)
+                rows[i] = (pair[i, :].sum(dim=0) + pair[:, i].sum(dim=0)) / (K - 1)
+        return rows.mean(dim=0).view(B, 1, H, W)
+
+    def forward(self, data, label, **kw):
+        data, label = data.clone().detach().to(self.device), label.clone().detach().to(self.device)
+        ce = nn.CrossEntropyLoss()
+        K, members = self.K, self.model.models
+        momentum = 0.
+        delta = torch.zeros_like(data).to(self.device) + 0.001 * torch.randn(data.shape, device=self.device)
+        delta.requires_grad = True
+        for _ in range(self.epoch):
+            outs = [members[k](delta + data) for k in range(K)]
+            grads = [torch.autograd.grad(ce(outs[k], label), delta, retain_graph=True, create_graph=False)[0] for k in range(K)]
+            adv = [self._one_step(data, data + delta, grads[k]) for k in range(K)]                       # agm, adaea.py:87-113
+            own = [ce(members[k](adv[k]), label) for k in range(K)]
+            w = torch.zeros(size=(K,), device=self.device)
+            for j in range(K):
+                for i in range(K):
+                    if i != j:
+                        w[j] += ce(members[i](adv[j]), label) / own[i] * self.beta
+            w = torch.softmax(w, dim=0)
+            mp = self.drf_map(grads, data.shape)
+            mp[mp >= self.threshold] = 1.
+            mp[mp < self.threshold] = 0.
+            out = (torch.stack(outs, dim=0) * w.view(K, 1, 1)).sum(dim=0)
+            grad = torch.autograd.grad(ce(out, label).sum(dim=0), delta)[0] * mp
+            momentum = self.get_momentum(grad, momentum)
+            delta = self.update_delta(delta, data, momentum, self.alpha)
+        return delta.detach()
+
+
 REF_ZOO = {
     "fgsm": ref_fgsm, "ifgsm": ref_ifgsm, "mifgsm": ref_mifgsm, "nifgsm": RefNIFGSM, "dim": RefDIM,
     "tim": RefTIM, "sim": RefSIM, "admix": RefAdmix, "ditimi": RefDITIMI, "vmifgsm": RefVMIFGSM,
     "vnifgsm": RefVNIFGSM, "emifgsm": RefEMIFGSM, "ens": ref_mifgsm, "pifgsm": RefPIFGSM, "siditimi": RefSIDITIMI,
+    "gra": RefGRA, "adaea": RefAdaEA,
 }
 
 

@@ -157,6 +157,16 @@ class OracleBackend:
                                      float(lo), float(hi))
         return _t(a), _t(d)
 
+    def gra_update(self, M, last, cur, eta, alpha, delta, data, eps, lo, hi):
+        self._log("gra_update")
+        m, d = oracle.gra_update(_np(M), _np(last), _np(cur), float(eta), float(alpha), _np(delta), _np(data), float(eps), float(lo), float(hi))
+        return _t(m), _t(d)
+
+    def adaea_drf(self, grads, threshold, grad=None, want_map=False):
+        self._log("adaea_drf")
+        mp, out = oracle.adaea_drf([_np(g) for g in grads], float(threshold), _np(grad))
+        return (None if out is None else _t(out)), (_t(mp) if (want_map or grad is None) else None)
+
     def lin_sample(self, x, gbar, coefs, forward=True):
         self._log("lin_sample")
         if forward:

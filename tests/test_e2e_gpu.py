@@ -246,6 +246,28 @@ def test_pifgsm_native_matches_restatement_on_gpu():
         assert float(d.abs().max()) <= 16 / 255 + 1e-7
 
 
+def test_gra_and_adaea_native_match_restatement_on_gpu():
+    """SURVEY §8 f4 on the GPU: native GRA (ta_gra_update, in-kernel Philox neighbours) bit-identical to the restatement of
+    gradient/gra.py; native AdaEA (ta_adaea_drf) equal to the restatement of ensemble/adaea.py up to pixels whose map value is
+    within rounding of the threshold."""
+    net = _net()
+    x, y = _data()
+    kw = {"num_neighbor": 3, "epoch": 4}
+    seed_all(2); torch.cuda.manual_seed_all(2)
+    ref = torch_ref.RefGRA(torch_ref.ref_wrap_model(net), **kw)(x, y)
+    seed_all(2); torch.cuda.manual_seed_all(2)
+    d = make_attack(tab, "gra", net, **kw)(x, y)
+    REPORT["gra"] = _stats(d, ref, x)
+    assert torch.equal(d, ref), REPORT["gra"]
+    nets = [_net("resnet18", 0), _net("mobilenet_v2", 3), _net("resnet18", 5)]
+    seed_all(3); torch.cuda.manual_seed_all(3)
+    ref = torch_ref.RefAdaEA(torch_ref.RefEnsemble([torch_ref.ref_wrap_model(n) for n in nets]), epoch=3)(x, y)
+    seed_all(3); torch.cuda.manual_seed_all(3)
+    d = make_attack(tab, "adaea", nets, epoch=3)(x, y)
+    REPORT["adaea"] = _stats(d, ref, x)
+    assert REPORT["adaea"]["n_gt_1e-5"] <= 1e-5 * d.numel(), REPORT["adaea"]
+
+
 def test_cuda_graph_is_refused_for_host_rng_transforms():
     net = _net()
     x, y = _data(2)

@@ -118,6 +118,33 @@ def test_normalize_fold_is_bit_identical(oracle_backend, name, mean_mode):
         assert bits_equal(d_fold.numpy(), ref.numpy())
 
 
+def test_gra_and_adaea_native_match_restatement(E, oracle_backend):
+    """native GRA (ta_gra_update: decay indicator + tensor-step update in one launch) and AdaEA (ta_adaea_drf: the
+    whole disparity-reduced filter in one launch) against the eager restatements of gradient/gra.py and ensemble/adaea.py
+    (pinned to the live reference in tests/test_reference_live.py). GRA's ops are all bit-determined; AdaEA's filter enters
+    through a 0/1 threshold on the map, so only pixels whose map value sits within rounding of the threshold could differ."""
+    x, y = _inputs(E)
+    kw = {"num_neighbor": 3, "epoch": 3}
+    seed_all(2); ref = torch_ref.RefGRA(torch_ref.ref_wrap_model(tiny_net(0)), **kw)(x, y)
+    oracle_backend.calls.clear()
+    seed_all(2); d = make_attack(tab, "gra", tiny_net(0), **kw)(x, y)
+    assert oracle_backend.calls.count("gra_update") == 3 and "update_linf" not in oracle_backend.calls
+    assert bits_equal(d.numpy(), ref.numpy()), n_diff_bits(d.numpy(), ref.numpy())
+    # the public hook alone (plugins that call get_decay_indicator themselves, e.g. the reference's fgsra.py)
+    atk = make_attack(tab, "gra", tiny_net(0), **kw)
+    M = torch.full_like(x, 1 / 0.94); cur = torch.randn_like(x); last = torch.randn_like(x)
+    for lst in (0, last):
+        lt = torch.zeros_like(cur) if isinstance(lst, int) else lst
+        eq = (lt.sign() == cur.sign()).float()
+        assert bits_equal(atk.get_decay_indicator(M, x, cur, lst, 0.94).numpy(), (M * (eq + (torch.ones_like(x) - eq) * 0.94)).numpy())
+    nets = [tiny_net(0), tiny_net(3), tiny_net(5)]
+    seed_all(4); ref = torch_ref.RefAdaEA(torch_ref.RefEnsemble([torch_ref.ref_wrap_model(n) for n in nets]), epoch=2)(x, y)
+    oracle_backend.calls.clear()
+    seed_all(4); d = make_attack(tab, "adaea", nets, epoch=2)(x, y)
+    assert oracle_backend.calls.count("adaea_drf") == 2
+    assert int((d != ref).sum()) <= 1e-5 * d.numel()
+
+
 def test_pifgsm_native_matches_restatement(E, oracle_backend):
     """PI-FGSM on the kernels (ta_pi_cut_noise → ta_dwconv2d → ta_pi_update_linf) against the eager restatement
     of gradient/pifgsm.py. Every op is bit-exact except the 3x3 projection convolution, whose 8-term sums torch may add in
@@ -297,9 +324,10 @@ def test_save_images_quantisation(tmp_path):
 def test_graph_capture_is_opt_in_per_hook_owner():
     """A CUDA graph replays what ran at capture time; a transform that flips a host coin per call must therefore never
     be captured. Every class defining a loop hook has to declare graph_safe itself — inheriting the flag is not enough."""
-    ok = {n: make_attack(tab, n, [tiny_net(0), tiny_net(1)] if n == "ens" else tiny_net(0))._graph_ok() for n in tab.attack_zoo}
+    ok = {n: make_attack(tab, n, [tiny_net(0), tiny_net(1)] if n in ("ens", "adaea") else tiny_net(0))._graph_ok() for n in tab.attack_zoo}
     assert ok == {"fgsm": True, "ifgsm": True, "mifgsm": True, "nifgsm": True, "tim": True, "sim": True, "ens": True,
-                  "dim": False, "admix": False, "ditimi": False, "vmifgsm": False, "vnifgsm": False, "emifgsm": False, "pifgsm": False, "siditimi": False}
+                  "dim": False, "admix": False, "ditimi": False, "vmifgsm": False, "vnifgsm": False, "emifgsm": False, "pifgsm": False, "siditimi": False,
+                  "gra": False, "adaea": False}
     base = tab.load_attack_class("mifgsm")
 
     class Custom(base):                          # a user plugin overriding a hook without declaring anything

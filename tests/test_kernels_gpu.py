@@ -511,6 +511,61 @@ def test_fused_all_zero_gradient_sample(be):
     assert bits_equal(npy(gm), mo) and bits_equal(npy(dd), do)
 
 
+# ---------------------------------------------------------------------------------------------- GRA / AdaEA
+@pytest.mark.parametrize("shape", [(4, 3, 224, 224), (2, 3, 17, 19), (64, 3, 224, 224)])
+def test_gra_update_matches_oracle(be, shape):
+    """ta_gra_update (gra.py:74-93 + 149) — every op has a determined order: bit-exact, incl. NaN / zero momentum entries, the
+    first iteration's python-0 `last`, and in place on M and delta"""
+    rng = np.random.default_rng(sum(shape))
+    M = (1 / 0.94 * 0.94 ** rng.integers(0, 4, shape)).astype(np.float32)
+    cur = rng.standard_normal(shape).astype(np.float32); last = rng.standard_normal(shape).astype(np.float32)
+    cur.reshape(-1)[:5] = 0.0; last.reshape(-1)[3:8] = 0.0; cur.reshape(-1)[9] = np.nan; last.reshape(-1)[10] = np.nan
+    x = rng.random(shape, dtype=np.float32)
+    d = ((rng.random(shape, dtype=np.float32) * 2 - 1) * EPS).astype(np.float32)
+    for lst in (None, last):
+        m1, d1 = be.gra_update(cu(M), cu(lst), cu(cur), 0.94, ALPHA, cu(d), cu(x), EPS, 0.0, 1.0)
+        om, od = oracle.gra_update(M, lst, cur, 0.94, ALPHA, d, x, EPS)
+        assert bits_equal(npy(m1), om) and bits_equal(npy(d1), od), (shape, lst is None)
+        if lst is not None:      # against the reference's own ops on the GPU
+            tM, tl, tc, td, tx = cu(M), cu(last), cu(cur), cu(d), cu(x)
+            eq = (tl.sign() == tc.sign()).float()
+            M2 = tM * (eq + (torch.ones_like(td) - eq) * 0.94)
+            d2 = torch.clamp(td + (M2 * ALPHA) * tc.sign(), -EPS, EPS)
+            d2 = torch.min(torch.max(d2, 0 - tx), 1.0 - tx)
+            assert bits_equal(npy(m1), npy(M2)) and bits_equal(npy(d1), npy(d2))
+
+
+@pytest.mark.parametrize("K,shape", [(4, (3, 3, 224, 224)), (2, (2, 3, 17, 19)), (3, (8, 3, 64, 64)), (8, (2, 3, 32, 32))])
+def test_adaea_drf_matches_oracle_and_torch(be, K, shape):
+    """ta_adaea_drf (adaea.py:115-136, 74-76, 82): the map within 2e-6 of the C oracle and of torch's own op chain (torch's order
+    inside its 3-element norms / dot products is not specified), the thresholded product equal wherever the map is not within
+    2e-6 of the threshold."""
+    import torch.nn.functional as F
+    rng = np.random.default_rng(K)
+    grads = [(rng.standard_normal(shape) * 10.0 ** rng.integers(-6, 0)).astype(np.float32) for _ in range(K)]
+    grads[0][0, :, 0, :5] = 0.0                                   # all-zero pixels: normalize → 0, cosine → 0
+    grad = rng.standard_normal(shape).astype(np.float32)
+    thr = -0.3
+    out, mp = be.adaea_drf([cu(g) for g in grads], thr, cu(grad), want_map=True)
+    omp, oout = oracle.adaea_drf(grads, thr, grad)
+    assert np.abs(npy(mp) - omp).max() <= 2e-6
+    tg = [cu(g) for g in grads]
+    B, _, H, W = shape
+    pair = torch.zeros(K, K, B, H, W, device="cuda"); rows = torch.zeros(K, B, H, W, device="cuda")
+    cos = torch.nn.CosineSimilarity(dim=1, eps=1e-8)
+    for i in range(K):
+        for j in range(i + 1, K):
+            pair[i][j] = cos(F.normalize(tg[i], dim=1), F.normalize(tg[j], dim=1))
+        if i < K - 1:
+            rows[i] = (pair[i, :].sum(dim=0) + pair[:, i].sum(dim=0)) / (K - 1)
+    tmap = rows.mean(dim=0).view(B, 1, H, W)
+    assert float((mp - tmap).abs().max()) <= 2e-6
+    mask = (tmap >= thr).float()
+    safe = ((tmap - thr).abs() > 2e-6).expand(-1, shape[1], -1, -1)
+    assert torch.equal(out[safe], (cu(grad) * mask)[safe])
+    assert bits_equal(npy(out)[np.abs(omp - thr).repeat(shape[1], 1) > 2e-6], oout[np.abs(omp - thr).repeat(shape[1], 1) > 2e-6])
+
+
 # ---------------------------------------------------------------------------------------------- PI-FGSM (SURVEY §8 f4)
 @pytest.mark.parametrize("shape", [(4, 3, 224, 224), (2, 3, 17, 19), (1, 3, 8, 8)])
 def test_pifgsm_kernels_match_oracle(be, shape):

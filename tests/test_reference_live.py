@@ -77,6 +77,28 @@ def test_torch_ref_pifgsm_equals_live_reference(ref, monkeypatch):
         assert bits_equal(d.numpy(), d_ref.numpy()), (kw, n_diff_bits(d.numpy(), d_ref.numpy()))
 
 
+def test_torch_ref_gra_and_adaea_equal_live_reference(ref):
+    """the restatements of gradient/gra.py and ensemble/adaea.py that the native plugins are tested against"""
+    from oracle import torch_ref
+    x, y = _data()
+    kw = {"num_neighbor": 3, "epoch": 3}
+    seed_all(3); d_ref = make_attack(ref, "gra", _net(), **kw)(x, y)
+    seed_all(3); d = torch_ref.RefGRA(torch_ref.ref_wrap_model(_net()), **kw)(x, y)
+    assert bits_equal(d.numpy(), d_ref.numpy()), n_diff_bits(d.numpy(), d_ref.numpy())
+    nets = [_net(0), _net(3), _net(5), _net(7)]
+    seed_all(5); d_ref = make_attack(ref, "adaea", nets, epoch=2)(x, y)
+    seed_all(5); d = torch_ref.RefAdaEA(torch_ref.RefEnsemble([torch_ref.ref_wrap_model(n) for n in nets]), epoch=2)(x, y)
+    assert bits_equal(d.numpy(), d_ref.numpy()), n_diff_bits(d.numpy(), d_ref.numpy())
+    # and the native plugins (kernels replaced by the C oracle on this box) against the live reference itself
+    import transferattack_b200 as tab
+    seed_all(3); d_ref = make_attack(ref, "gra", _net(), **kw)(x, y)
+    seed_all(3); d = make_attack(tab, "gra", _net(), **kw)(x, y)
+    assert bits_equal(d.numpy(), d_ref.numpy())
+    seed_all(5); d_ref = make_attack(ref, "adaea", nets, epoch=2)(x, y)
+    seed_all(5); d = make_attack(tab, "adaea", nets, epoch=2)(x, y)
+    assert int((d != d_ref).sum()) <= 1e-5 * d.numel()
+
+
 def test_torch_ref_ens_and_composite(ref):
     from oracle import torch_ref
     x, y = _data()

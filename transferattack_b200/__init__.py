@@ -12,9 +12,9 @@ def _zoo():
     """name → (relative module, class); same keys and classes as the reference registry for the accelerated attacks."""
     table = {
         "gradient": ["fgsm:FGSM", "ifgsm:IFGSM", "mifgsm:MIFGSM", "nifgsm:NIFGSM", "vmifgsm:VMIFGSM", "vnifgsm:VNIFGSM",
-                     "emifgsm:EMIFGSM", "pifgsm:PIFGSM"],
+                     "emifgsm:EMIFGSM", "pifgsm:PIFGSM", "gra:GRA"],
         "input_transformation": ["dim:DIM", "tim:TIM", "sim:SIM", "admix:Admix", "di_ti_mi:DITIMI=ditimi", "di_ti_mi:SIDITIMI=siditimi"],
-        "ensemble": ["ens:ENS"],
+        "ensemble": ["ens:ENS", "adaea:AdaEA"],
     }
     zoo = {}
     for package, entries in table.items():

@@ -318,6 +318,28 @@ class CudaBackend:
                                                   _stream()), "ta_pi_update_linf")
         return amp_out, d_out
 
+    def gra_update(self, M, last, cur, eta, alpha, delta, data, eps, lo, hi):
+        """GRA (gra.py:74-93, 149): returns (M * (eq + (1-eq)*eta), update_delta(delta, data, cur, M' * alpha)); last None = python 0"""
+        M = _f32c(M, "M"); last = _f32c(last, "last_momentum"); cur = _f32c(cur, "momentum"); delta = _f32c(delta, "delta"); data = _f32c(data, "data")
+        M_out, d_out = torch.empty_like(M), torch.empty_like(M)
+        with _DeviceOf(M):
+            _lib.check(self.lib.ta_gra_update(_ptr(M), _ptr(last), _ptr(cur), float(eta), float(alpha), _ptr(delta), _ptr(data), float(eps),
+                                              float(lo), float(hi), _ptr(M_out), _ptr(d_out), M.numel(), _stream()), "ta_gra_update")
+        return M_out, d_out
+
+    def adaea_drf(self, grads, threshold, grad=None, want_map=False):
+        """AdaEA (adaea.py:115-136, 74-76, 82): returns (grad * mask or None, map [B,1,H,W] or None) in one launch"""
+        grads = [_f32c(g, "grads") for g in grads]; grad = _f32c(grad, "grad")
+        B, C = grads[0].shape[0], grads[0].shape[1]
+        plane = grads[0].numel() // (B * C)
+        arr = (ctypes.c_void_p * len(grads))(*[g.data_ptr() for g in grads])
+        out = torch.empty_like(grad) if grad is not None else None
+        mp = torch.empty((B, 1) + tuple(grads[0].shape[2:]), device=grads[0].device, dtype=torch.float32) if (want_map or grad is None) else None
+        with _DeviceOf(grads[0]):
+            _lib.check(self.lib.ta_adaea_drf(arr, len(grads), float(threshold), _ptr(grad), _ptr(out), _ptr(mp), B, C, plane, _stream()),
+                       "ta_adaea_drf")
+        return out, mp
+
     def lin_sample(self, x, gbar, coefs, forward=True):
         x = _f32c(x, "x"); K = len(coefs)
         with _DeviceOf(x):
