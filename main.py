@@ -5,8 +5,10 @@ reports the attack success rate of saved PNGs on the eight victim models.
 Differences from the reference driver, none visible in the outputs:
   * `--eps --alpha --epoch --momentum --random_start` ARE forwarded to the attack constructor when given (the reference parses
     them and then builds the attacker with only model_name / targeted, main.py:41); unset flags keep each attack's defaults;
-  * batches go up from pinned host memory; the uint8 quantisation + NHWC transpose of save_images runs on the device
-    (`ta_quantize_u8`) and only bytes come back;
+  * batches are uploaded one batch AHEAD from pinned host memory on a side stream (`PrefetchLoader`); the uint8 quantisation +
+    NHWC transpose of save_images runs on the device (`ta_quantize_u8`), only bytes come back, on a side stream, and the PNGs
+    are encoded by a thread pool while the next batch is attacked (`AsyncImageWriter`; `--sync_io` restores the serial path);
+  * `--eval` under torchrun deals the batches round-robin over the ranks (`multigpu.sharded_asr`), same ASR row;
   * `--gpus N` (under torchrun) shards every batch across ranks with `multigpu.run_sharded` (no data-path collective);
   * `--random_weights` builds surrogates / victims with `weights=None` (offline smoke tests; there is no network here).
 """
@@ -39,6 +41,8 @@ def get_parser():
     p.add_argument('--GPU_ID', default='0', type=str)
     p.add_argument('--random_weights', action='store_true', help='weights=None surrogates/victims (offline smoke test)')
     p.add_argument('--num_workers', default=4, type=int)
+    p.add_argument('--sync_io', action='store_true', help='serial upload / save_images as in the reference (no prefetch, no async writer)')
+    p.add_argument('--eval_bf16', action='store_true', help='run the victim models under bf16 autocast in --eval (inference only)')
     return p.parse_args()
 
 
@@ -79,17 +83,28 @@ def main():
     dataset = AdvDataset(input_dir=args.input_dir, output_dir=args.output_dir, targeted=args.targeted, eval=args.eval)
     loader = torch.utils.data.DataLoader(dataset, batch_size=args.batchsize, shuffle=False, num_workers=args.num_workers,
                                          pin_memory=True)
+    device = torch.device("cuda", torch.cuda.current_device())
     if not args.eval:
         attacker = _build_attacker(args)
-        for batch_idx, (images, labels, filenames) in tqdm.tqdm(enumerate(loader), disable=rank != 0):
-            if args.targeted and isinstance(labels, (list, tuple)):
-                labels = torch.stack(list(labels))
-            if world > 1:
-                delta = multigpu.run_sharded(attacker, images, labels, seed=batch_idx, gather=True)
-            else:
-                delta = attacker(images, labels)
-            if rank == 0:
-                save_images(args.output_dir, images.to(delta.device, non_blocking=True), filenames, delta=delta)
+        batches = loader if (args.sync_io or world > 1) else PrefetchLoader(loader, device)
+        writer = None if args.sync_io else AsyncImageWriter(workers=max(2, args.num_workers))
+        try:
+            for batch_idx, (images, labels, filenames) in tqdm.tqdm(enumerate(batches), disable=rank != 0):
+                if args.targeted and isinstance(labels, (list, tuple)):
+                    labels = torch.stack(list(labels))
+                if world > 1:
+                    delta = multigpu.run_sharded(attacker, images, labels, seed=batch_idx, gather=True)
+                else:
+                    delta = attacker(images, labels)
+                if rank == 0:
+                    x_dev = images.to(delta.device, non_blocking=True)
+                    if writer is None:
+                        save_images(args.output_dir, x_dev, filenames, delta=delta)
+                    else:
+                        writer.submit(args.output_dir, x_dev, filenames, delta=delta)
+        finally:
+            if writer is not None:
+                writer.close()
     else:
         res = '|'
         victims = [(n, models.__dict__[n](weights=None if args.random_weights else "DEFAULT")) for n in cnn_model_paper] \
@@ -98,25 +113,17 @@ def main():
             model = wrap_model(model.eval().cuda())
             for p_ in model.parameters():
                 p_.requires_grad = False
-            asr = evaluate(model, loader, args.targeted)
-            print(f'{model_name}: {asr:.1f}')
+            asr = multigpu.sharded_asr(model, loader, args.targeted, device, dtype=torch.bfloat16 if args.eval_bf16 else None)
+            if rank == 0:
+                print(f'{model_name}: {asr:.1f}')
             res += f' {asr:.1f} |'
-        print(res)
-        with open('results_eval.txt', 'a') as f:
-            f.write(args.output_dir + res + '\n')
-
-
-@torch.no_grad()
-def evaluate(model, loader, is_targeted):
-    """attack success rate in percent (reference main.py:80-94)"""
-    correct, total = 0, 0
-    for images, labels, _ in loader:
-        if is_targeted:
-            labels = labels[1]
-        pred = model(images.cuda(non_blocking=True)).argmax(dim=1).cpu()
-        correct += int((labels == pred).sum())
-        total += labels.shape[0]
-    return (correct / total) * 100 if is_targeted else (1 - correct / total) * 100
+        if rank == 0:
+            print(res)
+            with open('results_eval.txt', 'a') as f:
+                f.write(args.output_dir + res + '\n')
+    if world > 1:
+        import torch.distributed as dist
+        dist.destroy_process_group()
 
 
 if __name__ == '__main__':

@@ -339,3 +339,29 @@ def test_graph_capture_is_opt_in_per_hook_owner():
         def load_model(self, n):
             return super().load_model(n)
     assert make_attack(tab, OnlyCtor, tiny_net(0))._graph_ok()
+
+
+def test_async_writer_and_prefetch_loader_match_the_serial_path(tmp_path):
+    """SURVEY §8 f2 on CPU tensors: AsyncImageWriter produces the files save_images produces (same bytes in, same PNG out),
+    errors surface at flush; PrefetchLoader yields the loader's batches unchanged, one ahead."""
+    from PIL import Image
+    from transferattack_b200.utils import AsyncImageWriter, PrefetchLoader, save_images
+    g = torch.Generator().manual_seed(3)
+    x = torch.rand(5, 3, 32, 32, generator=g); d = (torch.rand(5, 3, 32, 32, generator=g) - 0.5) * 0.1
+    a, b = tmp_path / "sync", tmp_path / "async"
+    a.mkdir(); b.mkdir()
+    names = ["im%d.png" % i for i in range(5)]
+    save_images(str(a), x, names, delta=d)
+    with AsyncImageWriter(workers=3, max_pending=1) as w:
+        w.submit(str(b), x[:2], names[:2], delta=d[:2])
+        w.submit(str(b), x[2:], names[2:], delta=d[2:])
+    for n in names:
+        assert np.array_equal(np.array(Image.open(a / n)), np.array(Image.open(b / n)))
+    w = AsyncImageWriter(workers=1)
+    w.submit(str(tmp_path / "missing_dir"), x[:1], names[:1])
+    with pytest.raises(Exception):
+        w.flush()
+    batches = [(x[i:i + 2], torch.arange(i, min(i + 2, 5)), names[i:i + 2]) for i in range(0, 5, 2)]
+    got = list(PrefetchLoader(batches, "cpu"))
+    assert len(got) == 3 and all(torch.equal(p[0], q[0]) and torch.equal(p[1], q[1]) and p[2] == q[2] for p, q in zip(got, batches))
+    assert list(PrefetchLoader([], "cpu")) == []

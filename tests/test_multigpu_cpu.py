@@ -46,10 +46,16 @@ def _worker(rank, world, init_file, out_dir, case):
                 out = torch.zeros(1)
             except RuntimeError as e:
                 out = torch.ones(1) if "replicas" in str(e) else torch.zeros(1)
-        elif case == "ens":
+        elif case in ("ens", "ens_rs"):
             member = tab.utils.wrap_model(tiny_net(0 if rank == 0 else 3))
-            atk = multigpu.make_ens_attack(tab.load_attack_class("ens"), member, epoch=4)
+            torch.manual_seed(100 + rank)          # different generator states per rank: a random start must still agree
+            atk = multigpu.make_ens_attack(tab.load_attack_class("ens"), member, epoch=4, random_start=(case == "ens_rs"))
             out = atk(x, y)
+        elif case == "asr":
+            model = tab.utils.wrap_model(tiny_net(0))
+            batches = [(x[i:i + 1], y[i:i + 1], ["f%d" % i]) for i in range(x.shape[0])] + [(x[:3], y[:3], ["a", "b", "c"])]
+            out = torch.tensor([multigpu.sharded_asr(model, batches, False, "cpu"),
+                                multigpu.sharded_asr(model, [(b[0], torch.stack([b[1], b[1]]), b[2]) for b in batches], True, "cpu")])
         else:
             raise ValueError(case)
         np.save(os.path.join(out_dir, "%s_rank%d.npy" % (case, rank)), out.detach().cpu().numpy())
@@ -129,3 +135,32 @@ def test_sharded_ensemble_matches_single_device_ensemble():
     ens = torch_ref.RefEnsemble([torch_ref.ref_wrap_model(tiny_net(0)), torch_ref.ref_wrap_model(tiny_net(3))])
     ref = torch_ref.ref_mifgsm(ens, epoch=4)(x, y).numpy()
     assert np.array_equal(outs[0], ref)              # K = 2: two-term sums commute → bit-identical
+
+
+def test_sharded_ensemble_random_start_is_broadcast():
+    """with random_start every rank drew its own delta; the sharded-ensemble attack now broadcasts rank 0's draw,
+    so the replicated updates stay in lockstep (different per-rank generator states on purpose)."""
+    outs = _run("ens_rs")
+    assert np.array_equal(outs[0], outs[1])
+    assert np.abs(outs[0]).max() <= 16 / 255 + 1e-7
+
+
+def test_sharded_asr_equals_single_process_pass():
+    """--eval with the batches dealt round-robin over the ranks returns the ASR a single pass returns"""
+    import transferattack_b200 as tab
+    from transferattack_b200 import multigpu, ops
+    from oracle_backend import OracleBackend
+    from helpers import tiny_net
+    outs = _run("asr")
+    assert np.array_equal(outs[0], outs[1])
+    ops._install_backend_for_tests(OracleBackend())
+    try:
+        x, y = _inputs()
+        model = tab.utils.wrap_model(tiny_net(0))
+        with torch.no_grad():
+            pred = torch.cat([model(x[i:i + 1]).argmax(1) for i in range(4)] + [model(x[:3]).argmax(1)])
+        lab = torch.cat([y, y[:3]])
+        acc = float((pred == lab).sum()) / 7
+        assert abs(outs[0][0] - (1 - acc) * 100) < 1e-9 and abs(outs[0][1] - acc * 100) < 1e-9
+    finally:
+        ops._install_backend_for_tests(None)

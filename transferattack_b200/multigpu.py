@@ -86,6 +86,33 @@ def run_sharded(attacker, data, label, seed=None, gather=False, group=None, **kw
     return torch.cat([p[:n] for p, n in zip(parts, sizes)], dim=0)
 
 
+@torch.no_grad()
+def sharded_asr(model, loader, is_targeted, device, group=None, dtype=None):
+    """Attack success rate in percent (reference main.py:80-94) with the BATCHES dealt round-robin over the ranks of `group`
+    (evaluation is pure inference on independent images → batch-sharded, no data-path collective; two scalars
+    are all-reduced at the end). Every rank returns the same number — the one a single-process pass over `loader` returns.
+    `dtype` (e.g. torch.bfloat16) runs the victim under autocast: inference only, optional, off by default."""
+    rank, world = _world(group)
+    counts = torch.zeros(2, dtype=torch.float64, device=device)
+    for i, (images, labels, _) in enumerate(loader):
+        if i % world != rank:
+            continue
+        if is_targeted:
+            labels = labels[1]
+        x = images.to(device, non_blocking=True)
+        if dtype is not None and torch.device(device).type == "cuda":
+            with torch.autocast("cuda", dtype=dtype):
+                pred = model(x).argmax(dim=1)
+        else:
+            pred = model(x).argmax(dim=1)
+        counts[0] += (labels.to(pred.device) == pred).sum()
+        counts[1] += labels.shape[0]
+    if world > 1:
+        dist.all_reduce(counts, op=dist.ReduceOp.SUM, group=group)
+    correct, total = float(counts[0]), float(counts[1])
+    return (correct / total) * 100 if is_targeted else (1 - correct / total) * 100
+
+
 class _SumGradAcrossRanks(torch.autograd.Function):
     """identity forward; backward all_reduce(SUM)s the gradient wrt the (replicated) model input"""
 

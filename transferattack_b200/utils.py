@@ -7,7 +7,9 @@ Differences that are not visible to callers:
     clone/sub_/div_ and without its per-forward ``(std == 0).any()`` host sync; reference utils.py:72-79);
   * ``clamp`` on CUDA fp32 tensors with per-element bounds of the box form is left to the callers' kernels;
     the function itself keeps the reference's tensor semantics (utils.py:68-69);
-  * ``save_images`` quantises on the device with ``ta_quantize_u8`` before the single D2H copy (utils.py:63-66).
+  * ``save_images`` quantises on the device with ``ta_quantize_u8`` before the single D2H copy (utils.py:63-66);
+    ``AsyncImageWriter`` additionally takes the copy and the PNG encoding off the loop's critical path and
+    ``PrefetchLoader`` uploads the next batch while the current one is attacked.
 """
 import os
 import types
@@ -107,6 +109,131 @@ def save_images(output_dir, adversaries, filenames, delta=None):
         u8 = (adversaries.detach().permute((0, 2, 3, 1)).cpu().numpy() * 255).astype(np.uint8)
     for i, filename in enumerate(filenames):
         Image.fromarray(u8[i]).save(os.path.join(output_dir, filename))
+
+
+class AsyncImageWriter:
+    """``save_images`` off the attack loop's critical path (reference utils.py:63-66 encodes every PNG serially
+    between two batches). ``submit`` quantises on the device (``ta_quantize_u8``: add, *255, truncate, NHWC transpose — the
+    reference's bytes), starts the device→host copy of the BYTES into a pinned buffer on a side stream and returns at once;
+    a thread pool waits for the copy and encodes the PNGs in parallel (Pillow releases the GIL inside zlib). The next batch's
+    attack overlaps both. ``flush`` (or leaving the ``with`` block) waits for everything and re-raises the first error."""
+
+    def __init__(self, workers=8, max_pending=4):
+        import concurrent.futures as cf
+        self._pool = cf.ThreadPoolExecutor(max_workers=max(1, int(workers)))
+        self._pending = []
+        self._max_pending = max(1, int(max_pending))
+        self._streams = {}
+
+    @staticmethod
+    def _encode(u8_row, path):
+        Image.fromarray(u8_row).save(path)
+
+    def _finish(self, event, host_u8, output_dir, filenames):
+        if event is not None:
+            event.synchronize()
+        arr = host_u8.numpy()
+        futs = [self._pool.submit(self._encode, arr[i], os.path.join(output_dir, fn)) for i, fn in enumerate(filenames)]
+        for f in futs:
+            f.result()
+
+    def submit(self, output_dir, adversaries, filenames, delta=None):
+        filenames = list(filenames)
+        if adversaries.is_cuda:
+            dev = adversaries.device
+            zero = torch.zeros_like(adversaries) if delta is None else delta
+            u8 = ops.backend().quantize_u8(adversaries, zero, to_nhwc=True)
+            side = self._streams.get(dev.index)
+            if side is None:
+                side = self._streams[dev.index] = torch.cuda.Stream(device=dev)
+            side.wait_stream(torch.cuda.current_stream(dev))
+            host = torch.empty(u8.shape, dtype=torch.uint8, pin_memory=True)
+            with torch.cuda.stream(side):
+                host.copy_(u8, non_blocking=True)
+                event = torch.cuda.Event()
+                event.record(side)
+            u8.record_stream(side)
+        else:
+            if delta is not None:
+                adversaries = adversaries + delta
+            host = torch.from_numpy((adversaries.detach().permute((0, 2, 3, 1)).cpu().numpy() * 255).astype(np.uint8))
+            event = None
+        import threading
+        t = threading.Thread(target=self._run, args=(event, host, output_dir, filenames), daemon=True)
+        t.err = None
+        t.start()
+        self._pending.append(t)
+        while len(self._pending) > self._max_pending:       # bound the pinned memory in flight
+            self._join(self._pending.pop(0))
+
+    def _run(self, event, host, output_dir, filenames):
+        import threading
+        try:
+            self._finish(event, host, output_dir, filenames)
+        except BaseException as e:     # surfaced by flush()
+            threading.current_thread().err = e
+
+    @staticmethod
+    def _join(t):
+        t.join()
+        if t.err is not None:
+            raise t.err
+
+    def flush(self):
+        while self._pending:
+            self._join(self._pending.pop(0))
+
+    def close(self):
+        self.flush()
+        self._pool.shutdown(wait=True)
+
+    def __enter__(self):
+        return self
+
+    def __exit__(self, *exc):
+        self.close()
+
+
+class PrefetchLoader:
+    """Iterate a ``DataLoader`` one batch AHEAD on the device (reference main.py:41-52 hands the attack pageable
+    host tensors and pays the upload inside every call): while the attack works on batch i, batch i+1 is already pinned
+    (``pin_memory=True`` on the loader) and on its way up on a side stream. Yields ``(images_on_device, labels, filenames)``;
+    labels stay where the loader put them (the attack moves the few bytes itself)."""
+
+    def __init__(self, loader, device):
+        self.loader = loader
+        self.device = torch.device(device)
+        self._side = torch.cuda.Stream(device=self.device) if self.device.type == "cuda" else None
+
+    def __len__(self):
+        return len(self.loader)
+
+    def _upload(self, batch):
+        images = batch[0]
+        if self._side is None:
+            return (images.to(self.device),) + tuple(batch[1:]), None
+        with torch.cuda.stream(self._side):
+            dev = images.to(self.device, non_blocking=True)
+            ev = torch.cuda.Event()
+            ev.record(self._side)
+        return (dev,) + tuple(batch[1:]), ev
+
+    def __iter__(self):
+        it = iter(self.loader)
+        try:
+            nxt = self._upload(next(it))
+        except StopIteration:
+            return
+        while nxt is not None:
+            cur, ev = nxt
+            try:
+                nxt = self._upload(next(it))
+            except StopIteration:
+                nxt = None
+            if ev is not None:
+                torch.cuda.current_stream(self.device).wait_event(ev)
+                cur[0].record_stream(torch.cuda.current_stream(self.device))
+            yield cur
 
 
 def clamp(x, x_min, x_max):
