@@ -245,3 +245,71 @@ def dim_bwd_gather_model(g, rnd, R, top, left):
                     lx, cx = inv1[col]
                     gin[pl, sy, col] = gather(bufG, lo - q0, roww, lx, [tap_w(t1[lx + b], col) for b in range(cx)]) if nq else f32(0)
     return gin
+
+
+# ---- csrc/aten_mean.cuh: the TA_MEAN_TORCH replay, as the kernel executes it --------------------------------------------
+def _shfl_down(v, off, width):
+    """__shfl_down_sync(full, v, off, width) for one warp: lane l reads lane l + off inside its width-lane segment, else itself"""
+    out = v.copy()
+    for l in range(32):
+        if (l % width) + off < width:
+            out[l] = v[l + off]
+    return out
+
+
+def aten_mean_kernel_model(x, cfg, cl=8):
+    """mean of one sample x [n] (already |g|) exactly as csrc/aten_mean.cuh + the fused cluster kernel compute it: rows of S
+    elements, one thread per column (4 accumulators, rows in order), CTA r owning columns [r*W, (r+1)*W); then
+    aten_tree_mean: thread (warp, lane) <-> block position (ty = lane % bh, tx = warp*(32/bh) + lane/bh), y tree by
+    shfl_down inside bh-lane groups, shared-memory transpose, x tree (register halving + shfl_down 1..16), final tree over the
+    cpo block sums. `cl` only changes who owns which column (the DSMEM gather reads element vt from CTA vt // W)."""
+    f32 = np.float32
+    n = x.shape[0]
+    bw, bh, cpo, S = cfg["bw"], cfg["bh"], cfg["cpo"], cfg["stride"]
+    W = S // cl
+    assert S % cl == 0 and W % 4 == 0
+    J = (n + S - 1) // S
+    val = np.zeros(S, f32)
+    for r in range(cl):                                   # phase 1, per CTA and column
+        for col in range(W):
+            e0 = r * W + col
+            rows = (n - e0 + S - 1) // S if e0 < n else 0
+            a = [f32(0)] * 4
+            for j in range(rows):
+                a[j % 4] = f32(a[j % 4] + x[j * S + e0])
+            val[e0] = f32(f32(f32(a[0] + a[1]) + a[2]) + a[3])
+    s_tree = np.zeros(cpo * bw, f32)
+    s_blk = np.zeros(32, f32)
+    lanes = np.arange(32)
+    for warp in range(16):                                # phase 2a: gather + y tree
+        ty = lanes & (bh - 1); tx = warp * (32 // bh) + lanes // bh
+        pos = ty * bw + tx
+        for cb in range(cpo):
+            v = val[cb * 512 + pos].astype(f32)
+            h = bh >> 1
+            while h >= 1:
+                v = (v + _shfl_down(v, h, bh)).astype(f32); h >>= 1
+            s_tree[cb * bw + tx[ty == 0]] = v[ty == 0]
+    K = bw >> 5
+    for warp in range(16):                                # phase 2b: x tree per virtual block
+        for cb in range(warp, cpo, 16):
+            a = np.zeros((8, 32), f32)
+            for k in range(K):
+                a[k] = s_tree[cb * bw + lanes + 32 * k]
+            h = 4
+            while h >= 1:
+                if h < K:
+                    for k in range(h):
+                        a[k] = (a[k] + a[k + h]).astype(f32)
+                h >>= 1
+            v = a[0]
+            o = 1
+            while o < 32:
+                v = (v + _shfl_down(v, o, 32)).astype(f32); o <<= 1
+            s_blk[cb] = v[0]
+    v = np.where(lanes < cpo, s_blk, f32(0)).astype(f32)   # phase 2c: global_reduce's last block
+    if cpo > 1:
+        o = 1
+        while o < 32:
+            v = (v + _shfl_down(v, o, 32)).astype(f32); o <<= 1
+    return v[0]

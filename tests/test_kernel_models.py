@@ -35,3 +35,38 @@ def test_dim_direct_models(S, rnd, R, top, left):
         got = model(g, rnd, R, top, left)
         assert not np.isnan(got).any()
         np.testing.assert_allclose(got, want, rtol=0, atol=2e-6)
+
+
+@pytest.mark.parametrize("B,n,cl", [(64, 150528, 8), (5, 150528, 8), (2, 12288, 1), (9, 12288, 4), (256, 150528, 8), (16, 12288, 16)])
+def test_aten_mean_kernel_model_equals_the_aten_restatement(B, n, cl):
+    """The thread/lane mapping of csrc/aten_mean.cuh (columns per CTA, y tree by segmented shuffles, transposed x tree, final
+    tree) executed step by step in numpy reproduces oracle/aten_reduce.py's restatement of ATen's reduction bit for bit; the
+    restatement itself is pinned against torch on the GPU box (tests/test_kernels_gpu.py, tools/diag_aten_mean.py). Also: the C
+    policy (ta_aten_mean_policy, host-only) equals the Python restatement of setReduceConfig over a grid of shapes."""
+    import ctypes
+    from oracle import aten_reduce
+    from kernel_models import aten_mean_kernel_model
+    cfg = aten_reduce.config(B, n)
+    rng = np.random.default_rng(B + n)
+    x = np.abs(rng.standard_normal(n) * 10.0 ** rng.integers(-4, 3)).astype(np.float32)
+    tot = aten_mean_kernel_model(x, cfg, cl)
+    mine = np.float32(tot * np.float32(np.float32(B) / np.float32(B * n)))
+    ref = aten_reduce.emulate_numpy(np.repeat(x[None], B, 0))
+    assert mine == ref[0] and (ref == ref[0]).all()
+
+
+def test_aten_mean_policy_c_equals_python():
+    import ctypes
+    from oracle import aten_reduce
+    from transferattack_b200 import _lib
+    lib = _lib.load()
+    for sm, mt in ((148, 2048), (132, 2048), (108, 2048), (84, 1536)):
+        for B in (1, 2, 3, 4, 7, 8, 15, 16, 31, 32, 64, 65, 128, 256, 512, 592, 593, 600, 1024):
+            for n in (8, 31, 32, 37, 512, 1024, 1200, 3072, 12288, 50176, 150528, 268203, 442368, 786432):
+                bw, bh, cpo = ctypes.c_int(), ctypes.c_int(), ctypes.c_int()
+                rc = lib.ta_aten_mean_policy(B, n, sm, mt, ctypes.byref(bw), ctypes.byref(bh), ctypes.byref(cpo))
+                cfg = aten_reduce.config(B, n, sm, mt)
+                if cfg is None:
+                    assert rc == _lib.TA_EUNSUPPORTED, (B, n, sm)
+                else:
+                    assert rc == 0 and (bw.value, bh.value, cpo.value) == (cfg["bw"], cfg["bh"], cfg["cpo"]), (B, n, sm, cfg)

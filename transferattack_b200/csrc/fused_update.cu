@@ -194,7 +194,7 @@ __global__ void __launch_bounds__(kThreads, (U <= 2 ? 2 : 1)) fused_cluster_kern
       float* sp = sg + col;
       const int64_t gi0 = col0 + (col >> 2);
       ColAcc A;
-#pragma unroll
+#pragma unroll 1
       for (int q = 0; q < kChunks; ++q) {
         const int a = q * RG, b = (a + RG < rows) ? a + RG : rows;
         if (b > a) {
