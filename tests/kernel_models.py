@@ -248,8 +248,8 @@ def dim_bwd_gather_model(g, rnd, R, top, left):
 
 
 # ---- csrc/aten_mean.cuh: the TA_MEAN_TORCH replay, as the kernel executes it --------------------------------------------
-def _shfl_down(v, off, width):
-    """__shfl_down_sync(full, v, off, width) for one warp: lane l reads lane l + off inside its width-lane segment, else itself"""
+def _shfl_down(v, off, width=32):
+    """__shfl_down_sync(full, v, off) for one warp: lane l reads lane l + off, or itself when that is past the warp"""
     out = v.copy()
     for l in range(32):
         if (l % width) + off < width:
@@ -257,59 +257,62 @@ def _shfl_down(v, off, width):
     return out
 
 
+def _x_tree(a, K):
+    """aten_x_tree<16>: a[k][lane] = value[tx = lane + 32k]; register halving (the shared-memory levels), then shfl_down 16..1"""
+    f32 = np.float32
+    h = 8
+    while h >= 1:
+        if h < K:
+            for k in range(h):
+                a[k] = (a[k] + a[k + h]).astype(f32)
+        h >>= 1
+    v = a[0]
+    for o in (16, 8, 4, 2, 1):
+        v = (v + _shfl_down(v, o)).astype(f32)
+    return v[0]
+
+
 def aten_mean_kernel_model(x, cfg, cl=8):
-    """mean of one sample x [n] (already |g|) exactly as csrc/aten_mean.cuh + the fused cluster kernel compute it: rows of S
-    elements, one thread per column (4 accumulators, rows in order), CTA r owning columns [r*W, (r+1)*W); then
-    aten_tree_mean: thread (warp, lane) <-> block position (ty = lane % bh, tx = warp*(32/bh) + lane/bh), y tree by
-    shfl_down inside bh-lane groups, shared-memory transpose, x tree (register halving + shfl_down 1..16), final tree over the
-    cpo block sums. `cl` only changes who owns which column (the DSMEM gather reads element vt from CTA vt // W)."""
+    """mean-sum of one sample x [n] (already |g|) exactly as csrc/aten_mean.cuh + the fused cluster kernel compute it: rows of S
+    128-bit vectors, one thread per vector column (the 4 accumulators are the 4 components, rows in order), CTA r owning
+    columns [r*W4, (r+1)*W4); then aten_tree_mean: a warp per (virtual block, ty) row — lanes hold tx = lane + 32k —, one
+    thread per virtual block for the y tree, the final tree over the cpo block sums. `cl` only changes who owns which column
+    (the DSMEM gather reads virtual thread vt's value from CTA vt // W4)."""
     f32 = np.float32
     n = x.shape[0]
     bw, bh, cpo, S = cfg["bw"], cfg["bh"], cfg["cpo"], cfg["stride"]
-    W = S // cl
-    assert S % cl == 0 and W % 4 == 0
-    J = (n + S - 1) // S
+    assert n % 4 == 0 and S % cl == 0
+    nvec = n // 4
+    X = x.reshape(nvec, 4)
     val = np.zeros(S, f32)
-    for r in range(cl):                                   # phase 1, per CTA and column
-        for col in range(W):
-            e0 = r * W + col
-            rows = (n - e0 + S - 1) // S if e0 < n else 0
-            a = [f32(0)] * 4
-            for j in range(rows):
-                a[j % 4] = f32(a[j % 4] + x[j * S + e0])
-            val[e0] = f32(f32(f32(a[0] + a[1]) + a[2]) + a[3])
-    s_tree = np.zeros(cpo * bw, f32)
-    s_blk = np.zeros(32, f32)
-    lanes = np.arange(32)
-    for warp in range(16):                                # phase 2a: gather + y tree
-        ty = lanes & (bh - 1); tx = warp * (32 // bh) + lanes // bh
-        pos = ty * bw + tx
-        for cb in range(cpo):
-            v = val[cb * 512 + pos].astype(f32)
-            h = bh >> 1
-            while h >= 1:
-                v = (v + _shfl_down(v, h, bh)).astype(f32); h >>= 1
-            s_tree[cb * bw + tx[ty == 0]] = v[ty == 0]
+    for t in range(S):                                    # phase 1 (the owner CTA is t // (S // cl); irrelevant for the value)
+        a = np.zeros(4, f32)
+        for v in range(t, nvec, S):
+            a = (a + X[v]).astype(f32)
+        val[t] = f32(f32(f32(a[0] + a[1]) + a[2]) + a[3])
     K = bw >> 5
-    for warp in range(16):                                # phase 2b: x tree per virtual block
-        for cb in range(warp, cpo, 16):
-            a = np.zeros((8, 32), f32)
-            for k in range(K):
-                a[k] = s_tree[cb * bw + lanes + 32 * k]
-            h = 4
-            while h >= 1:
-                if h < K:
-                    for k in range(h):
-                        a[k] = (a[k] + a[k + h]).astype(f32)
-                h >>= 1
-            v = a[0]
-            o = 1
-            while o < 32:
-                v = (v + _shfl_down(v, o, 32)).astype(f32); o <<= 1
-            s_blk[cb] = v[0]
-    v = np.where(lanes < cpo, s_blk, f32(0)).astype(f32)   # phase 2c: global_reduce's last block
-    if cpo > 1:
-        o = 1
-        while o < 32:
-            v = (v + _shfl_down(v, o, 32)).astype(f32); o <<= 1
-    return v[0]
+    lanes = np.arange(32)
+    s_row = np.zeros(cpo * bh, f32)
+    for row in range(cpo * bh):                           # phase 2a: x tree per (virtual block, ty) row
+        base = row * bw
+        a = [np.zeros(32, f32) for _ in range(16)]
+        for k in range(K):
+            a[k] = val[base + lanes + 32 * k].astype(f32)
+        s_row[row] = _x_tree(a, K)
+    s_blk = np.zeros(max(cpo, 1), f32)
+    for cb in range(cpo):                                 # phase 2b: y tree, one thread per virtual block
+        a = [s_row[cb * bh + y] if y < bh else f32(0) for y in range(16)]
+        h = 8
+        while h >= 1:
+            if h < bh:
+                for y in range(h):
+                    a[y] = f32(a[y] + a[y + h])
+            h >>= 1
+        s_blk[cb] = a[0]
+    if cpo == 1:
+        return s_blk[0]
+    a = [np.zeros(32, f32) for _ in range(16)]            # phase 2c: global_reduce's last block
+    for k in range(K):
+        idx = lanes + 32 * k
+        a[k] = np.where(idx < cpo, s_blk[np.minimum(idx, cpo - 1)], f32(0)).astype(f32)
+    return _x_tree(a, K)

@@ -268,6 +268,36 @@ def test_gra_and_adaea_native_match_restatement_on_gpu():
     assert REPORT["adaea"]["n_gt_1e-5"] <= 1e-5 * d.numel(), REPORT["adaea"]
 
 
+def test_fast_mode_is_opt_in_and_keeps_the_attack_strength():
+    """The opt-in bf16 / channels_last surrogate (Attack.fast_mode) is NOT a parity path: its acceptance is that the
+    perturbation is a valid one (eps-ball, [0,1] box) and attacks the fp32 surrogate about as well as the strict path's —
+    white-box loss increase >= 90 % of the strict one. It is off unless asked for."""
+    net = _net("resnet50")
+    x, y = _data(16)
+    wrapped = tab.utils.wrap_model(net)
+    ce = torch.nn.CrossEntropyLoss()
+
+    def loss_of(d):
+        with torch.no_grad():
+            return float(ce(wrapped(x.cuda() + d), y.cuda()))
+    strict = make_attack(tab, "mifgsm", net)
+    assert strict.fast_mode == ""
+    d0 = strict(x, y)
+    res = {"clean": loss_of(torch.zeros_like(d0)), "strict": loss_of(d0)}
+    for name, kw in (("mifgsm", {}), ("vmifgsm", {"num_neighbor": 4, "epoch": 5})):
+        fast = make_attack(tab, name, net, **kw)
+        fast.fast_mode = "bf16"
+        d1 = fast(x, y)
+        assert d1.dtype == torch.float32 and float(d1.abs().max()) <= 16 / 255 + 1e-7
+        adv = x.cuda() + d1
+        assert float(adv.min()) >= 0.0 and float(adv.max()) <= 1.0
+        res["fast_" + name] = loss_of(d1)
+    REPORT["fast_mode"] = res
+    gain_strict = res["strict"] - res["clean"]
+    assert gain_strict > 0 and res["fast_mifgsm"] - res["clean"] >= 0.9 * gain_strict, res
+    assert res["fast_vmifgsm"] > res["clean"], res
+
+
 def test_cuda_graph_is_refused_for_host_rng_transforms():
     net = _net()
     x, y = _data(2)

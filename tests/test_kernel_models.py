@@ -37,10 +37,12 @@ def test_dim_direct_models(S, rnd, R, top, left):
         np.testing.assert_allclose(got, want, rtol=0, atol=2e-6)
 
 
-@pytest.mark.parametrize("B,n,cl", [(64, 150528, 8), (5, 150528, 8), (2, 12288, 1), (9, 12288, 4), (256, 150528, 8), (16, 12288, 16)])
+@pytest.mark.parametrize("B,n,cl", [(64, 150528, 8), (5, 150528, 8), (2, 12288, 1), (9, 12288, 4), (256, 150528, 8), (16, 12288, 16),
+                                    (1, 150528, 8), (600, 150528, 8)])
 def test_aten_mean_kernel_model_equals_the_aten_restatement(B, n, cl):
-    """The thread/lane mapping of csrc/aten_mean.cuh (columns per CTA, y tree by segmented shuffles, transposed x tree, final
-    tree) executed step by step in numpy reproduces oracle/aten_reduce.py's restatement of ATen's reduction bit for bit; the
+    """The thread/lane mapping of csrc/aten_mean.cuh (vector columns per CTA, x tree per block row in one warp, y tree per virtual
+    block in one thread, final tree) executed step by step in numpy reproduces oracle/aten_reduce.py's restatement of ATen's
+    reduction bit for bit; the
     restatement itself is pinned against torch on the GPU box (tests/test_kernels_gpu.py, tools/diag_aten_mean.py). Also: the C
     policy (ta_aten_mean_policy, host-only) equals the Python restatement of setReduceConfig over a grid of shapes."""
     import ctypes
@@ -62,7 +64,7 @@ def test_aten_mean_policy_c_equals_python():
     lib = _lib.load()
     for sm, mt in ((148, 2048), (132, 2048), (108, 2048), (84, 1536)):
         for B in (1, 2, 3, 4, 7, 8, 15, 16, 31, 32, 64, 65, 128, 256, 512, 592, 593, 600, 1024):
-            for n in (8, 31, 32, 37, 512, 1024, 1200, 3072, 12288, 50176, 150528, 268203, 442368, 786432):
+            for n in (8, 31, 32, 37, 128, 512, 1024, 1200, 2048, 3072, 12288, 50176, 150528, 268203, 268204, 442368, 786432):
                 bw, bh, cpo = ctypes.c_int(), ctypes.c_int(), ctypes.c_int()
                 rc = lib.ta_aten_mean_policy(B, n, sm, mt, ctypes.byref(bw), ctypes.byref(bh), ctypes.byref(cpo))
                 cfg = aten_reduce.config(B, n, sm, mt)

@@ -46,6 +46,34 @@ def _is_zero_scalar(v):
     return isinstance(v, _ZERO_TYPES) and not isinstance(v, bool) and v == 0
 
 
+class _FastMember(nn.Module):
+    """fast mode only: Preprocessing (fp32 kernels) → bf16 channels_last copy of the network → fp32 logits"""
+
+    def __init__(self, wrapped):
+        super().__init__()
+        import copy
+        if isinstance(wrapped, nn.Sequential) and len(wrapped) == 2 and isinstance(wrapped[0], PreprocessingModel):
+            self.pre, net = wrapped[0], wrapped[1]
+        else:
+            self.pre, net = None, wrapped
+        self.net = copy.deepcopy(net).to(dtype=torch.bfloat16).to(memory_format=torch.channels_last).eval()
+        for p_ in self.net.parameters():
+            p_.requires_grad_(False)
+
+    def forward(self, x):
+        h = x if self.pre is None else self.pre(x)
+        h = h.to(torch.bfloat16)
+        if h.dim() == 4:
+            h = h.contiguous(memory_format=torch.channels_last)
+        return self.net(h).float()
+
+
+def _fast_twin(model):
+    if isinstance(model, EnsembleModel):
+        return EnsembleModel([_FastMember(m) for m in model.models], mode=model.mode)
+    return _FastMember(model)
+
+
 class Attack(object):
     """Base class of every attack plugin (reference attack.py:8-169)."""
 
@@ -73,6 +101,14 @@ class Attack(object):
     #: strict mean mode (torch's own mean op needs the gradient w.r.t. delta in memory) and moves into the fused kernel too
     #: in 'exact' mode with the base ``get_grad``. Same arithmetic in the same order → same bits. Env TA_B200_FOLD=0 disables.
     fold_normalize = os.environ.get("TA_B200_FOLD", "1") == "1"
+    #: OPT-IN, NOT THE PARITY PATH. 'bf16': the surrogate's forward/backward runs on a bf16,
+    #: channels_last copy of the model (tensor-core convolutions, half the activation traffic); everything around it — staging,
+    #: mean|g|, momentum, update, clipping — stays the fp32 kernels. The perturbation is a valid one (eps-ball, [0,1] box) of the
+    #: same attack but NOT bit-comparable with the reference: acceptance is attack strength (tests/test_e2e_gpu.py, bench.py
+    #: `fast_mode`), never 1e-5 / uint8 identity. Off by default; env TA_B200_FAST=bf16 enables. VMI/VNI/GRA additionally batch
+    #: their neighbour evaluations in this mode (`fast_neighbor_images` images per forward).
+    fast_mode = os.environ.get("TA_B200_FAST", "")
+    fast_neighbor_images = 512
 
     def __init__(self, attack, model_name, epsilon, targeted, random_start, norm, loss, device=None):
         """attack.py:12-38 — same arguments, same attributes, same ``Unsupported norm`` exception."""
@@ -146,6 +182,18 @@ class Attack(object):
             return _lib.TA_MEAN_TORCH
         return None
 
+    def _surrogate(self):
+        """the module get_logits runs: `self.model`, or in fast mode its bf16 / channels_last twin (built once per model)"""
+        if not self.fast_mode:
+            return self.model
+        if self.fast_mode != 'bf16':
+            raise ValueError("unknown fast_mode {!r} (only 'bf16')".format(self.fast_mode))
+        cached = self.__dict__.get("_fast_twin")
+        if cached is None or cached[0] is not self.model:
+            cached = (self.model, _fast_twin(self.model))
+            self.__dict__["_fast_twin"] = cached
+        return cached[1]
+
     def _fusable(self):
         cls = type(self)
         return (self.fuse_update and self.norm == 'linfty'
@@ -157,7 +205,7 @@ class Attack(object):
         """(pre, net, mean, std, defer) when Normalize can be folded into the fused tail for this batch, else None.
         `kmode`: the in-kernel mean mode (``_mean_kernel_mode``); with one, Normalize's adjoint moves into the kernel too."""
         cls = type(self)
-        if not self.fold_normalize or cls.get_logits is not Attack.get_logits or cls.transform is not Attack.transform:
+        if not self.fold_normalize or self.fast_mode or cls.get_logits is not Attack.get_logits or cls.transform is not Attack.transform:
             return None
         m = self.model
         if not (isinstance(m, nn.Sequential) and len(m) == 2 and isinstance(m[0], PreprocessingModel)) or data.dim() != 4:
@@ -346,8 +394,8 @@ class Attack(object):
 
     # ------------------------------------------------------------------------------------------------
     def get_logits(self, x, **kwargs):
-        """attack.py:104-108"""
-        return self.model(x)
+        """attack.py:104-108 (fast mode: the bf16 twin, see ``fast_mode``)"""
+        return self._surrogate()(x)
 
     def get_loss(self, logits, label):
         """attack.py:110-115"""

@@ -8,30 +8,33 @@ namespace ta {
 static int last_pow2(int64_t n) { int p = 1; while ((int64_t)p * 2 <= n) p *= 2; return p; }
 static int64_t div_up(int64_t a, int64_t b) { return (a + b - 1) / b; }
 
-// PyTorch ATen/native/cuda/Reduce.cuh setReduceConfig<float, float, vt0 = 4> for a [B, n] fp32 iterator reduced over the
-// stride-1 dimension with B >= 2 outputs (restated; validated against torch on the GPU, oracle/aten_reduce.py).
+// PyTorch ATen/native/cuda/Reduce.cuh:1033-1178 setReduceConfig<float, float, vt0 = 4, input_vec_size = 4> for a contiguous
+// [B, n] fp32 iterator reduced over its stride-1 dimension, "vectorize along input" (restated; oracle/aten_reduce.py).
 bool aten_mean_policy(int B, int64_t n, int sm_count, int max_threads_per_sm, int* bw_, int* bh_, int* cpo_) {
   const int kMax = 512;
-  if (B < 2 || n < 32 || sm_count <= 0 || max_threads_per_sm < kMax) return false;
-  const int d0p = n < kMax ? last_pow2(n) : kMax;
+  if (B < 1 || n < 128 || n % 4 != 0 || sm_count <= 0 || max_threads_per_sm < kMax) return false;
+  const int64_t dim0 = n / 4;
+  const int d0p = dim0 < kMax ? last_pow2(dim0) : kMax;
   const int d1p = B < kMax ? last_pow2(B) : kMax;
   int bw = d0p < 32 ? d0p : 32;
   int bh = d1p < kMax / bw ? d1p : kMax / bw;
   bw = d0p < kMax / bh ? d0p : kMax / bh;
-  if (bw * bh != kMax || bh > 16 || bw < 32) return false;      // the replay kernels assume ATen's full 512-thread block
+  if (bw < 32 || bh > 16) return false;
+  const int nt = bw * bh;
   int64_t step = bw;
-  int64_t vpt = div_up(n, step);
-  if (!(vpt >= (int64_t)bh * 16 || vpt >= 256)) return false;   // warp rows own separate outputs: not restated
+  int64_t vpt = div_up(n, step);                                   // num_inputs counts elements, the steps count vectors (as in ATen)
+  const int64_t thr = (int64_t)bh * 16 < 256 ? (int64_t)bh * 16 : 256;
+  if (vpt < thr) return false;                                     // warp rows own separate outputs: not restated
   step *= bh;
   vpt = div_up(n, step);
-  const int64_t target = (int64_t)sm_count * (max_threads_per_sm / kMax);
+  const int64_t target = (int64_t)sm_count * (max_threads_per_sm / nt);
   int64_t cpo = 1;
   if (vpt >= 256 && B <= target) {
     const int64_t c1 = div_up(target, B), c2 = div_up(vpt, 16), c3 = div_up(vpt, 256);
     const int64_t mn = c1 < c2 ? c1 : c2;
     cpo = mn > c3 ? mn : c3;
   }
-  if (cpo > 32) return false;                                      // final tree here: one partial per lane of one warp
+  if (cpo > bw) return false;                                      // final tree here: the partials fill one block row
   *bw_ = bw; *bh_ = bh; *cpo_ = (int)cpo;
   return true;
 }
@@ -51,37 +54,34 @@ int aten_mean_plan(const char* who, int B, int64_t n, int cl, AtenMeanCfg* cfg) 
     set_error("%s: TA_MEAN_TORCH does not cover B=%d n=%lld (outside the replayed ATen launch family)", who, B, (long long)n);
     return TA_EUNSUPPORTED;
   }
-  const int S = kAtenThreads * cpo;
-  if (cl < 1 || S % cl != 0 || (S / cl) % 4 != 0 || S / cl > kAtenMaxW) {
+  const int S = bw * bh * cpo;
+  if (cl < 1 || S % cl != 0 || S / cl > kAtenMaxW) {
     set_error("%s: TA_MEAN_TORCH: cluster %d does not divide the %d virtual threads into <= %d columns", who, cl, S, kAtenMaxW);
     return TA_EUNSUPPORTED;
   }
-  cfg->bw = bw; cfg->bh = bh; cfg->cpo = cpo; cfg->S = S; cfg->W = S / cl;
+  cfg->bw = bw; cfg->bh = bh; cfg->cpo = cpo; cfg->nt = bw * bh; cfg->S = S; cfg->W4 = S / cl;
   cfg->factor = (float)B / (float)((int64_t)B * n);
   return TA_OK;
 }
 
 namespace {
 
-// grid = (cluster, B); dynamic smem = cpo*bw floats
+// grid = (cluster, B)
 __global__ void __launch_bounds__(kAtenThreads) aten_abs_mean_kernel(const float* __restrict__ g, float* __restrict__ mean_out,
                                                                      int64_t n, AtenMeanCfg c) {
-  extern __shared__ __align__(16) float s_tree[];
   __shared__ float s_val[kAtenMaxW];
-  __shared__ float s_blk[32];
-  const float* gp = g + (int64_t)blockIdx.y * n;
-  const int64_t col0 = (int64_t)cluster_ctarank() * c.W;
-  for (int col = threadIdx.x; col < c.W; col += kAtenThreads) {
-    const int64_t e0 = col0 + col;
-    const int rows = e0 < n ? (int)((n - e0 + c.S - 1) / c.S) : 0;
-    const float* p = gp + e0;
-    const int64_t S = c.S;
+  __shared__ float s_row[kAtenThreads];
+  __shared__ float s_blk[kAtenThreads];
+  const float4* gp = reinterpret_cast<const float4*>(g + (int64_t)blockIdx.y * n);
+  const int64_t nvec = n >> 2;
+  const int64_t col0 = (int64_t)cluster_ctarank() * c.W4;
+  for (int col = threadIdx.x; col < c.W4; col += kAtenThreads) {
     ColAcc A;
-    aten_column_rows(A, 0, rows, [p, S](int j) { return fabsf(__ldg(p + (int64_t)j * S)); });
+    for (int64_t v = col0 + col; v < nvec; v += c.S) aten_column_add(A, __ldg(gp + v));
     s_val[col] = aten_column_value(A);
   }
   cluster_sync_all();
-  const float mu = aten_tree_mean(c, s_val, s_tree, s_blk);
+  const float mu = aten_tree_mean(c, s_val, s_row, s_blk);
   if (cluster_ctarank() == 0 && threadIdx.x == 0) mean_out[blockIdx.y] = mu;
   cluster_sync_all();                         // s_val must outlive every remote read
 }
@@ -89,14 +89,13 @@ __global__ void __launch_bounds__(kAtenThreads) aten_abs_mean_kernel(const float
 }  // namespace
 
 int aten_abs_mean_launch(const float* g, float* mean_out, int B, int64_t n, cudaStream_t s) {
+  if (!aligned16(g)) { set_error("ta_abs_mean_per_sample: TA_MEAN_TORCH needs 16-byte aligned rows"); return TA_EUNSUPPORTED; }
   int cl = tune_get("reduce.cluster", 0);
   if (cl <= 0) cl = 8;
   AtenMeanCfg c;
   int rc = aten_mean_plan("ta_abs_mean_per_sample", B, n, cl, &c);
-  while (rc != TA_OK && cl > 1) { cl >>= 1; rc = aten_mean_plan("ta_abs_mean_per_sample", B, n, cl, &c); }   // W must fit s_val
   if (rc != TA_OK) return rc;
-  return launch_cluster("ta_abs_mean_per_sample[torch order]", aten_abs_mean_kernel, cl, B, kAtenThreads,
-                        sizeof(float) * (size_t)aten_mean_tree_floats(c), s, g, mean_out, n, c);
+  return launch_cluster("ta_abs_mean_per_sample[torch order]", aten_abs_mean_kernel, cl, B, kAtenThreads, 0, s, g, mean_out, n, c);
 }
 
 }  // namespace ta

@@ -72,7 +72,7 @@ __device__ __forceinline__ void sts_f32(uint32_t addr, float v) {
 struct FwdTabParam { DimTabF t; __device__ __forceinline__ const DimTabF& get() const { return t; } };
 struct FwdTabPtr { const DimTabF* p; __device__ __forceinline__ const DimTabF& get() const { return *p; } };
 
-template <int MODE, bool TMA_STAGE, class TR>
+template <int MODE, bool TMA_STAGE, class TR, bool REUSE = true>
 __global__ void __launch_bounds__(kThreads) dim_fwd_direct_kernel(const float* __restrict__ x, float* __restrict__ out,
                                                                   const __grid_constant__ TR tr, const Geo gm) {
   const DimTabF& tab = tr.get();
@@ -131,7 +131,9 @@ __global__ void __launch_bounds__(kThreads) dim_fwd_direct_kernel(const float* _
   if (any) {
     if (TMA_STAGE) mbar_wait(&s_bar, 0);
     // phase A: y1[q][qx] for q in [q0, q1]; inactive lanes of the last column chunk recompute column rnd-1 (same value,
-    // same address) so that the loop stays convergent
+    // same address) so that the loop stays convergent. Consecutive destination rows share source rows (the tap index moves
+    // by the resize scale, 0.9..1.1 rows per row): the horizontal lerp of a source row is kept in a two-entry register cache
+    // keyed by the row's byte offset and reused — same value as recomputing it, half the shared-memory loads (REUSE).
     for (int c0 = 0; c0 < rnd; c0 += kThreads) {
       const int col = min(c0 + tid, rnd - 1);
       const TapE tw = tab.t1[col];
@@ -139,18 +141,26 @@ __global__ void __launch_bounds__(kThreads) dim_fwd_direct_kernel(const float* _
       const uint32_t ca = smem_u32(bufA + tap_i0(tw)), cb = smem_u32(bufA + tap_i1(tw));
       uint32_t dst = smem_u32(bufC + col);
       const RowD* d = descA;
-#pragma unroll 4
+      int ka = -1, kb = -1;            // byte offsets of the cached rows (descriptor values are >= 0)
+      float ha = 0.0f, hb = 0.0f;
+#pragma unroll 2
       for (int q = 0; q < nq; ++q, ++d, dst += (uint32_t)CP * 4) {
         const int4 dd = *reinterpret_cast<const int4*>(d);
         const float hl1 = __int_as_float(dd.z), hl0 = sub_rn(1.0f, hl1);
-        const float t = hl<MODE>(wl0, wl1, lds_f32(ca + dd.x), lds_f32(cb + dd.x));
-        const float b = hl<MODE>(wl0, wl1, lds_f32(ca + dd.y), lds_f32(cb + dd.y));
+        float t, b;
+        if (REUSE && dd.x == kb) t = hb;
+        else if (REUSE && dd.x == ka) t = ha;
+        else t = hl<MODE>(wl0, wl1, lds_f32(ca + dd.x), lds_f32(cb + dd.x));
+        if (REUSE && dd.y == dd.x) b = t;
+        else if (REUSE && dd.y == kb) b = hb;
+        else b = hl<MODE>(wl0, wl1, lds_f32(ca + dd.y), lds_f32(cb + dd.y));
+        ka = dd.x; ha = t; kb = dd.y; hb = b;
         sts_f32(dst, vl<MODE>(hl0, hl1, t, b));
       }
     }
   }
   __syncthreads();
-  // phase B: out[oy][ox] for oy in [oy0, oy1]
+  // phase B: out[oy][ox] for oy in [oy0, oy1] (same two-entry row cache; the zero row of the padding is a row like any other)
   for (int c0 = 0; c0 < S; c0 += kThreads) {
     const int col = min(c0 + tid, S - 1);
     const TapE tw = tab.t2[col];
@@ -159,12 +169,20 @@ __global__ void __launch_bounds__(kThreads) dim_fwd_direct_kernel(const float* _
     const uint32_t ca = smem_u32(bufC + ((xa >= 0 && xa < rnd) ? xa : rnd)), cb = smem_u32(bufC + ((xb >= 0 && xb < rnd) ? xb : rnd));
     float* o = op + (int64_t)oy0 * S + col;
     const RowD* d = descB;
-#pragma unroll 4
+    int ka = -1, kb = -1;
+    float ha = 0.0f, hb = 0.0f;
+#pragma unroll 2
     for (int r = 0; r < nb; ++r, ++d, o += S) {
       const int4 dd = *reinterpret_cast<const int4*>(d);
       const float hl1 = __int_as_float(dd.z), hl0 = sub_rn(1.0f, hl1);
-      const float t = hl<MODE>(wl0, wl1, lds_f32(ca + dd.x), lds_f32(cb + dd.x));
-      const float b = hl<MODE>(wl0, wl1, lds_f32(ca + dd.y), lds_f32(cb + dd.y));
+      float t, b;
+      if (REUSE && dd.x == kb) t = hb;
+      else if (REUSE && dd.x == ka) t = ha;
+      else t = hl<MODE>(wl0, wl1, lds_f32(ca + dd.x), lds_f32(cb + dd.x));
+      if (REUSE && dd.y == dd.x) b = t;
+      else if (REUSE && dd.y == kb) b = hb;
+      else b = hl<MODE>(wl0, wl1, lds_f32(ca + dd.y), lds_f32(cb + dd.y));
+      ka = dd.x; ha = t; kb = dd.y; hb = b;
       *o = vl<MODE>(hl0, hl1, t, b);
     }
   }
@@ -506,6 +524,7 @@ size_t dim_direct_ws_bytes() { return sizeof(DimTabB) > sizeof(DimTabF) ? sizeof
 
 int dim_fwd_direct(const float* x, float* out, int planes, int S, int rnd, int R, int top, int left, int blend, bool tma, void* ws,
                    cudaStream_t stream) {
+  const bool reuse = tune_get("dim.reuse", 1) != 0;      // two-entry h-lerp row cache (bit-identical either way)
   static thread_local DimTabF tab;
   host_taps(R, S, tab.t2);
   host_taps(S, rnd, tab.t1);
@@ -524,19 +543,21 @@ int dim_fwd_direct(const float* x, float* out, int planes, int S, int rnd, int R
   const size_t smem = ((sizeof(float) * ((size_t)a_rows * S + (size_t)(c_rows + 1) * (rnd + 1)) + 15) & ~(size_t)15) + 16 * (size_t)(c_rows + RB);
   TA_REQUIRE(smem <= 200 * 1024, "ta_dim_fwd: image size S=%d needs %zu B of shared memory per CTA", S, smem);
   dim3 grid((unsigned)((S + RB - 1) / RB), (unsigned)planes);
-  static SmemOptIn optin[20] = {};
+  static SmemOptIn optin[40] = {};
 #define TA_DIM_FWD_LAUNCH(MODE_, SLOT_)                                                                             \
   do {                                                                                                              \
     if (ws) {                                                                                                       \
-      auto k = tma ? dim_fwd_direct_kernel<MODE_, true, FwdTabPtr> : dim_fwd_direct_kernel<MODE_, false, FwdTabPtr>; \
-      const int rc = ensure_dyn_smem("ta_dim_fwd", k, smem, optin[2 * SLOT_ + (tma ? 0 : 1)]);                      \
+      auto k = tma ? (reuse ? dim_fwd_direct_kernel<MODE_, true, FwdTabPtr, true> : dim_fwd_direct_kernel<MODE_, true, FwdTabPtr, false>) \
+                   : dim_fwd_direct_kernel<MODE_, false, FwdTabPtr, true>;                                           \
+      const int rc = ensure_dyn_smem("ta_dim_fwd", k, smem, optin[4 * SLOT_ + (tma ? (reuse ? 0 : 2) : 1)]);        \
       if (rc != TA_OK) return rc;                                                                                   \
       const int ru = upload_tab(tab, ws, stream);                                                                   \
       if (ru != TA_OK) return ru;                                                                                   \
       k<<<grid, kThreads, smem, stream>>>(x, out, FwdTabPtr{reinterpret_cast<const DimTabF*>(ws)}, gm);             \
     } else {                                                                                                        \
-      auto k = tma ? dim_fwd_direct_kernel<MODE_, true, FwdTabParam> : dim_fwd_direct_kernel<MODE_, false, FwdTabParam>; \
-      const int rc = ensure_dyn_smem("ta_dim_fwd", k, smem, optin[10 + 2 * SLOT_ + (tma ? 0 : 1)]);                 \
+      auto k = tma ? (reuse ? dim_fwd_direct_kernel<MODE_, true, FwdTabParam, true> : dim_fwd_direct_kernel<MODE_, true, FwdTabParam, false>) \
+                   : dim_fwd_direct_kernel<MODE_, false, FwdTabParam, true>;                                         \
+      const int rc = ensure_dyn_smem("ta_dim_fwd", k, smem, optin[20 + 4 * SLOT_ + (tma ? (reuse ? 0 : 2) : 1)]);   \
       if (rc != TA_OK) return rc;                                                                                   \
       k<<<grid, kThreads, smem, stream>>>(x, out, *reinterpret_cast<const FwdTabParam*>(&tab), gm);                 \
     }                                                                                                               \

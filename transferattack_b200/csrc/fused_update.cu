@@ -17,8 +17,9 @@
 //              TA_MEAN_TORCH — the fp32 summation tree of torch's own CUDA mean kernel (aten_mean.cuh), bit for bit;
 //   phase B: streams m, delta, x with 128-bit loads, takes g' from shared memory (so g crosses HBM once),
 //            and writes m', delta', xadv with 128-bit stores.
-// Layout: the sample is viewed as rows of S elements; CTA r owns columns [r*W, (r+1)*W) of every row (TORCH: S = ATen's
-// 512*ctas_per_output virtual threads, so a column is one virtual thread's elements; EXACT: S chosen for 16 rows).
+// Layout: the sample is viewed as rows of S 128-bit vectors; CTA r owns vector columns [r*W4, (r+1)*W4) of every row (TORCH:
+// S = ATen's block threads * ctas_per_output virtual threads, so a column is one virtual thread's vectors; EXACT: S chosen
+// for 16 rows).
 //
 // With `scale` given (torch computed mean|g| with the reference's own op) there is no phase A and the work is a flat 128-bit
 // streaming kernel.
@@ -109,7 +110,7 @@ constexpr int kThreads = kAtenThreads; // 512: ATen's block size (the TORCH tree
 
 struct TailLayout {
   int S4, W4;              // 128-bit vectors per row of the sample / per row of one CTA
-  int rows_per_group;      // rows per mbarrier group (multiple of 4)
+  int rows_per_group;      // rows per mbarrier group
   unsigned long long w4_magic;   // floor(2^32 / W4) + 1: i / W4 == (i * magic) >> 32 for the i that occur
 };
 
@@ -117,14 +118,15 @@ __device__ __forceinline__ float4 div4(float4 v, float s) { v.x = div_rn(v.x, s)
 __device__ __forceinline__ float4 add4(float4 a, const float4& b) { a.x = add_rn(a.x, b.x); a.y = add_rn(a.y, b.y); a.z = add_rn(a.z, b.z); a.w = add_rn(a.w, b.w); return a; }
 
 // MEAN: 0 = TA_MEAN_EXACT, 1 = TA_MEAN_TORCH.  grid = (cluster, B), 512 threads.
-// dynamic smem: [g' part of this CTA: rows x W4 float4][TORCH: cpo*bw floats for the tree]
+// dynamic smem: g' part of this CTA: rows x W4 float4
 template <int U, int MEAN, bool NF>
-__global__ void __launch_bounds__(kThreads, (U <= 2 ? 2 : 1)) fused_cluster_kernel(FusedParams p, TailLayout L, AtenMeanCfg c, int tree_off4) {
+__global__ void __launch_bounds__(kThreads, (U <= 2 ? 2 : 1)) fused_cluster_kernel(FusedParams p, TailLayout L, AtenMeanCfg c) {
   extern __shared__ __align__(128) unsigned char smem_raw[];
   __shared__ double s_scratch[32];
   __shared__ double s_part;
   __shared__ float s_val[MEAN == 1 ? kAtenMaxW : 1];
-  __shared__ float s_blk[32];
+  __shared__ float s_row[MEAN == 1 ? kAtenThreads : 1];
+  __shared__ float s_blk[MEAN == 1 ? kAtenThreads : 1];
   __shared__ __align__(8) uint64_t s_bar[kChunks];
 
   const int tid = threadIdx.x;
@@ -187,26 +189,24 @@ __global__ void __launch_bounds__(kThreads, (U <= 2 ? 2 : 1)) fused_cluster_kern
   // ---------------- phase A.2: mean|g'| ----------------
   float mu;
   if (MEAN == 1) {
-    float* sg = reinterpret_cast<float*>(smem_raw);
-    const int W = L.W4 * 4;
-    for (int col = tid; col < W; col += kThreads) {
-      const int rows = Jf + (col < 4 * last ? 1 : 0);
-      float* sp = sg + col;
-      const int64_t gi0 = col0 + (col >> 2);
+    // one thread per vector column: its virtual thread's vectors are rows 0, 1, 2, ... of that column; the 4 accumulators are
+    // the 4 components (ATen's input_vectorized_thread_reduce_impl)
+    for (int col = tid; col < L.W4; col += kThreads) {
+      const int rows = Jf + (col < last ? 1 : 0);
       ColAcc A;
 #pragma unroll 1
       for (int q = 0; q < kChunks; ++q) {
         const int a = q * RG, b = (a + RG < rows) ? a + RG : rows;
         if (b > a) {
           if (!fill) mbar_wait(&s_bar[q], 0);
-          if (nfb_pass)
-            aten_column_rows(A, a, b, [&](int j) {
-              const float v = div_rn(sp[j * W], pick4(p.nf.std, nf_channel(p.nf, (int64_t)j * L.S4 + gi0)));
-              sp[j * W] = v;
-              return fabsf(v);
-            });
-          else
-            aten_column_rows(A, a, b, [sp, W](int j) { return fabsf(sp[j * W]); });
+          for (int j = a; j < b; ++j) {
+            float4 v = sg4[j * L.W4 + col];
+            if (nfb_pass) {
+              v = div4(v, pick4(p.nf.std, nf_channel(p.nf, (int64_t)j * L.S4 + col0 + col)));
+              sg4[j * L.W4 + col] = v;
+            }
+            aten_column_add(A, v);
+          }
         }
       }
       s_val[col] = aten_column_value(A);
@@ -216,7 +216,7 @@ __global__ void __launch_bounds__(kThreads, (U <= 2 ? 2 : 1)) fused_cluster_kern
       for (int q = 0; q < kChunks; ++q) if (q * RG < Jtot) mbar_wait(&s_bar[q], 0);
     }
     cluster_sync_all();
-    mu = aten_tree_mean(c, s_val, reinterpret_cast<float*>(sg4 + tree_off4), s_blk);
+    mu = aten_tree_mean(c, s_val, s_row, s_blk);
     cluster_arrive();                     // "done reading remote shared memory"; matched by cluster_wait() at exit
   } else {
     double acc = 0.0;
@@ -301,8 +301,8 @@ __global__ void __launch_bounds__(kThreads, (U <= 2 ? 2 : 1)) fused_cluster_kern
 constexpr size_t kMaxStageBytes = 200 * 1024;   // per-CTA dynamic shared memory bound (227 KB/SM minus static + system use)
 
 template <int U, int MEAN, bool NF>
-int launch_fused(const char* who, const FusedParams& p, const TailLayout& L, const AtenMeanCfg& c, int tree_off4, int B, int cl,
-                 size_t smem, cudaStream_t s) {
+int launch_fused(const char* who, const FusedParams& p, const TailLayout& L, const AtenMeanCfg& c, int B, int cl, size_t smem,
+                 cudaStream_t s) {
   auto k = fused_cluster_kernel<U, MEAN, NF>;
   static SmemOptIn optin = {};
   static bool nonportable[64] = {};
@@ -321,7 +321,7 @@ int launch_fused(const char* who, const FusedParams& p, const TailLayout& L, con
       nonportable[dev] = true;
     }
   }
-  return launch_cluster(who, k, cl, B, kThreads, smem, s, p, L, c, tree_off4);
+  return launch_cluster(who, k, cl, B, kThreads, smem, s, p, L, c);
 }
 
 // ---- ENS, one surrogate per GPU: reduce-scatter + fused update + all-gather in ONE kernel over NVLink peer memory ------------
@@ -484,26 +484,22 @@ int fused_tail_impl(const ta_fused_tail_args& a, const NormFold* nf, ta_stream_t
   AtenMeanCfg c = {};
   TailLayout L = {};
   size_t smem = 0;
-  int tree_off4 = 0;
   bool staged = v4 && nvec < (int64_t)1 << 28;
   if (staged) {
-    int64_t rows;
     if (torch_order) {
       const int rc = aten_mean_plan(who, B, n, cl, &c);
       if (rc != TA_OK) return rc;
-      L.S4 = c.S / 4; L.W4 = c.W / 4;
+      L.S4 = c.S; L.W4 = c.W4;                       // a row = ATen's S virtual threads, one 128-bit vector each
     } else {
       int64_t w4 = (nvec + (int64_t)cl * 16 - 1) / ((int64_t)cl * 16);     // ~16 rows: 4 transfer groups of 4 rows
       if (w4 < 1) w4 = 1;
       L.W4 = (int)w4; L.S4 = (int)(w4 * cl);
     }
-    rows = (nvec + L.S4 - 1) / L.S4;
-    L.rows_per_group = (int)(4 * ((rows + 15) / 16));
+    const int64_t rows = (nvec + L.S4 - 1) / L.S4;
+    L.rows_per_group = (int)((rows + kChunks - 1) / kChunks);
     L.w4_magic = (1ull << 32) / (unsigned long long)L.W4 + 1ull;
-    const size_t slice = (size_t)rows * (size_t)L.W4 * 16;
-    tree_off4 = (int)(rows * L.W4);
-    smem = slice + (torch_order ? sizeof(float) * (size_t)aten_mean_tree_floats(c) : 0);
-    if (smem > kMaxStageBytes || rows > 0x3fffffff / (L.W4 > 0 ? L.W4 : 1)) staged = false;
+    smem = (size_t)rows * (size_t)L.W4 * 16;
+    if (smem > kMaxStageBytes || rows * L.W4 > 0x3fffffff) staged = false;
   }
 
   if (!staged) {
@@ -521,10 +517,10 @@ int fused_tail_impl(const ta_fused_tail_args& a, const NormFold* nf, ta_stream_t
 
 #define TA_FUSED_CASE(U_)                                                                                        \
   if (unroll == U_) {                                                                                            \
-    if (torch_order) return nf ? launch_fused<U_, 1, true>(who, p, L, c, tree_off4, B, cl, smem, s)              \
-                               : launch_fused<U_, 1, false>(who, p, L, c, tree_off4, B, cl, smem, s);            \
-    return nf ? launch_fused<U_, 0, true>(who, p, L, c, tree_off4, B, cl, smem, s)                               \
-              : launch_fused<U_, 0, false>(who, p, L, c, tree_off4, B, cl, smem, s);                             \
+    if (torch_order) return nf ? launch_fused<U_, 1, true>(who, p, L, c, B, cl, smem, s)              \
+                               : launch_fused<U_, 1, false>(who, p, L, c, B, cl, smem, s);            \
+    return nf ? launch_fused<U_, 0, true>(who, p, L, c, B, cl, smem, s)                               \
+              : launch_fused<U_, 0, false>(who, p, L, c, B, cl, smem, s);                             \
   }
   TA_FUSED_CASE(1)
   TA_FUSED_CASE(2)

@@ -25,8 +25,33 @@ class VMIFGSM(Attack):
         self.radius = beta * epsilon
         self.num_neighbor = num_neighbor
 
+    def _neighbor_sum_batched(self, data, delta, label, momentum):
+        """FAST MODE ONLY (Attack.fast_mode; not the parity path): the neighbours go through the surrogate several at a time.
+        d/d delta of sum_k CE_k is the sum of the neighbour gradients, formed by autograd in one backward per chunk (its
+        accumulation order, not the reference's running `grad +=`)."""
+        B = data.shape[0]
+        per = max(1, min(self.num_neighbor, self.fast_neighbor_images // max(B, 1)))
+        acc = None
+        for k0 in range(0, self.num_neighbor, per):
+            n = min(per, self.num_neighbor - k0)
+            xs = []
+            for _ in range(n):
+                if self.philox_noise and ops.philox_noise_available(delta):
+                    xs.append(ops.neighbor_stage_philox(data, delta, -self.radius, self.radius))
+                else:
+                    noise = torch.zeros_like(delta).uniform_(-self.radius, self.radius).to(self.device)
+                    xs.append(ops.neighbor_stage(data, delta, noise))
+            x_all = torch.cat(xs, dim=0)
+            mom = momentum.repeat(n, 1, 1, 1) if torch.is_tensor(momentum) else momentum
+            loss = self.get_loss(self.get_logits(self.transform(x_all, momentum=mom)), label.repeat(n)) * n
+            g = self.get_grad(loss, delta)
+            acc = g if acc is None else acc + g
+        return acc
+
     def get_variance(self, data, delta, label, cur_grad, momentum, **kwargs):
         be = ops.backend()
+        if self.fast_mode and self.num_neighbor > 1:
+            return be.variance_finalize(self._neighbor_sum_batched(data, delta, label, momentum), cur_grad, self.num_neighbor)
         acc = None
         for k in range(self.num_neighbor):
             if self.philox_noise and ops.philox_noise_available(delta):
