@@ -429,6 +429,9 @@ def test_fused_tail_addend_and_gbar(be, mean_mode):
                 sc, mode = None, (_lib.TA_MEAN_TORCH if mean_mode == "torch" else _lib.TA_MEAN_EXACT)
             ok = be.fused_tail(cu(g), gm, gm, dd, d_next, cu(x), xa, sc, so, 0.9, ALPHA, EPS, 0, 1.0, mean_mode=mode,
                                addend=cu(addend), gbar_out=gb)
+            if mean_mode == "torch" and not ok:        # outside the replayed ATen launch family: the caller passes torch's scale
+                assert be.abs_mean(cu(gsum), _lib.TA_MEAN_TORCH) is None, (B, shape)
+                continue
             assert ok, (B, shape, _lib.last_error())
             scale = npy(so)
             if mean_mode == "exact":
@@ -444,7 +447,7 @@ def test_fused_tail_addend_and_gbar(be, mean_mode):
             assert bits_equal(npy(gb), ref_gb), tag
 
 
-@pytest.mark.parametrize("tune", [dict(), {"fused.unroll": 1}, {"fused.cluster": 2}], ids=["default", "unroll1", "cluster2"])
+@pytest.mark.parametrize("tune", [dict(), {"fused.unroll": 1}, {"fused.cluster": 4}], ids=["default", "unroll1", "cluster4"])
 def test_fused_update_with_normalize_folded(be, tune):
     """ta_fused_update_linf_nf against the chain of reference ops it replaces (oracle.fused_update_linf_nf):
     strict (scale given) and exact (in-kernel mean) modes, gradient w.r.t. delta or w.r.t. the normalised input, first
@@ -475,7 +478,7 @@ def test_fused_update_with_normalize_folded(be, tune):
                                                      0.9, ALPHA, EPS, 0, 1.0, mean, std, wrt_xn,
                                                      _lib.TA_MEAN_TORCH if mmode == "torch" else _lib.TA_MEAN_EXACT)
                         if mmode == "torch" and not ok:
-                            assert be.abs_mean(cu(g_eff), _lib.TA_MEAN_TORCH) is None or tune.get("fused.cluster", 0) == 2, (B, shape)
+                            assert be.abs_mean(cu(g_eff), _lib.TA_MEAN_TORCH) is None, (B, shape)
                             continue
                         assert ok
                         scale = npy(so)

@@ -15,10 +15,17 @@ scale = be.abs_mean(g)
 flush = torch.empty(256 * 1024 * 1024 // 4, device="cuda")
 for it in range(6):
     flush.sum()
-    if which == "fused":
-        be.fused_update_linf(g, m, m2, d, d2, x, xa, None, so, 1.0, 1.6 / 255, 16 / 255, 0, 1.0)
+    if which == "fused":         # the kernel forms that SHIP (round 2): cluster + torch-order mean (+ Normalize fold + adjoint), streaming
+        from transferattack_b200 import _lib
+        MEAN, STD = [0.485, 0.456, 0.406], [0.229, 0.224, 0.225]
+        be.fused_tail(g, m, m2, d, d2, x, xa, None, so, 1.0, 1.6 / 255, 16 / 255, 0, 1.0, mean_mode=_lib.TA_MEAN_TORCH, mean=MEAN, std=STD,
+                      emit_normalized=True, grad_wrt_xn=True)
         flush.sum()
-        be.fused_update_linf(g, m, m2, d, d2, x, xa, scale, None, 1.0, 1.6 / 255, 16 / 255, 0, 1.0)
+        be.fused_tail(g, m, m2, d, d2, x, xa, None, so, 1.0, 1.6 / 255, 16 / 255, 0, 1.0, mean_mode=_lib.TA_MEAN_TORCH)
+        flush.sum()
+        be.fused_tail(g, m, m2, d, d2, x, xa, scale, None, 1.0, 1.6 / 255, 16 / 255, 0, 1.0, mean=MEAN, std=STD, emit_normalized=True)
+        flush.sum()
+        be.abs_mean(g, _lib.TA_MEAN_TORCH)
     elif which == "dim":
         be.dim(x, 235, 246, 5, 6, True); be.dim(g, 235, 246, 5, 6, False)
     elif which == "timdim":      # one launch each: TIM with factors as parameters / from device arrays, DIM forward, DIM adjoint
