@@ -266,6 +266,18 @@ int ta_gra_update(const float* M, const float* last, const float* cur, float eta
 int ta_adaea_drf(const float* const* grads, int K, float threshold, const float* grad, float* out,
                  float* map_out, int B, int C, int64_t plane, ta_stream_t stream);
 
+/* ---- SSM / FGSRA spectrum transform (input_transformation/ssm.py:41-55, 101-200) ----------------------------
+ *   out = idct_2d(dct_2d(x + gauss) * mask) per [N x N] plane, with the reference's un-normalised DCT-II
+ *   (X_k = 2 sum_n x_n cos(pi (2n+1) k / 2N)) and its exact inverse, evaluated as four tensor-core GEMMs (tcgen05, tf32
+ *   operands, fp32 accumulation in TMEM):  T(X) = E ((D X D^T) . mask) E^T,  D[k][n] = 2 cos(pi (2n+1) k / 2N),  E = D^-1.
+ *   D, E: [N, N] fp32 DEVICE matrices (row-major) supplied by the caller (built once per N); gauss / mask nullable;
+ *   planes = B*C; N a multiple of 16 in [16, 256]. precision 1 (default) = "3xTF32": every operand is split hi + lo on the
+ *   way into shared memory and hi*hi + lo*hi + hi*lo is accumulated (fp32-level products); precision 0 = one tf32 product.
+ *   ws: scratch of ta_spectrum_ws_bytes(planes, N) bytes. 4 launches for the reference's ~40, no FFT.                      */
+int64_t ta_spectrum_ws_bytes(int planes, int N);
+int ta_spectrum_transform(const float* x, const float* gauss, const float* mask, const float* D, const float* E,
+                          float* out, int planes, int N, int precision, void* ws, ta_stream_t stream);
+
 /* ---- EMI (gradient/emifgsm.py:53-58, 86-103) ---------------------------------------------------------
  *   out[k*N + i] = x[i] + coef[k] * gbar[i]  (coef[k] = (float)(factor_k * alpha), host array, K <= 32)
  *   gbar == NULL is the first iteration (`bar_grad = 0`): out[k*N+i] = x[i] + 0.

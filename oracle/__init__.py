@@ -298,3 +298,24 @@ def adaea_drf(grads, threshold, grad=None):
     out = np.empty_like(grad) if grad is not None else None
     lib().orc_adaea_drf(arr, len(grads), ctypes.c_float(threshold), _fp(grad), _fp(out), _fp(mp), B, C, ctypes.c_int64(plane))
     return mp, out
+
+
+def dct_matrices(N):
+    """float64 (D, E): D[k][n] = 2 cos(pi (2n+1) k / 2N) — input_transformation/ssm.py:101-133 `dct` with norm=None written as a
+    matrix (X = D x) — and E = D^-1 — ssm.py:135-172 `idct`. Pinned against the reference's FFT formulation in
+    tests/test_reference_live.py."""
+    k = np.arange(N, dtype=np.float64)[:, None]; n = np.arange(N, dtype=np.float64)[None, :]
+    D = 2.0 * np.cos(np.pi * (2.0 * n + 1.0) * k / (2.0 * N))
+    return D, np.linalg.inv(D)
+
+
+def spectrum_transform(x, gauss=None, mask=None):
+    """ssm.py:41-55 in float64: idct_2d(dct_2d(x + gauss) * mask) = E ((D X D^T) . M) E^T per plane; returns float64"""
+    x = np.asarray(x, np.float64)
+    N = x.shape[-1]
+    D, E = dct_matrices(N)
+    X = x if gauss is None else (np.asarray(x, np.float32) + np.asarray(gauss, np.float32)).astype(np.float64)
+    Y = D @ X @ D.T
+    if mask is not None:
+        Y = Y * np.asarray(mask, np.float64)
+    return E @ Y @ E.T

@@ -460,11 +460,64 @@ class RefAdaEA(RefAttack):            # ensemble/adaea.py:10-150 (model: RefEnse
         return delta.detach()
 
 
+class RefSSM(RefAttack):              # input_transformation/ssm.py:8-200 (device-agnostic: the reference hard-codes .cuda())
+    def __init__(self, model, num_spectrum=20, rho=0.5, **kw):
+        super().__init__(model, **kw)
+        self.num_spectrum, self.rho = num_spectrum, rho
+
+    @staticmethod
+    def dct(x):                                                                                      # ssm.py:101-133, norm=None
+        shape, N = x.shape, x.shape[-1]
+        x = x.contiguous().view(-1, N)
+        Vc = torch.fft.fft(torch.cat([x[:, ::2], x[:, 1::2].flip([1])], dim=1))
+        k = -torch.arange(N, dtype=x.dtype, device=x.device)[None, :] * np.pi / (2 * N)
+        return 2 * (Vc.real * torch.cos(k) - Vc.imag * torch.sin(k)).view(*shape)
+
+    @staticmethod
+    def idct(X):                                                                                     # ssm.py:135-172, norm=None
+        shape, N = X.shape, X.shape[-1]
+        Xv = X.contiguous().view(-1, N) / 2
+        k = torch.arange(N, dtype=X.dtype, device=X.device)[None, :] * np.pi / (2 * N)
+        Wr, Wi = torch.cos(k), torch.sin(k)
+        Vti = torch.cat([Xv[:, :1] * 0, -Xv.flip([1])[:, :-1]], dim=1)
+        v = torch.fft.ifft(torch.complex(real=Xv * Wr - Vti * Wi, imag=Xv * Wi + Vti * Wr))
+        x = v.new_zeros(v.shape)
+        x[:, ::2] += v[:, :N - (N // 2)]
+        x[:, 1::2] += v.flip([1])[:, :N // 2]
+        return x.view(*shape).real
+
+    def dct_2d(self, x):
+        return self.dct(self.dct(x).transpose(-1, -2)).transpose(-1, -2)
+
+    def idct_2d(self, X):
+        return self.idct(self.idct(X).transpose(-1, -2)).transpose(-1, -2)
+
+    def transform(self, x, **kw):                                                                    # ssm.py:41-55
+        gauss = (torch.randn(x.size()[0], 3, 224, 224) * self.epsilon).to(x.device)
+        x_dct = self.dct_2d(x + gauss)
+        mask = torch.rand_like(x) * 2 * self.rho + 1 - self.rho
+        return self.idct_2d(x_dct * mask)
+
+    def forward(self, data, label, **kw):
+        data, label = self._prep(data, label)
+        delta = self.init_delta(data)
+        momentum = 0
+        for _ in range(self.epoch):
+            grads = 0
+            for _k in range(self.num_spectrum):
+                x_idct = self.transform(data + delta)
+                grads += self.get_grad(self.get_loss(self.get_logits(x_idct), label), x_idct)
+            grads /= self.num_spectrum
+            momentum = self.get_momentum(grads, momentum)
+            delta = self.update_delta(delta, data, momentum, self.alpha)
+        return delta.detach()
+
+
 REF_ZOO = {
     "fgsm": ref_fgsm, "ifgsm": ref_ifgsm, "mifgsm": ref_mifgsm, "nifgsm": RefNIFGSM, "dim": RefDIM,
     "tim": RefTIM, "sim": RefSIM, "admix": RefAdmix, "ditimi": RefDITIMI, "vmifgsm": RefVMIFGSM,
     "vnifgsm": RefVNIFGSM, "emifgsm": RefEMIFGSM, "ens": ref_mifgsm, "pifgsm": RefPIFGSM, "siditimi": RefSIDITIMI,
-    "gra": RefGRA, "adaea": RefAdaEA,
+    "gra": RefGRA, "adaea": RefAdaEA, "ssm": RefSSM,
 }
 
 

@@ -167,6 +167,10 @@ class OracleBackend:
         mp, out = oracle.adaea_drf([_np(g) for g in grads], float(threshold), _np(grad))
         return (None if out is None else _t(out)), (_t(mp) if (want_map or grad is None) else None)
 
+    def spectrum_transform(self, x, gauss, mask, precision=1):
+        self._log("spectrum_transform")
+        return _t(oracle.spectrum_transform(_np(x), _np(gauss), _np(mask)).astype(np.float32))
+
     def lin_sample(self, x, gbar, coefs, forward=True):
         self._log("lin_sample")
         if forward:

@@ -77,6 +77,31 @@ def test_torch_ref_pifgsm_equals_live_reference(ref, monkeypatch):
         assert bits_equal(d.numpy(), d_ref.numpy()), (kw, n_diff_bits(d.numpy(), d_ref.numpy()))
 
 
+def test_torch_ref_ssm_and_the_matrix_form_equal_live_reference(ref, monkeypatch):
+    """input_transformation/ssm.py hard-codes .cuda(); with the shim the UNMODIFIED file pins (a) the device-agnostic
+    restatement RefSSM bit for bit and (b) the float64 MATRIX form of its transform (oracle.spectrum_transform — what the
+    tcgen05 kernel is tested against) to 2e-6."""
+    import oracle
+    from oracle import torch_ref
+    monkeypatch.setattr(torch.Tensor, "cuda", lambda self, *a, **k: self)
+    monkeypatch.setattr(torch.nn.Module, "cuda", lambda self, *a, **k: self)
+    x, y = _data()
+    kw = {"num_spectrum": 2, "epoch": 2}
+    net = _net()
+    seed_all(3); d_ref = make_attack(ref, "ssm", net, **kw)(x, y)
+    seed_all(3); d = torch_ref.RefSSM(torch_ref.ref_wrap_model(net), **kw)(x, y)
+    assert bits_equal(d.numpy(), d_ref.numpy()), n_diff_bits(d.numpy(), d_ref.numpy())
+    live = make_attack(ref, "ssm", net, **kw)
+    g = torch.Generator().manual_seed(9)
+    img = torch.rand(2, 3, 224, 224, generator=g); mask = torch.rand(2, 3, 224, 224, generator=g) + 0.5
+    fft = live.idct_2d(live.dct_2d(img) * mask).numpy()
+    assert np.abs(fft - oracle.spectrum_transform(img.numpy(), None, mask.numpy())).max() <= 2e-6
+    # the native plugin on this box (transform = the float64 matrix form through the stand-in backend): same draws, same loop
+    import transferattack_b200 as tab
+    seed_all(3); d_new = make_attack(tab, "ssm", net, **kw)(x, y)
+    assert float((d_new == d_ref).float().mean()) >= 0.9
+
+
 def test_torch_ref_gra_and_adaea_equal_live_reference(ref):
     """the restatements of gradient/gra.py and ensemble/adaea.py that the native plugins are tested against"""
     from oracle import torch_ref

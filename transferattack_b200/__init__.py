@@ -13,7 +13,7 @@ def _zoo():
     table = {
         "gradient": ["fgsm:FGSM", "ifgsm:IFGSM", "mifgsm:MIFGSM", "nifgsm:NIFGSM", "vmifgsm:VMIFGSM", "vnifgsm:VNIFGSM",
                      "emifgsm:EMIFGSM", "pifgsm:PIFGSM", "gra:GRA"],
-        "input_transformation": ["dim:DIM", "tim:TIM", "sim:SIM", "admix:Admix", "di_ti_mi:DITIMI=ditimi", "di_ti_mi:SIDITIMI=siditimi"],
+        "input_transformation": ["dim:DIM", "tim:TIM", "sim:SIM", "admix:Admix", "di_ti_mi:DITIMI=ditimi", "di_ti_mi:SIDITIMI=siditimi", "ssm:SSM"],
         "ensemble": ["ens:ENS", "adaea:AdaEA"],
     }
     zoo = {}

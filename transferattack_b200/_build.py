@@ -12,7 +12,7 @@ HERE = os.path.dirname(os.path.abspath(__file__))
 CSRC = os.path.join(HERE, "csrc")
 OBJ = os.path.join(CSRC, "build")
 SO = os.path.join(HERE, "libta_b200.so")
-SOURCES = ["lib.cu", "elementwise.cu", "reduce.cu", "aten_mean.cu", "fused_update.cu", "dim.cu", "dim_direct.cu", "dwconv.cu", "philox.cu", "longtail.cu"]
+SOURCES = ["lib.cu", "elementwise.cu", "reduce.cu", "aten_mean.cu", "fused_update.cu", "dim.cu", "dim_direct.cu", "dwconv.cu", "philox.cu", "longtail.cu", "spectrum.cu"]
 NVCC = os.environ.get("NVCC", "/usr/local/cuda/bin/nvcc")
 FLAGS = [
     "-gencode", "arch=compute_100a,code=sm_100a",

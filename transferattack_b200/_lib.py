@@ -68,6 +68,8 @@ SIGNATURES = {
     "ta_pi_update_linf": (_i, [_p, _p, _p, _p, _p, _f, _f, _f, _f, _f, _p, _p, _l, _p]),
     "ta_gra_update": (_i, [_p, _p, _p, _f, _f, _p, _p, _f, _f, _f, _p, _p, _l, _p]),
     "ta_adaea_drf": (_i, [ctypes.POINTER(_p), _i, _f, _p, _p, _p, _i, _i, _l, _p]),
+    "ta_spectrum_ws_bytes": (_l, [_i, _i]),
+    "ta_spectrum_transform": (_i, [_p, _p, _p, _p, _p, _p, _i, _i, _i, _p, _p]),
     "ta_lin_sample_fwd": (_i, [_p, _p, ctypes.POINTER(_f), _i, _p, _l, _p]),
     "ta_lin_sample_bwd": (_i, [_p, _p, _i, _l, _p]),
     "ta_neighbor_stage": (_i, [_p, _p, _p, _p, _f, _p, _l, _p]),

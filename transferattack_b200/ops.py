@@ -340,6 +340,37 @@ class CudaBackend:
                        "ta_adaea_drf")
         return out, mp
 
+    _dct_cache = {}
+
+    def dct_matrices(self, N, device):
+        """(D, E) fp32 [N, N] on `device`: D[k][n] = 2 cos(pi (2n+1) k / 2N) (the reference's un-normalised DCT-II, ssm.py:101-133),
+        E = D^-1 (its idct, ssm.py:135-172), both formed in float64 on the host once per (N, device)"""
+        key = (int(N), str(device))
+        hit = self._dct_cache.get(key)
+        if hit is None:
+            k = np.arange(N, dtype=np.float64)[:, None]; n = np.arange(N, dtype=np.float64)[None, :]
+            D = 2.0 * np.cos(np.pi * (2.0 * n + 1.0) * k / (2.0 * N))
+            E = np.cos(np.pi * (2.0 * k + 1.0) * n / (2.0 * N)) / N           # E[n][k] = cos(pi (2n+1) k / 2N) / N ...
+            E[:, 0] *= 0.5                                                    # ... with the k = 0 column halved: E @ D = I
+            hit = (torch.from_numpy(D.astype(np.float32)).to(device), torch.from_numpy(E.astype(np.float32)).to(device))
+            self._dct_cache[key] = hit
+        return hit
+
+    def spectrum_transform(self, x, gauss, mask, precision=1):
+        """SSM (ssm.py:41-55): idct_2d(dct_2d(x + gauss) * mask) per plane as four tcgen05 GEMMs (``ta_spectrum_transform``)"""
+        x = _f32c(x, "x"); gauss = _f32c(gauss, "gauss"); mask = _f32c(mask, "mask")
+        N = x.shape[-1]
+        if x.shape[-2] != N:
+            raise ValueError("the spectrum transform needs square planes (the reference hard-codes 224 x 224)")
+        planes = x.numel() // (N * N)
+        D, E = self.dct_matrices(N, x.device)
+        out = torch.empty_like(x)
+        with _DeviceOf(x):
+            ws = torch.empty(int(self.lib.ta_spectrum_ws_bytes(planes, N)), dtype=torch.uint8, device=x.device)
+            _lib.check(self.lib.ta_spectrum_transform(_ptr(x), _ptr(gauss), _ptr(mask), _ptr(D), _ptr(E), _ptr(out), planes, N,
+                                                      int(precision), _ptr(ws), _stream()), "ta_spectrum_transform")
+        return out
+
     def lin_sample(self, x, gbar, coefs, forward=True):
         x = _f32c(x, "x"); K = len(coefs)
         with _DeviceOf(x):
