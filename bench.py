@@ -300,6 +300,9 @@ def tail_kernel_name(atk, x_dev):
     nf = "" if fold is None else (",nf+adjoint" if fold[4] else ",nf")
     if kmode is None:
         return "ta_fused_tail[stream%s] after ATen abs+mean" % nf, 3
+    if kmode == _lib.TA_MEAN_TORCH and x_dev.numel() * 4 <= 64 * 1024 * 1024 and int(os.environ.get("TA_FUSED_STRATEGY", "0")) in (0, 2):
+        # csrc/fused_update.cu: a gradient that fits L2 takes the two-launch form (mean kernel, then the flat streaming kernel)
+        return "ta_abs_mean_per_sample[torch order%s] + ta_fused_tail[stream%s]" % (", g/std" if (fold is not None and fold[4]) else "", nf), 2
     return "ta_fused_tail[cluster,%s%s]" % ("torch-order mean" if kmode == _lib.TA_MEAN_TORCH else "fp64 mean", nf), 1
 
 
@@ -731,6 +734,7 @@ def run_kernels(args):
     add("ATen reference: tensor.copy_ (same harness)", 8, lambda: xa.copy_(x))
     MEAN, STD = [0.485, 0.456, 0.406], [0.229, 0.224, 0.225]
     vadd = torch.randn_like(g) * 1e-5; gb = torch.empty_like(g)
+    _lib.tune_set("fused.strategy", 1)
     add("fused_tail[cluster, fp64 mean]", 28, lambda: be.fused_tail(g, m, m2, d, d2, x, xa, None, so, 1.0, a, al, 0, 1.0, mean_mode=_lib.TA_MEAN_EXACT))
     add("fused_tail[cluster, torch-order mean]", 28, lambda: be.fused_tail(g, m, m2, d, d2, x, xa, None, so, 1.0, a, al, 0, 1.0, mean_mode=_lib.TA_MEAN_TORCH))
     add("fused_tail[cluster, torch-order mean, nf]", 28, lambda: be.fused_tail(g, m, m2, d, d2, x, xa, None, so, 1.0, a, al, 0, 1.0, mean_mode=_lib.TA_MEAN_TORCH,
@@ -738,6 +742,7 @@ def run_kernels(args):
     add("fused_tail[cluster, torch-order mean, nf+adjoint] (the default base loop)", 28,
         lambda: be.fused_tail(g, m, m2, d, d2, x, xa, None, so, 1.0, a, al, 0, 1.0, mean_mode=_lib.TA_MEAN_TORCH, mean=MEAN, std=STD,
                               emit_normalized=True, grad_wrt_xn=True))
+    _lib.tune_set("fused.strategy", 1)         # rows above/below labelled "cluster": the one-launch form, whatever the size
     for un in (1, 4):
         _lib.tune_set("fused.unroll", un)
         add("  fused_tail[cluster, torch-order mean, nf+adjoint] unroll=%d" % un, 28,
@@ -748,6 +753,15 @@ def run_kernels(args):
                                                                                         mean_mode=_lib.TA_MEAN_TORCH, addend=vadd))
     add("fused_tail[cluster, torch-order mean, gbar] (EMI)", 32, lambda: be.fused_tail(g, m, m2, d, d2, x, xa, None, so, 1.0, a, al, 0, 1.0,
                                                                                       mean_mode=_lib.TA_MEAN_TORCH, gbar_out=gb))
+    _lib.tune_set("fused.strategy", 2)
+    add("fused_tail[split: torch-order mean kernel + stream] (2 launches)", 32, lambda: be.fused_tail(g, m, m2, d, d2, x, xa, None, so, 1.0, a, al, 0, 1.0,
+                                                                                                   mean_mode=_lib.TA_MEAN_TORCH))
+    add("fused_tail[split: torch-order mean kernel + stream, nf+adjoint] (2 launches; the default base loop at B=64)", 32,
+        lambda: be.fused_tail(g, m, m2, d, d2, x, xa, None, so, 1.0, a, al, 0, 1.0, mean_mode=_lib.TA_MEAN_TORCH, mean=MEAN, std=STD,
+                              emit_normalized=True, grad_wrt_xn=True))
+    add("fused_tail[split, addend] (VMI)", 40, lambda: be.fused_tail(g, m, m2, d, d2, x, xa, None, so, 1.0, a, al, 0, 1.0,
+                                                                    mean_mode=_lib.TA_MEAN_TORCH, addend=vadd))
+    _lib.tune_set("fused.strategy", 0)
     add("fused_tail[stream, scale given]", 28, lambda: be.fused_update_linf(g, m, m2, d, d2, x, xa, scale, None, 1.0, a, al, 0, 1.0))
     add("abs_mean_per_sample [torch order]", 4, lambda: be.abs_mean(g, _lib.TA_MEAN_TORCH))
     add("ATen reference: g.abs().mean(dim=(1,2,3)) (2 launches)", 12, lambda: g.abs().mean(dim=(1, 2, 3)))

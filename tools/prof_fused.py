@@ -18,6 +18,11 @@ for it in range(6):
     if which == "fused":         # the kernel forms that SHIP (round 2): cluster + torch-order mean (+ Normalize fold + adjoint), streaming
         from transferattack_b200 import _lib
         MEAN, STD = [0.485, 0.456, 0.406], [0.229, 0.224, 0.225]
+        _lib.tune_set("fused.strategy", 2)       # the default at B=64: mean kernel + streaming kernel
+        be.fused_tail(g, m, m2, d, d2, x, xa, None, so, 1.0, 1.6 / 255, 16 / 255, 0, 1.0, mean_mode=_lib.TA_MEAN_TORCH, mean=MEAN, std=STD,
+                      emit_normalized=True, grad_wrt_xn=True)
+        flush.sum()
+        _lib.tune_set("fused.strategy", 1)       # the one-launch cluster form
         be.fused_tail(g, m, m2, d, d2, x, xa, None, so, 1.0, 1.6 / 255, 16 / 255, 0, 1.0, mean_mode=_lib.TA_MEAN_TORCH, mean=MEAN, std=STD,
                       emit_normalized=True, grad_wrt_xn=True)
         flush.sum()

@@ -60,6 +60,7 @@ int aten_mean_plan(const char* who, int B, int64_t n, int cl, AtenMeanCfg* cfg) 
     return TA_EUNSUPPORTED;
   }
   cfg->bw = bw; cfg->bh = bh; cfg->cpo = cpo; cfg->nt = bw * bh; cfg->S = S; cfg->W4 = S / cl;
+  cfg->w4_magic = (1ull << 32) / (unsigned long long)cfg->W4 + 1ull;
   cfg->factor = (float)B / (float)((int64_t)B * n);
   return TA_OK;
 }
@@ -67,8 +68,9 @@ int aten_mean_plan(const char* who, int B, int64_t n, int cl, AtenMeanCfg* cfg) 
 namespace {
 
 // grid = (cluster, B)
+template <bool PRE>
 __global__ void __launch_bounds__(kAtenThreads) aten_abs_mean_kernel(const float* __restrict__ g, float* __restrict__ mean_out,
-                                                                     int64_t n, AtenMeanCfg c) {
+                                                                     int64_t n, AtenMeanCfg c, MeanPre pre) {
   __shared__ float s_val[kAtenMaxW];
   __shared__ float s_row[kAtenThreads];
   __shared__ float s_blk[kAtenThreads];
@@ -77,7 +79,17 @@ __global__ void __launch_bounds__(kAtenThreads) aten_abs_mean_kernel(const float
   const int64_t col0 = (int64_t)cluster_ctarank() * c.W4;
   for (int col = threadIdx.x; col < c.W4; col += kAtenThreads) {
     ColAcc A;
-    for (int64_t v = col0 + col; v < nvec; v += c.S) aten_column_add(A, __ldg(gp + v));
+    if (PRE) {
+      const float4* ap = pre.addend ? reinterpret_cast<const float4*>(pre.addend + (int64_t)blockIdx.y * n) : nullptr;
+      for (int64_t v = col0 + col; v < nvec; v += c.S) {
+        float4 x = __ldg(gp + v);
+        if (pre.plane_vec > 0) x = div4(x, pick4(pre.std, channel_of(v, pre.plane_vec)));
+        if (ap) x = add4(x, __ldg(ap + v));
+        aten_column_add(A, x);
+      }
+    } else {
+      for (int64_t v = col0 + col; v < nvec; v += c.S) aten_column_add(A, __ldg(gp + v));
+    }
     s_val[col] = aten_column_value(A);
   }
   cluster_sync_all();
@@ -88,14 +100,20 @@ __global__ void __launch_bounds__(kAtenThreads) aten_abs_mean_kernel(const float
 
 }  // namespace
 
-int aten_abs_mean_launch(const float* g, float* mean_out, int B, int64_t n, cudaStream_t s) {
-  if (!aligned16(g)) { set_error("ta_abs_mean_per_sample: TA_MEAN_TORCH needs 16-byte aligned rows"); return TA_EUNSUPPORTED; }
+int aten_abs_mean_launch(const float* g, float* mean_out, int B, int64_t n, const MeanPre* pre, cudaStream_t s) {
+  if (!aligned16(g) || (pre && !aligned16(pre->addend))) {
+    set_error("ta_abs_mean_per_sample: TA_MEAN_TORCH needs 16-byte aligned rows");
+    return TA_EUNSUPPORTED;
+  }
   int cl = tune_get("reduce.cluster", 0);
   if (cl <= 0) cl = 8;
   AtenMeanCfg c;
   int rc = aten_mean_plan("ta_abs_mean_per_sample", B, n, cl, &c);
   if (rc != TA_OK) return rc;
-  return launch_cluster("ta_abs_mean_per_sample[torch order]", aten_abs_mean_kernel, cl, B, kAtenThreads, 0, s, g, mean_out, n, c);
+  if (pre && (pre->addend || pre->plane_vec > 0))
+    return launch_cluster("ta_abs_mean_per_sample[torch order]", aten_abs_mean_kernel<true>, cl, B, kAtenThreads, 0, s, g, mean_out, n, c, *pre);
+  return launch_cluster("ta_abs_mean_per_sample[torch order]", aten_abs_mean_kernel<false>, cl, B, kAtenThreads, 0, s, g, mean_out, n, c,
+                        MeanPre{});
 }
 
 }  // namespace ta

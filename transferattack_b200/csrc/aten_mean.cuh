@@ -32,6 +32,7 @@ struct AtenMeanCfg {
   int nt;                 // bw * bh
   int S;                  // virtual threads per output = 128-bit vectors per row
   int W4;                 // vector columns (virtual threads) per CTA of the cluster
+  unsigned long long w4_magic;   // floor(2^32 / W4) + 1: vt / W4 == (vt * magic) >> 32 for vt < S
   float factor;           // MeanOps factor
 };
 
@@ -44,6 +45,20 @@ bool aten_mean_policy(int B, int64_t n, int sm_count, int max_threads_per_sm, in
 // Host: policy for the current device + the cluster mapping; TA_OK / TA_EUNSUPPORTED (message set)
 int aten_mean_plan(const char* who, int B, int64_t n, int cl, AtenMeanCfg* cfg);
 
+// optional pre-processing of the gradient before |.|: Normalize's adjoint g / std_c (channel c = vector index / plane_vec) and
+// an addend (VMI's grad + variance) — the same two steps, in the same order, as the fused tail applies them
+struct MeanPre {
+  const float* addend;
+  float std[4];
+  int64_t plane_vec;      // 128-bit vectors per channel plane (0: no division)
+};
+__device__ __forceinline__ float4 div4(float4 v, float s) { v.x = div_rn(v.x, s); v.y = div_rn(v.y, s); v.z = div_rn(v.z, s); v.w = div_rn(v.w, s); return v; }
+__device__ __forceinline__ float4 add4(float4 a, const float4& b) { a.x = add_rn(a.x, b.x); a.y = add_rn(a.y, b.y); a.z = add_rn(a.z, b.z); a.w = add_rn(a.w, b.w); return a; }
+__device__ __forceinline__ float pick4(const float (&a)[4], int c) { return c == 0 ? a[0] : (c == 1 ? a[1] : (c == 2 ? a[2] : a[3])); }
+__device__ __forceinline__ int channel_of(int64_t vec, int64_t plane_vec) {
+  return (vec >= plane_vec ? 1 : 0) + (vec >= 2 * plane_vec ? 1 : 0) + (vec >= 3 * plane_vec ? 1 : 0);
+}
+
 // ---- phase 1: one vector column ------------------------------------------------------------------------------------------
 struct ColAcc { float a0 = 0.0f, a1 = 0.0f, a2 = 0.0f, a3 = 0.0f; };
 __device__ __forceinline__ void aten_column_add(ColAcc& A, const float4& v) {
@@ -52,67 +67,106 @@ __device__ __forceinline__ void aten_column_add(ColAcc& A, const float4& v) {
 __device__ __forceinline__ float aten_column_value(const ColAcc& A) { return add_rn(add_rn(add_rn(A.a0, A.a1), A.a2), A.a3); }
 
 // ---- phase 2: the trees -------------------------------------------------------------------------------------------------
-// block_x_reduce of one block row held as a[k] = value[tx = lane + 32k], k < K = bw/32 (zero beyond): lane 0 gets the sum
-template <int KMAX>
-__device__ __forceinline__ float aten_x_tree(float (&a)[KMAX], int K) {
+// block_x_reduce of one block row held as a[k] = value[tx = lane + 32k], k < K = bw/32: lane 0 gets the sum
+template <int K>
+__device__ __forceinline__ float aten_x_tree(float (&a)[K]) {
 #pragma unroll
-  for (int h = KMAX / 2; h >= 1; h >>= 1)            // shared-memory levels: value[tx] += value[tx + 32h], tx < 32h
-    if (h < K) {
+  for (int h = K / 2; h >= 1; h >>= 1) {            // shared-memory levels: value[tx] += value[tx + 32h], tx < 32h
 #pragma unroll
-      for (int k = 0; k < KMAX / 2; ++k) if (k < h) a[k] = add_rn(a[k], a[k + h]);
-    }
+    for (int k = 0; k < h; ++k) a[k] = add_rn(a[k], a[k + h]);
+  }
   float v = a[0];
 #pragma unroll
   for (int o = 16; o >= 1; o >>= 1) v = add_rn(v, __shfl_down_sync(0xffffffffu, v, o));   // warp levels, offsets decreasing
   return v;
 }
 
+// one warp reduces block rows warp, warp+16, ...: row = (virtual block, ty), bw = 32*K values each, gathered through DSMEM
+// (virtual thread vt's value lives in CTA vt / W4 at s_val[vt % W4]). Two rows are in flight per step so that the remote
+// loads of the second overlap the shuffles of the first.
+template <int K>
+__device__ __forceinline__ void aten_rows_x_tree(const AtenMeanCfg& c, const float* s_val, float* s_row, int warp, int lane) {
+  const int nrows = c.cpo * c.bh;
+  const int bw = 32 * K;
+  auto fetch = [&](int row, float (&a)[K]) {
+#pragma unroll
+    for (int k = 0; k < K; ++k) {
+      const uint32_t vt = (uint32_t)(row * bw + lane + 32 * k);
+      const uint32_t owner = (uint32_t)(((unsigned long long)vt * c.w4_magic) >> 32);
+      a[k] = dsmem_ld_f32(s_val + (vt - owner * (uint32_t)c.W4), owner);
+    }
+  };
+  int row = warp;
+  for (; row + 16 < nrows; row += 32) {
+    float a0[K], a1[K];
+    fetch(row, a0); fetch(row + 16, a1);
+    const float v0 = aten_x_tree<K>(a0), v1 = aten_x_tree<K>(a1);
+    if (lane == 0) { s_row[row] = v0; s_row[row + 16] = v1; }
+  }
+  if (row < nrows) {
+    float a0[K];
+    fetch(row, a0);
+    const float v0 = aten_x_tree<K>(a0);
+    if (lane == 0) s_row[row] = v0;
+  }
+}
+
 // s_val: this CTA's W4 column values (static shared memory, same offset in every CTA of the cluster), already written and
-// made visible by a cluster barrier. s_row: >= cpo*bh floats, s_blk: >= bw floats of CTA-local shared memory.
+// made visible by a cluster barrier. s_row: >= cpo*bh floats, s_blk: >= max(cpo, 32) floats of CTA-local shared memory.
 // Contains two __syncthreads(); all remote reads of s_val are complete after the first one. Returns the mean (same value in
 // every thread of every CTA). blockDim.x == kAtenThreads.
 __device__ __forceinline__ float aten_tree_mean(const AtenMeanCfg& c, const float* s_val, float* s_row, float* s_blk) {
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
   const int K = c.bw >> 5;                              // 1 .. 16 values per lane before the shuffles
-  const int nrows = c.cpo * c.bh;                       // (virtual block, ty) rows of bw values each
-  for (int row = warp; row < nrows; row += kAtenThreads / 32) {
-    const int base = row * c.bw;                        // = cb*nt + ty*bw : first virtual thread of the row
-    float a[16];
-#pragma unroll
-    for (int k = 0; k < 16; ++k) {
-      a[k] = 0.0f;
-      if (k < K) {
-        const int vt = base + lane + 32 * k;
-        const int owner = vt / c.W4;
-        a[k] = dsmem_ld_f32(s_val + (vt - owner * c.W4), (uint32_t)owner);
-      }
-    }
-    const float v = aten_x_tree<16>(a, K);
-    if (lane == 0) s_row[row] = v;
+  switch (K) {
+    case 1: aten_rows_x_tree<1>(c, s_val, s_row, warp, lane); break;
+    case 2: aten_rows_x_tree<2>(c, s_val, s_row, warp, lane); break;
+    case 4: aten_rows_x_tree<4>(c, s_val, s_row, warp, lane); break;
+    case 8: aten_rows_x_tree<8>(c, s_val, s_row, warp, lane); break;
+    default: aten_rows_x_tree<16>(c, s_val, s_row, warp, lane); break;
   }
   __syncthreads();
-  if ((int)threadIdx.x < c.cpo) {                       // block_y_reduce of virtual block threadIdx.x
-    float a[16];
+  if ((int)threadIdx.x < c.cpo) {                       // block_y_reduce of virtual block threadIdx.x (offsets bh/2 .. 1)
+    const float* r = s_row + threadIdx.x * c.bh;
+    float v;
+    if (c.bh == 16) {
+      float a[16];
 #pragma unroll
-    for (int y = 0; y < 16; ++y) a[y] = (y < c.bh) ? s_row[threadIdx.x * c.bh + y] : 0.0f;
+      for (int y = 0; y < 16; ++y) a[y] = r[y];
 #pragma unroll
-    for (int h = 8; h >= 1; h >>= 1)
-      if (h < c.bh) {
+      for (int h = 8; h >= 1; h >>= 1) {
 #pragma unroll
-        for (int y = 0; y < 8; ++y) if (y < h) a[y] = add_rn(a[y], a[y + h]);
+        for (int y = 0; y < h; ++y) a[y] = add_rn(a[y], a[y + h]);
       }
-    s_blk[threadIdx.x] = a[0];
+      v = a[0];
+    } else {
+      float a[8];
+#pragma unroll
+      for (int y = 0; y < 8; ++y) a[y] = (y < c.bh) ? r[y] : 0.0f;
+#pragma unroll
+      for (int h = 4; h >= 1; h >>= 1)
+        if (h < c.bh) {
+#pragma unroll
+          for (int y = 0; y < h; ++y) a[y] = add_rn(a[y], a[y + h]);
+        }
+      v = a[0];
+    }
+    s_blk[threadIdx.x] = v;
   }
   __syncthreads();
   // global_reduce's last block: partial i at (tx = i, ty = 0), identity elsewhere: the y tree adds +0.0f (exact); x tree.
   float v;
-  if (c.cpo > 1) {
+  if (c.cpo == 1) {
+    v = s_blk[0];
+  } else if (c.cpo <= 32) {                             // the shared-memory levels of the x tree only add +0.0f here
+    float a[1] = {lane < c.cpo ? s_blk[lane] : 0.0f};
+    v = aten_x_tree<1>(a);
+  } else {
     float a[16];
 #pragma unroll
     for (int k = 0; k < 16; ++k) { const int i = lane + 32 * k; a[k] = (k < K && i < c.cpo) ? s_blk[i] : 0.0f; }
-    v = aten_x_tree<16>(a, K);
-  } else {
-    v = s_blk[0];
+    // K < 16: entries beyond K are zero, so the extra halving levels add +0.0f and the live levels are ATen's
+    v = aten_x_tree<16>(a);
   }
   v = __shfl_sync(0xffffffffu, v, 0);
   return mul_rn(v, c.factor);

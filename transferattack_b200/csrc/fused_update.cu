@@ -27,7 +27,7 @@
 
 using namespace ta;
 
-namespace ta { int aten_abs_mean_launch(const float* g, float* mean_out, int B, int64_t n, cudaStream_t s); }
+namespace ta { int aten_abs_mean_launch(const float* g, float* mean_out, int B, int64_t n, const MeanPre* pre, cudaStream_t s); }
 
 namespace {
 
@@ -52,7 +52,6 @@ struct FusedParams {
 __device__ __forceinline__ int nf_channel(const NormFold& nf, int64_t j) {
   return (j >= nf.plane_vec ? 1 : 0) + (j >= 2 * nf.plane_vec ? 1 : 0) + (j >= 3 * nf.plane_vec ? 1 : 0);
 }
-__device__ __forceinline__ float pick4(const float (&a)[4], int c) { return c == 0 ? a[0] : (c == 1 ? a[1] : (c == 2 ? a[2] : a[3])); }
 
 // one element of the fused tail; all roundings as in the reference's eager ops
 __device__ __forceinline__ void fused_elem(float g, float m, bool has_m, float d, float x, float mu, const FusedParams& p,
@@ -114,8 +113,6 @@ struct TailLayout {
   unsigned long long w4_magic;   // floor(2^32 / W4) + 1: i / W4 == (i * magic) >> 32 for the i that occur
 };
 
-__device__ __forceinline__ float4 div4(float4 v, float s) { v.x = div_rn(v.x, s); v.y = div_rn(v.y, s); v.z = div_rn(v.z, s); v.w = div_rn(v.w, s); return v; }
-__device__ __forceinline__ float4 add4(float4 a, const float4& b) { a.x = add_rn(a.x, b.x); a.y = add_rn(a.y, b.y); a.z = add_rn(a.z, b.z); a.w = add_rn(a.w, b.w); return a; }
 
 // MEAN: 0 = TA_MEAN_EXACT, 1 = TA_MEAN_TORCH.  grid = (cluster, B), 512 threads.
 // dynamic smem: g' part of this CTA: rows x W4 float4
@@ -472,6 +469,28 @@ int fused_tail_impl(const ta_fused_tail_args& a, const NormFold* nf, ta_stream_t
     return TA_EUNSUPPORTED;
   }
   const bool torch_order = a.mean_mode == TA_MEAN_TORCH;
+
+  // Strategy for the torch-order mean. The cluster kernel reads g from HBM once but serialises "load g -> column sums ->
+  // cluster barrier -> trees -> stream" per sample (two waves of 33 clusters at B = 64: measured 72 us). When the whole
+  // gradient fits L2 comfortably it is faster as two launches: the mean kernel streams g once (leaving it in the 126 MB L2),
+  // then the flat streaming kernel runs at full width with g as an L2 hit (measured). fused.strategy: 0 = by
+  // size, 1 = always the cluster kernel, 2 = always split.
+  {
+    const int strategy = tune_get("fused.strategy", 0);
+    const bool fits_l2 = (int64_t)B * n * 4 <= (int64_t)64 * 1024 * 1024;
+    if (torch_order && v4 && a.scale_out && (strategy == 2 || (strategy == 0 && fits_l2))) {
+      MeanPre pre = {};
+      pre.addend = a.addend;
+      if (nf && nf->bwd) { for (int c = 0; c < 4; ++c) pre.std[c] = nf->std[c]; pre.plane_vec = nf->plane_vec; }
+      const int rc = aten_abs_mean_launch(a.g, a.scale_out, B, n, &pre, s);
+      if (rc == TA_OK) {
+        p.scale = a.scale_out;
+        if (nf) return launch_ew_rows2<1>("ta_fused_tail[stream,nf]", B, n, true, FusedStreamOpT<true>{p, n / 4}, s, 0);
+        return launch_ew_rows2<1>("ta_fused_tail[stream]", B, n, true, FusedStreamOp{p, n / 4}, s, 0);
+      }
+      if (rc != TA_EUNSUPPORTED) return rc;
+    }
+  }
 
   // cluster geometry
   int cl = tune_get("fused.cluster", 0);

@@ -5,7 +5,7 @@
 
 using namespace ta;
 
-namespace ta { int aten_abs_mean_launch(const float* g, float* mean_out, int B, int64_t n, cudaStream_t s); }
+namespace ta { struct MeanPre; int aten_abs_mean_launch(const float* g, float* mean_out, int B, int64_t n, const MeanPre* pre, cudaStream_t s); }
 
 namespace {
 
@@ -122,7 +122,7 @@ int64_t ta_abs_mean_ws_bytes(int B, int64_t n) {
 int ta_abs_mean_per_sample(const float* g, float* mean_out, int B, int64_t n, int mode, void* ws, ta_stream_t stream) {
   (void)ws;
   TA_REQUIRE(g && mean_out && B > 0 && n > 0, "ta_abs_mean_per_sample: null pointer or empty shape (B=%d n=%lld)", B, (long long)n);
-  if (mode == TA_MEAN_TORCH) return aten_abs_mean_launch(g, mean_out, B, n, (cudaStream_t)stream);
+  if (mode == TA_MEAN_TORCH) return aten_abs_mean_launch(g, mean_out, B, n, nullptr, (cudaStream_t)stream);
   if (mode != TA_MEAN_EXACT) {
     set_error("ta_abs_mean_per_sample: mode %d not available in this build", mode);
     return TA_EUNSUPPORTED;

@@ -4,7 +4,14 @@ gaussian / uniform / linear, ``self.kernel`` is the same [3,1,k,k] fp32 tensor).
 
 ``get_grad`` runs ``ta_dwconv2d_sep`` when ``self.kernel`` is still the generated (rank-1) kernel — row pass + column
 pass in one CTA, 2k instead of k*k FMAs per element, HBM-bound — and ``ta_dwconv2d`` (direct k x k) otherwise or when
-``conv_mode='direct'``."""
+``conv_mode='direct'``.
+
+Numerical contract (stated, not bit-parity): the reference convolves with the fp32 2-D kernel through ``F.conv2d`` (cuDNN /
+ATen pick the summation order); the separable form multiplies by fp32(k1/sqrt(sum)) twice and sums 15 + 15 terms in tap order,
+the direct form sums the 225 products in row-major tap order. Either way the smoothed gradient is within 1e-6 (relative to its
+largest entry) of ``F.conv2d``'s (tests/test_kernels_gpu.py, golden tim.npz); the perturbation can therefore differ from the
+reference's only where a momentum entry is zero to rounding (a sign tie) — measured: 0 differing elements over 10 iterations at
+ResNet-50 B = 32 (profiles/e2e_parity_baseline_r2.json), asserted against the reference's own run-to-run floor."""
 import numpy as np
 import scipy.stats as st
 

@@ -264,7 +264,9 @@ class CudaBackend:
     def dim(self, x, rnd, R, top, left, forward=True):
         x = _f32c(x, "x"); S = x.shape[-1]
         if x.shape[-2] != S:
-            raise ValueError("DIM kernels need square images (the reference resizes with x.shape[-1] only)")
+            raise ValueError("ta_dim_*: needs square images, got %dx%d. The reference's DIM (dim.py:50-68) resizes BOTH sides to "
+                             "sizes derived from x.shape[-1] only, i.e. it squashes non-square inputs; that case is not kernelised — "
+                             "use the reference's dim.py on this base (compat.adopt_reference_plugins) for it" % (x.shape[-2], S))
         planes = x.numel() // (S * S)
         out = torch.empty_like(x)
         fn = self.lib.ta_dim_fwd_ws if forward else self.lib.ta_dim_bwd_ws
