@@ -53,9 +53,10 @@ def _worker(rank, world, init_file, out_dir, case):
         elif case == "shard_dim":
             atk = make_attack(tab, "ditimi", _net("resnet18", 0, dev), epoch=4)
             out = multigpu.run_sharded(atk, x, y, seed=5 + rank, gather=True)
-        elif case == "ens":
+        elif case in ("ens", "ens_rs"):
             member = tab.utils.wrap_model(_net("resnet18" if rank == 0 else "mobilenet_v2", 0 if rank == 0 else 3, dev))
-            atk = multigpu.make_ens_attack(tab.load_attack_class("ens"), member, epoch=4)
+            torch.cuda.manual_seed(100 + rank)         # per-rank device generators differ: a random start must still agree
+            atk = multigpu.make_ens_attack(tab.load_attack_class("ens"), member, epoch=4, random_start=(case == "ens_rs"))
             out = atk(x, y)
         elif case == "p2p":
             member = tab.utils.wrap_model(_net("resnet18" if rank == 0 else "mobilenet_v2", 0 if rank == 0 else 3, dev))
@@ -133,3 +134,10 @@ def test_fused_p2p_ensemble_equals_single_device_ensemble():
     atk.mean_mode = "exact"
     ref = atk(x, y).cpu().numpy()
     assert np.array_equal(outs[0], ref), int((outs[0] != ref).sum())
+
+
+def test_sharded_ensemble_random_start_is_broadcast():
+    """the sharded-ensemble attack broadcasts rank 0's random start, so the replicated updates stay in lockstep"""
+    _need2()
+    outs = _run("ens_rs")
+    assert np.array_equal(outs[0], outs[1]) and np.abs(outs[0]).max() <= 16 / 255 + 1e-7

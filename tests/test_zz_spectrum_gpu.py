@@ -13,7 +13,13 @@ import transferattack_b200 as tab
 from oracle import torch_ref
 from helpers import make_attack, seed_all
 
-pytestmark = pytest.mark.gpu
+# Opt-in: after the GPU call in which these tests first ran (all 6 passed on a B200; profiles/pytest_spectrum_r2.log) the box was
+# reported unhealthy by the runner's post-call probe. The cause is not established (nothing in the run failed), so the
+# tensor-core tests are kept out of the default `-m gpu` run until it is: TA_B200_TEST_TCGEN05=1 enables them.
+import os
+pytestmark = [pytest.mark.gpu,
+              pytest.mark.skipif(os.environ.get("TA_B200_TEST_TCGEN05", "0") != "1",
+                                 reason="tcgen05 spectrum tests are opt-in (TA_B200_TEST_TCGEN05=1), see the comment above")]
 
 
 @pytest.fixture(scope="module")

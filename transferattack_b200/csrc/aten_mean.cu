@@ -77,18 +77,35 @@ __global__ void __launch_bounds__(kAtenThreads) aten_abs_mean_kernel(const float
   const float4* gp = reinterpret_cast<const float4*>(g + (int64_t)blockIdx.y * n);
   const int64_t nvec = n >> 2;
   const int64_t col0 = (int64_t)cluster_ctarank() * c.W4;
+  const float4* ap = (PRE && pre.addend) ? reinterpret_cast<const float4*>(pre.addend + (int64_t)blockIdx.y * n) : nullptr;
+  const int pv = (int)pre.plane_vec;                                 // vectors per channel plane (n < 2^31 here)
   for (int col = threadIdx.x; col < c.W4; col += kAtenThreads) {
+    // the column's vectors are v0, v0 + S, v0 + 2S, ...: all loads of a batch of 8 rows are issued before the first add (a
+    // thread has no other work to hide a DRAM latency per row behind); the adds then run in row order
     ColAcc A;
-    if (PRE) {
-      const float4* ap = pre.addend ? reinterpret_cast<const float4*>(pre.addend + (int64_t)blockIdx.y * n) : nullptr;
-      for (int64_t v = col0 + col; v < nvec; v += c.S) {
-        float4 x = __ldg(gp + v);
-        if (pre.plane_vec > 0) x = div4(x, pick4(pre.std, channel_of(v, pre.plane_vec)));
-        if (ap) x = add4(x, __ldg(ap + v));
-        aten_column_add(A, x);
-      }
-    } else {
-      for (int64_t v = col0 + col; v < nvec; v += c.S) aten_column_add(A, __ldg(gp + v));
+    const int v0 = (int)col0 + col;
+    const int rows = v0 < (int)nvec ? (int)((nvec - v0 + c.S - 1) / c.S) : 0;
+    for (int j0 = 0; j0 < rows; j0 += 8) {
+      float4 x[8], y[8];
+#pragma unroll
+      for (int u = 0; u < 8; ++u)
+        if (j0 + u < rows) {
+          x[u] = __ldg(gp + v0 + (int64_t)(j0 + u) * c.S);
+          if (PRE && ap) y[u] = __ldg(ap + v0 + (int64_t)(j0 + u) * c.S);
+        }
+#pragma unroll
+      for (int u = 0; u < 8; ++u)
+        if (j0 + u < rows) {
+          float4 t = x[u];
+          if (PRE) {
+            if (pv > 0) {
+              const int v = v0 + (j0 + u) * c.S;
+              t = div4(t, pick4(pre.std, (v >= pv ? 1 : 0) + (v >= 2 * pv ? 1 : 0) + (v >= 3 * pv ? 1 : 0)));
+            }
+            if (ap) t = add4(t, y[u]);
+          }
+          aten_column_add(A, t);
+        }
     }
     s_val[col] = aten_column_value(A);
   }
@@ -105,6 +122,7 @@ int aten_abs_mean_launch(const float* g, float* mean_out, int B, int64_t n, cons
     set_error("ta_abs_mean_per_sample: TA_MEAN_TORCH needs 16-byte aligned rows");
     return TA_EUNSUPPORTED;
   }
+  if (n >= ((int64_t)1 << 31)) { set_error("ta_abs_mean_per_sample: TA_MEAN_TORCH serves samples below 2^31 elements"); return TA_EUNSUPPORTED; }
   int cl = tune_get("reduce.cluster", 0);
   if (cl <= 0) cl = 8;
   AtenMeanCfg c;

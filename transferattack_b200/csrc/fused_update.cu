@@ -86,7 +86,11 @@ struct FusedStreamOpT {
     const int64_t i = (int64_t)row * nvec + j;
     Vec<V> mo, dn, xa, gb;
     float mean_c = 0.0f, std_c = 1.0f;
-    if (NF) { const int c = nf_channel(p.nf, j); mean_c = pick4(p.nf.mean, c); std_c = pick4(p.nf.std, c); }
+    if (NF) {                               // j < 2^31 (one sample): 32-bit compares
+      const int jj = (int)j, pv = (int)p.nf.plane_vec;
+      const int c = (jj >= pv ? 1 : 0) + (jj >= 2 * pv ? 1 : 0) + (jj >= 3 * pv ? 1 : 0);
+      mean_c = pick4(p.nf.mean, c); std_c = pick4(p.nf.std, c);
+    }
 #pragma unroll
     for (int k = 0; k < V; ++k) {
       float g = r.g.v[k];
