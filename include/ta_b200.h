@@ -222,6 +222,20 @@ int ta_dim_fwd_ws(const float* x, float* out, int planes, int S, int rnd, int R,
 int ta_dim_bwd_ws(const float* gout, float* gin, int planes, int S, int rnd, int R, int pad_top, int pad_left,
                   void* ws, ta_stream_t stream);
 
+/* DIM with the draw in DEVICE memory (for CUDA-graph replay; dim.py:47-62 draws a new (coin, rnd, pad_top, pad_left) per call):
+ * `packs` is a device array of n_packs records of ta_dim_pack_bytes() bytes each, built on the HOST by ta_dim_pack_build (one per
+ * pre-drawn iteration; identity != 0 = the coin said "return x") and uploaded by the caller; `it` is a device int32 holding the
+ * index of the record to use (clamped to [0, n_packs-1]); ta_counter_add advances / resets it in stream order. The kernels are the
+ * ones behind ta_dim_fwd_ws / ta_dim_bwd_ws reading geometry and tables from packs[*it] — bit-identical results. R = int(S*rate). */
+int64_t ta_dim_pack_bytes(void);
+int ta_dim_pack_build(void* host_pack, int S, int rnd, int R, int pad_top, int pad_left, int identity);
+int ta_dim_fwd_dyn(const float* x, float* out, int planes, int S, int R, const void* packs, int n_packs,
+                   const int* it, ta_stream_t stream);
+int ta_dim_bwd_dyn(const float* gout, float* gin, int planes, int S, int R, const void* packs, int n_packs,
+                   const int* it, ta_stream_t stream);
+/* *counter = set_to >= 0 ? set_to : *counter + delta   (one-thread kernel, stream-ordered, capturable) */
+int ta_counter_add(int* counter, int delta, int set_to, ta_stream_t stream);
+
 /* ---- TIM (input_transformation/tim.py:68-73) ------------------------------------------------------
  *   out = conv2d(g, K[C,1,ks,ks], stride 1, zero padding 'same', groups=C)  (cross-correlation)
  *   k: [C, ks, ks] DEVICE array, ks odd, ks <= 31.

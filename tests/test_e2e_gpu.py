@@ -298,14 +298,33 @@ def test_fast_mode_is_opt_in_and_keeps_the_attack_strength():
     assert res["fast_vmifgsm"] > res["clean"], res
 
 
-def test_cuda_graph_is_refused_for_host_rng_transforms():
+def test_dim_runs_inside_the_cuda_graph_with_the_reference_draws():
+    """DIM / DI-TI-MI draw per call from the host generator. The graph path makes all `epoch` draws up front (same calls, same
+    order), uploads per-iteration table records and lets the captured kernels read record *it (ta_dim_*_dyn): one captured graph,
+    a new draw per replay, the same bits as the eager loop and as the reference restatement — also on a second batch."""
     net = _net()
     x, y = _data(2)
-    atk = make_attack(tab, "dim", net, epoch=2)
+    for name, kw in (("dim", {"epoch": 4}), ("dim", {"epoch": 5, "diversity_prob": 1.0}), ("ditimi", {"epoch": 4}), ("siditimi", {"epoch": 2})):
+        eager = make_attack(tab, name, net, **kw); eager.use_cuda_graph = False
+        graph = make_attack(tab, name, net, **kw); graph.use_cuda_graph = True
+        for seed, (xx, yy) in ((4, (x, y)), (9, _data(2, seed=7))):
+            seed_all(seed); d_e = eager(xx, yy); r_e = torch.rand(1)
+            seed_all(seed); d_g = graph(xx, yy); r_g = torch.rand(1)
+            assert getattr(graph, "_graphs", None), getattr(graph, "_graph_error", None)
+            assert torch.equal(d_e, d_g), (name, kw, seed)
+            assert torch.equal(r_e, r_g)                  # the host generator was consumed identically
+        REPORT["graph/" + name + "_" + "_".join("%s%s" % kv for kv in kw.items())] = {"bit_identical_to_eager": True}
+
+
+def test_cuda_graph_is_refused_for_host_rng_transforms():
+    """Admix draws a permutation per call and declares nothing: it must stay eager (and still equal an eager twin)"""
+    net = _net()
+    x, y = _data(2)
+    atk = make_attack(tab, "admix", net, epoch=2)
     atk.use_cuda_graph = True
     seed_all(4); d = atk(x, y)
-    assert not getattr(atk, "_graphs", None)          # DIM draws per call → eager loop
-    ref = make_attack(tab, "dim", net, epoch=2)
+    assert not getattr(atk, "_graphs", None)
+    ref = make_attack(tab, "admix", net, epoch=2)
     seed_all(4)
     assert torch.equal(d, ref(x, y))
 

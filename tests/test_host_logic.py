@@ -326,7 +326,7 @@ def test_graph_capture_is_opt_in_per_hook_owner():
     be captured. Every class defining a loop hook has to declare graph_safe itself — inheriting the flag is not enough."""
     ok = {n: make_attack(tab, n, [tiny_net(0), tiny_net(1)] if n in ("ens", "adaea") else tiny_net(0))._graph_ok() for n in tab.attack_zoo}
     assert ok == {"fgsm": True, "ifgsm": True, "mifgsm": True, "nifgsm": True, "tim": True, "sim": True, "ens": True,
-                  "dim": False, "admix": False, "ditimi": False, "vmifgsm": False, "vnifgsm": False, "emifgsm": False, "pifgsm": False, "siditimi": False,
+                  "dim": True, "admix": False, "ditimi": True, "vmifgsm": False, "vnifgsm": False, "emifgsm": False, "pifgsm": False, "siditimi": True,
                   "gra": False, "adaea": False, "ssm": False}
     base = tab.load_attack_class("mifgsm")
 

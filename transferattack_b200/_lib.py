@@ -61,6 +61,11 @@ SIGNATURES = {
     "ta_dim_ws_bytes": (_l, []),
     "ta_dim_fwd_ws": (_i, [_p, _p, _i, _i, _i, _i, _i, _i, _p, _p]),
     "ta_dim_bwd_ws": (_i, [_p, _p, _i, _i, _i, _i, _i, _i, _p, _p]),
+    "ta_dim_pack_bytes": (_l, []),
+    "ta_dim_pack_build": (_i, [_p, _i, _i, _i, _i, _i, _i]),
+    "ta_dim_fwd_dyn": (_i, [_p, _p, _i, _i, _i, _p, _i, _p, _p]),
+    "ta_dim_bwd_dyn": (_i, [_p, _p, _i, _i, _i, _p, _i, _p, _p]),
+    "ta_counter_add": (_i, [_p, _i, _i, _p]),
     "ta_dwconv2d": (_i, [_p, _p, _i, _p, _i, _i, _i, _i, _p]),
     "ta_dwconv2d_sep": (_i, [_p, _p, _p, _i, _p, _i, _i, _i, _i, _p]),
     "ta_dwconv2d_sep_hw": (_i, [_p, _p, _p, _i, _p, _i, _i, _i, _i, _p]),

@@ -101,6 +101,9 @@ class Attack(object):
     #: strict mean mode (torch's own mean op needs the gradient w.r.t. delta in memory) and moves into the fused kernel too
     #: in 'exact' mode with the base ``get_grad``. Same arithmetic in the same order → same bits. Env TA_B200_FOLD=0 disables.
     fold_normalize = os.environ.get("TA_B200_FOLD", "1") == "1"
+    #: with an in-kernel mean and the base get_grad, Normalize's ADJOINT (g / std) is applied inside the tail kernels too instead
+    #: of as a `ta_normalize_bwd` launch at the end of the backward pass. Same bits either way; False keeps the separate launch.
+    fold_adjoint = os.environ.get("TA_B200_FOLD_ADJOINT", "1") == "1"
     #: OPT-IN, NOT THE PARITY PATH. 'bf16': the surrogate's forward/backward runs on a bf16,
     #: channels_last copy of the model (tensor-core convolutions, half the activation traffic); everything around it — staging,
     #: mean|g|, momentum, update, clipping — stays the fp32 kernels. The perturbation is a valid one (eps-ball, [0,1] box) of the
@@ -219,7 +222,7 @@ class Attack(object):
         if pre.mean.numel() != C or C > 4 or (H * W) % 4 != 0 or data.data_ptr() % 16 != 0:
             return None
         # Normalize's adjoint inside the kernel needs the staged (cluster) form: the sample must fit 8 CTAs' shared memory
-        defer = kmode is not None and cls.get_grad is Attack.get_grad and C * H * W <= 384 * 1024
+        defer = self.fold_adjoint and kmode is not None and cls.get_grad is Attack.get_grad and C * H * W <= 384 * 1024
         return pre, m[1], [float(v) for v in pre.mean.tolist()], [float(v) for v in pre.std.tolist()], defer
 
     @staticmethod
@@ -340,6 +343,9 @@ class Attack(object):
         grad = self.get_grad(loss, st["delta"])
         self._tail(ops.backend(), grad, st["m"], st["m"], st["delta"], st["delta"], st["data"], st["xadv"], st["scale_out"],
                    st["kmode"], fold)
+        step = getattr(self, "_graph_step", None)       # plugins with per-iteration state on the device (DIM's draw index)
+        if step is not None:
+            step()
 
     def _graph_reset(self, st, data, label, delta0):
         with torch.no_grad():
@@ -351,12 +357,15 @@ class Attack(object):
                 self._first_normalized(st["fold"][0], st["data"], st["delta"], out=st["xadv"])
             else:
                 ops.backend().stage_add(st["data"], st["delta"], out=st["xadv"])
+            rewind = getattr(self, "_graph_rewind", None)
+            if rewind is not None:
+                rewind()
 
     def _graph_for(self, data, label, delta0):
         kmode = self._mean_kernel_mode(data)
         fold = self._fold_plan(data, kmode)
         key = (tuple(data.shape), str(data.device), tuple(label.shape), self.mean_mode, kmode, float(self.alpha), float(self.decay),
-               float(self.epsilon), bool(self.targeted), id(self.model), fold is not None, bool(fold[4]) if fold else False)
+               float(self.epsilon), bool(self.targeted), id(self.model), fold is not None, bool(fold[4]) if fold else False, self.fast_mode)
         cache = self.__dict__.setdefault("_graphs", {})
         st = cache.get(key)
         if st is not None:
@@ -386,11 +395,21 @@ class Attack(object):
         return st
 
     def _loop_graph(self, data, label, delta0):
-        st = self._graph_for(data, label, delta0.detach())
-        self._graph_reset(st, data, label, delta0.detach())
-        for _ in range(self.epoch):
-            st["graph"].replay()
-        return st["delta"].detach().clone()
+        begin, end = getattr(self, "_graph_begin", None), getattr(self, "_graph_end", None)
+        if begin is not None:                       # e.g. DIM: draw all `epoch` transforms now, in the reference's order
+            begin(data)
+        ok = False
+        try:
+            st = self._graph_for(data, label, delta0.detach())
+            self._graph_reset(st, data, label, delta0.detach())
+            for _ in range(self.epoch):
+                st["graph"].replay()
+            out = st["delta"].detach().clone()
+            ok = True
+            return out
+        finally:
+            if end is not None:
+                end(ok)
 
     # ------------------------------------------------------------------------------------------------
     def get_logits(self, x, **kwargs):

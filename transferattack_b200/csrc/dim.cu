@@ -361,4 +361,34 @@ int ta_dim_bwd_ws(const float* gout, float* gin, int planes, int S, int rnd, int
   return ta_dim_bwd(gout, gin, planes, S, rnd, R, pad_top, pad_left, stream);
 }
 
+
+// ---- the draw in DEVICE memory: one captured CUDA graph serves every iteration's (coin, rnd, top, left) -----------------------
+int64_t ta_dim_pack_bytes(void) { return (int64_t)sizeof(DimPack); }
+
+int ta_dim_pack_build(void* host_pack, int S, int rnd, int R, int pad_top, int pad_left, int identity) {
+  TA_REQUIRE(host_pack, "ta_dim_pack_build: null pointer");
+  if (!identity) {
+    const int rc = check_geom("ta_dim_pack_build", 1, S, rnd, R, pad_top, pad_left);
+    if (rc != TA_OK) return rc;
+    if (!dim_direct_ok(S, rnd, R)) { set_error("ta_dim_pack_build: S=%d R=%d beyond the direct kernels' tables", S, R); return TA_EUNSUPPORTED; }
+  }
+  return dim_pack_build(reinterpret_cast<DimPack*>(host_pack), S, rnd, R, pad_top, pad_left, identity);
+}
+
+int ta_dim_fwd_dyn(const float* x, float* out, int planes, int S, int R, const void* packs, int n_packs, const int* it,
+                   ta_stream_t stream) {
+  TA_REQUIRE(x && out && packs && it && n_packs > 0 && planes > 0 && planes <= 65535, "ta_dim_fwd_dyn: bad arguments");
+  if (!dim_direct_ok(S, S, R) || !aligned16(packs)) { set_error("ta_dim_fwd_dyn: S=%d R=%d unsupported or misaligned packs", S, R); return TA_EUNSUPPORTED; }
+  return dim_fwd_dyn(x, out, planes, S, R, reinterpret_cast<const DimPack*>(packs), n_packs, it,
+                     (S % 4 == 0) && aligned16(x) && tune_get("dim.tma", 1) != 0, (cudaStream_t)stream);
+}
+
+int ta_dim_bwd_dyn(const float* gout, float* gin, int planes, int S, int R, const void* packs, int n_packs, const int* it,
+                   ta_stream_t stream) {
+  TA_REQUIRE(gout && gin && packs && it && n_packs > 0 && planes > 0 && planes <= 65535, "ta_dim_bwd_dyn: bad arguments");
+  if (!dim_direct_ok(S, S, R) || !aligned16(packs)) { set_error("ta_dim_bwd_dyn: S=%d R=%d unsupported or misaligned packs", S, R); return TA_EUNSUPPORTED; }
+  return dim_bwd_dyn(gout, gin, planes, S, R, reinterpret_cast<const DimPack*>(packs), n_packs, it,
+                     (S % 4 == 0) && aligned16(gout) && tune_get("dim.tma", 1) != 0, (cudaStream_t)stream);
+}
+
 }  // extern "C"

@@ -30,7 +30,7 @@ constexpr int RB = kDimRB;      // destination rows per CTA
 constexpr int kThreads = 256;
 constexpr int kMaxW = 3;        // inverse-range weights kept in registers (bilinear at DIM's rates needs <= 3)
 
-struct Geo { int S, rnd, R, top, left, a_rows, c_rows; };
+using Geo = DimGeo;
 
 __device__ __forceinline__ int tap_i0(const TapE& e) { return e.i01 & 0xffff; }
 __device__ __forceinline__ int tap_i1(const TapE& e) { return (int)((unsigned)e.i01 >> 16); }
@@ -69,15 +69,41 @@ __device__ __forceinline__ void sts_f32(uint32_t addr, float v) {
 // row nq and column rnd are zero | descA [c_rows] | descB [RB]
 // table source of the forward kernel: the 8.7 KB struct itself as a kernel parameter (default: the forward reads 2 column
 // taps per thread and phase, measured 34 us against 38 us with the extra upload launch) or a pointer into the workspace
-struct FwdTabParam { DimTabF t; __device__ __forceinline__ const DimTabF& get() const { return t; } };
-struct FwdTabPtr { const DimTabF* p; __device__ __forceinline__ const DimTabF& get() const { return *p; } };
+struct FwdTabParam {
+  DimTabF t;
+  __device__ __forceinline__ const DimTabF& get() const { return t; }
+  __device__ __forceinline__ Geo geo(const Geo& g) const { return g; }
+  __device__ __forceinline__ bool identity() const { return false; }
+};
+struct FwdTabPtr {
+  const DimTabF* p;
+  __device__ __forceinline__ const DimTabF& get() const { return *p; }
+  __device__ __forceinline__ Geo geo(const Geo& g) const { return g; }
+  __device__ __forceinline__ bool identity() const { return false; }
+};
+// the draw comes from device memory: packs[min(*it, n - 1)] (one captured graph, a new draw per replay)
+struct FwdTabDyn {
+  const DimPack* packs; const int* it; int n;
+  __device__ __forceinline__ const DimPack& pk() const { const int i = *it; return packs[i < n - 1 ? (i < 0 ? 0 : i) : n - 1]; }
+  __device__ __forceinline__ const DimTabF& get() const { return pk().tf; }
+  __device__ __forceinline__ Geo geo(const Geo&) const { return pk().gf; }
+  __device__ __forceinline__ bool identity() const { return pk().identity != 0; }
+};
 
 template <int MODE, bool TMA_STAGE, class TR, bool REUSE = true>
 __global__ void __launch_bounds__(kThreads) dim_fwd_direct_kernel(const float* __restrict__ x, float* __restrict__ out,
-                                                                  const __grid_constant__ TR tr, const Geo gm) {
+                                                                  const __grid_constant__ TR tr, const Geo gm_in) {
   const DimTabF& tab = tr.get();
+  const Geo gm = tr.geo(gm_in);
   extern __shared__ __align__(128) unsigned char smem_raw[];
   __shared__ __align__(8) uint64_t s_bar;
+  if (tr.identity()) {                                   // the coin said "return x" (dim.py:47-48): this band is a copy
+    const int S0 = gm.S, r0 = blockIdx.x * RB, r1 = min(r0 + RB, S0);
+    const float* xp0 = x + (int64_t)blockIdx.y * S0 * S0;
+    float* op0 = out + (int64_t)blockIdx.y * S0 * S0;
+    for (int e = r0 * S0 + threadIdx.x; e < r1 * S0; e += kThreads) op0[e] = __ldg(xp0 + e);
+    return;
+  }
   const int S = gm.S, rnd = gm.rnd, top = gm.top, left = gm.left;
   const int CP = rnd + 1;
   float* bufA = reinterpret_cast<float*>(smem_raw);
@@ -275,12 +301,23 @@ __device__ __forceinline__ void gather_scatter(uint32_t src, uint32_t pitch_byte
 
 // smem: bufU [u_rows * S] gout band (offset 0: the bulk-TMA destination) | bufG [g_rows * rnd] g1 band | descU [u_rows] |
 // descQ [g_rows]
-template <bool TMA_STAGE>
+template <bool TMA_STAGE, bool DYN = false>
 __global__ void __launch_bounds__(kThreads) dim_bwd_direct_kernel(const float* __restrict__ gout, float* __restrict__ gin,
-                                                                  const DimTabB* __restrict__ tabp, const Geo gm) {
-  const DimTabB& tab = *tabp;
+                                                                  const DimTabB* __restrict__ tabp, const Geo gm_in,
+                                                                  const DimPack* __restrict__ packs, const int* __restrict__ it, int n_packs) {
+  const DimPack* pk = nullptr;
+  if (DYN) { const int i = *it; pk = packs + (i < n_packs - 1 ? (i < 0 ? 0 : i) : n_packs - 1); }
+  const DimTabB& tab = DYN ? pk->tb : *tabp;
+  const Geo gm = DYN ? pk->gb : gm_in;
   extern __shared__ __align__(128) unsigned char smem_raw[];
   __shared__ __align__(8) uint64_t s_bar;
+  if (DYN && pk->identity) {                             // identity forward → identity adjoint
+    const int S0 = gm.S, r0 = blockIdx.x * RB, r1 = min(r0 + RB, S0);
+    const float* gp0 = gout + (int64_t)blockIdx.y * S0 * S0;
+    float* ip0 = gin + (int64_t)blockIdx.y * S0 * S0;
+    for (int e = r0 * S0 + threadIdx.x; e < r1 * S0; e += kThreads) ip0[e] = __ldg(gp0 + e);
+    return;
+  }
   const int S = gm.S, rnd = gm.rnd, top = gm.top, left = gm.left;
   float* bufU = reinterpret_cast<float*>(smem_raw);
   float* bufG = bufU + (size_t)gm.a_rows * S;
@@ -522,6 +559,124 @@ bool dim_direct_ok(int S, int rnd, int R) { return S <= kDimMaxS && R <= kDimMax
 
 size_t dim_direct_ws_bytes() { return sizeof(DimTabB) > sizeof(DimTabF) ? sizeof(DimTabB) : sizeof(DimTabF); }
 
+// exact band maxima of one draw (rows of y1 / of the source a forward band needs; rows of g1 / of gout an adjoint band needs)
+static void fwd_tables(int S, int rnd, int R, int top, DimTabF& tab, int* a_rows_, int* c_rows_) {
+  host_taps(R, S, tab.t2);
+  host_taps(S, rnd, tab.t1);
+  int c_rows = 0, a_rows = 1;
+  for (int oy0 = 0; oy0 < S; oy0 += RB) {
+    const int oy1 = (oy0 + RB < S ? oy0 + RB : S) - 1;
+    const int pr0 = h_i0(tab.t2[oy0]), pr1 = h_i1(tab.t2[oy1]);
+    const int q0 = pr0 - top > 0 ? pr0 - top : 0, q1 = pr1 - top < rnd - 1 ? pr1 - top : rnd - 1;
+    if (q0 > q1) continue;
+    if (q1 - q0 + 1 > c_rows) c_rows = q1 - q0 + 1;
+    const int nsr = h_i1(tab.t1[q1]) - h_i0(tab.t1[q0]) + 1;
+    if (nsr > a_rows) a_rows = nsr;
+  }
+  *a_rows_ = a_rows; *c_rows_ = c_rows;
+}
+static void bwd_tables(int S, int rnd, int R, int top, DimTabB& tab, int* u_rows_, int* g_rows_) {
+  host_taps(R, S, tab.t2);
+  host_taps(S, rnd, tab.t1);
+  host_inverse(tab.t2, S, R, tab.inv2);
+  host_inverse(tab.t1, rnd, S, tab.inv1);
+  int g_rows = 1, u_rows = 1;
+  for (int sy0 = 0; sy0 < S; sy0 += RB) {
+    const int sy1 = (sy0 + RB < S ? sy0 + RB : S) - 1;
+    tab.band[sy0 / RB] = make_short4(0, 0, 0, 0);
+    int q0 = 0x7fffffff, q1 = -1;
+    for (int sy = sy0; sy <= sy1; ++sy)
+      if (tab.inv1[sy].cnt > 0) {
+        if (tab.inv1[sy].lo < q0) q0 = tab.inv1[sy].lo;
+        if (tab.inv1[sy].lo + tab.inv1[sy].cnt - 1 > q1) q1 = tab.inv1[sy].lo + tab.inv1[sy].cnt - 1;
+      }
+    if (q0 > q1) continue;
+    if (q1 - q0 + 1 > g_rows) g_rows = q1 - q0 + 1;
+    int a = 0x7fffffff, b = -1;
+    for (int q = q0; q <= q1; ++q) {
+      const InvE& iv = tab.inv2[q + top];
+      if (iv.cnt > 0) { if (iv.lo < a) a = iv.lo; if (iv.lo + iv.cnt - 1 > b) b = iv.lo + iv.cnt - 1; }
+    }
+    if (a <= b && b - a + 1 > u_rows) u_rows = b - a + 1;
+    tab.band[sy0 / RB] = make_short4((short)q0, (short)(q1 - q0 + 1), (short)(a <= b ? a : 0), (short)(a <= b ? b - a + 1 : 0));
+  }
+  *u_rows_ = u_rows; *g_rows_ = g_rows;
+}
+static size_t fwd_smem(int S, int rnd, int a_rows, int c_rows) {
+  return ((sizeof(float) * ((size_t)a_rows * S + (size_t)(c_rows + 1) * (rnd + 1)) + 15) & ~(size_t)15) + 16 * (size_t)(c_rows + RB);
+}
+static size_t bwd_smem(int S, int rnd, int u_rows, int g_rows) {
+  return ((sizeof(float) * ((size_t)u_rows * S + (size_t)g_rows * rnd) + 15) & ~(size_t)15) + 16 * (size_t)(u_rows + g_rows);
+}
+
+int dim_pack_build(DimPack* pack, int S, int rnd, int R, int top, int left, int identity) {
+  memset(pack, 0, sizeof(DimPack));
+  pack->identity = identity ? 1 : 0;
+  if (identity) { pack->gf = Geo{S, S, S, 0, 0, 1, 1, 0}; pack->gb = pack->gf; return TA_OK; }
+  int a = 1, c = 0, u = 1, g = 1;
+  fwd_tables(S, rnd, R, top, pack->tf, &a, &c);
+  bwd_tables(S, rnd, R, top, pack->tb, &u, &g);
+  pack->gf = Geo{S, rnd, R, top, left, a, c, 0};
+  pack->gb = Geo{S, rnd, R, top, left, u, g, 0};
+  return TA_OK;
+}
+
+// shared memory that serves every draw (rnd, top) DIM can make at (S, R): scanned once per (S, R)
+void dim_dyn_smem(int S, int R, size_t* fwd_bytes, size_t* bwd_bytes) {
+  static thread_local int cS = 0, cR = 0;
+  static thread_local size_t cf = 0, cb = 0;
+  if (cS != S || cR != R) {
+    static thread_local DimTabF tf;
+    static thread_local DimTabB tb;
+    size_t mf = 0, mb = 0;
+    const int lo = S < R ? S : R, hi = S < R ? R : S;
+    const int hi_excl = hi > lo ? hi : lo + 1;              // dim.py:54 draws rnd from [min(S,R), max(S,R)), top / left from [0, R - rnd)
+    for (int rnd = lo; rnd < hi_excl; ++rnd) {
+      const int ntop = R - rnd > 1 ? R - rnd : 1;
+      for (int top = 0; top < ntop; ++top) {
+        int a, c, u, g;
+        fwd_tables(S, rnd, R, top, tf, &a, &c);
+        bwd_tables(S, rnd, R, top, tb, &u, &g);
+        const size_t f = fwd_smem(S, rnd, a, c), b = bwd_smem(S, rnd, u, g);
+        if (f > mf) mf = f;
+        if (b > mb) mb = b;
+      }
+    }
+    cS = S; cR = R; cf = mf; cb = mb;
+  }
+  *fwd_bytes = cf; *bwd_bytes = cb;
+}
+
+int dim_fwd_dyn(const float* x, float* out, int planes, int S, int R, const DimPack* packs, int n_packs, const int* it, bool tma,
+                cudaStream_t stream) {
+  size_t smem, sb;
+  dim_dyn_smem(S, R, &smem, &sb);
+  TA_REQUIRE(smem <= 200 * 1024, "ta_dim_fwd_dyn: image size S=%d needs %zu B of shared memory per CTA", S, smem);
+  auto k = tma ? dim_fwd_direct_kernel<1, true, FwdTabDyn, true> : dim_fwd_direct_kernel<1, false, FwdTabDyn, true>;
+  static SmemOptIn optin[2] = {};
+  const int rc = ensure_dyn_smem("ta_dim_fwd_dyn", k, smem, optin[tma ? 0 : 1]);
+  if (rc != TA_OK) return rc;
+  dim3 grid((unsigned)((S + RB - 1) / RB), (unsigned)planes);
+  k<<<grid, kThreads, smem, stream>>>(x, out, FwdTabDyn{packs, it, n_packs}, Geo{});
+  count_launch();
+  return check_launch("ta_dim_fwd_dyn");
+}
+
+int dim_bwd_dyn(const float* gout, float* gin, int planes, int S, int R, const DimPack* packs, int n_packs, const int* it, bool tma,
+                cudaStream_t stream) {
+  size_t sf, smem;
+  dim_dyn_smem(S, R, &sf, &smem);
+  TA_REQUIRE(smem <= 200 * 1024, "ta_dim_bwd_dyn: image size S=%d needs %zu B of shared memory per CTA", S, smem);
+  auto k = tma ? dim_bwd_direct_kernel<true, true> : dim_bwd_direct_kernel<false, true>;
+  static SmemOptIn optin[2] = {};
+  const int rc = ensure_dyn_smem("ta_dim_bwd_dyn", k, smem, optin[tma ? 0 : 1]);
+  if (rc != TA_OK) return rc;
+  dim3 grid((unsigned)((S + RB - 1) / RB), (unsigned)planes);
+  k<<<grid, kThreads, smem, stream>>>(gout, gin, nullptr, Geo{}, packs, it, n_packs);
+  count_launch();
+  return check_launch("ta_dim_bwd_dyn");
+}
+
 int dim_fwd_direct(const float* x, float* out, int planes, int S, int rnd, int R, int top, int left, int blend, bool tma, void* ws,
                    cudaStream_t stream) {
   const bool reuse = tune_get("dim.reuse", 1) != 0;      // two-entry h-lerp row cache (bit-identical either way)
@@ -539,7 +694,7 @@ int dim_fwd_direct(const float* x, float* out, int planes, int S, int rnd, int R
     const int nsr = h_i1(tab.t1[q1]) - h_i0(tab.t1[q0]) + 1;
     if (nsr > a_rows) a_rows = nsr;
   }
-  Geo gm{S, rnd, R, top, left, a_rows, c_rows};
+  Geo gm{S, rnd, R, top, left, a_rows, c_rows, 0};
   const size_t smem = ((sizeof(float) * ((size_t)a_rows * S + (size_t)(c_rows + 1) * (rnd + 1)) + 15) & ~(size_t)15) + 16 * (size_t)(c_rows + RB);
   TA_REQUIRE(smem <= 200 * 1024, "ta_dim_fwd: image size S=%d needs %zu B of shared memory per CTA", S, smem);
   dim3 grid((unsigned)((S + RB - 1) / RB), (unsigned)planes);
@@ -601,7 +756,7 @@ int dim_bwd_direct(const float* gout, float* gin, int planes, int S, int rnd, in
     if (a <= b && b - a + 1 > u_rows) u_rows = b - a + 1;
     tab.band[sy0 / RB] = make_short4((short)q0, (short)(q1 - q0 + 1), (short)(a <= b ? a : 0), (short)(a <= b ? b - a + 1 : 0));
   }
-  Geo gm{S, rnd, R, top, left, u_rows, g_rows};
+  Geo gm{S, rnd, R, top, left, u_rows, g_rows, 0};
   const int ru = upload_tab(tab, ws, stream);
   if (ru != TA_OK) return ru;
   const DimTabB* dtab = reinterpret_cast<const DimTabB*>(ws);
@@ -624,12 +779,12 @@ int dim_bwd_direct(const float* gout, float* gin, int planes, int S, int rnd, in
   }
   const size_t smem = ((sizeof(float) * ((size_t)u_rows * S + (size_t)g_rows * rnd) + 15) & ~(size_t)15) + 16 * (size_t)(u_rows + g_rows);
   TA_REQUIRE(smem <= 200 * 1024, "ta_dim_bwd: image size S=%d needs %zu B of shared memory per CTA", S, smem);
-  auto k = tma ? dim_bwd_direct_kernel<true> : dim_bwd_direct_kernel<false>;
+  auto k = tma ? dim_bwd_direct_kernel<true, false> : dim_bwd_direct_kernel<false, false>;
   static SmemOptIn optin[2] = {};
   const int rc = ensure_dyn_smem("ta_dim_bwd", k, smem, optin[tma ? 0 : 1]);
   if (rc != TA_OK) return rc;
   dim3 grid((unsigned)((S + RB - 1) / RB), (unsigned)planes);
-  k<<<grid, kThreads, smem, stream>>>(gout, gin, dtab, gm);
+  k<<<grid, kThreads, smem, stream>>>(gout, gin, dtab, gm, nullptr, nullptr, 0);
   count_launch();
   return check_launch("ta_dim_bwd[direct]");
 }

@@ -26,7 +26,25 @@ struct DimTabB {                              // adjoint: 13 KB
   short4 band[kDimMaxS / kDimRB];             //   per band of source rows: {q0, nq, oyA, nu} (y1 rows / gout rows it needs)
 };
 
+// One draw of DIM (dim.py:47-62: coin, rnd, pad_top, pad_left) with everything the direct kernels derive from it, as plain data:
+// an array of these in DEVICE memory plus a device iteration counter lets ONE captured CUDA graph serve every iteration's draw.
+struct DimGeo { int S, rnd, R, top, left, a_rows, c_rows, pad; };
+struct DimPack {
+  int identity;            // the coin said "do not transform": both directions copy
+  int pad[3];
+  DimGeo gf, gb;           // forward / adjoint geometry (band row maxima of THIS draw)
+  DimTabF tf;
+  DimTabB tb;
+};
+
 bool dim_direct_ok(int S, int rnd, int R);
+// host: fill `pack` for one draw; shared-memory bytes per CTA that serve EVERY possible draw at (S, R)
+int dim_pack_build(DimPack* pack, int S, int rnd, int R, int top, int left, int identity);
+void dim_dyn_smem(int S, int R, size_t* fwd_bytes, size_t* bwd_bytes);
+int dim_fwd_dyn(const float* x, float* out, int planes, int S, int R, const DimPack* packs, int n_packs, const int* it, bool tma,
+                cudaStream_t stream);
+int dim_bwd_dyn(const float* gout, float* gin, int planes, int S, int R, const DimPack* packs, int n_packs, const int* it, bool tma,
+                cudaStream_t stream);
 size_t dim_direct_ws_bytes();              // device workspace the direct kernels need for their tables (16-byte aligned)
 int dim_fwd_direct(const float* x, float* out, int planes, int S, int rnd, int R, int top, int left, int blend, bool tma, void* ws,
                    cudaStream_t stream);

@@ -503,4 +503,14 @@ int ta_quantize_u8(const float* data, const float* delta, uint8_t* out, int B, i
   return check_launch("ta_quantize_u8");
 }
 
+
+// *counter = (set_to >= 0) ? set_to : *counter + delta — the device-side iteration index of loops replayed from a CUDA graph
+__global__ void counter_kernel(int* counter, int delta, int set_to) { *counter = set_to >= 0 ? set_to : *counter + delta; }
+int ta_counter_add(int* counter, int delta, int set_to, ta_stream_t stream) {
+  TA_REQUIRE(counter, "ta_counter_add: null pointer");
+  counter_kernel<<<1, 1, 0, (cudaStream_t)stream>>>(counter, delta, set_to);
+  count_launch();
+  return check_launch("ta_counter_add");
+}
+
 }  // extern "C"

@@ -9,6 +9,7 @@ from .tim import TIM
 
 
 class DITIMI(DIM):
+    graph_safe = True       # DIM's pre-drawn tables + TIM's deterministic convolution → capturable (see dim.py)
     conv_mode = TIM.conv_mode
 
     def __init__(self, model_name, epsilon=16/255, alpha=1.6/255, epoch=10, decay=1., resize_rate=1.1, diversity_prob=0.5,
@@ -28,6 +29,8 @@ class SIDITIMI(DITIMI):
     DIM draw resizes / pads the whole S*B batch (dim.py:42-68 uses one (rnd, top, left) per call), TIM smooths the gradient —
     exactly what composing the reference's own hooks gives (``DIM.transform(SIM.transform(x))``, SIM's ``get_loss``,
     TIM's ``get_grad``). Kernels: ``ta_sim_fwd`` → ``ta_dim_fwd`` on S*B*3 planes, adjoints in reverse, ``ta_dwconv2d_sep``."""
+
+    graph_safe = True
 
     def __init__(self, model_name, epsilon=16/255, alpha=1.6/255, epoch=10, decay=1., resize_rate=1.1, diversity_prob=0.5,
                  kernel_type='gaussian', kernel_size=15, num_scale=5, targeted=False, random_start=False, norm='linfty',

@@ -277,6 +277,34 @@ class CudaBackend:
             _lib.check(fn(_ptr(x), _ptr(out), planes, S, int(rnd), int(R), int(top), int(left), _ptr(ws), _stream()), "ta_dim")
         return out
 
+    def dim_dyn(self, x, R, packs, n_packs, it, forward=True):
+        """DIM with the draw read from device memory: packs[min(*it, n_packs-1)] (``ta_dim_fwd_dyn`` / ``ta_dim_bwd_dyn``)"""
+        x = _f32c(x, "x"); S = x.shape[-1]
+        if x.shape[-2] != S:
+            raise ValueError("ta_dim_*: needs square images, got %dx%d" % (x.shape[-2], S))
+        planes = x.numel() // (S * S)
+        out = torch.empty_like(x)
+        fn = self.lib.ta_dim_fwd_dyn if forward else self.lib.ta_dim_bwd_dyn
+        with _DeviceOf(x):
+            _lib.check(fn(_ptr(x), _ptr(out), planes, S, int(R), _ptr(packs), int(n_packs), _ptr(it), _stream()), "ta_dim_dyn")
+        return out
+
+    def dim_packs(self, draws, S, R):
+        """host: one ta_dim_pack record per pre-drawn iteration; draws[i] = None (identity) or (rnd, top, left). Returns a pinned
+        uint8 tensor [len(draws), pack_bytes]."""
+        nb = int(self.lib.ta_dim_pack_bytes())
+        host = torch.empty((len(draws), nb), dtype=torch.uint8, pin_memory=True)
+        base = host.data_ptr()
+        for i, d in enumerate(draws):
+            rnd, top, left = (S, 0, 0) if d is None else d
+            _lib.check(self.lib.ta_dim_pack_build(ctypes.c_void_p(base + i * nb), int(S), int(rnd), int(R), int(top), int(left),
+                                                  1 if d is None else 0), "ta_dim_pack_build")
+        return host
+
+    def counter_add(self, counter, delta=1, set_to=-1):
+        with _DeviceOf(counter):
+            _lib.check(self.lib.ta_counter_add(_ptr(counter), int(delta), int(set_to), _stream()), "ta_counter_add")
+
     def dwconv2d(self, g, k):
         g = _f32c(g, "grad"); k = _f32c(k, "kernel"); B, C, H, W = g.shape; ks = k.shape[-1]
         out = torch.empty_like(g)
@@ -591,6 +619,20 @@ class DimResizePad(torch.autograd.Function):
         return backend().dim(gout, rnd, R, top, left, False), None, None, None, None
 
 
+class DimResizePadDyn(torch.autograd.Function):
+    """DimResizePad whose draw lives in device memory (packs[*it]): the same kernels, capturable in a CUDA graph"""
+
+    @staticmethod
+    def forward(ctx, x, R, packs, n_packs, it):
+        ctx.cfg = (R, packs, n_packs, it)
+        return backend().dim_dyn(x, R, packs, n_packs, it, True)
+
+    @staticmethod
+    def backward(ctx, gout):
+        R, packs, n_packs, it = ctx.cfg
+        return backend().dim_dyn(gout, R, packs, n_packs, it, False), None, None, None, None
+
+
 class LinSample(torch.autograd.Function):
     @staticmethod
     def forward(ctx, x, gbar, coefs):
@@ -676,6 +718,10 @@ def admix_mix(x, perm, strength, S, A):
 
 def dim_resize_pad(x, rnd, R, top, left):
     return DimResizePad.apply(x, rnd, R, top, left)
+
+
+def dim_resize_pad_dyn(x, R, packs, n_packs, it):
+    return DimResizePadDyn.apply(x, R, packs, n_packs, it)
 
 
 def lin_sample(x, gbar, coefs):
