@@ -521,6 +521,32 @@ def test_fused_all_zero_gradient_sample(be):
     assert bits_equal(npy(gm), mo) and bits_equal(npy(dd), do)
 
 
+def test_dim_dyn_kernels_equal_the_static_ones(be):
+    """ta_dim_fwd_dyn / ta_dim_bwd_dyn (draw read from device memory at index *it, for CUDA-graph replay) against ta_dim_*_ws with
+    the same draw: bit-identical in both directions, for every record incl. the identity coin, with the counter advanced on the
+    device and clamped at the last record."""
+    rng = np.random.default_rng(3)
+    S, R = 224, 246
+    x = cu(rng.random((2, 3, S, S), dtype=np.float32)); g = cu(rng.standard_normal((2, 3, S, S)).astype(np.float32))
+    draws = [(235, 5, 6), None, (224, 0, 21), (245, 0, 0), (230, 16, 3)]
+    host = be.dim_packs(draws, S, R)
+    packs = host.cuda()
+    it = torch.zeros(1, dtype=torch.int32, device="cuda")
+    for i in range(len(draws) + 2):
+        d = draws[min(i, len(draws) - 1)]
+        f_dyn = be.dim_dyn(x, R, packs, len(draws), it, True)
+        b_dyn = be.dim_dyn(g, R, packs, len(draws), it, False)
+        if d is None:
+            assert torch.equal(f_dyn, x) and torch.equal(b_dyn, g)
+        else:
+            assert torch.equal(f_dyn, be.dim(x, d[0], R, d[1], d[2], True)), (i, d)
+            assert torch.equal(b_dyn, be.dim(g, d[0], R, d[1], d[2], False)), (i, d)
+        be.counter_add(it, delta=1)
+    assert int(it.item()) == len(draws) + 2
+    be.counter_add(it, set_to=0)
+    assert int(it.item()) == 0
+
+
 # ---------------------------------------------------------------------------------------------- GRA / AdaEA (SURVEY §8 f4)
 @pytest.mark.parametrize("shape", [(4, 3, 224, 224), (2, 3, 17, 19), (64, 3, 224, 224)])
 def test_gra_update_matches_oracle(be, shape):

@@ -68,8 +68,10 @@ int aten_mean_plan(const char* who, int B, int64_t n, int cl, AtenMeanCfg* cfg) 
 namespace {
 
 // grid = (cluster, B)
+// 4-CTA clusters: 4 x B CTAs of 512 threads — one wave at 2 CTAs/SM for B = 64 (an 8-CTA cluster would need 4 CTAs/SM, i.e. a
+// 32-register budget that cannot hold a batch of loads)
 template <bool PRE>
-__global__ void __launch_bounds__(kAtenThreads) aten_abs_mean_kernel(const float* __restrict__ g, float* __restrict__ mean_out,
+__global__ void __launch_bounds__(kAtenThreads, 2) aten_abs_mean_kernel(const float* __restrict__ g, float* __restrict__ mean_out,
                                                                      int64_t n, AtenMeanCfg c, MeanPre pre) {
   __shared__ float s_val[kAtenMaxW];
   __shared__ float s_row[kAtenThreads];
@@ -85,16 +87,17 @@ __global__ void __launch_bounds__(kAtenThreads) aten_abs_mean_kernel(const float
     ColAcc A;
     const int v0 = (int)col0 + col;
     const int rows = v0 < (int)nvec ? (int)((nvec - v0 + c.S - 1) / c.S) : 0;
-    for (int j0 = 0; j0 < rows; j0 += 8) {
-      float4 x[8], y[8];
+    constexpr int NB = PRE ? 4 : 8;                                  // rows per batch of loads in flight
+    for (int j0 = 0; j0 < rows; j0 += NB) {
+      float4 x[NB], y[PRE ? NB : 1];
 #pragma unroll
-      for (int u = 0; u < 8; ++u)
+      for (int u = 0; u < NB; ++u)
         if (j0 + u < rows) {
           x[u] = __ldg(gp + v0 + (int64_t)(j0 + u) * c.S);
           if (PRE && ap) y[u] = __ldg(ap + v0 + (int64_t)(j0 + u) * c.S);
         }
 #pragma unroll
-      for (int u = 0; u < 8; ++u)
+      for (int u = 0; u < NB; ++u)
         if (j0 + u < rows) {
           float4 t = x[u];
           if (PRE) {
@@ -124,9 +127,10 @@ int aten_abs_mean_launch(const float* g, float* mean_out, int B, int64_t n, cons
   }
   if (n >= ((int64_t)1 << 31)) { set_error("ta_abs_mean_per_sample: TA_MEAN_TORCH serves samples below 2^31 elements"); return TA_EUNSUPPORTED; }
   int cl = tune_get("reduce.cluster", 0);
-  if (cl <= 0) cl = 8;
+  if (cl <= 0) cl = 4;
   AtenMeanCfg c;
   int rc = aten_mean_plan("ta_abs_mean_per_sample", B, n, cl, &c);
+  if (rc != TA_OK && cl < 8 && tune_get("reduce.cluster", 0) <= 0) rc = aten_mean_plan("ta_abs_mean_per_sample", B, n, 8, &c), cl = 8;   // more columns than s_val holds
   if (rc != TA_OK) return rc;
   if (pre && (pre->addend || pre->plane_vec > 0))
     return launch_cluster("ta_abs_mean_per_sample[torch order]", aten_abs_mean_kernel<true>, cl, B, kAtenThreads, 0, s, g, mean_out, n, c, *pre);
