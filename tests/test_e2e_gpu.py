@@ -204,7 +204,7 @@ def test_cuda_graph_replay_is_bit_identical(name, kw):
 
 
 @pytest.mark.parametrize("graph", [False, True], ids=["eager", "graph"])
-@pytest.mark.parametrize("mean_mode", ["torch", "aten", "exact"])
+@pytest.mark.parametrize("mean_mode", ["torch", "aten", "exact", "torch+adjoint"])
 @pytest.mark.parametrize("name", ["mifgsm", "ifgsm", "tim"])
 def test_normalize_fold_is_bit_identical(name, mean_mode, graph):
     """SURVEY §8 f1 on the GPU: fused tail emitting the normalised model input (+ Normalize's adjoint in 'exact' mode with
@@ -215,7 +215,11 @@ def test_normalize_fold_is_bit_identical(name, mean_mode, graph):
     res = {}
     for fold in (False, True):
         atk = make_attack(tab, name, net, epoch=4)
-        atk.mean_mode = mean_mode; atk.fold_normalize = fold; atk.use_cuda_graph = graph
+        if mean_mode == "torch+adjoint":                     # the in-kernel torch-order mean WITH Normalize's adjoint in the kernels
+            atk.mean_mode = "torch"; atk.fold_adjoint = True
+        else:
+            atk.mean_mode = mean_mode
+        atk.fold_normalize = fold; atk.use_cuda_graph = graph
         assert (atk._fold_plan(x.cuda()) is not None) == fold
         before = _lib.launch_count()
         res[fold] = atk(x, y)
@@ -225,7 +229,7 @@ def test_normalize_fold_is_bit_identical(name, mean_mode, graph):
     if not graph:       # launches of OUR kernels per attack: the fold removes the Normalize forward (and adjoint when deferred)
         deferred = mean_mode != "aten" and name != "tim"       # in-kernel mean + base get_grad → Normalize's adjoint in the kernel too
         assert res[False, "launches"] - res[True, "launches"] == 4 * (2 if deferred else 1) - 1      # one extra Normalize forward up front
-    if mean_mode in ("torch", "aten"):
+    if mean_mode in ("torch", "aten", "torch+adjoint"):
         ref = torch_ref.REF_ZOO[name](torch_ref.ref_wrap_model(net), epoch=4)(x, y)
         assert torch.equal(res[True], ref)
     REPORT["fold/%s_%s_%s" % (name, mean_mode, "graph" if graph else "eager")] = {"bit_identical": True}
@@ -284,18 +288,20 @@ def test_fast_mode_is_opt_in_and_keeps_the_attack_strength():
     assert strict.fast_mode == ""
     d0 = strict(x, y)
     res = {"clean": loss_of(torch.zeros_like(d0)), "strict": loss_of(d0)}
-    for name, kw in (("mifgsm", {}), ("vmifgsm", {"num_neighbor": 4, "epoch": 5})):
+    for name, kw, mode in (("mifgsm", {}, "bnfold"), ("mifgsm", {}, "bf16"), ("vmifgsm", {"num_neighbor": 4, "epoch": 5}, "bnfold+bf16")):
         fast = make_attack(tab, name, net, **kw)
-        fast.fast_mode = "bf16"
+        fast.fast_mode = mode
         d1 = fast(x, y)
         assert d1.dtype == torch.float32 and float(d1.abs().max()) <= 16 / 255 + 1e-7
         adv = x.cuda() + d1
         assert float(adv.min()) >= 0.0 and float(adv.max()) <= 1.0
-        res["fast_" + name] = loss_of(d1)
+        res["fast_%s_%s" % (name, mode)] = loss_of(d1)
     REPORT["fast_mode"] = res
     gain_strict = res["strict"] - res["clean"]
-    assert gain_strict > 0 and res["fast_mifgsm"] - res["clean"] >= 0.9 * gain_strict, res
-    assert res["fast_vmifgsm"] > res["clean"], res
+    assert gain_strict > 0, res
+    for mode in ("bnfold", "bf16"):
+        assert res["fast_mifgsm_" + mode] - res["clean"] >= 0.9 * gain_strict, res
+    assert res["fast_vmifgsm_bnfold+bf16"] > res["clean"], res
 
 
 def test_dim_runs_inside_the_cuda_graph_with_the_reference_draws():

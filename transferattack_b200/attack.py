@@ -46,32 +46,63 @@ def _is_zero_scalar(v):
     return isinstance(v, _ZERO_TYPES) and not isinstance(v, bool) and v == 0
 
 
-class _FastMember(nn.Module):
-    """fast mode only: Preprocessing (fp32 kernels) → bf16 channels_last copy of the network → fp32 logits"""
+def _fold_bn(module):
+    """In place on a COPY of the surrogate: every eval-mode BatchNorm2d that directly follows a Conv2d — `convK`/`bnK` attribute
+    pairs of one parent (torchvision ResNet / Inception blocks) or neighbours inside an nn.Sequential (downsample, VGG-BN,
+    MobileNet ConvNormActivation) — is folded into the convolution's weights and bias (torch.nn.utils.fusion) and replaced by
+    Identity. Exact algebra, different rounding: fast mode only."""
+    from torch.nn.utils.fusion import fuse_conv_bn_eval
+    n = 0
+    for parent in list(module.modules()):
+        kids = dict(parent.named_children())
+        if isinstance(parent, nn.Sequential):
+            names = list(kids)
+            for a, b in zip(names, names[1:]):
+                ca, cb = getattr(parent, a), getattr(parent, b)
+                if isinstance(ca, nn.Conv2d) and isinstance(cb, nn.BatchNorm2d) and cb.track_running_stats:
+                    setattr(parent, a, fuse_conv_bn_eval(ca, cb)); setattr(parent, b, nn.Identity()); n += 1
+        for name, child in kids.items():
+            if name.startswith("conv") and isinstance(child, nn.Conv2d):
+                bn_name = "bn" + name[4:]
+                bn = kids.get(bn_name)
+                if isinstance(bn, nn.BatchNorm2d) and bn.track_running_stats and isinstance(getattr(parent, name), nn.Conv2d):
+                    setattr(parent, name, fuse_conv_bn_eval(child, bn)); setattr(parent, bn_name, nn.Identity()); n += 1
+    return n
 
-    def __init__(self, wrapped):
+
+class _FastMember(nn.Module):
+    """fast mode only: Preprocessing (fp32 kernels) → a private copy of the network (BatchNorm folded into the convolutions and /
+    or bf16 channels_last, per `mode`) → fp32 logits"""
+
+    def __init__(self, wrapped, mode):
         super().__init__()
         import copy
         if isinstance(wrapped, nn.Sequential) and len(wrapped) == 2 and isinstance(wrapped[0], PreprocessingModel):
             self.pre, net = wrapped[0], wrapped[1]
         else:
             self.pre, net = None, wrapped
-        self.net = copy.deepcopy(net).to(dtype=torch.bfloat16).to(memory_format=torch.channels_last).eval()
+        net = copy.deepcopy(net).eval()
+        self.folded = _fold_bn(net) if "bnfold" in mode else 0
+        self.bf16 = "bf16" in mode
+        if self.bf16:
+            net = net.to(dtype=torch.bfloat16).to(memory_format=torch.channels_last)
+        self.net = net
         for p_ in self.net.parameters():
             p_.requires_grad_(False)
 
     def forward(self, x):
         h = x if self.pre is None else self.pre(x)
-        h = h.to(torch.bfloat16)
-        if h.dim() == 4:
-            h = h.contiguous(memory_format=torch.channels_last)
+        if self.bf16:
+            h = h.to(torch.bfloat16)
+            if h.dim() == 4:
+                h = h.contiguous(memory_format=torch.channels_last)
         return self.net(h).float()
 
 
-def _fast_twin(model):
+def _fast_twin(model, mode):
     if isinstance(model, EnsembleModel):
-        return EnsembleModel([_FastMember(m) for m in model.models], mode=model.mode)
-    return _FastMember(model)
+        return EnsembleModel([_FastMember(m, mode) for m in model.models], mode=model.mode)
+    return _FastMember(model, mode)
 
 
 class Attack(object):
@@ -101,15 +132,19 @@ class Attack(object):
     #: strict mean mode (torch's own mean op needs the gradient w.r.t. delta in memory) and moves into the fused kernel too
     #: in 'exact' mode with the base ``get_grad``. Same arithmetic in the same order → same bits. Env TA_B200_FOLD=0 disables.
     fold_normalize = os.environ.get("TA_B200_FOLD", "1") == "1"
-    #: with an in-kernel mean and the base get_grad, Normalize's ADJOINT (g / std) is applied inside the tail kernels too instead
-    #: of as a `ta_normalize_bwd` launch at the end of the backward pass. Same bits either way; False keeps the separate launch.
-    fold_adjoint = os.environ.get("TA_B200_FOLD_ADJOINT", "1") == "1"
-    #: OPT-IN, NOT THE PARITY PATH. 'bf16': the surrogate's forward/backward runs on a bf16,
-    #: channels_last copy of the model (tensor-core convolutions, half the activation traffic); everything around it — staging,
-    #: mean|g|, momentum, update, clipping — stays the fp32 kernels. The perturbation is a valid one (eps-ball, [0,1] box) of the
-    #: same attack but NOT bit-comparable with the reference: acceptance is attack strength (tests/test_e2e_gpu.py, bench.py
-    #: `fast_mode`), never 1e-5 / uint8 identity. Off by default; env TA_B200_FAST=bf16 enables. VMI/VNI/GRA additionally batch
-    #: their neighbour evaluations in this mode (`fast_neighbor_images` images per forward).
+    #: with an in-kernel mean and the base get_grad, Normalize's ADJOINT (g / std) can be applied inside the tail kernels too
+    #: instead of as a `ta_normalize_bwd` launch at the end of the backward pass. Same bits either way. Measured on B200 at B = 64
+    #:: folded = 2 launches, 64 us of tail; not folded = 3 launches, 13 us (inside autograd.grad) + 55 us of tail —
+    #: the IEEE division has to be done in the mean kernel AND in the streaming kernel when folded, so the saving is 4 us per
+    #: iteration. Default: not folded for mean_mode 'torch' (the division-free mean kernel), folded for 'exact' (one cluster launch).
+    fold_adjoint = {"1": True, "0": False}.get(os.environ.get("TA_B200_FOLD_ADJOINT", ""), None)
+    #: OPT-IN, NOT THE PARITY PATH. The surrogate's forward/backward runs on a private copy of
+    #: the model: 'bnfold' = every eval-mode BatchNorm folded into its convolution (the launch list shows BN inference + BN backward
+    #: at 30 % of an iteration), 'bf16' = bf16 / channels_last, 'bnfold+bf16' = both; everything around it — staging, mean|g|,
+    #: momentum, update, clipping — stays the fp32 kernels. The perturbation is a valid one (eps-ball, [0,1] box) of the same attack
+    #: but NOT bit-comparable with the reference: acceptance is attack strength (tests/test_e2e_gpu.py, bench.py `fast_mode`),
+    #: never 1e-5 / uint8 identity. Off by default; env TA_B200_FAST enables. VMI/VNI additionally batch their neighbour
+    #: evaluations in this mode (`fast_neighbor_images` images per forward).
     fast_mode = os.environ.get("TA_B200_FAST", "")
     fast_neighbor_images = 512
 
@@ -189,11 +224,11 @@ class Attack(object):
         """the module get_logits runs: `self.model`, or in fast mode its bf16 / channels_last twin (built once per model)"""
         if not self.fast_mode:
             return self.model
-        if self.fast_mode != 'bf16':
-            raise ValueError("unknown fast_mode {!r} (only 'bf16')".format(self.fast_mode))
+        if self.fast_mode not in ('bnfold', 'bf16', 'bnfold+bf16'):
+            raise ValueError("unknown fast_mode {!r} ('bnfold', 'bf16' or 'bnfold+bf16')".format(self.fast_mode))
         cached = self.__dict__.get("_fast_twin")
-        if cached is None or cached[0] is not self.model:
-            cached = (self.model, _fast_twin(self.model))
+        if cached is None or cached[0] is not self.model or cached[2] != self.fast_mode:
+            cached = (self.model, _fast_twin(self.model, self.fast_mode), self.fast_mode)
             self.__dict__["_fast_twin"] = cached
         return cached[1]
 
@@ -222,7 +257,8 @@ class Attack(object):
         if pre.mean.numel() != C or C > 4 or (H * W) % 4 != 0 or data.data_ptr() % 16 != 0:
             return None
         # Normalize's adjoint inside the kernel needs the staged (cluster) form: the sample must fit 8 CTAs' shared memory
-        defer = self.fold_adjoint and kmode is not None and cls.get_grad is Attack.get_grad and C * H * W <= 384 * 1024
+        fa = self.fold_adjoint if self.fold_adjoint is not None else (kmode == _lib.TA_MEAN_EXACT)
+        defer = fa and kmode is not None and cls.get_grad is Attack.get_grad and C * H * W <= 384 * 1024
         return pre, m[1], [float(v) for v in pre.mean.tolist()], [float(v) for v in pre.std.tolist()], defer
 
     @staticmethod
