@@ -158,15 +158,18 @@ def _dim_cases():
     return D, sorted({k.rsplit("_", 1)[0] for k in D.files})
 
 
-@pytest.fixture(params=[(1, 0, 0), (1, 1, 1), (0, 0, 0)], ids=["direct", "direct-gather-wstab", "fourpass"])
+@pytest.fixture(params=[(2, 0, 0, 1), (2, 0, 1, 0), (1, 0, 0, 1), (1, 1, 1, 1), (0, 0, 0, 1)],
+                ids=["sep", "sep-wstab-rtpitch", "direct", "direct-gather-wstab", "fourpass"])
 def dim_impl(request):
-    """All generations of the DIM kernels must meet the same parity bar: csrc/dim_direct.cu (default: forward with its tables as
+    """All generations of the DIM kernels must meet the same parity bar: the separable-pass kernels of csrc/dim_direct.cu (default; with
+    compile-time and with run-time pitches), the second-generation kernels of the same file (forward with its tables as
     kernel parameters, adjoint = gather + scatter with the tables in the workspace; alternative: forward tables in the workspace,
     adjoint = independent gather) and the four-pass kernels of csrc/dim.cu."""
     from transferattack_b200 import _lib
     _lib.tune_set("dim.impl", request.param[0]); _lib.tune_set("dim.bwd", request.param[1]); _lib.tune_set("dim.fwdtab", request.param[2])
+    _lib.tune_set("dim.sepconst", request.param[3])
     yield request.param
-    _lib.tune_set("dim.impl", 1); _lib.tune_set("dim.bwd", 0); _lib.tune_set("dim.fwdtab", 0)
+    _lib.tune_set("dim.impl", 2); _lib.tune_set("dim.bwd", 0); _lib.tune_set("dim.fwdtab", 0); _lib.tune_set("dim.sepconst", 1)
 
 
 @pytest.mark.parametrize("tma", [1, 0])
@@ -263,7 +266,8 @@ def test_tim_generic_kernel_sizes(be):
 
 @pytest.mark.parametrize("ks", [3, 5, 7, 15])
 def test_tim_sep_all_launch_paths_bit_identical(be, ks):
-    """The separable convolution has several launch paths (register-sliding fed from global memory or from bulk-TMA-staged
+    """The separable convolution has several launch paths (the fully unrolled interior / edge walk with paired weights — the default
+    for host factors and H % 32 == 0 —, register-sliding fed from global memory or from bulk-TMA-staged
     shared memory, each with the factors as kernel parameters or loaded from device arrays, band height 32 / 56; two-pass
     band kernel; 32x32 tiles): all must equal the C oracle bit for bit,
     including ragged heights (last band partly / wholly outside the image) and channel-specific factors."""
@@ -279,14 +283,17 @@ def test_tim_sep_all_launch_paths_bit_identical(be, ks):
             distinct = (rng.random((C, ks), dtype=np.float32), rng.random((C, ks), dtype=np.float32))
             for kc, kr in (shared, distinct):
                 want = oracle.dwconv2d_sep(x, kc, kr)
-                for band, bh, f2 in ((3, 32, 1), (3, 56, 1), (3, 32, 0), (3, 56, 0), (2, 32, 0), (2, 56, 0), (1, 32, 0), (0, 32, 0)):
+                for band, bh, f2 in ((4, 32, 1), (3, 32, 1), (3, 56, 1), (3, 32, 0), (3, 56, 0), (2, 32, 0), (2, 56, 0), (1, 32, 0), (0, 32, 0)):
                     _lib.tune_set("tim.band", band); _lib.tune_set("tim.bh", bh); _lib.tune_set("tim.f2", f2)
                     got = npy(be.dwconv2d_sep(cu(x), cu(kc), cu(kr)))
                     assert bits_equal(got, want), (shp, "device factors", band, bh, f2)
-                    got = npy(be.dwconv2d_sep(cu(x), cu(kc), cu(kr), host=(kc, kr)))
-                    assert bits_equal(got, want), (shp, "host factors", band, bh, f2)
+                    for split in ((0, 1) if band == 4 else (0,)):
+                        _lib.tune_set("tim.split", split)
+                        got = npy(be.dwconv2d_sep(cu(x), cu(kc), cu(kr), host=(kc, kr)))
+                        assert bits_equal(got, want), (shp, "host factors", band, bh, f2, split)
+                    _lib.tune_set("tim.split", 0)
     finally:
-        _lib.tune_set("tim.band", 3); _lib.tune_set("tim.bh", 32); _lib.tune_set("tim.f2", 1)
+        _lib.tune_set("tim.band", 4); _lib.tune_set("tim.bh", 32); _lib.tune_set("tim.f2", 1)
 
 
 def test_tim_sep_hw_refuses_what_it_cannot_serve(be):

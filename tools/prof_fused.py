@@ -43,6 +43,12 @@ for it in range(6):
         be.dwconv2d_sep(g, kc3, kr3); flush.sum()
         be.dim(x, 235, 246, 5, 6, True); flush.sum()
         be.dim(g, 235, 246, 5, 6, False)
+    elif which == "tim2":        # the default TIM launch (host factors as kernel parameters)
+        import numpy as np
+        import transferattack_b200.input_transformation.tim as tim
+        k2d, kcol, krow = tim.make_kernel("gaussian", 15)
+        hc, hr = np.stack([kcol] * 3), np.stack([krow] * 3)
+        be.dwconv2d_sep(g, torch.from_numpy(hc).cuda(), torch.from_numpy(hr).cuda(), host=(hc, hr))
     elif which == "tim":
         import numpy as np
         import transferattack_b200.input_transformation.tim as tim

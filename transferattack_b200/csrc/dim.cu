@@ -341,7 +341,7 @@ int ta_dim_fwd_ws(const float* x, float* out, int planes, int S, int rnd, int R,
   TA_REQUIRE(x && out, "ta_dim_fwd_ws: null pointer");
   int rc = check_geom("ta_dim_fwd_ws", planes, S, rnd, R, pad_top, pad_left);
   if (rc != TA_OK) return rc;
-  if (ws && aligned16(ws) && tune_get("dim.impl", 1) != 0 && dim_direct_ok(S, rnd, R))
+  if (ws && aligned16(ws) && tune_get("dim.impl", 2) != 0 && dim_direct_ok(S, rnd, R))
     return dim_fwd_direct(x, out, planes, S, rnd, R, pad_top, pad_left, tune_get("dim.blend", 1),
                           (S % 4 == 0) && aligned16(x) && tune_get("dim.tma", 1) != 0,
                           tune_get("dim.fwdtab", 0) != 0 ? ws : nullptr,      // forward: tables as kernel parameters by default
@@ -354,7 +354,7 @@ int ta_dim_bwd_ws(const float* gout, float* gin, int planes, int S, int rnd, int
   TA_REQUIRE(gout && gin, "ta_dim_bwd_ws: null pointer");
   int rc = check_geom("ta_dim_bwd_ws", planes, S, rnd, R, pad_top, pad_left);
   if (rc != TA_OK) return rc;
-  if (ws && aligned16(ws) && tune_get("dim.impl", 1) != 0 && dim_direct_ok(S, rnd, R))
+  if (ws && aligned16(ws) && tune_get("dim.impl", 2) != 0 && dim_direct_ok(S, rnd, R))
     return dim_bwd_direct(gout, gin, planes, S, rnd, R, pad_top, pad_left,
                           (S % 4 == 0) && aligned16(gout) && tune_get("dim.tma", 1) != 0, tune_get("dim.bwd", 0) != 0, ws,
                           (cudaStream_t)stream);

@@ -506,6 +506,331 @@ __global__ void __launch_bounds__(kThreads) dim_bwd_gather_kernel(const float* _
   }
 }
 
+// ---- third generation: separable passes (default) ----------------------------------------------------------------------------
+// ncu on the two kernels above (profiles/ncu_tim_dim_r2.md): 73 (forward) and 149 (adjoint) issued instructions per output
+// element at 73 % / 86 % issue-slot utilisation — per element they decode a row descriptor, test a two-entry cache, compute
+// two shared addresses and walk a pointer, all per THREAD-column. The bilinear expression is separable in VALUE, not only in
+// form: hl(row) = wl0*p[row][i0] + wl1*p[row][i1] depends on (row, column) alone, and the result is vl(hl(row a), hl(row b)),
+// so the band is processed as four plain passes over shared memory with nothing carried between elements:
+//   h1  H[r][c]  = hl(A[r][i0(c)], A[r][i1(c)])          one thread per destination column, rows unrolled (2 LDS + 2 FP + 1 STS)
+//   v1  Y1[q][c] = vl(H[ra(q)][c], H[rb(q)][c])           one thread per 4 adjacent columns (2 LDS.128 + 8 FP + 1 STS.128)
+//   h2  H[q][o]  = hl(Y1[q][xa(o)], Y1[q][xb(o)])         (zero column rnd / zero row nq of Y1 are the padding)
+//   v2  out[oy][o] = vl(H[ya][o], H[yb][o])               128-bit coalesced global stores
+// Every value is produced by the same hl / vl expression on the same operands as in the kernels above → bit-identical.
+// The adjoint is the four passes transposed, each a gather over the (<= 3 long) inverse range: vT2, hT2, vT1, hT1.
+__host__ __device__ __forceinline__ int sep_pitch(int S, int R) { const int m = (R > S ? R : S) + 1; return (m + 3) & ~3; }
+
+// The passes. SC / PC > 0: image side and row pitch are compile-time constants (the hot shape 224 -> 246: 224 / 248), so that the
+// unrolled row loops address shared memory as [register + immediate] and carry no integer arithmetic; 0: run-time values.
+template <int MODE, int SC, int PC>
+__device__ __forceinline__ void sep_hpass(const float* __restrict__ ca, const float* __restrict__ cb, float* __restrict__ dst,
+                                          float wl0, float wl1, int rows, int src_pitch_rt, int dst_pitch_rt) {
+  const int sp = SC ? SC : src_pitch_rt, dp = PC ? PC : dst_pitch_rt;
+  int r = 0;
+  for (; r + 4 <= rows; r += 4, ca += 4 * sp, cb += 4 * sp, dst += 4 * dp) {
+#pragma unroll
+    for (int k = 0; k < 4; ++k) dst[k * dp] = hl<MODE>(wl0, wl1, ca[k * sp], cb[k * sp]);
+  }
+  for (; r < rows; ++r, ca += sp, cb += sp, dst += dp) dst[0] = hl<MODE>(wl0, wl1, ca[0], cb[0]);
+}
+
+template <int MODE>
+__device__ __forceinline__ float4 vl4(float hl0, float hl1, const float4& t, const float4& b) {
+  return make_float4(vl<MODE>(hl0, hl1, t.x, b.x), vl<MODE>(hl0, hl1, t.y, b.y), vl<MODE>(hl0, hl1, t.z, b.z), vl<MODE>(hl0, hl1, t.w, b.w));
+}
+
+// smem: bufA [a_rows * S] (bulk-TMA destination) | bufH [max(a_rows, c_rows + 1) * P] | bufY [(c_rows + 1) * P] | descA | descB
+template <int MODE, class TR, int SC, int PC>
+__global__ void __launch_bounds__(kThreads) dim_fwd_sep_kernel(const float* __restrict__ x, float* __restrict__ out,
+                                                               const __grid_constant__ TR tr, const Geo gm_in) {
+  const DimTabF& tab = tr.get();
+  const Geo gm = tr.geo(gm_in);
+  extern __shared__ __align__(128) unsigned char smem_raw[];
+  __shared__ __align__(8) uint64_t s_bar;
+  const int tid = threadIdx.x;
+  if (tr.identity()) {                                   // the coin said "return x" (dim.py:47-48): this band is a copy
+    const int S0 = gm.S, r0 = blockIdx.x * RB, r1 = min(r0 + RB, S0);
+    const float4* xp0 = reinterpret_cast<const float4*>(x + (int64_t)blockIdx.y * S0 * S0);
+    float4* op0 = reinterpret_cast<float4*>(out + (int64_t)blockIdx.y * S0 * S0);
+    for (int e = (r0 * S0 >> 2) + tid; e < (r1 * S0 >> 2); e += kThreads) op0[e] = __ldg(xp0 + e);
+    return;
+  }
+  const int S = SC ? SC : gm.S, rnd = gm.rnd, top = gm.top, left = gm.left;
+  const int P = PC ? PC : sep_pitch(S, gm.R);
+  const int HR = max(gm.a_rows, gm.c_rows + 1);
+  float* bufA = reinterpret_cast<float*>(smem_raw);
+  float* bufH = bufA + (size_t)gm.a_rows * S;
+  float* bufY = bufH + (size_t)HR * P;
+  RowD* descA = reinterpret_cast<RowD*>(bufY + (size_t)(gm.c_rows + 1) * P);
+  RowD* descB = descA + gm.c_rows;
+
+  const int oy0 = blockIdx.x * RB;
+  const int oy1 = min(oy0 + RB, S) - 1;                 // inclusive
+  const int nb = oy1 - oy0 + 1;
+  const float* xp = x + (int64_t)blockIdx.y * S * S;
+  float* op = out + (int64_t)blockIdx.y * S * S;
+
+  const int pr0 = tap_i0(tab.t2[oy0]), pr1 = tap_i1(tab.t2[oy1]);
+  const int q0 = max(pr0 - top, 0), q1 = min(pr1 - top, rnd - 1);
+  if (q0 > q1) {                                         // the band maps entirely into the padding: vl(hl(0,0), hl(0,0)) = +0
+    float4* o4 = reinterpret_cast<float4*>(op + (int64_t)oy0 * S);
+    for (int e = tid; e < (nb * S >> 2); e += kThreads) o4[e] = make_float4(0.f, 0.f, 0.f, 0.f);
+    return;
+  }
+  const int nq = q1 - q0 + 1;
+  const int sr0 = tap_i0(tab.t1[q0]);
+  const int nsr = tap_i1(tab.t1[q1]) - sr0 + 1;
+
+  if (tid == 0) {
+    mbar_init(&s_bar, 1);
+    mbar_fence_init();
+    const uint32_t bytes = (uint32_t)(nsr * S * 4);
+    mbar_expect_tx(&s_bar, bytes);
+    tma_bulk_g2s(bufA, xp + (int64_t)sr0 * S, bytes, &s_bar);
+  }
+  for (int e = tid; e < P; e += kThreads) bufY[nq * P + e] = 0.0f;                     // the zero row (padding rows of y2)
+  for (int q = tid; q < nq; q += kThreads) {
+    const TapE th = tab.t1[q0 + q];
+    descA[q] = RowD{(tap_i0(th) - sr0) * P * 4, (tap_i1(th) - sr0) * P * 4, th.l1, 0};
+  }
+  for (int r = tid; r < nb; r += kThreads) {
+    const TapE th = tab.t2[oy0 + r];
+    const int ya = tap_i0(th) - top - q0, yb = tap_i1(th) - top - q0;
+    descB[r] = RowD{((ya >= 0 && ya < nq) ? ya : nq) * P * 4, ((yb >= 0 && yb < nq) ? yb : nq) * P * 4, th.l1, 0};
+  }
+  __syncthreads();
+  mbar_wait(&s_bar, 0);
+
+  const int PW1 = (rnd + 1 + 3) & ~3;                   // columns of H / Y1 that are written: [rnd, PW1) = 0 (the zero column)
+  // h1
+  for (int c = tid; c < PW1; c += kThreads) {
+    if (c < rnd) {
+      const TapE tw = tab.t1[c];
+      const float wl1 = tw.l1, wl0 = sub_rn(1.0f, wl1);
+      sep_hpass<MODE, SC, PC>(bufA + tap_i0(tw), bufA + tap_i1(tw), bufH + c, wl0, wl1, nsr, S, P);
+    } else {
+      for (int r = 0; r < nsr; ++r) bufH[r * P + c] = 0.0f;
+    }
+  }
+  __syncthreads();
+  // v1
+  {
+    const int ncg = PW1 >> 2;
+    for (int cg = (tid & 63); cg < ncg; cg += 64) {
+      const unsigned char* hb = reinterpret_cast<const unsigned char*>(bufH + 4 * cg);
+      float* yo = bufY + 4 * cg + (tid >> 6) * P;
+#pragma unroll 2
+      for (int q = tid >> 6; q < nq; q += kThreads / 64, yo += (kThreads / 64) * P) {
+        const int4 dd = *reinterpret_cast<const int4*>(descA + q);
+        const float hl1 = __int_as_float(dd.z), hl0 = sub_rn(1.0f, hl1);
+        const float4 t = *reinterpret_cast<const float4*>(hb + dd.x), b = *reinterpret_cast<const float4*>(hb + dd.y);
+        *reinterpret_cast<float4*>(yo) = vl4<MODE>(hl0, hl1, t, b);
+      }
+    }
+  }
+  __syncthreads();
+  // h2 (rows 0 .. nq: the last one is the zero row)
+  for (int c = tid; c < S; c += kThreads) {
+    const TapE tw = tab.t2[c];
+    const float wl1 = tw.l1, wl0 = sub_rn(1.0f, wl1);
+    const int xa = tap_i0(tw) - left, xb = tap_i1(tw) - left;
+    sep_hpass<MODE, PC, PC>(bufY + ((xa >= 0 && xa < rnd) ? xa : rnd), bufY + ((xb >= 0 && xb < rnd) ? xb : rnd), bufH + c, wl0, wl1,
+                            nq + 1, P, P);
+  }
+  __syncthreads();
+  // v2
+  {
+    const int ncg = S >> 2;
+    for (int cg = (tid & 63); cg < ncg; cg += 64) {
+      const unsigned char* hb = reinterpret_cast<const unsigned char*>(bufH + 4 * cg);
+      float4* o = reinterpret_cast<float4*>(op + (int64_t)(oy0 + (tid >> 6)) * S) + cg;
+#pragma unroll 2
+      for (int r = tid >> 6; r < nb; r += kThreads / 64, o += (kThreads / 64) * (S >> 2)) {
+        const int4 dd = *reinterpret_cast<const int4*>(descB + r);
+        const float hl1 = __int_as_float(dd.z), hl0 = sub_rn(1.0f, hl1);
+        const float4 t = *reinterpret_cast<const float4*>(hb + dd.x), b = *reinterpret_cast<const float4*>(hb + dd.y);
+        *o = vl4<MODE>(hl0, hl1, t, b);
+      }
+    }
+  }
+}
+
+// 4 adjacent columns of one destination row of a transposed vertical pass: sum over the row's inverse range
+__device__ __forceinline__ float4 fma4(float w, const float4& v, const float4& a) {
+  return make_float4(fmaf(w, v.x, a.x), fmaf(w, v.y, a.y), fmaf(w, v.z, a.z), fmaf(w, v.w, a.w));
+}
+__device__ __forceinline__ float4 vgather4(const RowG* __restrict__ d, const float* __restrict__ wext, int wpitch, int row,
+                                           const unsigned char* __restrict__ colbase, int pitch_bytes) {
+  const int4 dd = *reinterpret_cast<const int4*>(d + row);
+  const int cy = dd.y;
+  const unsigned char* addr = colbase + dd.x;
+  float4 acc = make_float4(0.f, 0.f, 0.f, 0.f);
+  if (cy > 0) acc = fma4(__int_as_float(dd.z), *reinterpret_cast<const float4*>(addr), acc);
+  if (cy > 1) acc = fma4(__int_as_float(dd.w), *reinterpret_cast<const float4*>(addr + pitch_bytes), acc);
+  if (cy > 2) {
+    addr += 2 * pitch_bytes;
+#pragma unroll 1
+    for (int a = 2; a < cy; ++a, addr += pitch_bytes) acc = fma4(wext[row * wpitch + (a - 2)], *reinterpret_cast<const float4*>(addr), acc);
+  }
+  return acc;
+}
+// one destination column of a transposed horizontal pass, all rows: <= 3 register weights + tail
+template <int SPC, int DPC>
+__device__ __forceinline__ void sep_htpass(const float* __restrict__ src, float* __restrict__ dst, int rows, int cx, const float (&wx)[3],
+                                           const TapE* __restrict__ tab, int lo, int col, int src_pitch_rt, int dst_pitch_rt) {
+  const int sp = SPC ? SPC : src_pitch_rt;
+  const int64_t dp = DPC ? DPC : dst_pitch_rt;
+  if (cx <= 3) {                                         // weights beyond the range are 0 and the extra columns exist (finite or not read)
+    int r = 0;
+    for (; r + 4 <= rows; r += 4, src += 4 * sp, dst += 4 * dp) {
+#pragma unroll
+      for (int k = 0; k < 4; ++k) {
+        float h = 0.0f;
+        if (cx > 0) h = fmaf(wx[0], src[k * sp], h);
+        if (cx > 1) h = fmaf(wx[1], src[k * sp + 1], h);
+        if (cx > 2) h = fmaf(wx[2], src[k * sp + 2], h);
+        dst[k * dp] = h;
+      }
+    }
+    for (; r < rows; ++r, src += sp, dst += dp) {
+      float h = 0.0f;
+      if (cx > 0) h = fmaf(wx[0], src[0], h);
+      if (cx > 1) h = fmaf(wx[1], src[1], h);
+      if (cx > 2) h = fmaf(wx[2], src[2], h);
+      dst[0] = h;
+    }
+  } else {
+    for (int r = 0; r < rows; ++r, src += sp, dst += dp) {
+      float h = fmaf(wx[2], src[2], fmaf(wx[1], src[1], fmaf(wx[0], src[0], 0.0f)));
+#pragma unroll 1
+      for (int b = 3; b < cx; ++b) h = fmaf(tap_w(tab[lo + b], col), src[b], h);
+      dst[0] = h;
+    }
+  }
+}
+
+__host__ __device__ __forceinline__ size_t bwd_sep_first(int S, int P, int u_rows) {     // floats: gout band, later W[RB][P]
+  const size_t a = (size_t)u_rows * S, b = (size_t)RB * P;
+  return a > b ? a : b;
+}
+
+// smem: bufU [max(u_rows * S, RB * P)] (bulk-TMA destination; reused as W) | bufV [g_rows * S] | bufG [g_rows * P] |
+//       descQ [g_rows] | descS [RB] | wextQ [g_rows * wext] | wextS [RB * wext];   P = sep_pitch(S, R), wext = gm.pad
+template <bool DYN, int SC, int PC>
+__global__ void __launch_bounds__(kThreads) dim_bwd_sep_kernel(const float* __restrict__ gout, float* __restrict__ gin,
+                                                               const DimTabB* __restrict__ tabp, const Geo gm_in,
+                                                               const DimPack* __restrict__ packs, const int* __restrict__ it, int n_packs) {
+  const DimPack* pk = nullptr;
+  if (DYN) { const int i = *it; pk = packs + (i < n_packs - 1 ? (i < 0 ? 0 : i) : n_packs - 1); }
+  const DimTabB& tab = DYN ? pk->tb : *tabp;
+  const Geo gm = DYN ? pk->gb : gm_in;
+  extern __shared__ __align__(128) unsigned char smem_raw[];
+  __shared__ __align__(8) uint64_t s_bar;
+  const int tid = threadIdx.x;
+  if (DYN && pk->identity) {                             // identity forward → identity adjoint
+    const int S0 = gm.S, r0 = blockIdx.x * RB, r1 = min(r0 + RB, S0);
+    const float4* gp0 = reinterpret_cast<const float4*>(gout + (int64_t)blockIdx.y * S0 * S0);
+    float4* ip0 = reinterpret_cast<float4*>(gin + (int64_t)blockIdx.y * S0 * S0);
+    for (int e = (r0 * S0 >> 2) + tid; e < (r1 * S0 >> 2); e += kThreads) ip0[e] = __ldg(gp0 + e);
+    return;
+  }
+  const int S = SC ? SC : gm.S, rnd = gm.rnd, top = gm.top, left = gm.left, wext = gm.pad;
+  const int P = PC ? PC : sep_pitch(S, gm.R);
+  float* bufU = reinterpret_cast<float*>(smem_raw);
+  float* bufV = bufU + bwd_sep_first(S, P, gm.a_rows);
+  float* bufG = bufV + (size_t)gm.c_rows * S;
+  RowG* descQ = reinterpret_cast<RowG*>(bufG + (size_t)gm.c_rows * P);
+  RowG* descS = descQ + gm.c_rows;
+  float* wextQ = reinterpret_cast<float*>(descS + RB);
+  float* wextS = wextQ + (size_t)gm.c_rows * wext;
+
+  const int sy0 = blockIdx.x * RB;
+  const int nb = min(sy0 + RB, S) - sy0;
+  const float* gp = gout + (int64_t)blockIdx.y * S * S;
+  float* ip = gin + (int64_t)blockIdx.y * S * S;
+  const short4 bd = tab.band[blockIdx.x];
+  const int q0 = bd.x, nq = bd.y, oyA = bd.z, nu = bd.w;
+  if (nq == 0) {                                         // no y1 row reads this band of source rows
+    float4* o4 = reinterpret_cast<float4*>(ip + (int64_t)sy0 * S);
+    for (int e = tid; e < (nb * S >> 2); e += kThreads) o4[e] = make_float4(0.f, 0.f, 0.f, 0.f);
+    return;
+  }
+  if (tid == 0) {
+    mbar_init(&s_bar, 1);
+    mbar_fence_init();
+    if (nu > 0) {
+      const uint32_t bytes = (uint32_t)(nu * S * 4);
+      mbar_expect_tx(&s_bar, bytes);
+      tma_bulk_g2s(bufU, gp + (int64_t)oyA * S, bytes, &s_bar);
+    }
+  }
+  // row descriptors: V row q gathers gout rows inv2[q0 + q + top]; W row r gathers g1 rows inv1[sy0 + r]
+  for (int q = tid; q < nq; q += kThreads) {
+    const int p = q0 + q + top;
+    const InvE iv = tab.inv2[p];
+    RowG d{(iv.lo - oyA) * S * 4, iv.cnt, 0.0f, 0.0f};
+    if (iv.cnt > 0) d.w0 = tap_w(tab.t2[iv.lo], p);
+    if (iv.cnt > 1) d.w1 = tap_w(tab.t2[iv.lo + 1], p);
+    for (int a = 2; a < iv.cnt; ++a) wextQ[q * wext + (a - 2)] = tap_w(tab.t2[iv.lo + a], p);
+    descQ[q] = d;
+  }
+  for (int r = tid; r < nb; r += kThreads) {
+    const int sy = sy0 + r;
+    const InvE iv = tab.inv1[sy];
+    RowG d{(iv.lo - q0) * P * 4, iv.cnt, 0.0f, 0.0f};
+    if (iv.cnt > 0) d.w0 = tap_w(tab.t1[iv.lo], sy);
+    if (iv.cnt > 1) d.w1 = tap_w(tab.t1[iv.lo + 1], sy);
+    for (int a = 2; a < iv.cnt; ++a) wextS[r * wext + (a - 2)] = tap_w(tab.t1[iv.lo + a], sy);
+    descS[r] = d;
+  }
+  __syncthreads();
+  if (nu > 0) mbar_wait(&s_bar, 0);
+
+  // vT2: V[q][ox] = sum over the output rows that read y2 row q0 + q + top
+  {
+    const int ncg = S >> 2;
+    for (int cg = (tid & 63); cg < ncg; cg += 64) {
+      const unsigned char* ub = reinterpret_cast<const unsigned char*>(bufU + 4 * cg);
+      float* vo = bufV + 4 * cg + (tid >> 6) * S;
+#pragma unroll 2
+      for (int q = tid >> 6; q < nq; q += kThreads / 64, vo += (kThreads / 64) * S)
+        *reinterpret_cast<float4*>(vo) = vgather4(descQ, wextQ, wext, q, ub, S * 4);
+    }
+  }
+  __syncthreads();
+  // hT2: g1[q][qx] = sum over the output columns that read y2 column qx + left (crop = the pad's adjoint)
+  for (int c = tid; c < rnd; c += kThreads) {
+    const int px = c + left;
+    const InvE iv = tab.inv2[px];
+    float wx[3];
+#pragma unroll
+    for (int b = 0; b < 3; ++b) wx[b] = (b < iv.cnt) ? tap_w(tab.t2[iv.lo + b], px) : 0.0f;
+    sep_htpass<SC, PC>(bufV + iv.lo, bufG + c, nq, iv.cnt, wx, tab.t2, iv.lo, px, S, P);
+  }
+  __syncthreads();
+  // vT1: W[r][qx] = sum over the y1 rows that read source row sy0 + r   (W reuses the gout band's storage)
+  float* bufW = bufU;
+  {
+    const int ncg = (rnd + 3) >> 2;
+    for (int cg = (tid & 63); cg < ncg; cg += 64) {
+      const unsigned char* gb = reinterpret_cast<const unsigned char*>(bufG + 4 * cg);
+      float* wo = bufW + 4 * cg + (tid >> 6) * P;
+#pragma unroll 2
+      for (int r = tid >> 6; r < nb; r += kThreads / 64, wo += (kThreads / 64) * P)
+        *reinterpret_cast<float4*>(wo) = vgather4(descS, wextS, wext, r, gb, P * 4);
+    }
+  }
+  __syncthreads();
+  // hT1: gin[sy][sx] = sum over the y1 columns that read source column sx (coalesced stores)
+  for (int c = tid; c < S; c += kThreads) {
+    const InvE iv = tab.inv1[c];
+    float wx[3];
+#pragma unroll
+    for (int b = 0; b < 3; ++b) wx[b] = (b < iv.cnt) ? tap_w(tab.t1[iv.lo + b], c) : 0.0f;
+    sep_htpass<PC, SC>(bufW + iv.lo, ip + (int64_t)sy0 * S + c, nb, iv.cnt, wx, tab.t1, iv.lo, c, P, S);
+  }
+}
+
 // ---- table upload -------------------------------------------------------------------------------------------------------
 // The tables are built on the host per call and must reach GLOBAL memory in stream order without a host-side staging buffer
 // whose lifetime the library would have to manage: they travel as the parameter of this one-wave copy kernel (128-bit
@@ -608,6 +933,24 @@ static size_t fwd_smem(int S, int rnd, int a_rows, int c_rows) {
 static size_t bwd_smem(int S, int rnd, int u_rows, int g_rows) {
   return ((sizeof(float) * ((size_t)u_rows * S + (size_t)g_rows * rnd) + 15) & ~(size_t)15) + 16 * (size_t)(u_rows + g_rows);
 }
+// the separable kernels (dim_fwd_sep_kernel / dim_bwd_sep_kernel): S % 4 == 0
+static bool sep_enabled(int S, bool tma) { return tma && S % 4 == 0 && tune_get("dim.impl", 2) == 2; }
+static bool sep_hot(int S, int R) { return S == 224 && sep_pitch(S, R) == 248 && tune_get("dim.sepconst", 1) != 0; }
+static size_t fwd_sep_smem(int S, int R, int a_rows, int c_rows) {
+  const size_t P = (size_t)sep_pitch(S, R), hr = (size_t)(a_rows > c_rows + 1 ? a_rows : c_rows + 1);
+  return sizeof(float) * ((size_t)a_rows * S + hr * P + (size_t)(c_rows + 1) * P) + 16 * (size_t)(c_rows + RB);
+}
+static int inverse_wext(const DimTabB& tab, int S, int R) {       // weights beyond the two a row descriptor holds
+  int cmax = 2;
+  for (int i = 0; i < R; ++i) if (tab.inv2[i].cnt > cmax) cmax = tab.inv2[i].cnt;
+  for (int i = 0; i < S; ++i) if (tab.inv1[i].cnt > cmax) cmax = tab.inv1[i].cnt;
+  return cmax - 2 > 1 ? cmax - 2 : 1;
+}
+static size_t bwd_sep_smem(int S, int R, int u_rows, int g_rows, int wext) {
+  const size_t P = (size_t)sep_pitch(S, R);
+  return sizeof(float) * (bwd_sep_first(S, (int)P, u_rows) + (size_t)g_rows * S + (size_t)g_rows * P) + 16 * (size_t)(g_rows + RB) +
+         sizeof(float) * (size_t)wext * (size_t)(g_rows + RB);
+}
 
 int dim_pack_build(DimPack* pack, int S, int rnd, int R, int top, int left, int identity) {
   memset(pack, 0, sizeof(DimPack));
@@ -617,18 +960,18 @@ int dim_pack_build(DimPack* pack, int S, int rnd, int R, int top, int left, int 
   fwd_tables(S, rnd, R, top, pack->tf, &a, &c);
   bwd_tables(S, rnd, R, top, pack->tb, &u, &g);
   pack->gf = Geo{S, rnd, R, top, left, a, c, 0};
-  pack->gb = Geo{S, rnd, R, top, left, u, g, 0};
+  pack->gb = Geo{S, rnd, R, top, left, u, g, inverse_wext(pack->tb, S, R)};
   return TA_OK;
 }
 
 // shared memory that serves every draw (rnd, top) DIM can make at (S, R): scanned once per (S, R)
-void dim_dyn_smem(int S, int R, size_t* fwd_bytes, size_t* bwd_bytes) {
+void dim_dyn_smem(int S, int R, size_t* fwd_bytes, size_t* bwd_bytes, size_t* fwd_sep_bytes, size_t* bwd_sep_bytes) {
   static thread_local int cS = 0, cR = 0;
-  static thread_local size_t cf = 0, cb = 0;
+  static thread_local size_t cf = 0, cb = 0, cfs = 0, cbs = 0;
   if (cS != S || cR != R) {
     static thread_local DimTabF tf;
     static thread_local DimTabB tb;
-    size_t mf = 0, mb = 0;
+    size_t mf = 0, mb = 0, mfs = 0, mbs = 0;
     const int lo = S < R ? S : R, hi = S < R ? R : S;
     const int hi_excl = hi > lo ? hi : lo + 1;              // dim.py:54 draws rnd from [min(S,R), max(S,R)), top / left from [0, R - rnd)
     for (int rnd = lo; rnd < hi_excl; ++rnd) {
@@ -640,17 +983,35 @@ void dim_dyn_smem(int S, int R, size_t* fwd_bytes, size_t* bwd_bytes) {
         const size_t f = fwd_smem(S, rnd, a, c), b = bwd_smem(S, rnd, u, g);
         if (f > mf) mf = f;
         if (b > mb) mb = b;
+        if (S % 4 == 0) {
+          const size_t fs = fwd_sep_smem(S, R, a, c), bs = bwd_sep_smem(S, R, u, g, inverse_wext(tb, S, R));
+          if (fs > mfs) mfs = fs;
+          if (bs > mbs) mbs = bs;
+        }
       }
     }
-    cS = S; cR = R; cf = mf; cb = mb;
+    cS = S; cR = R; cf = mf; cb = mb; cfs = mfs; cbs = mbs;
   }
   *fwd_bytes = cf; *bwd_bytes = cb;
+  if (fwd_sep_bytes) *fwd_sep_bytes = cfs;
+  if (bwd_sep_bytes) *bwd_sep_bytes = cbs;
 }
 
 int dim_fwd_dyn(const float* x, float* out, int planes, int S, int R, const DimPack* packs, int n_packs, const int* it, bool tma,
                 cudaStream_t stream) {
-  size_t smem, sb;
-  dim_dyn_smem(S, R, &smem, &sb);
+  size_t smem, sb, smem_s, sb_s;
+  dim_dyn_smem(S, R, &smem, &sb, &smem_s, &sb_s);
+  dim3 grid_s((unsigned)((S + RB - 1) / RB), (unsigned)planes);
+  if (sep_enabled(S, tma) && aligned16(out) && smem_s <= 200 * 1024) {
+    const bool hot = sep_hot(S, R);
+    auto ks = hot ? dim_fwd_sep_kernel<1, FwdTabDyn, 224, 248> : dim_fwd_sep_kernel<1, FwdTabDyn, 0, 0>;
+    static SmemOptIn optin_s[2] = {};
+    const int rcs = ensure_dyn_smem("ta_dim_fwd_dyn", ks, smem_s, optin_s[hot ? 0 : 1]);
+    if (rcs != TA_OK) return rcs;
+    ks<<<grid_s, kThreads, smem_s, stream>>>(x, out, FwdTabDyn{packs, it, n_packs}, Geo{});
+    count_launch();
+    return check_launch("ta_dim_fwd_dyn[sep]");
+  }
   TA_REQUIRE(smem <= 200 * 1024, "ta_dim_fwd_dyn: image size S=%d needs %zu B of shared memory per CTA", S, smem);
   auto k = tma ? dim_fwd_direct_kernel<1, true, FwdTabDyn, true> : dim_fwd_direct_kernel<1, false, FwdTabDyn, true>;
   static SmemOptIn optin[2] = {};
@@ -664,8 +1025,19 @@ int dim_fwd_dyn(const float* x, float* out, int planes, int S, int R, const DimP
 
 int dim_bwd_dyn(const float* gout, float* gin, int planes, int S, int R, const DimPack* packs, int n_packs, const int* it, bool tma,
                 cudaStream_t stream) {
-  size_t sf, smem;
-  dim_dyn_smem(S, R, &sf, &smem);
+  size_t sf, smem, sf_s, smem_s;
+  dim_dyn_smem(S, R, &sf, &smem, &sf_s, &smem_s);
+  if (sep_enabled(S, tma) && aligned16(gin) && smem_s <= 200 * 1024) {
+    const bool hot = sep_hot(S, R);
+    auto ks = hot ? dim_bwd_sep_kernel<true, 224, 248> : dim_bwd_sep_kernel<true, 0, 0>;
+    static SmemOptIn optin_s[2] = {};
+    const int rcs = ensure_dyn_smem("ta_dim_bwd_dyn", ks, smem_s, optin_s[hot ? 0 : 1]);
+    if (rcs != TA_OK) return rcs;
+    dim3 grid_s((unsigned)((S + RB - 1) / RB), (unsigned)planes);
+    ks<<<grid_s, kThreads, smem_s, stream>>>(gout, gin, nullptr, Geo{}, packs, it, n_packs);
+    count_launch();
+    return check_launch("ta_dim_bwd_dyn[sep]");
+  }
   TA_REQUIRE(smem <= 200 * 1024, "ta_dim_bwd_dyn: image size S=%d needs %zu B of shared memory per CTA", S, smem);
   auto k = tma ? dim_bwd_direct_kernel<true, true> : dim_bwd_direct_kernel<false, true>;
   static SmemOptIn optin[2] = {};
@@ -695,9 +1067,40 @@ int dim_fwd_direct(const float* x, float* out, int planes, int S, int rnd, int R
     if (nsr > a_rows) a_rows = nsr;
   }
   Geo gm{S, rnd, R, top, left, a_rows, c_rows, 0};
+  dim3 grid((unsigned)((S + RB - 1) / RB), (unsigned)planes);
+  if (sep_enabled(S, tma) && aligned16(out) && fwd_sep_smem(S, R, a_rows, c_rows) <= 200 * 1024) {
+    const size_t smem_s = fwd_sep_smem(S, R, a_rows, c_rows);
+    const bool hot = sep_hot(S, R);
+    static SmemOptIn optin_s[20] = {};
+#define TA_DIM_FWD_SEP(MODE_, SLOT_)                                                                                \
+  do {                                                                                                              \
+    if (ws) {                                                                                                       \
+      auto k = hot ? dim_fwd_sep_kernel<MODE_, FwdTabPtr, 224, 248> : dim_fwd_sep_kernel<MODE_, FwdTabPtr, 0, 0>;   \
+      const int rc = ensure_dyn_smem("ta_dim_fwd", k, smem_s, optin_s[4 * SLOT_ + (hot ? 0 : 1)]);                  \
+      if (rc != TA_OK) return rc;                                                                                   \
+      const int ru = upload_tab(tab, ws, stream);                                                                   \
+      if (ru != TA_OK) return ru;                                                                                   \
+      k<<<grid, kThreads, smem_s, stream>>>(x, out, FwdTabPtr{reinterpret_cast<const DimTabF*>(ws)}, gm);           \
+    } else {                                                                                                        \
+      auto k = hot ? dim_fwd_sep_kernel<MODE_, FwdTabParam, 224, 248> : dim_fwd_sep_kernel<MODE_, FwdTabParam, 0, 0>; \
+      const int rc = ensure_dyn_smem("ta_dim_fwd", k, smem_s, optin_s[4 * SLOT_ + 2 + (hot ? 0 : 1)]);              \
+      if (rc != TA_OK) return rc;                                                                                   \
+      k<<<grid, kThreads, smem_s, stream>>>(x, out, *reinterpret_cast<const FwdTabParam*>(&tab), gm);               \
+    }                                                                                                               \
+  } while (0)
+    switch (blend) {
+      case 1: TA_DIM_FWD_SEP(1, 0); break;
+      case 0: TA_DIM_FWD_SEP(0, 1); break;
+      case 2: TA_DIM_FWD_SEP(2, 2); break;
+      case 3: TA_DIM_FWD_SEP(3, 3); break;
+      default: TA_DIM_FWD_SEP(4, 4); break;
+    }
+#undef TA_DIM_FWD_SEP
+    count_launch();
+    return check_launch("ta_dim_fwd[sep]");
+  }
   const size_t smem = ((sizeof(float) * ((size_t)a_rows * S + (size_t)(c_rows + 1) * (rnd + 1)) + 15) & ~(size_t)15) + 16 * (size_t)(c_rows + RB);
   TA_REQUIRE(smem <= 200 * 1024, "ta_dim_fwd: image size S=%d needs %zu B of shared memory per CTA", S, smem);
-  dim3 grid((unsigned)((S + RB - 1) / RB), (unsigned)planes);
   static SmemOptIn optin[40] = {};
 #define TA_DIM_FWD_LAUNCH(MODE_, SLOT_)                                                                             \
   do {                                                                                                              \
@@ -760,6 +1163,22 @@ int dim_bwd_direct(const float* gout, float* gin, int planes, int S, int rnd, in
   const int ru = upload_tab(tab, ws, stream);
   if (ru != TA_OK) return ru;
   const DimTabB* dtab = reinterpret_cast<const DimTabB*>(ws);
+  if (sep_enabled(S, tma) && aligned16(gin)) {
+    gm.pad = inverse_wext(tab, S, R);
+    const size_t smem_s = bwd_sep_smem(S, R, u_rows, g_rows, gm.pad);
+    if (smem_s <= 200 * 1024) {
+      const bool hot = sep_hot(S, R);
+      auto ks = hot ? dim_bwd_sep_kernel<false, 224, 248> : dim_bwd_sep_kernel<false, 0, 0>;
+      static SmemOptIn optin_s[2] = {};
+      const int rcs = ensure_dyn_smem("ta_dim_bwd", ks, smem_s, optin_s[hot ? 0 : 1]);
+      if (rcs != TA_OK) return rcs;
+      dim3 grid_s((unsigned)((S + RB - 1) / RB), (unsigned)planes);
+      ks<<<grid_s, kThreads, smem_s, stream>>>(gout, gin, dtab, gm, nullptr, nullptr, 0);
+      count_launch();
+      return check_launch("ta_dim_bwd[sep]");
+    }
+    gm.pad = 0;
+  }
   if (gather) {
     int cmax = 2;
     for (int i = 0; i < R; ++i) if (tab.inv2[i].cnt > cmax) cmax = tab.inv2[i].cnt;

@@ -500,6 +500,211 @@ int launch_rg(const float* g, const float* kcol, const float* krow, const SepWei
   return check_launch("ta_dwconv2d_sep[rg]");
 }
 
+// ---- third form of the register-sliding walk: interior / edge split, fully unrolled band ----------------------------------------
+// ncu on dwconv_sep_rg_kernel<15,32> (profiles/ncu_tim_dim_r2.md): 17.3 M issued instructions of which only 6.5 M are FFMA2 —
+// per input row a thread spent 60 FFMA2 + 38 MOV (building the odd-aligned operand pairs v[j], v[j+1] of the row pass) + 10 CS2R
+// (zero-filling the destination of its five predicated loads) + ~35 integer / predicate instructions, and ran all KS column taps
+// on the 2 x (KS - 1) halo rows although a halo row feeds only part of the band. Here:
+//  * row pass with the DATA broadcast and the WEIGHTS paired: (out[x], out[x+1]) += (w[m], w[m-1]) * v[x+m] — SASS
+//    `FFMA2 R, R.F32, UR.F32x2, R`: the pair operand is a uniform-register pair of kernel parameters, no per-row register moves;
+//    per output the products still arrive in tap order 0..KS-1 from +0 (the end taps of a pair are scalar FFMAs), so the result
+//    is the same fma chain as before, bit for bit;
+//  * the band's BHR + KS - 1 rows are unrolled completely, so which column taps a row feeds (i <= r at the top, i >= r - BHR + 1 at
+//    the bottom) is decided at compile time: 2 * BHR * KS column FFMA2s per thread instead of 2 * (BHR + KS - 1) * KS, and the
+//    first tap of every output row takes +0 as its addend instead of a zeroed accumulator;
+//  * threads whose 4-output window (KS + 3 columns, as NV 128-bit loads) lies inside the row — all but 2 + 2 per row at ks = 15 —
+//    run in their own CTAs with unconditional loads; the edge windows get CTAs of their own with the predicated form. Rows outside
+//    the image are skipped (their products are exact zeros and an accumulator is never -0).
+template <int KS> struct SepWeights2 { float kr[KS]; float kc[KS]; float wp[KS + 1][2]; };   // wp[m] = (w[m], w[m-1]), w[-1] = w[KS] = 0
+
+__device__ __forceinline__ f32x2_t ffma2_bc(float2 wpair, float v, f32x2_t c) {   // (c.lo, c.hi) + (wpair.x, wpair.y) * v
+  return ffma2(pack2(v, v), pack2(wpair.x, wpair.y), c);
+}
+
+// Zero rows for the constant-width walk: a window quarter that lies outside the image row reads HERE instead (same row stride, so
+// the unrolled walk keeps its [base + immediate] addressing and every load is unconditional). 64 rows x 224 floats of zeros.
+__device__ __align__(16) float g_rg2_zero_rows[64 * 224 + 8];
+
+// 128-bit read-only load under a predicate that leaves the destination registers untouched when false: a window quarter that lies
+// outside the row keeps the zeros it was initialised with for the whole walk (no per-row zero fill, no select)
+__device__ __forceinline__ void ldg4_if(float4& d, const float4* p, int pred) {
+  asm volatile("{\n\t.reg .pred p;\n\tsetp.ne.s32 p, %5, 0;\n\t@p ld.global.nc.v4.f32 {%0,%1,%2,%3}, [%4];\n\t}"
+               : "+f"(d.x), "+f"(d.y), "+f"(d.z), "+f"(d.w) : "l"(p), "r"(pred));
+}
+
+// WC > 0: the image width is a compile-time constant (224, the hot shape): every load, store and prefetch of the walk is
+// [base register + immediate] — no per-row pointer arithmetic and no constant-bank reads of W behind a scoreboard.
+template <int KS, int BHR, bool EDGE, int WC>
+__device__ __forceinline__ void rg2_walk(const float* __restrict__ g, float* __restrict__ out, const SepWeights2<KS>& wp,
+                                         int plane, int band, int nbands, int q, int H, int W_rt, int prefetch) {
+  const int W = WC ? WC : W_rt;
+  using G = RsGeom<KS>;
+  constexpr int R = G::R, PADX = G::PADX, OFF = G::OFF, NV = G::NV;
+  constexpr int ROWS = BHR + KS - 1;
+  const int y0 = band * BHR;                              // H % BHR == 0 (host-checked): every band is full, only the first R rows of
+  const bool top_ok = band > 0, bot_ok = band < nbands - 1;   // band 0 and the last R rows of the last band lie outside the image
+  int cv[NV];
+#pragma unroll
+  for (int k = 0; k < NV; ++k) { const int col = 4 * q - PADX + 4 * k; cv[k] = (!EDGE || (col >= 0 && col < W)) ? 1 : 0; }
+  const float4* ip0 = reinterpret_cast<const float4*>(g + (int64_t)plane * H * W + (int64_t)(y0 - R) * W + 4 * q - PADX);
+  float* op0 = out + (int64_t)plane * H * W + (int64_t)y0 * W + 4 * q;
+  const int pitch4 = W >> 2;
+  f32x2_t acc0[KS], acc1[KS];
+#pragma unroll
+  for (int s = 0; s < KS; ++s) { acc0[s] = pack2(0.f, 0.f); acc1[s] = pack2(0.f, 0.f); }
+  float4 buf[2][NV];
+#pragma unroll
+  for (int k = 0; k < NV; ++k) { buf[0][k] = make_float4(0.f, 0.f, 0.f, 0.f); buf[1][k] = make_float4(0.f, 0.f, 0.f, 0.f); }
+  constexpr bool ZB = EDGE && WC == 224 && ROWS <= 64;      // out-of-row window quarters read the zero rows: no predicates at all
+  const float4* bk[NV];
+#pragma unroll
+  for (int k = 0; k < NV; ++k) bk[k] = (!ZB || cv[k]) ? ip0 + k : reinterpret_cast<const float4*>(g_rg2_zero_rows);
+#define TA_RG2_LOAD(SLOT_, ROW_)                                                               \
+  do {                                                                                         \
+    _Pragma("unroll") for (int k = 0; k < NV; ++k) {                                           \
+      if (ZB) buf[SLOT_][k] = __ldg(bk[k] + (ROW_) * pitch4);                                  \
+      else if (EDGE) ldg4_if(buf[SLOT_][k], ip0 + (ROW_) * pitch4 + k, cv[k]);                 \
+      else buf[SLOT_][k] = __ldg(ip0 + (ROW_) * pitch4 + k);                                   \
+    }                                                                                          \
+  } while (0)
+  if (top_ok) TA_RG2_LOAD(0, 0);
+  // The walk is serial per thread with one row of loads in flight ahead of the FMAs, i.e. a cold row costs one DRAM latency.
+  // prefetch 3 (default): every row step asks L2 for this thread's own 16 bytes of the row PD rows further down (the band's
+  // threads cover each row once) — a rolling request stream PD row-times ahead of the demand loads instead of one burst;
+  // 1 / 2: the whole band up front (the earlier kernels' scheme; measured slower here), 2 also the row three ahead into L1.
+  constexpr int PD = 6;
+  if (prefetch == 1 || prefetch == 2) {
+    const float* pp = g + (int64_t)plane * H * W + (int64_t)(y0 - R + 1) * W + 4 * q;
+#pragma unroll 1
+    for (int r = 1; r < ROWS; ++r, pp += W)
+      if ((unsigned)(y0 - R + r) < (unsigned)H) asm volatile("prefetch.global.L2 [%0];" ::"l"(pp));
+  } else if (prefetch == 3) {
+#pragma unroll
+    for (int r = 2; r < PD; ++r)
+      if ((r >= R || top_ok) && (r < ROWS - R || bot_ok)) asm volatile("prefetch.global.L2 [%0];" ::"l"(ip0 + r * pitch4 + (PADX >> 2)));
+  }
+#pragma unroll
+  for (int r = 0; r < ROWS; ++r) {
+    if (prefetch == 2 && r + 3 < ROWS && (r + 3 >= R || top_ok) && (r + 3 < ROWS - R || bot_ok))
+      asm volatile("prefetch.global.L1 [%0];" ::"l"(ip0 + (r + 3) * pitch4 + (PADX >> 2)));
+    if (prefetch == 3 && r + PD < ROWS && (r + PD >= R || top_ok) && (r + PD < ROWS - R || bot_ok))
+      asm volatile("prefetch.global.L2 [%0];" ::"l"(ip0 + (r + PD) * pitch4 + (PADX >> 2)));
+    if (r + 1 < ROWS) {
+      if (r + 1 < R) {
+        if (top_ok) TA_RG2_LOAD((r + 1) & 1, r + 1);
+      } else if (r + 1 >= ROWS - R) {
+        if (bot_ok) TA_RG2_LOAD((r + 1) & 1, r + 1);
+      } else {
+        TA_RG2_LOAD((r + 1) & 1, r + 1);
+      }
+    }
+    const bool rv = r < R ? top_ok : (r >= ROWS - R ? bot_ok : true);
+    if (rv) {
+      float v[4 * NV];
+#pragma unroll
+      for (int t = 0; t < NV; ++t) {
+        v[4 * t] = buf[r & 1][t].x; v[4 * t + 1] = buf[r & 1][t].y; v[4 * t + 2] = buf[r & 1][t].z; v[4 * t + 3] = buf[r & 1][t].w;
+      }
+      // row pass: pair 0 = outputs (0, 1), pair 1 = outputs (2, 3); tap index m, data v[OFF + m (+ 2)]
+      float lo0 = fmaf(wp.kr[0], v[OFF], 0.f), lo1 = fmaf(wp.kr[0], v[OFF + 2], 0.f);
+      f32x2_t p0 = pack2(lo0, 0.f), p1 = pack2(lo1, 0.f);
+#pragma unroll
+      for (int m = 1; m < KS; ++m) {
+        const float2 w2 = make_float2(wp.wp[m][0], wp.wp[m][1]);
+        p0 = ffma2_bc(w2, v[OFF + m], p0);
+        p1 = ffma2_bc(w2, v[OFF + 2 + m], p1);
+      }
+      float a0, a1, b0, b1;
+      unpack2(p0, a0, a1); unpack2(p1, b0, b1);
+      a1 = fmaf(wp.kr[KS - 1], v[OFF + KS], a1);
+      b1 = fmaf(wp.kr[KS - 1], v[OFF + 2 + KS], b1);
+      const f32x2_t t0 = pack2(a0, a1), t1 = pack2(b0, b1);
+      // column pass: this row is tap i of output row y = r - i
+#pragma unroll
+      for (int i = 0; i < KS; ++i) {
+        const int y = r - i;
+        if (y >= 0 && y < BHR) {
+          const int s = y % KS;
+          const f32x2_t ww = pack2(wp.kc[i], wp.kc[i]);
+          if (i == 0) { acc0[s] = ffma2(ww, t0, pack2(0.f, 0.f)); acc1[s] = ffma2(ww, t1, pack2(0.f, 0.f)); }
+          else { acc0[s] = ffma2(ww, t0, acc0[s]); acc1[s] = ffma2(ww, t1, acc1[s]); }
+        }
+      }
+    } else if (r < BHR) {                                  // the first tap of output row r never comes: start it at +0
+      acc0[r % KS] = pack2(0.f, 0.f); acc1[r % KS] = pack2(0.f, 0.f);
+    }
+    if (r >= KS - 1) {
+      const int s = (r - (KS - 1)) % KS;
+      float o0, o1, o2, o3;
+      unpack2(acc0[s], o0, o1); unpack2(acc1[s], o2, o3);
+      *reinterpret_cast<float4*>(op0 + (r - (KS - 1)) * W) = make_float4(o0, o1, o2, o3);
+    }
+  }
+#undef TA_RG2_LOAD
+}
+
+// SPLIT = false (default): one code path, every thread with the predicated loads. SPLIT = true: the interior windows in CTAs of
+// their own with unconditional loads, the edge windows in trailing CTAs — measured slower: the few edge warps stream 70 KB of
+// straight-line code that no other warp on their SM has brought into the instruction cache (ncu: 83 % of their stall samples
+// are no_instruction) and run 4x longer than the interior warps.
+template <int KS, int BHR, bool SPLIT, int WC>
+__global__ void __launch_bounds__(128, 4) dwconv_sep_rg2_kernel(const float* __restrict__ g, const __grid_constant__ SepWeights2<KS> wp,
+                                                             float* __restrict__ out, int H, int W, int nbands, int n_int_blocks,
+                                                             int64_t n_int, int64_t n_edge, int prefetch) {
+  using G = RsGeom<KS>;
+  constexpr int NEL = G::PADX / 4, NER = G::NV - 1 - G::PADX / 4;     // edge windows per row, left / right
+  const int Q = W >> 2;
+  if (!SPLIT) {
+    const int64_t item = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (item >= n_int) return;
+    const int q = (int)(item % Q);
+    const int64_t pb = item / Q;
+    rg2_walk<KS, BHR, true, WC>(g, out, wp, (int)(pb / nbands), (int)(pb % nbands), nbands, q, H, W, prefetch);
+  } else if ((int)blockIdx.x < n_int_blocks) {
+    const int64_t item = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (item >= n_int) return;
+    const int QI = Q - NEL - NER;
+    const int q = NEL + (int)(item % QI);
+    const int64_t pb = item / QI;
+    rg2_walk<KS, BHR, false, WC>(g, out, wp, (int)(pb / nbands), (int)(pb % nbands), nbands, q, H, W, prefetch);
+  } else {
+    const int64_t item = (int64_t)(blockIdx.x - n_int_blocks) * blockDim.x + threadIdx.x;
+    if (item >= n_edge) return;
+    const int e = (int)(item % (NEL + NER));
+    const int64_t pb = item / (NEL + NER);
+    const int q = e < NEL ? e : Q - (NEL + NER) + e;
+    rg2_walk<KS, BHR, true, WC>(g, out, wp, (int)(pb / nbands), (int)(pb % nbands), nbands, q, H, W, prefetch);
+  }
+}
+
+template <int KS, int BHR>
+int launch_rg2(const float* g, const float* kcol_host, const float* krow_host, float* out, int B, int C, int H, int W, cudaStream_t s) {
+  using G = RsGeom<KS>;
+  constexpr int NE = G::NV - 1;
+  SepWeights2<KS> w;
+  for (int j = 0; j < KS; ++j) { w.kr[j] = krow_host[j]; w.kc[j] = kcol_host[j]; }
+  for (int m = 0; m <= KS; ++m) { w.wp[m][0] = m < KS ? krow_host[m] : 0.0f; w.wp[m][1] = m >= 1 ? krow_host[m - 1] : 0.0f; }
+  const int nbands = (H + BHR - 1) / BHR, Q = W / 4;
+  const int64_t pbs = (int64_t)B * C * nbands;
+  const int pf = tune_get("tim.prefetch2", 3);
+  if (tune_get("tim.split", 0) != 0) {
+    const int64_t n_int = pbs * (Q - NE), n_edge = pbs * NE;
+    const int64_t bi = (n_int + 127) / 128, be = (n_edge + 127) / 128;
+    TA_REQUIRE(bi + be <= 0x7fffffff, "ta_dwconv2d_sep: too many work items");
+    dwconv_sep_rg2_kernel<KS, BHR, true, 0><<<(unsigned)(bi + be), 128, 0, s>>>(g, w, out, H, W, nbands, (int)bi, n_int, n_edge, pf);
+  } else {
+    const int64_t items = pbs * Q;
+    const int64_t blocks = (items + 127) / 128;
+    TA_REQUIRE(blocks <= 0x7fffffff, "ta_dwconv2d_sep: too many work items");
+    if (W == 224 && tune_get("tim.wconst", 1) != 0)
+      dwconv_sep_rg2_kernel<KS, BHR, false, 224><<<(unsigned)blocks, 128, 0, s>>>(g, w, out, H, W, nbands, 0, items, 0, pf);
+    else
+      dwconv_sep_rg2_kernel<KS, BHR, false, 0><<<(unsigned)blocks, 128, 0, s>>>(g, w, out, H, W, nbands, 0, items, 0, pf);
+  }
+  count_launch();
+  return check_launch("ta_dwconv2d_sep[rg2]");
+}
+
 template <int KS, int BHR, bool PW>
 int launch_rs(const float* g, const float* kcol, const float* krow, const SepWeights<KS>& wp, float* out, int B, int C, int H,
               int W, cudaStream_t s) {
@@ -520,7 +725,7 @@ template <int KS, bool PW>
 int launch_rs_bh(const float* g, const float* kcol, const float* krow, const SepWeights<KS>& wp, float* out, int B, int C,
                  int H, int W, cudaStream_t s) {
   const int bh = tune_get("tim.bh", 32);
-  if (tune_get("tim.band", 3) == 3) {       // straight from global memory; tim.f2: packed fp32x2 FMAs
+  if (tune_get("tim.band", 4) >= 3) {       // straight from global memory; tim.f2: packed fp32x2 FMAs
     if (tune_get("tim.f2", 1) != 0) {
       if (bh == 56) return launch_rg<KS, 56, PW, true>(g, kcol, krow, wp, out, B, C, H, W, s);
       return launch_rg<KS, 32, PW, true>(g, kcol, krow, wp, out, B, C, H, W, s);
@@ -667,8 +872,11 @@ int ta_dwconv2d_sep_hw(const float* g, const float* kcol_host, const float* krow
     return TA_EUNSUPPORTED;
   }
   cudaStream_t bs = (cudaStream_t)stream;
+  const int band_mode = tune_get("tim.band", 4);
 #define TA_HW_CASE(K)                                                                     \
   case K: {                                                                               \
+    if (band_mode == 4 && W / 4 > RsGeom<K>::NV - 1 && H % 32 == 0 && H >= 64)            \
+      return launch_rg2<K, 32>(g, kcol_host, krow_host, out, B, C, H, W, bs);             \
     SepWeights<K> w;                                                                      \
     for (int j = 0; j < K; ++j) { w.kr[j] = krow_host[j]; w.kc[j] = kcol_host[j]; }      \
     return launch_rs_bh<K, true>(g, nullptr, nullptr, w, out, B, C, H, W, bs);            \
