@@ -800,22 +800,25 @@ def run_kernels(args):
     add("stage_add", 12, lambda: be.stage_add(x, d, out=xa))
     add("sim_fwd S=5", 24, lambda: be.sim(x, 5, True))
     add("sim_bwd S=5", 24, lambda: be.sim(g5, 5, False))
-    for impl, bwd, fwdtab, tag in ((2, 0, 0, "separable passes in shared memory (default)"), (2, 0, 1, "separable passes; fwd tables in workspace"),
+    for impl, bwd, fwdtab, tag in ((2, 0, 0, "default: register-carried forward, separable-pass adjoint"), (3, 0, 0, "separable passes in shared memory"),
                                    (1, 0, 0, "direct; fwd tables = kernel parameters; adjoint = gather + scatter, tables in workspace"),
                                    (1, 1, 1, "direct; fwd tables in workspace; adjoint = independent gather"), (0, 0, 0, "4-pass")):
         _lib.tune_set("dim.impl", impl); _lib.tune_set("dim.bwd", bwd); _lib.tune_set("dim.fwdtab", fwdtab)
         add("dim_fwd [%s]" % tag, 8, lambda: be.dim(x, 235, 246, 5, 6, True))
         add("dim_bwd [%s]" % tag, 8, lambda: be.dim(g, 235, 246, 5, 6, False))
-    _lib.tune_set("dim.impl", 2); _lib.tune_set("dim.sepconst", 0)
+    _lib.tune_set("dim.impl", 3); _lib.tune_set("dim.sepconst", 0)
     add("dim_fwd [separable passes, run-time pitches]", 8, lambda: be.dim(x, 235, 246, 5, 6, True))
     add("dim_bwd [separable passes, run-time pitches]", 8, lambda: be.dim(g, 235, 246, 5, 6, False))
-    _lib.tune_set("dim.sepconst", 1); _lib.tune_set("dim.bwd", 0); _lib.tune_set("dim.fwdtab", 0)
+    _lib.tune_set("dim.impl", 2); _lib.tune_set("dim.sepconst", 1); _lib.tune_set("dim.bwd", 0); _lib.tune_set("dim.fwdtab", 0)
     hc, hr = kc3.cpu().numpy(), kr3.cpu().numpy()
     _lib.tune_set("tim.band", 4)
     add("dwconv2d_sep k=15 [unrolled band walk, paired weights, tap-exact column pass (default)]", 8, lambda: be.dwconv2d_sep(g, kc3, kr3, host=(hc, hr)))
     _lib.tune_set("tim.split", 1)
     add("dwconv2d_sep k=15 [unrolled band walk, interior / edge windows in separate CTAs]", 8, lambda: be.dwconv2d_sep(g, kc3, kr3, host=(hc, hr)))
     _lib.tune_set("tim.split", 0)
+    _lib.tune_set("tim.deep", 0)
+    add("dwconv2d_sep k=15 [unrolled band walk, loads one row ahead]", 8, lambda: be.dwconv2d_sep(g, kc3, kr3, host=(hc, hr)))
+    _lib.tune_set("tim.deep", 1)
     for pf in (2, 1, 0):
         _lib.tune_set("tim.prefetch2", pf)
         add("dwconv2d_sep k=15 [unrolled band walk, prefetch mode %d]" % pf, 8, lambda: be.dwconv2d_sep(g, kc3, kr3, host=(hc, hr)))

@@ -934,7 +934,13 @@ static size_t bwd_smem(int S, int rnd, int u_rows, int g_rows) {
   return ((sizeof(float) * ((size_t)u_rows * S + (size_t)g_rows * rnd) + 15) & ~(size_t)15) + 16 * (size_t)(u_rows + g_rows);
 }
 // the separable kernels (dim_fwd_sep_kernel / dim_bwd_sep_kernel): S % 4 == 0
-static bool sep_enabled(int S, bool tma) { return tma && S % 4 == 0 && tune_get("dim.impl", 2) == 2; }
+// dim.impl 2 (default): the separable passes where they measured faster — the adjoint (50 us against 56 us at B = 64) — and the
+// register-carried forward of the second generation (34 us against 40 us); 3: separable passes in both directions; 1: second generation
+// in both directions; 0: the four-pass kernels of dim.cu
+static bool sep_enabled(int S, bool tma, bool forward) {
+  const int impl = tune_get("dim.impl", 2);
+  return tma && S % 4 == 0 && (impl == 3 || (impl == 2 && !forward));
+}
 static bool sep_hot(int S, int R) { return S == 224 && sep_pitch(S, R) == 248 && tune_get("dim.sepconst", 1) != 0; }
 static size_t fwd_sep_smem(int S, int R, int a_rows, int c_rows) {
   const size_t P = (size_t)sep_pitch(S, R), hr = (size_t)(a_rows > c_rows + 1 ? a_rows : c_rows + 1);
@@ -1002,7 +1008,7 @@ int dim_fwd_dyn(const float* x, float* out, int planes, int S, int R, const DimP
   size_t smem, sb, smem_s, sb_s;
   dim_dyn_smem(S, R, &smem, &sb, &smem_s, &sb_s);
   dim3 grid_s((unsigned)((S + RB - 1) / RB), (unsigned)planes);
-  if (sep_enabled(S, tma) && aligned16(out) && smem_s <= 200 * 1024) {
+  if (sep_enabled(S, tma, true) && aligned16(out) && smem_s <= 200 * 1024) {
     const bool hot = sep_hot(S, R);
     auto ks = hot ? dim_fwd_sep_kernel<1, FwdTabDyn, 224, 248> : dim_fwd_sep_kernel<1, FwdTabDyn, 0, 0>;
     static SmemOptIn optin_s[2] = {};
@@ -1027,7 +1033,7 @@ int dim_bwd_dyn(const float* gout, float* gin, int planes, int S, int R, const D
                 cudaStream_t stream) {
   size_t sf, smem, sf_s, smem_s;
   dim_dyn_smem(S, R, &sf, &smem, &sf_s, &smem_s);
-  if (sep_enabled(S, tma) && aligned16(gin) && smem_s <= 200 * 1024) {
+  if (sep_enabled(S, tma, false) && aligned16(gin) && smem_s <= 200 * 1024) {
     const bool hot = sep_hot(S, R);
     auto ks = hot ? dim_bwd_sep_kernel<true, 224, 248> : dim_bwd_sep_kernel<true, 0, 0>;
     static SmemOptIn optin_s[2] = {};
@@ -1068,7 +1074,7 @@ int dim_fwd_direct(const float* x, float* out, int planes, int S, int rnd, int R
   }
   Geo gm{S, rnd, R, top, left, a_rows, c_rows, 0};
   dim3 grid((unsigned)((S + RB - 1) / RB), (unsigned)planes);
-  if (sep_enabled(S, tma) && aligned16(out) && fwd_sep_smem(S, R, a_rows, c_rows) <= 200 * 1024) {
+  if (sep_enabled(S, tma, true) && aligned16(out) && fwd_sep_smem(S, R, a_rows, c_rows) <= 200 * 1024) {
     const size_t smem_s = fwd_sep_smem(S, R, a_rows, c_rows);
     const bool hot = sep_hot(S, R);
     static SmemOptIn optin_s[20] = {};
@@ -1163,7 +1169,7 @@ int dim_bwd_direct(const float* gout, float* gin, int planes, int S, int rnd, in
   const int ru = upload_tab(tab, ws, stream);
   if (ru != TA_OK) return ru;
   const DimTabB* dtab = reinterpret_cast<const DimTabB*>(ws);
-  if (sep_enabled(S, tma) && aligned16(gin)) {
+  if (sep_enabled(S, tma, false) && aligned16(gin)) {
     gm.pad = inverse_wext(tab, S, R);
     const size_t smem_s = bwd_sep_smem(S, R, u_rows, g_rows, gm.pad);
     if (smem_s <= 200 * 1024) {

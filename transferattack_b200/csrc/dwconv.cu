@@ -534,7 +534,7 @@ __device__ __forceinline__ void ldg4_if(float4& d, const float4* p, int pred) {
 
 // WC > 0: the image width is a compile-time constant (224, the hot shape): every load, store and prefetch of the walk is
 // [base register + immediate] — no per-row pointer arithmetic and no constant-bank reads of W behind a scoreboard.
-template <int KS, int BHR, bool EDGE, int WC>
+template <int KS, int BHR, bool EDGE, int WC, bool DEEP>
 __device__ __forceinline__ void rg2_walk(const float* __restrict__ g, float* __restrict__ out, const SepWeights2<KS>& wp,
                                          int plane, int band, int nbands, int q, int H, int W_rt, int prefetch) {
   const int W = WC ? WC : W_rt;
@@ -567,7 +567,18 @@ __device__ __forceinline__ void rg2_walk(const float* __restrict__ g, float* __r
       else buf[SLOT_][k] = __ldg(ip0 + (ROW_) * pitch4 + k);                                   \
     }                                                                                          \
   } while (0)
-  if (top_ok) TA_RG2_LOAD(0, 0);
+#define TA_RG2_LOAD_ROW(ROW_)                                                                  \
+  do {                                                                                         \
+    if ((ROW_) < ROWS) {                                                                       \
+      if ((ROW_) < R) { if (top_ok) TA_RG2_LOAD((ROW_) & 1, ROW_); }                           \
+      else if ((ROW_) >= ROWS - R) { if (bot_ok) TA_RG2_LOAD((ROW_) & 1, ROW_); }              \
+      else TA_RG2_LOAD((ROW_) & 1, ROW_);                                                      \
+    }                                                                                          \
+  } while (0)
+  // DEEP: the loads of row r + 2 go out as soon as the row pass of row r has consumed its buffer (before the column pass), i.e.
+  // ~1.4 row-times ahead of their use instead of 1.0
+  TA_RG2_LOAD_ROW(0);
+  if (DEEP) TA_RG2_LOAD_ROW(1);
   // The walk is serial per thread with one row of loads in flight ahead of the FMAs, i.e. a cold row costs one DRAM latency.
   // prefetch 3 (default): every row step asks L2 for this thread's own 16 bytes of the row PD rows further down (the band's
   // threads cover each row once) — a rolling request stream PD row-times ahead of the demand loads instead of one burst;
@@ -589,15 +600,7 @@ __device__ __forceinline__ void rg2_walk(const float* __restrict__ g, float* __r
       asm volatile("prefetch.global.L1 [%0];" ::"l"(ip0 + (r + 3) * pitch4 + (PADX >> 2)));
     if (prefetch == 3 && r + PD < ROWS && (r + PD >= R || top_ok) && (r + PD < ROWS - R || bot_ok))
       asm volatile("prefetch.global.L2 [%0];" ::"l"(ip0 + (r + PD) * pitch4 + (PADX >> 2)));
-    if (r + 1 < ROWS) {
-      if (r + 1 < R) {
-        if (top_ok) TA_RG2_LOAD((r + 1) & 1, r + 1);
-      } else if (r + 1 >= ROWS - R) {
-        if (bot_ok) TA_RG2_LOAD((r + 1) & 1, r + 1);
-      } else {
-        TA_RG2_LOAD((r + 1) & 1, r + 1);
-      }
-    }
+    if (!DEEP) TA_RG2_LOAD_ROW(r + 1);
     const bool rv = r < R ? top_ok : (r >= ROWS - R ? bot_ok : true);
     if (rv) {
       float v[4 * NV];
@@ -619,6 +622,7 @@ __device__ __forceinline__ void rg2_walk(const float* __restrict__ g, float* __r
       a1 = fmaf(wp.kr[KS - 1], v[OFF + KS], a1);
       b1 = fmaf(wp.kr[KS - 1], v[OFF + 2 + KS], b1);
       const f32x2_t t0 = pack2(a0, a1), t1 = pack2(b0, b1);
+      if (DEEP) TA_RG2_LOAD_ROW(r + 2);
       // column pass: this row is tap i of output row y = r - i
 #pragma unroll
       for (int i = 0; i < KS; ++i) {
@@ -630,8 +634,11 @@ __device__ __forceinline__ void rg2_walk(const float* __restrict__ g, float* __r
           else { acc0[s] = ffma2(ww, t0, acc0[s]); acc1[s] = ffma2(ww, t1, acc1[s]); }
         }
       }
-    } else if (r < BHR) {                                  // the first tap of output row r never comes: start it at +0
-      acc0[r % KS] = pack2(0.f, 0.f); acc1[r % KS] = pack2(0.f, 0.f);
+    } else {
+      if (DEEP) TA_RG2_LOAD_ROW(r + 2);
+      if (r < BHR) {                                       // the first tap of output row r never comes: start it at +0
+        acc0[r % KS] = pack2(0.f, 0.f); acc1[r % KS] = pack2(0.f, 0.f);
+      }
     }
     if (r >= KS - 1) {
       const int s = (r - (KS - 1)) % KS;
@@ -640,6 +647,7 @@ __device__ __forceinline__ void rg2_walk(const float* __restrict__ g, float* __r
       *reinterpret_cast<float4*>(op0 + (r - (KS - 1)) * W) = make_float4(o0, o1, o2, o3);
     }
   }
+#undef TA_RG2_LOAD_ROW
 #undef TA_RG2_LOAD
 }
 
@@ -647,7 +655,7 @@ __device__ __forceinline__ void rg2_walk(const float* __restrict__ g, float* __r
 // their own with unconditional loads, the edge windows in trailing CTAs — measured slower: the few edge warps stream 70 KB of
 // straight-line code that no other warp on their SM has brought into the instruction cache (ncu: 83 % of their stall samples
 // are no_instruction) and run 4x longer than the interior warps.
-template <int KS, int BHR, bool SPLIT, int WC>
+template <int KS, int BHR, bool SPLIT, int WC, bool DEEP>
 __global__ void __launch_bounds__(128, 4) dwconv_sep_rg2_kernel(const float* __restrict__ g, const __grid_constant__ SepWeights2<KS> wp,
                                                              float* __restrict__ out, int H, int W, int nbands, int n_int_blocks,
                                                              int64_t n_int, int64_t n_edge, int prefetch) {
@@ -659,21 +667,21 @@ __global__ void __launch_bounds__(128, 4) dwconv_sep_rg2_kernel(const float* __r
     if (item >= n_int) return;
     const int q = (int)(item % Q);
     const int64_t pb = item / Q;
-    rg2_walk<KS, BHR, true, WC>(g, out, wp, (int)(pb / nbands), (int)(pb % nbands), nbands, q, H, W, prefetch);
+    rg2_walk<KS, BHR, true, WC, DEEP>(g, out, wp, (int)(pb / nbands), (int)(pb % nbands), nbands, q, H, W, prefetch);
   } else if ((int)blockIdx.x < n_int_blocks) {
     const int64_t item = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
     if (item >= n_int) return;
     const int QI = Q - NEL - NER;
     const int q = NEL + (int)(item % QI);
     const int64_t pb = item / QI;
-    rg2_walk<KS, BHR, false, WC>(g, out, wp, (int)(pb / nbands), (int)(pb % nbands), nbands, q, H, W, prefetch);
+    rg2_walk<KS, BHR, false, WC, DEEP>(g, out, wp, (int)(pb / nbands), (int)(pb % nbands), nbands, q, H, W, prefetch);
   } else {
     const int64_t item = (int64_t)(blockIdx.x - n_int_blocks) * blockDim.x + threadIdx.x;
     if (item >= n_edge) return;
     const int e = (int)(item % (NEL + NER));
     const int64_t pb = item / (NEL + NER);
     const int q = e < NEL ? e : Q - (NEL + NER) + e;
-    rg2_walk<KS, BHR, true, WC>(g, out, wp, (int)(pb / nbands), (int)(pb % nbands), nbands, q, H, W, prefetch);
+    rg2_walk<KS, BHR, true, WC, DEEP>(g, out, wp, (int)(pb / nbands), (int)(pb % nbands), nbands, q, H, W, prefetch);
   }
 }
 
@@ -691,15 +699,19 @@ int launch_rg2(const float* g, const float* kcol_host, const float* krow_host, f
     const int64_t n_int = pbs * (Q - NE), n_edge = pbs * NE;
     const int64_t bi = (n_int + 127) / 128, be = (n_edge + 127) / 128;
     TA_REQUIRE(bi + be <= 0x7fffffff, "ta_dwconv2d_sep: too many work items");
-    dwconv_sep_rg2_kernel<KS, BHR, true, 0><<<(unsigned)(bi + be), 128, 0, s>>>(g, w, out, H, W, nbands, (int)bi, n_int, n_edge, pf);
+    dwconv_sep_rg2_kernel<KS, BHR, true, 0, false><<<(unsigned)(bi + be), 128, 0, s>>>(g, w, out, H, W, nbands, (int)bi, n_int, n_edge, pf);
   } else {
     const int64_t items = pbs * Q;
     const int64_t blocks = (items + 127) / 128;
     TA_REQUIRE(blocks <= 0x7fffffff, "ta_dwconv2d_sep: too many work items");
-    if (W == 224 && tune_get("tim.wconst", 1) != 0)
-      dwconv_sep_rg2_kernel<KS, BHR, false, 224><<<(unsigned)blocks, 128, 0, s>>>(g, w, out, H, W, nbands, 0, items, 0, pf);
-    else
-      dwconv_sep_rg2_kernel<KS, BHR, false, 0><<<(unsigned)blocks, 128, 0, s>>>(g, w, out, H, W, nbands, 0, items, 0, pf);
+    if (W == 224 && tune_get("tim.wconst", 1) != 0) {
+      if (tune_get("tim.deep", 1) != 0)
+        dwconv_sep_rg2_kernel<KS, BHR, false, 224, true><<<(unsigned)blocks, 128, 0, s>>>(g, w, out, H, W, nbands, 0, items, 0, pf);
+      else
+        dwconv_sep_rg2_kernel<KS, BHR, false, 224, false><<<(unsigned)blocks, 128, 0, s>>>(g, w, out, H, W, nbands, 0, items, 0, pf);
+    } else {
+      dwconv_sep_rg2_kernel<KS, BHR, false, 0, false><<<(unsigned)blocks, 128, 0, s>>>(g, w, out, H, W, nbands, 0, items, 0, pf);
+    }
   }
   count_launch();
   return check_launch("ta_dwconv2d_sep[rg2]");
