@@ -806,6 +806,12 @@ def run_kernels(args):
         _lib.tune_set("dim.impl", impl); _lib.tune_set("dim.bwd", bwd); _lib.tune_set("dim.fwdtab", fwdtab)
         add("dim_fwd [%s]" % tag, 8, lambda: be.dim(x, 235, 246, 5, 6, True))
         add("dim_bwd [%s]" % tag, 8, lambda: be.dim(g, 235, 246, 5, 6, False))
+    _lib.tune_set("dim.impl", 4)
+    for rb, st in ((16, 1), (16, 0), (32, 1), (32, 0)):
+        _lib.tune_set("dim.walk_rb", rb); _lib.tune_set("dim.walk_stage", st)
+        add("dim_fwd [source-driven walk, %d-row bands, source rows %s]" % (rb, "staged by TMA" if st else "from global memory"), 8,
+            lambda: be.dim(x, 235, 246, 5, 6, True))
+    _lib.tune_set("dim.walk_rb", 16); _lib.tune_set("dim.walk_stage", 1)
     _lib.tune_set("dim.impl", 3); _lib.tune_set("dim.sepconst", 0)
     add("dim_fwd [separable passes, run-time pitches]", 8, lambda: be.dim(x, 235, 246, 5, 6, True))
     add("dim_bwd [separable passes, run-time pitches]", 8, lambda: be.dim(g, 235, 246, 5, 6, False))

@@ -158,10 +158,10 @@ def _dim_cases():
     return D, sorted({k.rsplit("_", 1)[0] for k in D.files})
 
 
-@pytest.fixture(params=[(2, 0, 0, 1), (3, 0, 0, 1), (3, 0, 1, 0), (1, 0, 0, 1), (1, 1, 1, 1), (0, 0, 0, 1)],
-                ids=["default", "sep", "sep-wstab-rtpitch", "direct", "direct-gather-wstab", "fourpass"])
+@pytest.fixture(params=[(2, 0, 0, 1), (4, 0, 0, 1), (4, 0, 1, 0), (3, 0, 0, 1), (3, 0, 1, 0), (1, 0, 0, 1), (1, 1, 1, 1), (0, 0, 0, 1)],
+                ids=["default", "walk", "walk-wstab-rtpitch", "sep", "sep-wstab-rtpitch", "direct", "direct-gather-wstab", "fourpass"])
 def dim_impl(request):
-    """All generations of the DIM kernels must meet the same parity bar: the default (register-carried forward, separable-pass adjoint),
+    """All generations of the DIM kernels must meet the same parity bar: the default (register-carried forward, separable-pass adjoint), the source-driven forward walk,
     the separable-pass kernels of csrc/dim_direct.cu in both directions (with compile-time and with run-time pitches), the
     second-generation kernels of the same file (forward with its tables as
     kernel parameters, adjoint = gather + scatter with the tables in the workspace; alternative: forward tables in the workspace,

@@ -73,12 +73,14 @@ struct FwdTabParam {
   DimTabF t;
   __device__ __forceinline__ const DimTabF& get() const { return t; }
   __device__ __forceinline__ Geo geo(const Geo& g) const { return g; }
+  __device__ __forceinline__ Geo geow(const Geo& g) const { return g; }
   __device__ __forceinline__ bool identity() const { return false; }
 };
 struct FwdTabPtr {
   const DimTabF* p;
   __device__ __forceinline__ const DimTabF& get() const { return *p; }
   __device__ __forceinline__ Geo geo(const Geo& g) const { return g; }
+  __device__ __forceinline__ Geo geow(const Geo& g) const { return g; }
   __device__ __forceinline__ bool identity() const { return false; }
 };
 // the draw comes from device memory: packs[min(*it, n - 1)] (one captured graph, a new draw per replay)
@@ -87,6 +89,7 @@ struct FwdTabDyn {
   __device__ __forceinline__ const DimPack& pk() const { const int i = *it; return packs[i < n - 1 ? (i < 0 ? 0 : i) : n - 1]; }
   __device__ __forceinline__ const DimTabF& get() const { return pk().tf; }
   __device__ __forceinline__ Geo geo(const Geo&) const { return pk().gf; }
+  __device__ __forceinline__ Geo geow(const Geo&) const { return pk().gw; }
   __device__ __forceinline__ bool identity() const { return pk().identity != 0; }
 };
 
@@ -655,6 +658,165 @@ __global__ void __launch_bounds__(kThreads) dim_fwd_sep_kernel(const float* __re
   }
 }
 
+// ---- forward, source-driven walk (default) ----------------------------------------------------------------------------------
+// Same data movement as dim_fwd_direct_kernel (every horizontal lerp computed once and carried in a register to the destination
+// rows that use it; the intermediate written once), but driven by the SOURCE rows: a thread owns one destination column and walks
+// the band's source rows in order with static addressing (hot shape: [register + immediate]); hcur = hl(row r) costs 2 LDS + 2
+// FP; a per-CTA step table says which destination rows complete at source row r (those whose second tap is r: at most two at
+// DIM's resize rates — checked on the host, other geometries keep the kernel above) and with which vertical weight, so a step
+// is one broadcast LDS.128, two uniform branches and, per emitted row, 1 FADD + 2 FP + 1 store. No tap decoding, row cache or
+// address arithmetic per element. The intermediate band is laid out as rows / columns of the PADDED image y2 (zero-filled first),
+// so the second resize addresses it with its taps directly. Same hl / vl expressions on the same operands → bit-identical.
+struct __align__(16) StepF { int n; float l1a; float l0a; float l1b; };    // destination rows completing at this source row (0..2)
+
+struct SinkS {                                     // destination rows in shared memory
+  uint32_t cur, pitch;
+  __device__ __forceinline__ void put(float v) { sts_f32(cur, v); cur += pitch; }
+};
+struct SinkG {                                     // destination rows in global memory (coalesced across the CTA's columns)
+  float* cur; int pitch;
+  __device__ __forceinline__ void put(float v) { *cur = v; cur += pitch; }
+};
+
+template <int MODE, class Sink>
+__device__ __forceinline__ void walk_step(const int4& d, float hprev, float hcur, Sink& sink) {
+  if (d.x != 0) {
+    sink.put(vl<MODE>(__int_as_float(d.z), __int_as_float(d.y), hprev, hcur));
+    if (d.x > 1) {
+      const float l1 = __int_as_float(d.w), l0 = sub_rn(1.0f, l1);
+      sink.put(vl<MODE>(l0, l1, hprev, hcur));
+    }
+  }
+}
+
+// tail_l1 >= 0: the band ends with the destination row whose two taps are both the LAST source row (ATen clamps i1 at the image
+// edge): it completes after everything else, from hcur alone
+template <int MODE, int SPC, bool GSRC, class Sink>
+__device__ __forceinline__ void walk_rows(const float* __restrict__ pa, const float* __restrict__ pb, float w0, float w1, int rows,
+                                          const StepF* __restrict__ prog, int src_pitch_rt, float tail_l1, Sink sink) {
+  const int sp = SPC ? SPC : src_pitch_rt;
+  float hprev = 0.0f, hcur = 0.0f;
+  int r = 0;
+  for (; r + 4 <= rows; r += 4, pa += 4 * sp, pb += 4 * sp, prog += 4) {
+    float a[4], b[4];
+#pragma unroll
+    for (int k = 0; k < 4; ++k) { a[k] = GSRC ? __ldg(pa + k * sp) : pa[k * sp]; b[k] = GSRC ? __ldg(pb + k * sp) : pb[k * sp]; }
+#pragma unroll
+    for (int k = 0; k < 4; ++k) {
+      hprev = hcur; hcur = hl<MODE>(w0, w1, a[k], b[k]);
+      walk_step<MODE>(*reinterpret_cast<const int4*>(prog + k), hprev, hcur, sink);
+    }
+  }
+  for (; r < rows; ++r, pa += sp, pb += sp, ++prog) {
+    hprev = hcur; hcur = hl<MODE>(w0, w1, GSRC ? __ldg(pa) : pa[0], GSRC ? __ldg(pb) : pb[0]);
+    walk_step<MODE>(*reinterpret_cast<const int4*>(prog), hprev, hcur, sink);
+  }
+  if (tail_l1 >= 0.0f) sink.put(vl<MODE>(sub_rn(1.0f, tail_l1), tail_l1, hcur, hcur));
+}
+
+// smem: bufC [c2_rows * P] y2 band | progA [a_rows] | progB [c2_rows];  c2_rows = gm.pad. The source rows are read straight from
+// global memory (read-only path; a column's two taps and its neighbours' share L1 lines): staging them cost 33 KB per CTA, i.e.
+// 3 instead of 5 resident CTAs per SM at 32-row bands.
+// RBW: output rows per CTA (16 or 32); STAGE: the source rows are staged in shared memory by one bulk-TMA copy (else read straight
+// from global memory)
+template <int MODE, class TR, int SC, int PC, int RBW, bool STAGE>
+__global__ void __launch_bounds__(kThreads) dim_fwd_walk_kernel(const float* __restrict__ x, float* __restrict__ out,
+                                                                const __grid_constant__ TR tr, const Geo gm_in) {
+  const DimTabF& tab = tr.get();
+  const Geo gm = tr.geow(gm_in);
+  extern __shared__ __align__(128) unsigned char smem_raw[];
+  __shared__ float s_tail[2];
+  __shared__ __align__(8) uint64_t s_bar;
+  const int tid = threadIdx.x;
+  if (tr.identity()) {                                   // the coin said "return x" (dim.py:47-48): this band is a copy
+    const int S0 = gm.S, r0 = blockIdx.x * RBW, r1 = min(r0 + RBW, S0);
+    const float4* xp0 = reinterpret_cast<const float4*>(x + (int64_t)blockIdx.y * S0 * S0);
+    float4* op0 = reinterpret_cast<float4*>(out + (int64_t)blockIdx.y * S0 * S0);
+    for (int e = (r0 * S0 >> 2) + tid; e < (r1 * S0 >> 2); e += kThreads) op0[e] = __ldg(xp0 + e);
+    return;
+  }
+  const int S = SC ? SC : gm.S, rnd = gm.rnd, top = gm.top, left = gm.left;
+  const int P = PC ? PC : sep_pitch(S, gm.R);
+  const int c2_rows = gm.pad;
+  float* bufA = reinterpret_cast<float*>(smem_raw);
+  float* bufC = bufA + (STAGE ? (size_t)gm.a_rows * S : 0);
+  StepF* progA = reinterpret_cast<StepF*>(bufC + (size_t)c2_rows * P);
+  StepF* progB = progA + gm.a_rows;
+
+  const int oy0 = blockIdx.x * RBW;
+  const int oy1 = min(oy0 + RBW, S) - 1;                 // inclusive
+  const int nb = oy1 - oy0 + 1;
+  const float* xp = x + (int64_t)blockIdx.y * S * S;
+  float* op = out + (int64_t)blockIdx.y * S * S;
+
+  const int pr0 = tap_i0(tab.t2[oy0]), pr1 = tap_i1(tab.t2[oy1]);
+  const int nC = pr1 - pr0 + 1;                         // rows of y2 this band reads
+  const int q0 = max(pr0 - top, 0), q1 = min(pr1 - top, rnd - 1);
+  if (q0 > q1) {                                         // the band maps entirely into the padding: vl(hl(0,0), hl(0,0)) = +0
+    float4* o4 = reinterpret_cast<float4*>(op + (int64_t)oy0 * S);
+    for (int e = tid; e < (nb * S >> 2); e += kThreads) o4[e] = make_float4(0.f, 0.f, 0.f, 0.f);
+    return;
+  }
+  const int nq = q1 - q0 + 1;
+  const int sr0 = tap_i0(tab.t1[q0]);
+  const int nsr = tap_i1(tab.t1[q1]) - sr0 + 1;
+
+  if (STAGE && tid == 0) {
+    mbar_init(&s_bar, 1);
+    mbar_fence_init();
+    const uint32_t bytes = (uint32_t)(nsr * S * 4);
+    mbar_expect_tx(&s_bar, bytes);
+    tma_bulk_g2s(bufA, xp + (int64_t)sr0 * S, bytes, &s_bar);
+  }
+  {                                                      // zero the y2 band (the padding) and the step tables
+    float4* c4 = reinterpret_cast<float4*>(bufC);
+    for (int e = tid; e < (nC * P >> 2); e += kThreads) c4[e] = make_float4(0.f, 0.f, 0.f, 0.f);
+    int4* p4 = reinterpret_cast<int4*>(progA);
+    for (int e = tid; e < gm.a_rows + c2_rows; e += kThreads) p4[e] = make_int4(0, 0, 0, 0);
+    if (tid < 2) s_tail[tid] = -1.0f;
+  }
+  __syncthreads();
+  for (int q = tid; q < nq; q += kThreads) {             // y1 row q0 + q completes at source row i1
+    const TapE th = tab.t1[q0 + q];
+    const int ra = tap_i0(th) - sr0, rb = tap_i1(th) - sr0;
+    if (ra == rb) { s_tail[0] = th.l1; continue; }       // clamped at the image edge: the band's last row (host-checked: at most one)
+    const int rank = (q > 0 && tap_i1(tab.t1[q0 + q - 1]) - sr0 == rb) ? 1 : 0;
+    if (rank) progA[rb].l1b = th.l1; else { progA[rb].l1a = th.l1; progA[rb].l0a = sub_rn(1.0f, th.l1); }
+    atomicAdd(&progA[rb].n, 1);
+  }
+  for (int r = tid; r < nb; r += kThreads) {             // output row oy0 + r completes at y2 row i1
+    const TapE th = tab.t2[oy0 + r];
+    const int ya = tap_i0(th) - pr0, yb = tap_i1(th) - pr0;
+    if (ya == yb) { s_tail[1] = th.l1; continue; }
+    const int rank = (r > 0 && tap_i1(tab.t2[oy0 + r - 1]) - pr0 == yb) ? 1 : 0;
+    if (rank) progB[yb].l1b = th.l1; else { progB[yb].l1a = th.l1; progB[yb].l0a = sub_rn(1.0f, th.l1); }
+    atomicAdd(&progB[yb].n, 1);
+  }
+  __syncthreads();
+  if (STAGE) mbar_wait(&s_bar, 0);
+
+  // phase A: y1 rows q0 .. q1 into rows (q + top - pr0), columns (left + c) of the y2 band
+  for (int c = tid; c < rnd; c += kThreads) {
+    const TapE tw = tab.t1[c];
+    const float wl1 = tw.l1, wl0 = sub_rn(1.0f, wl1);
+    SinkS sink{smem_u32(bufC + (size_t)(q0 + top - pr0) * P + left + c), (uint32_t)P * 4};
+    if (STAGE) {
+      walk_rows<MODE, SC, false>(bufA + tap_i0(tw), bufA + tap_i1(tw), wl0, wl1, nsr, progA, S, s_tail[0], sink);
+    } else {
+      const float* src = xp + (int64_t)sr0 * S;
+      walk_rows<MODE, SC, true>(src + tap_i0(tw), src + tap_i1(tw), wl0, wl1, nsr, progA, S, s_tail[0], sink);
+    }
+  }
+  __syncthreads();
+  // phase B: output rows oy0 .. oy1 straight to global memory
+  for (int c = tid; c < S; c += kThreads) {
+    const TapE tw = tab.t2[c];
+    const float wl1 = tw.l1, wl0 = sub_rn(1.0f, wl1);
+    SinkG sink{op + (int64_t)oy0 * S + c, S};
+    walk_rows<MODE, PC, false>(bufC + tap_i0(tw), bufC + tap_i1(tw), wl0, wl1, nC, progB, P, s_tail[1], sink);
+  }
+}
+
 // 4 adjacent columns of one destination row of a transposed vertical pass: sum over the row's inverse range
 __device__ __forceinline__ float4 fma4(float w, const float4& v, const float4& a) {
   return make_float4(fmaf(w, v.x, a.x), fmaf(w, v.y, a.y), fmaf(w, v.z, a.z), fmaf(w, v.w, a.w));
@@ -885,6 +1047,40 @@ bool dim_direct_ok(int S, int rnd, int R) { return S <= kDimMaxS && R <= kDimMax
 size_t dim_direct_ws_bytes() { return sizeof(DimTabB) > sizeof(DimTabF) ? sizeof(DimTabB) : sizeof(DimTabF); }
 
 // exact band maxima of one draw (rows of y1 / of the source a forward band needs; rows of g1 / of gout an adjoint band needs)
+// band maxima of the walk (RBW output rows per CTA): source rows and y2 rows one band reads; false when some source row
+// completes more than two destination rows (then the source-driven walk does not apply)
+static bool walk_geo(const DimTabF& tab, int S, int rnd, int top, int RBW, int* a_rows_, int* c2_rows_) {
+  int c2 = 1, a_rows = 1;
+  for (int oy0 = 0; oy0 < S; oy0 += RBW) {
+    const int oy1 = (oy0 + RBW < S ? oy0 + RBW : S) - 1;
+    const int pr0 = h_i0(tab.t2[oy0]), pr1 = h_i1(tab.t2[oy1]);
+    if (pr1 - pr0 + 1 > c2) c2 = pr1 - pr0 + 1;
+    const int q0 = pr0 - top > 0 ? pr0 - top : 0, q1 = pr1 - top < rnd - 1 ? pr1 - top : rnd - 1;
+    if (q0 > q1) continue;
+    const int nsr = h_i1(tab.t1[q1]) - h_i0(tab.t1[q0]) + 1;
+    if (nsr > a_rows) a_rows = nsr;
+  }
+  for (int stage = 0; stage < 2; ++stage) {
+    const TapE* t = stage ? tab.t2 : tab.t1;
+    const int n = stage ? S : rnd;
+    int run = 1;
+    for (int d = 1; d < n; ++d) {
+      run = (h_i1(t[d]) == h_i1(t[d - 1])) ? run + 1 : 1;
+      if (run > 2) return false;
+    }
+    for (int d = 0; d + 1 < n; ++d)
+      if (h_i0(t[d]) == h_i1(t[d])) return false;           // a clamped tap (i0 == i1) anywhere but at the last destination index
+  }
+  *a_rows_ = a_rows; *c2_rows_ = c2;
+  return true;
+}
+constexpr int kWalkRB = 16;          // defaults of the walk (the draw packs carry the geometry of THIS configuration)
+constexpr bool kWalkStage = true;
+static size_t fwd_walk_smem(int S, int R, int a_rows, int c2_rows, bool stage) {
+  return sizeof(float) * ((stage ? (size_t)a_rows * S : 0) + (size_t)c2_rows * sep_pitch(S, R)) + 16 * (size_t)(a_rows + c2_rows);
+}
+static bool walk_enabled(int S, bool tma) { return tma && S % 4 == 0 && tune_get("dim.impl", 2) == 4; }
+
 static void fwd_tables(int S, int rnd, int R, int top, DimTabF& tab, int* a_rows_, int* c_rows_) {
   host_taps(R, S, tab.t2);
   host_taps(S, rnd, tab.t1);
@@ -934,12 +1130,12 @@ static size_t bwd_smem(int S, int rnd, int u_rows, int g_rows) {
   return ((sizeof(float) * ((size_t)u_rows * S + (size_t)g_rows * rnd) + 15) & ~(size_t)15) + 16 * (size_t)(u_rows + g_rows);
 }
 // the separable kernels (dim_fwd_sep_kernel / dim_bwd_sep_kernel): S % 4 == 0
-// dim.impl 2 (default): the separable passes where they measured faster — the adjoint (50 us against 56 us at B = 64) — and the
-// register-carried forward of the second generation (34 us against 40 us); 3: separable passes in both directions; 1: second generation
-// in both directions; 0: the four-pass kernels of dim.cu
+// dim.impl 2 (default): forward = second-generation register-carried kernel (34 us at B = 64; the separable passes need 40 us, the
+// source-driven walk 32-34 us), adjoint = separable passes (48-50 us against 56 us); 3: separable passes in both directions;
+// 4: source-driven walk forward + separable adjoint; 1: second generation in both directions; 0: the four-pass kernels of dim.cu
 static bool sep_enabled(int S, bool tma, bool forward) {
   const int impl = tune_get("dim.impl", 2);
-  return tma && S % 4 == 0 && (impl == 3 || (impl == 2 && !forward));
+  return tma && S % 4 == 0 && (impl == 3 || ((impl == 2 || impl == 4) && !forward));
 }
 static bool sep_hot(int S, int R) { return S == 224 && sep_pitch(S, R) == 248 && tune_get("dim.sepconst", 1) != 0; }
 static size_t fwd_sep_smem(int S, int R, int a_rows, int c_rows) {
@@ -961,23 +1157,25 @@ static size_t bwd_sep_smem(int S, int R, int u_rows, int g_rows, int wext) {
 int dim_pack_build(DimPack* pack, int S, int rnd, int R, int top, int left, int identity) {
   memset(pack, 0, sizeof(DimPack));
   pack->identity = identity ? 1 : 0;
-  if (identity) { pack->gf = Geo{S, S, S, 0, 0, 1, 1, 0}; pack->gb = pack->gf; return TA_OK; }
+  if (identity) { pack->gf = Geo{S, S, S, 0, 0, 1, 1, 0}; pack->gb = pack->gf; pack->gw = pack->gf; return TA_OK; }
   int a = 1, c = 0, u = 1, g = 1;
   fwd_tables(S, rnd, R, top, pack->tf, &a, &c);
   bwd_tables(S, rnd, R, top, pack->tb, &u, &g);
   pack->gf = Geo{S, rnd, R, top, left, a, c, 0};
+  { int aw = 1, cw = 0; const bool ok = walk_geo(pack->tf, S, rnd, top, kWalkRB, &aw, &cw); pack->gw = Geo{S, rnd, R, top, left, aw, 0, ok ? cw : 0}; }
   pack->gb = Geo{S, rnd, R, top, left, u, g, inverse_wext(pack->tb, S, R)};
   return TA_OK;
 }
 
 // shared memory that serves every draw (rnd, top) DIM can make at (S, R): scanned once per (S, R)
-void dim_dyn_smem(int S, int R, size_t* fwd_bytes, size_t* bwd_bytes, size_t* fwd_sep_bytes, size_t* bwd_sep_bytes) {
+void dim_dyn_smem(int S, int R, size_t* fwd_bytes, size_t* bwd_bytes, size_t* fwd_sep_bytes, size_t* bwd_sep_bytes, size_t* fwd_walk_bytes) {
   static thread_local int cS = 0, cR = 0;
-  static thread_local size_t cf = 0, cb = 0, cfs = 0, cbs = 0;
+  static thread_local size_t cf = 0, cb = 0, cfs = 0, cbs = 0, cfw = 0;
   if (cS != S || cR != R) {
     static thread_local DimTabF tf;
     static thread_local DimTabB tb;
-    size_t mf = 0, mb = 0, mfs = 0, mbs = 0;
+    size_t mf = 0, mb = 0, mfs = 0, mbs = 0, mfw = 0;
+    bool walk_ok = S % 4 == 0;
     const int lo = S < R ? S : R, hi = S < R ? R : S;
     const int hi_excl = hi > lo ? hi : lo + 1;              // dim.py:54 draws rnd from [min(S,R), max(S,R)), top / left from [0, R - rnd)
     for (int rnd = lo; rnd < hi_excl; ++rnd) {
@@ -993,21 +1191,36 @@ void dim_dyn_smem(int S, int R, size_t* fwd_bytes, size_t* bwd_bytes, size_t* fw
           const size_t fs = fwd_sep_smem(S, R, a, c), bs = bwd_sep_smem(S, R, u, g, inverse_wext(tb, S, R));
           if (fs > mfs) mfs = fs;
           if (bs > mbs) mbs = bs;
+          int aw = 1, c2 = 0;
+          if (!walk_geo(tf, S, rnd, top, kWalkRB, &aw, &c2)) walk_ok = false;
+          else { const size_t fw = fwd_walk_smem(S, R, aw, c2, kWalkStage); if (fw > mfw) mfw = fw; }
         }
       }
     }
-    cS = S; cR = R; cf = mf; cb = mb; cfs = mfs; cbs = mbs;
+    cS = S; cR = R; cf = mf; cb = mb; cfs = mfs; cbs = mbs; cfw = walk_ok ? mfw : 0;   // 0: some draw does not fit the walk
   }
   *fwd_bytes = cf; *bwd_bytes = cb;
   if (fwd_sep_bytes) *fwd_sep_bytes = cfs;
   if (bwd_sep_bytes) *bwd_sep_bytes = cbs;
+  if (fwd_walk_bytes) *fwd_walk_bytes = cfw;
 }
 
 int dim_fwd_dyn(const float* x, float* out, int planes, int S, int R, const DimPack* packs, int n_packs, const int* it, bool tma,
                 cudaStream_t stream) {
-  size_t smem, sb, smem_s, sb_s;
-  dim_dyn_smem(S, R, &smem, &sb, &smem_s, &sb_s);
+  size_t smem, sb, smem_s, sb_s, smem_w;
+  dim_dyn_smem(S, R, &smem, &sb, &smem_s, &sb_s, &smem_w);
   dim3 grid_s((unsigned)((S + RB - 1) / RB), (unsigned)planes);
+  if (walk_enabled(S, tma) && smem_w > 0 && smem_w <= 200 * 1024) {
+    const bool hot = sep_hot(S, R);
+    auto kw = hot ? dim_fwd_walk_kernel<1, FwdTabDyn, 224, 248, kWalkRB, kWalkStage> : dim_fwd_walk_kernel<1, FwdTabDyn, 0, 0, kWalkRB, kWalkStage>;
+    static SmemOptIn optin_w[2] = {};
+    const int rcw = ensure_dyn_smem("ta_dim_fwd_dyn", kw, smem_w, optin_w[hot ? 0 : 1]);
+    if (rcw != TA_OK) return rcw;
+    dim3 grid_w((unsigned)((S + kWalkRB - 1) / kWalkRB), (unsigned)planes);
+    kw<<<grid_w, kThreads, smem_w, stream>>>(x, out, FwdTabDyn{packs, it, n_packs}, Geo{});
+    count_launch();
+    return check_launch("ta_dim_fwd_dyn[walk]");
+  }
   if (sep_enabled(S, tma, true) && aligned16(out) && smem_s <= 200 * 1024) {
     const bool hot = sep_hot(S, R);
     auto ks = hot ? dim_fwd_sep_kernel<1, FwdTabDyn, 224, 248> : dim_fwd_sep_kernel<1, FwdTabDyn, 0, 0>;
@@ -1074,6 +1287,52 @@ int dim_fwd_direct(const float* x, float* out, int planes, int S, int rnd, int R
   }
   Geo gm{S, rnd, R, top, left, a_rows, c_rows, 0};
   dim3 grid((unsigned)((S + RB - 1) / RB), (unsigned)planes);
+  int a_w = 1, c2_rows = 0;
+  const int wrb = tune_get("dim.walk_rb", kWalkRB) == 32 ? 32 : 16;
+  const bool wstage = tune_get("dim.walk_stage", kWalkStage ? 1 : 0) != 0;
+  if (walk_enabled(S, tma) && walk_geo(tab, S, rnd, top, wrb, &a_w, &c2_rows) && fwd_walk_smem(S, R, a_w, c2_rows, wstage) <= 200 * 1024) {
+    const size_t smem_w = fwd_walk_smem(S, R, a_w, c2_rows, wstage);
+    const bool hot = sep_hot(S, R);
+    gm.a_rows = a_w; gm.pad = c2_rows;
+    grid = dim3((unsigned)((S + wrb - 1) / wrb), (unsigned)planes);
+    static SmemOptIn optin_w[80] = {};
+    const int cfg = (wrb == 32 ? 2 : 0) + (wstage ? 1 : 0);
+#define TA_DIM_FWD_WALK_K(MODE_, TR_, ARG_)                                                                        \
+  do {                                                                                                              \
+    void (*k)(const float*, float*, TR_, Geo) = nullptr;                                                            \
+    if (hot) {                                                                                                      \
+      k = cfg == 3 ? dim_fwd_walk_kernel<MODE_, TR_, 224, 248, 32, true> : cfg == 2 ? dim_fwd_walk_kernel<MODE_, TR_, 224, 248, 32, false> \
+        : cfg == 1 ? dim_fwd_walk_kernel<MODE_, TR_, 224, 248, 16, true> : dim_fwd_walk_kernel<MODE_, TR_, 224, 248, 16, false>; \
+    } else {                                                                                                        \
+      k = cfg == 3 ? dim_fwd_walk_kernel<MODE_, TR_, 0, 0, 32, true> : cfg == 2 ? dim_fwd_walk_kernel<MODE_, TR_, 0, 0, 32, false> \
+        : cfg == 1 ? dim_fwd_walk_kernel<MODE_, TR_, 0, 0, 16, true> : dim_fwd_walk_kernel<MODE_, TR_, 0, 0, 16, false>; \
+    }                                                                                                               \
+    const int rc = ensure_dyn_smem("ta_dim_fwd", k, smem_w, optin_w[(MODE_ * 2 + (ws ? 1 : 0)) * 8 + cfg * 2 + (hot ? 0 : 1)]); \
+    if (rc != TA_OK) return rc;                                                                                     \
+    k<<<grid, kThreads, smem_w, stream>>>(x, out, ARG_, gm);                                                        \
+  } while (0)
+#define TA_DIM_FWD_WALK(MODE_, SLOT_)                                                                               \
+  do {                                                                                                              \
+    if (ws) {                                                                                                       \
+      const int ru = upload_tab(tab, ws, stream);                                                                   \
+      if (ru != TA_OK) return ru;                                                                                   \
+      TA_DIM_FWD_WALK_K(MODE_, FwdTabPtr, FwdTabPtr{reinterpret_cast<const DimTabF*>(ws)});                         \
+    } else {                                                                                                        \
+      TA_DIM_FWD_WALK_K(MODE_, FwdTabParam, *reinterpret_cast<const FwdTabParam*>(&tab));                           \
+    }                                                                                                               \
+  } while (0)
+    switch (blend) {
+      case 1: TA_DIM_FWD_WALK(1, 0); break;
+      case 0: TA_DIM_FWD_WALK(0, 1); break;
+      case 2: TA_DIM_FWD_WALK(2, 2); break;
+      case 3: TA_DIM_FWD_WALK(3, 3); break;
+      default: TA_DIM_FWD_WALK(4, 4); break;
+    }
+#undef TA_DIM_FWD_WALK_K
+#undef TA_DIM_FWD_WALK
+    count_launch();
+    return check_launch("ta_dim_fwd[walk]");
+  }
   if (sep_enabled(S, tma, true) && aligned16(out) && fwd_sep_smem(S, R, a_rows, c_rows) <= 200 * 1024) {
     const size_t smem_s = fwd_sep_smem(S, R, a_rows, c_rows);
     const bool hot = sep_hot(S, R);

@@ -33,6 +33,7 @@ struct DimPack {
   int identity;            // the coin said "do not transform": both directions copy
   int pad[3];
   DimGeo gf, gb;           // forward / adjoint geometry (band row maxima of THIS draw)
+  DimGeo gw;               // forward, source-driven walk (32-row bands): a_rows = source rows, pad = y2 rows per band (0: not applicable)
   DimTabF tf;
   DimTabB tb;
 };
@@ -40,7 +41,8 @@ struct DimPack {
 bool dim_direct_ok(int S, int rnd, int R);
 // host: fill `pack` for one draw; shared-memory bytes per CTA that serve EVERY possible draw at (S, R)
 int dim_pack_build(DimPack* pack, int S, int rnd, int R, int top, int left, int identity);
-void dim_dyn_smem(int S, int R, size_t* fwd_bytes, size_t* bwd_bytes, size_t* fwd_sep_bytes = nullptr, size_t* bwd_sep_bytes = nullptr);
+void dim_dyn_smem(int S, int R, size_t* fwd_bytes, size_t* bwd_bytes, size_t* fwd_sep_bytes = nullptr, size_t* bwd_sep_bytes = nullptr,
+                  size_t* fwd_walk_bytes = nullptr);
 int dim_fwd_dyn(const float* x, float* out, int planes, int S, int R, const DimPack* packs, int n_packs, const int* it, bool tma,
                 cudaStream_t stream);
 int dim_bwd_dyn(const float* gout, float* gin, int planes, int S, int R, const DimPack* packs, int n_packs, const int* it, bool tma,
