@@ -227,7 +227,8 @@ def test_normalize_fold_is_bit_identical(name, mean_mode, graph):
         assert bool(getattr(atk, "_graphs", None)) == graph
     assert torch.equal(res[False], res[True])
     if not graph:       # launches of OUR kernels per attack: the fold removes the Normalize forward (and adjoint when deferred)
-        deferred = mean_mode != "aten" and name != "tim"       # in-kernel mean + base get_grad → Normalize's adjoint in the kernel too
+        # Normalize's adjoint inside the tail kernels: default with the 'exact' cluster kernel, opt-in (fold_adjoint) with the torch-order mean
+        deferred = mean_mode in ("exact", "torch+adjoint") and name != "tim"
         assert res[False, "launches"] - res[True, "launches"] == 4 * (2 if deferred else 1) - 1      # one extra Normalize forward up front
     if mean_mode in ("torch", "aten", "torch+adjoint"):
         ref = torch_ref.REF_ZOO[name](torch_ref.ref_wrap_model(net), epoch=4)(x, y)

@@ -31,6 +31,22 @@ for it in range(6):
         be.fused_tail(g, m, m2, d, d2, x, xa, scale, None, 1.0, 1.6 / 255, 16 / 255, 0, 1.0, mean=MEAN, std=STD, emit_normalized=True)
         flush.sum()
         be.abs_mean(g, _lib.TA_MEAN_TORCH)
+    elif which == "final":       # what ships at the end of round 2: the default tail (mean kernel, then the streaming kernel with Normalize
+        # folded, its adjoint left to the backward), the TIM walk, DIM forward / adjoint — captured from the LAST loop iteration
+        import numpy as np
+        from transferattack_b200 import _lib
+        import transferattack_b200.input_transformation.tim as tim
+        MEAN, STD = [0.485, 0.456, 0.406], [0.229, 0.224, 0.225]
+        if it < 5:
+            continue
+        be.fused_tail(g, m, m2, d, d2, x, xa, None, so, 1.0, 1.6 / 255, 16 / 255, 0, 1.0, mean_mode=_lib.TA_MEAN_TORCH, mean=MEAN, std=STD,
+                      emit_normalized=True)
+        flush.sum()
+        k2d, kcol, krow = tim.make_kernel("gaussian", 15)
+        hc, hr = np.stack([kcol] * 3), np.stack([krow] * 3)
+        be.dwconv2d_sep(g, torch.from_numpy(hc).cuda(), torch.from_numpy(hr).cuda(), host=(hc, hr)); flush.sum()
+        be.dim(x, 235, 246, 5, 6, True); flush.sum()
+        be.dim(g, 235, 246, 5, 6, False)
     elif which == "dim":
         be.dim(x, 235, 246, 5, 6, True); be.dim(g, 235, 246, 5, 6, False)
     elif which == "timdim":      # one launch each: TIM with factors as parameters / from device arrays, DIM forward, DIM adjoint
