@@ -298,12 +298,26 @@ def tail_kernel_name(atk, x_dev):
     kmode = atk._mean_kernel_mode(x_dev)
     fold = atk._fold_plan(x_dev, kmode)
     nf = "" if fold is None else (",nf+adjoint" if fold[4] else ",nf")
+    if fold is not None and fold[5]:
+        # the Normalize-adjoint kernel at the end of the backward left the column sums of |g|: the tail only finishes the mean from them
+        return "ta_abs_mean_from_colsums + ta_fused_tail[stream,nf]", 2
     if kmode is None:
         return "ta_fused_tail[stream%s] after ATen abs+mean" % nf, 3
     if kmode == _lib.TA_MEAN_TORCH and x_dev.numel() * 4 <= 64 * 1024 * 1024 and int(os.environ.get("TA_FUSED_STRATEGY", "0")) in (0, 2):
         # csrc/fused_update.cu: a gradient that fits L2 takes the two-launch form (mean kernel, then the flat streaming kernel)
         return "ta_abs_mean_per_sample[torch order%s] + ta_fused_tail[stream%s]" % (", g/std" if (fold is not None and fold[4]) else "", nf), 2
     return "ta_fused_tail[cluster,%s%s]" % ("torch-order mean" if kmode == _lib.TA_MEAN_TORCH else "fp64 mean", nf), 1
+
+
+def outside_note(atk, x_dev):
+    fold = atk._fold_plan(x_dev, atk._mean_kernel_mode(x_dev))
+    if fold is None or fold[4]:
+        return None
+    if fold[5]:
+        return ("Normalize's adjoint g/std at the end of autograd.grad: one ta_normalize_bwd_colsum launch (8 B/elem) that also leaves "
+                "the per-column sums of |g| (20 KB per sample) from which the tail finishes torch's mean — the gradient is not read a "
+                "second time for the mean; standalone timings of that kernel and of plain ta_normalize_bwd: bench.py --kernels")
+    return "Normalize's adjoint g/std: one ta_normalize_bwd launch (8 B/elem) at the end of autograd.grad"
 
 
 def graph_status(atk, requested):
@@ -393,8 +407,7 @@ def run_ours(args, rank, local_rank, world, dist):
                 traffic, traffic_src = ent.get("dram_bytes"), ent.get("source")
         roof = {"bound": "hbm", "kernel": kname, "bracket": "the whole tail of an iteration: everything between autograd.grad and the "
                 "next forward (%d launch%s)" % (tail_launches, "" if tail_launches == 1 else "es"),
-                "outside_the_bracket": ("Normalize's adjoint g/std: one ta_normalize_bwd launch (8 B/elem) at the end of autograd.grad"
-                                        if (atk._fold_plan(x_dev, atk._mean_kernel_mode(x_dev)) or (0, 0, 0, 0, True))[4] is False else None),
+                "outside_the_bracket": outside_note(atk, x_dev),
                 "achieved": achieved, "peak": hbm_peak, "unit": "GB/s", "frac": achieved / hbm_peak, "traffic": traffic,
                 "traffic_source": traffic_src, "peak_source": peak_src, "avg_launch_us": avg_ms * 1e3, "launches_timed": len(k_ms),
                 "algorithmic_bytes_per_launch": FUSED_BYTES_PER_ELEM * n_elem, "share_of_step": float(np.sum(k_ms)) / ms_ev}
@@ -416,6 +429,16 @@ def run_ours(args, rank, local_rank, world, dist):
                            "roofline": {"achieved": ach2, "frac": ach2 / hbm_peak if ach2 else None,
                                         "avg_tail_us": float(np.mean(k2)) * 1e3 if k2 else None}}
         atk.mean_mode = args.mean_mode
+        # same mean mode with the separate torch-order mean kernel (the adjoint kernel does not leave column sums)
+        prev_cs = atk.colsum_adjoint
+        atk.colsum_adjoint = False
+        ms2 = time_attack(atk, x_dev, y_dev, max(3, args.steps // 2), 2, None, device)
+        k2, _ = tail_events(atk, x_dev, y_dev, 3, None, device)
+        ach2 = FUSED_BYTES_PER_ELEM * n_elem / (float(np.mean(k2)) * 1e-3) / 1e9 if k2 else None
+        alts["%s, separate mean kernel (plain ta_normalize_bwd in the backward)" % args.mean_mode] = {
+            "value": B * max(3, args.steps // 2) / (ms2 / 1e3), "kernel": tail_kernel_name(atk, x_dev)[0],
+            "roofline": {"achieved": ach2, "frac": ach2 / hbm_peak if ach2 else None, "avg_tail_us": float(np.mean(k2)) * 1e3 if k2 else None}}
+        atk.colsum_adjoint = prev_cs
         # same mean mode, Normalize's adjoint folded into the tail kernels (2 launches instead of 3; the division then runs twice)
         prev = atk.fold_adjoint
         atk.fold_adjoint = True
@@ -787,6 +810,14 @@ def run_kernels(args):
     _lib.tune_set("fused.strategy", 0)
     add("fused_tail[stream, scale given]", 28, lambda: be.fused_update_linf(g, m, m2, d, d2, x, xa, scale, None, 1.0, a, al, 0, 1.0))
     add("abs_mean_per_sample [torch order]", 4, lambda: be.abs_mean(g, _lib.TA_MEAN_TORCH))
+    std_dev = torch.tensor(STD, device=dev)
+    cs_n = be.colsum_size(B, g[0].numel(), g.device)
+    if cs_n is not None:
+        cs = torch.empty(B * cs_n, device=dev)
+        add("normalize_bwd (Normalize's adjoint, plain)", 8, lambda: be.normalize(g, None, std_dev, False))
+        add("normalize_bwd_colsum (the adjoint + ATen's column sums of |g|)", 8, lambda: be.normalize_bwd_colsum(g, std_dev, cs))
+        add("abs_mean_from_colsums (trees over the column sums; %d floats per sample)" % cs_n, 4, lambda: be.abs_mean_from_colsums(cs, so, B, g[0].numel()),
+            elems=B * cs_n)
     add("ATen reference: g.abs().mean(dim=(1,2,3)) (2 launches)", 12, lambda: g.abs().mean(dim=(1, 2, 3)))
     for cap in (0, 4, 8, 16):
         for un in (1, 2, 4):

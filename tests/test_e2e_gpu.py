@@ -204,7 +204,7 @@ def test_cuda_graph_replay_is_bit_identical(name, kw):
 
 
 @pytest.mark.parametrize("graph", [False, True], ids=["eager", "graph"])
-@pytest.mark.parametrize("mean_mode", ["torch", "aten", "exact", "torch+adjoint"])
+@pytest.mark.parametrize("mean_mode", ["torch", "torch-meankernel", "aten", "exact", "torch+adjoint"])
 @pytest.mark.parametrize("name", ["mifgsm", "ifgsm", "tim"])
 def test_normalize_fold_is_bit_identical(name, mean_mode, graph):
     """SURVEY §8 f1 on the GPU: fused tail emitting the normalised model input (+ Normalize's adjoint in 'exact' mode with
@@ -217,10 +217,14 @@ def test_normalize_fold_is_bit_identical(name, mean_mode, graph):
         atk = make_attack(tab, name, net, epoch=4)
         if mean_mode == "torch+adjoint":                     # the in-kernel torch-order mean WITH Normalize's adjoint in the kernels
             atk.mean_mode = "torch"; atk.fold_adjoint = True
+        elif mean_mode == "torch-meankernel":                # the separate torch-order mean kernel (no column sums from the adjoint)
+            atk.mean_mode = "torch"; atk.colsum_adjoint = False
         else:
             atk.mean_mode = mean_mode
         atk.fold_normalize = fold; atk.use_cuda_graph = graph
         assert (atk._fold_plan(x.cuda()) is not None) == fold
+        if fold:    # the default for 'torch' with the base get_grad: the adjoint kernel leaves the column sums (TIM smooths the gradient → no)
+            assert bool(atk._fold_plan(x.cuda(), atk._mean_kernel_mode(x.cuda()))[5]) == (mean_mode == "torch" and name != "tim")
         before = _lib.launch_count()
         res[fold] = atk(x, y)
         res[fold, "launches"] = _lib.launch_count() - before
@@ -230,7 +234,7 @@ def test_normalize_fold_is_bit_identical(name, mean_mode, graph):
         # Normalize's adjoint inside the tail kernels: default with the 'exact' cluster kernel, opt-in (fold_adjoint) with the torch-order mean
         deferred = mean_mode in ("exact", "torch+adjoint") and name != "tim"
         assert res[False, "launches"] - res[True, "launches"] == 4 * (2 if deferred else 1) - 1      # one extra Normalize forward up front
-    if mean_mode in ("torch", "aten", "torch+adjoint"):
+    if mean_mode in ("torch", "torch-meankernel", "aten", "torch+adjoint"):
         ref = torch_ref.REF_ZOO[name](torch_ref.ref_wrap_model(net), epoch=4)(x, y)
         assert torch.equal(res[True], ref)
     REPORT["fold/%s_%s_%s" % (name, mean_mode, "graph" if graph else "eager")] = {"bit_identical": True}

@@ -349,6 +349,42 @@ def test_abs_mean_torch_order_is_bit_identical_to_torch(be, B, shape):
             assert bits_equal(em, ref), (B, shape, seed)
 
 
+@pytest.mark.parametrize("B,shape", [(1, (3, 224, 224)), (2, (3, 224, 224)), (5, (3, 224, 224)), (64, (3, 224, 224)), (65, (3, 224, 224)),
+                                     (256, (3, 224, 224)), (16, (3, 64, 64)), (8, (3, 384, 384)), (128, (1, 224, 224)), (32, (3, 300, 300)),
+                                     (600, (3, 224, 224)), (4, (4, 64, 64))])
+def test_normalize_adjoint_with_column_sums_is_bit_identical_to_torch(be, B, shape):
+    """ta_normalize_bwd_colsum = Normalize's adjoint (the bits of ta_normalize_bwd, i.e. of torchvision's div_ under autograd) that also
+    leaves ATen's per-virtual-thread column values of |g|; ta_abs_mean_from_colsums finishes the mean from them: together they must
+    equal `(gout / std).abs().mean(dim=(1,2,3))` of the installed torch BIT FOR BIT — the same contract as TA_MEAN_TORCH, with the
+    gradient read once instead of twice."""
+    C = shape[0]
+    std = torch.tensor([0.229, 0.224, 0.225, 0.31][:C], device="cuda")
+    n = int(np.prod(shape))
+    S = be.colsum_size(B, n, torch.device("cuda", 0))
+    assert S is not None, (B, shape)
+    for seed, scale in ((0, 1.0), (1, 1e-4), (2, 3e3)):
+        g = torch.randn((B,) + shape, device="cuda", generator=torch.Generator("cuda").manual_seed(B + seed)) * scale
+        cs = torch.full((B * S,), float("nan"), device="cuda")
+        out = torch.empty(B, device="cuda")
+        gin = be.normalize_bwd_colsum(g, std, cs)
+        assert gin is not None, (B, shape)
+        ref = g / std.view(1, C, 1, 1)
+        assert torch.equal(gin, ref) and torch.equal(gin, be.normalize(g, None, std, False)), (B, shape, seed)
+        mu = be.abs_mean_from_colsums(cs, out, B, n)
+        assert torch.equal(mu, ref.abs().mean(dim=(1, 2, 3))), (B, shape, seed)
+        got = be.abs_mean(gin, __import__("transferattack_b200")._lib.TA_MEAN_TORCH)
+        assert got is not None and torch.equal(mu, got)
+
+
+def test_normalize_adjoint_with_column_sums_declines_what_it_does_not_replay(be):
+    from transferattack_b200 import ops
+    assert be.colsum_size(2, 3 * 299 * 299, torch.device("cuda", 0)) is None           # n % 4 != 0
+    assert be.colsum_size(4, 3 * 32 * 32, torch.device("cuda", 0)) is None             # one warp row per output: not restated
+    std = torch.tensor([0.229, 0.224, 0.225], device="cuda")
+    assert ops.colsum_adjoint_ok(torch.zeros(2, 3, 299, 299, device="cuda"), std) is False
+    assert ops.colsum_adjoint_ok(torch.zeros(6, 3, 224, 224, device="cuda"), std) is True
+
+
 def test_abs_mean_torch_order_declines_what_it_does_not_replay(be):
     from transferattack_b200 import _lib
     # odd row length (head / tail elements take another ATen path), tiny rows (one warp row per output), more partials than fit

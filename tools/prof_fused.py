@@ -47,6 +47,18 @@ for it in range(6):
         be.dwconv2d_sep(g, torch.from_numpy(hc).cuda(), torch.from_numpy(hr).cuda(), host=(hc, hr)); flush.sum()
         be.dim(x, 235, 246, 5, 6, True); flush.sum()
         be.dim(g, 235, 246, 5, 6, False)
+    elif which == "colsum":      # the default tail at the end of round 2: adjoint + column sums, trees, streaming kernel (one iteration's worth)
+        from transferattack_b200 import _lib
+        MEAN, STD = [0.485, 0.456, 0.406], [0.229, 0.224, 0.225]
+        if it < 5:
+            continue
+        std_dev = torch.tensor(STD, device="cuda")
+        cs = torch.empty(B * be.colsum_size(B, g[0].numel(), g.device), device="cuda")
+        gin = be.normalize_bwd_colsum(g, std_dev, cs)
+        be.abs_mean_from_colsums(cs, so, B, g[0].numel())
+        be.fused_tail(gin, m, m2, d, d2, x, xa, so, so, 1.0, 1.6 / 255, 16 / 255, 0, 1.0, mean=MEAN, std=STD, emit_normalized=True)
+        flush.sum()
+        be.normalize(g, None, std_dev, False)
     elif which == "dim":
         be.dim(x, 235, 246, 5, 6, True); be.dim(g, 235, 246, 5, 6, False)
     elif which == "timdim":      # one launch each: TIM with factors as parameters / from device arrays, DIM forward, DIM adjoint

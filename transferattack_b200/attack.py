@@ -138,6 +138,11 @@ class Attack(object):
     #: the IEEE division has to be done in the mean kernel AND in the streaming kernel when folded, so the saving is 4 us per
     #: iteration. Default: not folded for mean_mode 'torch' (the division-free mean kernel), folded for 'exact' (one cluster launch).
     fold_adjoint = {"1": True, "0": False}.get(os.environ.get("TA_B200_FOLD_ADJOINT", ""), None)
+    #: with mean_mode 'torch', the folded Normalize and the base get_grad: the Normalize-adjoint kernel at the end of the backward
+    #: pass also leaves the per-column sums of |g| that torch's mean reduction would form (``ta_normalize_bwd_colsum``), and the
+    #: tail finishes mean|g| from those 20 KB per sample (``ta_abs_mean_from_colsums``) instead of reading the gradient once more.
+    #: Same bits (self-checked per device and shape against torch's ops); False keeps the separate mean kernel.
+    colsum_adjoint = os.environ.get("TA_B200_COLSUM_ADJOINT", "1") == "1"
     #: OPT-IN, NOT THE PARITY PATH. The surrogate's forward/backward runs on a private copy of
     #: the model: 'bnfold' = every eval-mode BatchNorm folded into its convolution (the launch list shows BN inference + BN backward
     #: at 30 % of an iteration), 'bf16' = bf16 / channels_last, 'bnfold+bf16' = both; everything around it — staging, mean|g|,
@@ -240,7 +245,8 @@ class Attack(object):
                 and isinstance(self.alpha, (int, float)) and isinstance(self.decay, (int, float)))
 
     def _fold_plan(self, data, kmode=None):
-        """(pre, net, mean, std, defer) when Normalize can be folded into the fused tail for this batch, else None.
+        """(pre, net, mean, std, defer, colsum) when Normalize can be folded into the fused tail for this batch, else None.
+        defer: Normalize's adjoint is applied inside the tail kernels; colsum: the adjoint kernel leaves the column sums of |g|.
         `kmode`: the in-kernel mean mode (``_mean_kernel_mode``); with one, Normalize's adjoint moves into the kernel too."""
         cls = type(self)
         if not self.fold_normalize or self.fast_mode or cls.get_logits is not Attack.get_logits or cls.transform is not Attack.transform:
@@ -259,7 +265,11 @@ class Attack(object):
         # Normalize's adjoint inside the kernel needs the staged (cluster) form: the sample must fit 8 CTAs' shared memory
         fa = self.fold_adjoint if self.fold_adjoint is not None else (kmode == _lib.TA_MEAN_EXACT)
         defer = fa and kmode is not None and cls.get_grad is Attack.get_grad and C * H * W <= 384 * 1024
-        return pre, m[1], [float(v) for v in pre.mean.tolist()], [float(v) for v in pre.std.tolist()], defer
+        colsum = False
+        if self.colsum_adjoint and not defer and kmode == _lib.TA_MEAN_TORCH and cls.get_grad is Attack.get_grad:
+            pre._buffers_on(data.device)
+            colsum = ops.colsum_adjoint_ok(data, pre.std)
+        return pre, m[1], [float(v) for v in pre.mean.tolist()], [float(v) for v in pre.std.tolist()], defer, colsum
 
     @staticmethod
     def _first_normalized(pre, data, delta, out=None):
@@ -314,13 +324,20 @@ class Attack(object):
             delta = self.update_delta(delta, data, momentum, self.alpha)
         return delta.detach()
 
-    def _tail(self, be, grad, momentum, m_out, delta, delta_out, data, xadv, scale_out, kmode, fold, addend=None, gbar_out=None):
+    def _tail(self, be, grad, momentum, m_out, delta, delta_out, data, xadv, scale_out, kmode, fold, addend=None, gbar_out=None,
+              col_sums=None):
         """get_momentum + update_delta + the next model input as ONE ``ta_fused_tail`` launch. `kmode` None (or a shape the
         in-kernel reduction does not serve): the scale comes from torch's own ``abs().mean`` op and the streaming form runs."""
         norm = {}
         if fold is not None:
             norm = dict(mean=fold[2], std=fold[3], emit_normalized=True, grad_wrt_xn=fold[4])
         with torch.no_grad():
+            if col_sums is not None:       # mean|g| from the column sums the adjoint kernel left (torch's bits), then the streaming form
+                be.abs_mean_from_colsums(col_sums, scale_out, grad.shape[0], grad[0].numel())
+                if not be.fused_tail(grad, momentum, m_out, delta, delta_out, data, xadv, scale_out, scale_out, self.decay, self.alpha,
+                                     self.epsilon, img_min, img_max, gbar_out=gbar_out, **norm):
+                    raise RuntimeError("ta_fused_tail refused the streaming form: %s" % _lib.last_error())
+                return
             if kmode is not None and be.fused_tail(grad, momentum, m_out, delta, delta_out, data, xadv, None, scale_out, self.decay,
                                                    self.alpha, self.epsilon, img_min, img_max, mean_mode=kmode, addend=addend,
                                                    gbar_out=gbar_out, **norm):
@@ -340,15 +357,19 @@ class Attack(object):
         scale_out = torch.empty(data.shape[0], device=data.device, dtype=torch.float32)
         kmode = self._mean_kernel_mode(data)
         fold = self._fold_plan(data, kmode)
+        col_sums = None
         if fold is not None:
-            pre, net, mean, std, defer = fold
+            pre, net, mean, std, defer, colsum = fold
             xadv = self._first_normalized(pre, data, delta)          # holds the NORMALISED model input from here on
+            if colsum:
+                col_sums = torch.empty(data.shape[0] * be.colsum_size(data.shape[0], data[0].numel(), data.device), device=data.device,
+                                       dtype=torch.float32)
         else:
             xadv = torch.empty_like(data)
         momentum, pre_x = None, None
         for _ in range(self.epoch):
             if fold is not None:
-                logits = net(ops.stage_normalized(delta, xadv, pre.std, defer))
+                logits = net(ops.stage_normalized(delta, xadv, pre.std, defer, col_sums))
             else:
                 x = ops.stage_add(data, delta, precomputed=pre_x)
                 logits = self.get_logits(self.transform(x, momentum=0 if momentum is None else momentum))
@@ -358,7 +379,7 @@ class Attack(object):
             if ev is not None:                               # autograd.grad and the next forward), on its stream
                 e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
                 e0.record()
-            self._tail(be, grad, momentum, m_buf, delta, delta, data, xadv, scale_out, kmode, fold)
+            self._tail(be, grad, momentum, m_buf, delta, delta, data, xadv, scale_out, kmode, fold, col_sums=col_sums)
             if ev is not None:
                 e1.record()
                 ev.append((e0, e1))
@@ -370,15 +391,15 @@ class Attack(object):
         """One iteration on the static buffers `st` (this body is what gets captured)."""
         fold = st.get("fold")
         if fold is not None:
-            pre, net, mean, std, defer = fold
-            logits = net(ops.stage_normalized(st["delta"], st["xadv"], pre.std, defer))
+            pre, net, mean, std, defer, colsum = fold
+            logits = net(ops.stage_normalized(st["delta"], st["xadv"], pre.std, defer, st.get("col_sums")))
         else:
             x = ops.stage_add(st["data"], st["delta"], precomputed=st["xadv"])
             logits = self.get_logits(self.transform(x, momentum=st["m"]))
         loss = self.get_loss(logits, st["label"])
         grad = self.get_grad(loss, st["delta"])
         self._tail(ops.backend(), grad, st["m"], st["m"], st["delta"], st["delta"], st["data"], st["xadv"], st["scale_out"],
-                   st["kmode"], fold)
+                   st["kmode"], fold, col_sums=st.get("col_sums"))
         step = getattr(self, "_graph_step", None)       # plugins with per-iteration state on the device (DIM's draw index)
         if step is not None:
             step()
@@ -401,7 +422,8 @@ class Attack(object):
         kmode = self._mean_kernel_mode(data)
         fold = self._fold_plan(data, kmode)
         key = (tuple(data.shape), str(data.device), tuple(label.shape), self.mean_mode, kmode, float(self.alpha), float(self.decay),
-               float(self.epsilon), bool(self.targeted), id(self.model), fold is not None, bool(fold[4]) if fold else False, self.fast_mode)
+               float(self.epsilon), bool(self.targeted), id(self.model), fold is not None, bool(fold[4]) if fold else False,
+               bool(fold[5]) if fold else False, self.fast_mode)
         cache = self.__dict__.setdefault("_graphs", {})
         st = cache.get(key)
         if st is not None:
@@ -412,6 +434,10 @@ class Attack(object):
               "delta": torch.zeros_like(data).requires_grad_(True), "m": torch.zeros_like(data),
               "xadv": torch.empty_like(data), "scale_out": torch.empty(data.shape[0], device=data.device, dtype=torch.float32),
               "fold": fold, "kmode": kmode}
+        if fold is not None and fold[5]:
+            be = ops.backend()
+            st["col_sums"] = torch.empty(data.shape[0] * be.colsum_size(data.shape[0], data[0].numel(), data.device), device=data.device,
+                                         dtype=torch.float32)
         self._graph_reset(st, data, label, delta0)
         cur = torch.cuda.current_stream(data.device)
         side = torch.cuda.Stream(device=data.device)

@@ -55,6 +55,12 @@ int aten_mean_plan(const char* who, int B, int64_t n, int cl, AtenMeanCfg* cfg) 
     return TA_EUNSUPPORTED;
   }
   const int S = bw * bh * cpo;
+  if (cl == 0) {                                   // no cluster mapping wanted (column sums in global memory)
+    cfg->bw = bw; cfg->bh = bh; cfg->cpo = cpo; cfg->nt = bw * bh; cfg->S = S; cfg->W4 = S;
+    cfg->w4_magic = (1ull << 32) / (unsigned long long)S + 1ull;
+    cfg->factor = (float)B / (float)((int64_t)B * n);
+    return TA_OK;
+  }
   if (cl < 1 || S % cl != 0 || S / cl > kAtenMaxW) {
     set_error("%s: TA_MEAN_TORCH: cluster %d does not divide the %d virtual threads into <= %d columns", who, cl, S, kAtenMaxW);
     return TA_EUNSUPPORTED;
@@ -118,7 +124,94 @@ __global__ void __launch_bounds__(kAtenThreads, 2) aten_abs_mean_kernel(const fl
   cluster_sync_all();                         // s_val must outlive every remote read
 }
 
+// Normalize's adjoint gin = gout / std[c] (the bits of ta_normalize_bwd) with the thread <-> data mapping of ATen's mean
+// reduction over gin: CTA (x, b) owns virtual threads [512 x, 512 x + 512) of sample b, thread t the 128-bit vectors t, t + S, ...
+// — so that besides storing gin it can leave that virtual thread's column value of |gin| in col_sums[b * S + t].
+__global__ void __launch_bounds__(kAtenThreads, 3) normalize_bwd_colsum_kernel(const float* __restrict__ gout, const float* __restrict__ std,
+                                                                            float* __restrict__ gin, float* __restrict__ col_sums,
+                                                                            int64_t n, int S, int plane_vec, int C) {
+  const int b = blockIdx.y;
+  const float4* gp = reinterpret_cast<const float4*>(gout + (int64_t)b * n);
+  float4* ip = reinterpret_cast<float4*>(gin + (int64_t)b * n);
+  const int nvec = (int)(n >> 2);
+  const int col = blockIdx.x * kAtenThreads + threadIdx.x;
+  if (col >= S) return;
+  float sd[4];
+#pragma unroll
+  for (int c = 0; c < 4; ++c) sd[c] = c < C ? __ldg(std + c) : 1.0f;
+  const int rows = col < nvec ? (nvec - col + S - 1) / S : 0;
+  ColAcc A;
+  constexpr int NB = 4;
+  for (int j0 = 0; j0 < rows; j0 += NB) {
+    float4 x[NB];
+#pragma unroll
+    for (int u = 0; u < NB; ++u)
+      if (j0 + u < rows) x[u] = __ldg(gp + col + (int64_t)(j0 + u) * S);
+#pragma unroll
+    for (int u = 0; u < NB; ++u)
+      if (j0 + u < rows) {
+        const int v = col + (j0 + u) * S;
+        const float4 t = div4(x[u], pick4(sd, (v >= plane_vec ? 1 : 0) + (v >= 2 * plane_vec ? 1 : 0) + (v >= 3 * plane_vec ? 1 : 0)));
+        ip[v] = t;
+        aten_column_add(A, t);
+      }
+  }
+  col_sums[(int64_t)b * S + col] = aten_column_value(A);
+}
+
+// block_x / block_y / final trees over the S column values of one sample (one CTA per sample)
+// STAGE: the S values are first copied into shared memory with one batch of independent 128-bit loads per thread (one global
+// latency instead of one per pair of block rows), then the trees read them from there
+template <bool STAGE>
+__global__ void __launch_bounds__(kAtenThreads) aten_colsum_tree_kernel(const float* __restrict__ col_sums, float* __restrict__ mean_out,
+                                                                       AtenMeanCfg c) {
+  extern __shared__ __align__(16) float s_cols[];
+  __shared__ float s_row[kAtenThreads];
+  __shared__ float s_blk[kAtenThreads];
+  const float* src = col_sums + (int64_t)blockIdx.x * c.S;
+  float mu;
+  if (STAGE) {
+    const float4* s4 = reinterpret_cast<const float4*>(src);
+    float4* d4 = reinterpret_cast<float4*>(s_cols);
+    for (int i = threadIdx.x; i < (c.S >> 2); i += kAtenThreads) d4[i] = __ldg(s4 + i);
+    __syncthreads();
+    mu = aten_tree_mean_src(c, ColSrcShared{s_cols}, s_row, s_blk);
+  } else {
+    mu = aten_tree_mean_src(c, ColSrcGlobal{src}, s_row, s_blk);
+  }
+  if (threadIdx.x == 0) mean_out[blockIdx.x] = mu;
+}
+
 }  // namespace
+
+int aten_colsum_normalize_bwd(const float* gout, const float* std, float* gin, float* col_sums, int B, int C, int64_t plane, cudaStream_t s) {
+  const int64_t n = (int64_t)C * plane;
+  if (C < 1 || C > 4 || plane % 4 != 0 || !aligned16(gout) || !aligned16(gin) || n >= ((int64_t)1 << 31) || B > 65535) {
+    set_error("ta_normalize_bwd_colsum: needs C <= 4, H*W %% 4 == 0, 16-byte aligned tensors, B <= 65535");
+    return TA_EUNSUPPORTED;
+  }
+  AtenMeanCfg c;
+  const int rc = aten_mean_plan("ta_normalize_bwd_colsum", B, n, 0, &c);
+  if (rc != TA_OK) return rc;
+  dim3 grid((unsigned)((c.S + kAtenThreads - 1) / kAtenThreads), (unsigned)B);
+  normalize_bwd_colsum_kernel<<<grid, kAtenThreads, 0, s>>>(gout, std, gin, col_sums, n, c.S, (int)(plane / 4), C);
+  count_launch();
+  return check_launch("ta_normalize_bwd_colsum");
+}
+
+int aten_colsum_tree(const float* col_sums, float* mean_out, int B, int64_t n, cudaStream_t s) {
+  AtenMeanCfg c;
+  const int rc = aten_mean_plan("ta_abs_mean_from_colsums", B, n, 0, &c);
+  if (rc != TA_OK) return rc;
+  if (c.cpo * c.bh > kAtenThreads) { set_error("ta_abs_mean_from_colsums: %d block rows exceed the tree kernel's %d", c.cpo * c.bh, kAtenThreads); return TA_EUNSUPPORTED; }
+  const size_t smem = sizeof(float) * (size_t)c.S;
+  if (smem <= 48 * 1024 && c.S % 4 == 0 && aligned16(col_sums) && tune_get("reduce.tree_stage", 1) != 0)
+    aten_colsum_tree_kernel<true><<<(unsigned)B, kAtenThreads, smem, s>>>(col_sums, mean_out, c);
+  else
+    aten_colsum_tree_kernel<false><<<(unsigned)B, kAtenThreads, 0, s>>>(col_sums, mean_out, c);
+  count_launch();
+  return check_launch("ta_abs_mean_from_colsums");
+}
 
 int aten_abs_mean_launch(const float* g, float* mean_out, int B, int64_t n, const MeanPre* pre, cudaStream_t s) {
   if (!aligned16(g) || (pre && !aligned16(pre->addend))) {
@@ -153,4 +246,18 @@ extern "C" int ta_aten_mean_policy(int B, int64_t n, int sm_count, int max_threa
   if (block_h) *block_h = bh;
   if (ctas_per_output) *ctas_per_output = cpo;
   return TA_OK;
+}
+
+// Normalize's adjoint gin = gout / std[c] (utils.py:72-79; same bits as ta_normalize_bwd) that ALSO leaves, per sample, the S
+// column values of |gin| of torch's `gin.abs().mean(dim=(1,2,3))` reduction (attack.py:128) in col_sums [B, S], S = block_w *
+// block_h * ctas_per_output of ta_aten_mean_policy: ta_abs_mean_from_colsums then finishes that mean (bit-identical to torch's)
+// from 4*S bytes per sample instead of a pass over the gradient. TA_EUNSUPPORTED outside the replayed launch family.
+extern "C" int ta_normalize_bwd_colsum(const float* gout, const float* std, float* gin, float* col_sums, int B, int C, int64_t plane,
+                                       ta_stream_t stream) {
+  TA_REQUIRE(gout && std && gin && col_sums && B > 0 && C > 0 && plane > 0, "ta_normalize_bwd_colsum: bad arguments");
+  return ta::aten_colsum_normalize_bwd(gout, std, gin, col_sums, B, C, plane, (cudaStream_t)stream);
+}
+extern "C" int ta_abs_mean_from_colsums(const float* col_sums, float* mean_out, int B, int64_t n, ta_stream_t stream) {
+  TA_REQUIRE(col_sums && mean_out && B > 0 && n > 0, "ta_abs_mean_from_colsums: bad arguments");
+  return ta::aten_colsum_tree(col_sums, mean_out, B, n, (cudaStream_t)stream);
 }

@@ -84,17 +84,31 @@ __device__ __forceinline__ float aten_x_tree(float (&a)[K]) {
 // one warp reduces block rows warp, warp+16, ...: row = (virtual block, ty), bw = 32*K values each, gathered through DSMEM
 // (virtual thread vt's value lives in CTA vt / W4 at s_val[vt % W4]). Two rows are in flight per step so that the remote
 // loads of the second overlap the shuffles of the first.
-template <int K>
-__device__ __forceinline__ void aten_rows_x_tree(const AtenMeanCfg& c, const float* s_val, float* s_row, int warp, int lane) {
+// where virtual thread vt's column value lives: in the cluster's shared memory (CTA vt / W4 at s_val[vt % W4]) or in a global
+// array of S values per sample (the column sums a previous kernel left: ta_normalize_bwd_colsum)
+struct ColSrcCluster {
+  const float* s_val; unsigned long long w4_magic; uint32_t W4;
+  __device__ __forceinline__ float ld(uint32_t vt) const {
+    const uint32_t owner = (uint32_t)(((unsigned long long)vt * w4_magic) >> 32);
+    return dsmem_ld_f32(s_val + (vt - owner * W4), owner);
+  }
+};
+struct ColSrcGlobal {
+  const float* cs;
+  __device__ __forceinline__ float ld(uint32_t vt) const { return __ldg(cs + vt); }
+};
+struct ColSrcShared {                                  // the sample's S values copied into this CTA's shared memory first
+  const float* s;
+  __device__ __forceinline__ float ld(uint32_t vt) const { return s[vt]; }
+};
+
+template <int K, class Src>
+__device__ __forceinline__ void aten_rows_x_tree(const AtenMeanCfg& c, const Src& src, float* s_row, int warp, int lane) {
   const int nrows = c.cpo * c.bh;
   const int bw = 32 * K;
   auto fetch = [&](int row, float (&a)[K]) {
 #pragma unroll
-    for (int k = 0; k < K; ++k) {
-      const uint32_t vt = (uint32_t)(row * bw + lane + 32 * k);
-      const uint32_t owner = (uint32_t)(((unsigned long long)vt * c.w4_magic) >> 32);
-      a[k] = dsmem_ld_f32(s_val + (vt - owner * (uint32_t)c.W4), owner);
-    }
+    for (int k = 0; k < K; ++k) a[k] = src.ld((uint32_t)(row * bw + lane + 32 * k));
   };
   int row = warp;
   for (; row + 16 < nrows; row += 32) {
@@ -115,15 +129,16 @@ __device__ __forceinline__ void aten_rows_x_tree(const AtenMeanCfg& c, const flo
 // made visible by a cluster barrier. s_row: >= cpo*bh floats, s_blk: >= max(cpo, 32) floats of CTA-local shared memory.
 // Contains two __syncthreads(); all remote reads of s_val are complete after the first one. Returns the mean (same value in
 // every thread of every CTA). blockDim.x == kAtenThreads.
-__device__ __forceinline__ float aten_tree_mean(const AtenMeanCfg& c, const float* s_val, float* s_row, float* s_blk) {
+template <class Src>
+__device__ __forceinline__ float aten_tree_mean_src(const AtenMeanCfg& c, const Src& src, float* s_row, float* s_blk) {
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
   const int K = c.bw >> 5;                              // 1 .. 16 values per lane before the shuffles
   switch (K) {
-    case 1: aten_rows_x_tree<1>(c, s_val, s_row, warp, lane); break;
-    case 2: aten_rows_x_tree<2>(c, s_val, s_row, warp, lane); break;
-    case 4: aten_rows_x_tree<4>(c, s_val, s_row, warp, lane); break;
-    case 8: aten_rows_x_tree<8>(c, s_val, s_row, warp, lane); break;
-    default: aten_rows_x_tree<16>(c, s_val, s_row, warp, lane); break;
+    case 1: aten_rows_x_tree<1>(c, src, s_row, warp, lane); break;
+    case 2: aten_rows_x_tree<2>(c, src, s_row, warp, lane); break;
+    case 4: aten_rows_x_tree<4>(c, src, s_row, warp, lane); break;
+    case 8: aten_rows_x_tree<8>(c, src, s_row, warp, lane); break;
+    default: aten_rows_x_tree<16>(c, src, s_row, warp, lane); break;
   }
   __syncthreads();
   if ((int)threadIdx.x < c.cpo) {                       // block_y_reduce of virtual block threadIdx.x (offsets bh/2 .. 1)
@@ -171,5 +186,15 @@ __device__ __forceinline__ float aten_tree_mean(const AtenMeanCfg& c, const floa
   v = __shfl_sync(0xffffffffu, v, 0);
   return mul_rn(v, c.factor);
 }
+
+__device__ __forceinline__ float aten_tree_mean(const AtenMeanCfg& c, const float* s_val, float* s_row, float* s_blk) {
+  return aten_tree_mean_src(c, ColSrcCluster{s_val, c.w4_magic, (uint32_t)c.W4}, s_row, s_blk);
+}
+
+// Normalize's adjoint that also leaves ATen's per-virtual-thread column sums of |gin| (ta_normalize_bwd_colsum), and the trees
+// over such column sums (ta_abs_mean_from_colsums): the mean kernel's two halves, the first riding on a pass over the gradient
+// that exists anyway
+int aten_colsum_normalize_bwd(const float* gout, const float* std, float* gin, float* col_sums, int B, int C, int64_t plane, cudaStream_t s);
+int aten_colsum_tree(const float* col_sums, float* mean_out, int B, int64_t n, cudaStream_t s);
 
 }  // namespace ta

@@ -237,6 +237,32 @@ class CudaBackend:
                 _lib.check(self.lib.ta_normalize_bwd(_ptr(x), _ptr(std), _ptr(out), B, C, plane, _stream()), "ta_normalize_bwd")
         return out
 
+    def colsum_size(self, B, n, device):
+        """floats per sample of the column sums ta_normalize_bwd_colsum leaves (S of ATen's mean reduction for [B, n] on this
+        device), or None when the shape is outside the replayed launch family"""
+        prop = _device_props(device)
+        bw, bh, cpo = ctypes.c_int(0), ctypes.c_int(0), ctypes.c_int(0)
+        rc = self.lib.ta_aten_mean_policy(int(B), int(n), prop[0], prop[1], ctypes.byref(bw), ctypes.byref(bh), ctypes.byref(cpo))
+        return bw.value * bh.value * cpo.value if rc == _lib.TA_OK else None
+
+    def normalize_bwd_colsum(self, gout, std, col_sums):
+        """Normalize's adjoint gout / std[c] (the bits of ``normalize(..., forward=False)``) that also fills `col_sums` [B, S] with
+        the column values of torch's ``gin.abs().mean(dim=(1,2,3))`` reduction; None when the library does not cover the shape."""
+        gout = _f32c(gout, "gout"); B, C = gout.shape[0], gout.shape[1]; plane = gout.numel() // (B * C)
+        out = torch.empty_like(gout)
+        with _DeviceOf(gout):
+            rc = self.lib.ta_normalize_bwd_colsum(_ptr(gout), _ptr(std), _ptr(out), _ptr(col_sums), B, C, plane, _stream())
+        if rc == _lib.TA_EUNSUPPORTED:
+            return None
+        _lib.check(rc, "ta_normalize_bwd_colsum")
+        return out
+
+    def abs_mean_from_colsums(self, col_sums, out, B, n):
+        """finishes mean|g| per sample (bit-identical to torch's op) from the column sums; returns `out` [B]"""
+        with _DeviceOf(col_sums):
+            _lib.check(self.lib.ta_abs_mean_from_colsums(_ptr(col_sums), _ptr(out), int(B), int(n), _stream()), "ta_abs_mean_from_colsums")
+        return out
+
     def sim(self, x, S, forward=True):
         x = _f32c(x, "x")
         with _DeviceOf(x):
@@ -461,6 +487,62 @@ def backend():
 _aten_replay_ok = {}
 
 
+_dev_props = {}
+
+
+def _device_props(device):
+    idx = torch.device(device).index
+    if idx is None:
+        idx = torch.cuda.current_device()
+    v = _dev_props.get(idx)
+    if v is None:
+        p = torch.cuda.get_device_properties(idx)
+        v = _dev_props[idx] = (int(p.multi_processor_count), int(p.max_threads_per_multi_processor))
+    return v
+
+
+_colsum_ok = {}
+
+
+def colsum_adjoint_ok(t, std):
+    """May ``normalize_bwd_colsum`` + ``abs_mean_from_colsums`` stand in for Normalize's adjoint followed by
+    ``abs().mean(dim=(1,2,3))`` for gradients shaped like `t` [B, C, H, W]? Same contract as ``aten_mean_replay_ok``: checked once
+    per (device, shape) against torch's own ops on random data, bit for bit (both the gradient and the mean); cached."""
+    if _test_backend is not None or not torch.is_tensor(t) or not t.is_cuda or t.dim() != 4 or t.dtype != torch.float32:
+        return False
+    key = (t.device.index, tuple(t.shape))
+    ok = _colsum_ok.get(key)
+    if ok is not None:
+        return ok
+    if torch.cuda.is_current_stream_capturing():
+        return False
+    be = backend()
+    B, n = t.shape[0], t[0].numel()
+    S = be.colsum_size(B, n, t.device)
+    ok = S is not None
+    if ok:
+        with torch.no_grad():
+            gen = torch.Generator(device=t.device).manual_seed(0x7B)
+            cs = torch.empty(B * S, device=t.device, dtype=torch.float32)
+            out = torch.empty(B, device=t.device, dtype=torch.float32)
+            for scale in (1.0, 1e-4):
+                g = torch.randn(t.shape, device=t.device, dtype=torch.float32, generator=gen) * scale
+                gin = be.normalize_bwd_colsum(g, std, cs)
+                if gin is None:
+                    ok = False
+                    break
+                ref = be.normalize(g, None, std, False)
+                mu = be.abs_mean_from_colsums(cs, out, B, n)
+                if not torch.equal(gin, ref) or not torch.equal(mu, ref.abs().mean(dim=(1, 2, 3))):
+                    ok = False
+                    import warnings
+                    warnings.warn("transferattack_b200: the column-sum form of Normalize's adjoint does not reproduce this torch "
+                                  "build's mean kernel for shape %s on %s; keeping the separate mean kernel" % (tuple(t.shape), t.device))
+                    break
+    _colsum_ok[key] = ok
+    return ok
+
+
 def aten_mean_replay_ok(t):
     """May TA_MEAN_TORCH stand in for ``t.abs().mean(dim=(1,2,3))`` on this device for tensors shaped like `t`?
 
@@ -523,17 +605,23 @@ class StageNormalized(torch.autograd.Function):
     — or the identity when the fused kernel will apply that division itself (`defer`)."""
 
     @staticmethod
-    def forward(ctx, delta, xn, std, defer):
+    def forward(ctx, delta, xn, std, defer, col_sums=None):
         ctx.defer = defer
+        ctx.col_sums = col_sums
         ctx.save_for_backward(std)
         return xn.view_as(delta)
 
     @staticmethod
     def backward(ctx, gout):
         if ctx.defer:
-            return gout, None, None, None
+            return gout, None, None, None, None
         (std,) = ctx.saved_tensors
-        return backend().normalize(gout, None, std, False), None, None, None
+        if ctx.col_sums is not None:          # the adjoint also leaves the column sums of |g| for the tail's mean (same gradient bits)
+            gin = backend().normalize_bwd_colsum(gout, std, ctx.col_sums)
+            if gin is None:
+                raise RuntimeError("ta_normalize_bwd_colsum refused a shape colsum_adjoint_ok accepted: %s" % _lib.last_error())
+            return gin, None, None, None, None
+        return backend().normalize(gout, None, std, False), None, None, None, None
 
 
 class LookAhead(torch.autograd.Function):
@@ -648,8 +736,8 @@ def stage_add(data, delta, look=None, coef=0.0, precomputed=None):
     return StageAdd.apply(data, delta, look, coef, precomputed)
 
 
-def stage_normalized(delta, xn, std, defer=False):
-    return StageNormalized.apply(delta, xn, std, defer)
+def stage_normalized(delta, xn, std, defer=False, col_sums=None):
+    return StageNormalized.apply(delta, xn, std, defer, col_sums)
 
 
 def look_ahead(x, momentum, coef):
