@@ -299,8 +299,9 @@ def tail_kernel_name(atk, x_dev):
     fold = atk._fold_plan(x_dev, kmode)
     nf = "" if fold is None else (",nf+adjoint" if fold[4] else ",nf")
     if fold is not None and fold[5]:
-        # the Normalize-adjoint kernel at the end of the backward left the column sums of |g|: the tail only finishes the mean from them
-        return "ta_abs_mean_from_colsums + ta_fused_tail[stream,nf]", 2
+        # the Normalize-adjoint kernel at the end of the backward formed ATen's column sums of |g| and its last CTA per sample finished
+        # the mean: the tail is the streaming kernel alone
+        return "ta_fused_tail[stream,nf] (mean|g| finished inside ta_normalize_bwd_colsum)", 1
     if kmode is None:
         return "ta_fused_tail[stream%s] after ATen abs+mean" % nf, 3
     if kmode == _lib.TA_MEAN_TORCH and x_dev.numel() * 4 <= 64 * 1024 * 1024 and int(os.environ.get("TA_FUSED_STRATEGY", "0")) in (0, 2):
@@ -314,9 +315,9 @@ def outside_note(atk, x_dev):
     if fold is None or fold[4]:
         return None
     if fold[5]:
-        return ("Normalize's adjoint g/std at the end of autograd.grad: one ta_normalize_bwd_colsum launch (8 B/elem) that also leaves "
-                "the per-column sums of |g| (20 KB per sample) from which the tail finishes torch's mean — the gradient is not read a "
-                "second time for the mean; standalone timings of that kernel and of plain ta_normalize_bwd: bench.py --kernels")
+        return ("Normalize's adjoint g/std at the end of autograd.grad: one ta_normalize_bwd_colsum launch (8 B/elem) that also forms "
+                "ATen's per-column sums of |g| and whose last CTA per sample finishes torch's mean from them — no separate mean kernel, "
+                "the gradient is not read a second time; standalone timings of that kernel and of plain ta_normalize_bwd: bench.py --kernels")
     return "Normalize's adjoint g/std: one ta_normalize_bwd launch (8 B/elem) at the end of autograd.grad"
 
 
@@ -816,6 +817,8 @@ def run_kernels(args):
         cs = torch.empty(B * cs_n, device=dev)
         add("normalize_bwd (Normalize's adjoint, plain)", 8, lambda: be.normalize(g, None, std_dev, False))
         add("normalize_bwd_colsum (the adjoint + ATen's column sums of |g|)", 8, lambda: be.normalize_bwd_colsum(g, std_dev, cs))
+        cnt = torch.zeros(B, dtype=torch.int32, device=dev)
+        add("normalize_bwd_colsum, mean finished in-launch (what the attack loop runs)", 8, lambda: be.normalize_bwd_colsum(g, std_dev, cs, so, cnt))
         add("abs_mean_from_colsums (trees over the column sums; %d floats per sample)" % cs_n, 4, lambda: be.abs_mean_from_colsums(cs, so, B, g[0].numel()),
             elems=B * cs_n)
     add("ATen reference: g.abs().mean(dim=(1,2,3)) (2 launches)", 12, lambda: g.abs().mean(dim=(1, 2, 3)))

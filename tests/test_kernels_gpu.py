@@ -374,6 +374,15 @@ def test_normalize_adjoint_with_column_sums_is_bit_identical_to_torch(be, B, sha
         assert torch.equal(mu, ref.abs().mean(dim=(1, 2, 3))), (B, shape, seed)
         got = be.abs_mean(gin, __import__("transferattack_b200")._lib.TA_MEAN_TORCH)
         assert got is not None and torch.equal(mu, got)
+        # the form the attack loop uses: the last CTA of every sample finishes the mean inside the launch; the ticket counters end at zero
+        cnt = torch.zeros(B, dtype=torch.int32, device="cuda")
+        for _ in range(2):
+            mu2 = torch.full((B,), float("nan"), device="cuda")
+            gin2 = be.normalize_bwd_colsum(g, std, cs, mu2, cnt)
+            if gin2 is None:          # more column values per sample than the finishing CTA stages (S > 16384): the two-launch form serves it
+                assert S > 16384, (B, shape, S)
+                break
+            assert torch.equal(gin2, ref) and torch.equal(mu2, mu) and int(cnt.abs().sum()) == 0, (B, shape, seed)
 
 
 def test_normalize_adjoint_with_column_sums_declines_what_it_does_not_replay(be):

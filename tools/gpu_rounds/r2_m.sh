@@ -16,5 +16,5 @@ tail -3 gpurun_out/bench.err
 echo "== reference arm"; timeout 900 python bench.py --impl reference --steps 2 --warmup 1 > gpurun_out/bench_ref.json 2> gpurun_out/bench_ref.err; echo "rc=$?"; tail -c 900 gpurun_out/bench_ref.json
 echo "== kernel table"; timeout 900 python bench.py --kernels > gpurun_out/kernels.log 2>&1; echo "rc=$?"; grep -E "us " gpurun_out/kernels.log | grep -vE "variant|prefetch mode|band 56|device arrays|FFMA,|TMA-staged"
 echo "== ncu launch list"; timeout 900 ncu --metrics gpu__time_duration.sum --clock-control none -c 1800 --csv --log-file gpurun_out/launches_r2.csv python bench.py --steps 1 --warmup 1 --graph 0 --no-cpu-baseline --no-eager-gpu --no-extras > gpurun_out/bench_under_ncu.log 2>&1; echo "rc=$?"; wc -l gpurun_out/launches_r2.csv
-echo "== ncu full: tail kernels + TIM + DIM"; timeout 900 ncu --set full --clock-control none --import-source on -k regex:"FusedStreamOpT|aten_abs_mean|dwconv_sep_rg2|dim_fwd_direct|dim_bwd_sep" -c 8 -o gpurun_out/prof_final_r2 -f python tools/prof_fused.py final > gpurun_out/ncu_final.log 2>&1; echo "rc=$?"; tail -2 gpurun_out/ncu_final.log
+echo "== ncu full: tail kernels + TIM + DIM"; timeout 900 ncu --set full --clock-control none --import-source on -k regex:"ew_rows_kernel|normalize_bwd_colsum|aten_abs_mean|dwconv_sep_rg2|dim_fwd_direct|dim_bwd_sep" -c 8 -o gpurun_out/prof_final_r2 -f python tools/prof_fused.py final > gpurun_out/ncu_final.log 2>&1; echo "rc=$?"; tail -2 gpurun_out/ncu_final.log
 python tools/ncu_summary.py gpurun_out/prof_final_r2.ncu-rep > gpurun_out/ncu_final_summary.txt 2>&1; grep -E "^====|gpu__time_duration|dram__bytes|smsp__inst_executed|issue_active" gpurun_out/ncu_final_summary.txt

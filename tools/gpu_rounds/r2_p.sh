@@ -11,5 +11,5 @@ print(json.dumps(d.get('alt_mean_modes'))[:1800])
 PY
 tail -3 gpurun_out/bench.err
 echo "== kernel table"; timeout 900 python bench.py --kernels > gpurun_out/kernels.log 2>&1; echo "rc=$?"; grep -E "us " gpurun_out/kernels.log | grep -E "normalize_bwd|colsums|abs_mean|stream, scale"
-echo "== ncu"; timeout 900 ncu --set full --clock-control none --import-source on -k regex:"normalize_bwd_colsum|aten_colsum_tree|FusedStreamOpT|NormalizeOp" -c 6 -o gpurun_out/prof_colsum_r2 -f python tools/prof_fused.py colsum > gpurun_out/ncu_colsum.log 2>&1; echo "rc=$?"; tail -2 gpurun_out/ncu_colsum.log
+echo "== ncu"; timeout 900 ncu --set full --clock-control none --import-source on -k regex:"normalize_bwd_colsum|aten_colsum_tree|ew_rows_kernel" -c 6 -o gpurun_out/prof_colsum_r2 -f python tools/prof_fused.py colsum > gpurun_out/ncu_colsum.log 2>&1; echo "rc=$?"; tail -2 gpurun_out/ncu_colsum.log
 python tools/ncu_summary.py gpurun_out/prof_colsum_r2.ncu-rep > gpurun_out/ncu_colsum_summary.txt 2>&1; grep -E "^====|gpu__time_duration|dram__bytes|smsp__inst_executed|issue_active|registers" gpurun_out/ncu_colsum_summary.txt

@@ -39,8 +39,13 @@ for it in range(6):
         MEAN, STD = [0.485, 0.456, 0.406], [0.229, 0.224, 0.225]
         if it < 5:
             continue
-        be.fused_tail(g, m, m2, d, d2, x, xa, None, so, 1.0, 1.6 / 255, 16 / 255, 0, 1.0, mean_mode=_lib.TA_MEAN_TORCH, mean=MEAN, std=STD,
-                      emit_normalized=True)
+        std_dev = torch.tensor(STD, device="cuda")
+        cs = torch.empty(B * be.colsum_size(B, g[0].numel(), g.device), device="cuda")
+        cnt = torch.zeros(B, dtype=torch.int32, device="cuda")
+        gin = be.normalize_bwd_colsum(g, std_dev, cs, so, cnt)                 # the adjoint at the end of the backward (+ mean|g|)
+        be.fused_tail(gin, m, m2, d, d2, x, xa, so, so, 1.0, 1.6 / 255, 16 / 255, 0, 1.0, mean=MEAN, std=STD, emit_normalized=True)   # the tail
+        flush.sum()
+        be.abs_mean(g, _lib.TA_MEAN_TORCH)                                       # the standalone torch-order mean kernel (public get_momentum hook)
         flush.sum()
         k2d, kcol, krow = tim.make_kernel("gaussian", 15)
         hc, hr = np.stack([kcol] * 3), np.stack([krow] * 3)
@@ -54,8 +59,8 @@ for it in range(6):
             continue
         std_dev = torch.tensor(STD, device="cuda")
         cs = torch.empty(B * be.colsum_size(B, g[0].numel(), g.device), device="cuda")
-        gin = be.normalize_bwd_colsum(g, std_dev, cs)
-        be.abs_mean_from_colsums(cs, so, B, g[0].numel())
+        cnt = torch.zeros(B, dtype=torch.int32, device="cuda")
+        gin = be.normalize_bwd_colsum(g, std_dev, cs, so, cnt)
         be.fused_tail(gin, m, m2, d, d2, x, xa, so, so, 1.0, 1.6 / 255, 16 / 255, 0, 1.0, mean=MEAN, std=STD, emit_normalized=True)
         flush.sum()
         be.normalize(g, None, std_dev, False)

@@ -52,7 +52,7 @@ SIGNATURES = {
     "ta_stage_add": (_i, [_p, _p, _p, _f, _p, _l, _p]),
     "ta_normalize_fwd": (_i, [_p, _p, _p, _p, _i, _i, _l, _p]),
     "ta_normalize_bwd": (_i, [_p, _p, _p, _i, _i, _l, _p]),
-    "ta_normalize_bwd_colsum": (_i, [_p, _p, _p, _p, _i, _i, _l, _p]),
+    "ta_normalize_bwd_colsum": (_i, [_p, _p, _p, _p, _p, _p, _i, _i, _l, _p]),
     "ta_abs_mean_from_colsums": (_i, [_p, _p, _i, _l, _p]),
     "ta_sim_fwd": (_i, [_p, _p, _i, _l, _p]),
     "ta_sim_bwd": (_i, [_p, _p, _i, _l, _p]),

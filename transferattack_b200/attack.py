@@ -139,8 +139,8 @@ class Attack(object):
     #: iteration. Default: not folded for mean_mode 'torch' (the division-free mean kernel), folded for 'exact' (one cluster launch).
     fold_adjoint = {"1": True, "0": False}.get(os.environ.get("TA_B200_FOLD_ADJOINT", ""), None)
     #: with mean_mode 'torch', the folded Normalize and the base get_grad: the Normalize-adjoint kernel at the end of the backward
-    #: pass also leaves the per-column sums of |g| that torch's mean reduction would form (``ta_normalize_bwd_colsum``), and the
-    #: tail finishes mean|g| from those 20 KB per sample (``ta_abs_mean_from_colsums``) instead of reading the gradient once more.
+    #: pass also forms the per-column sums of |g| of torch's mean reduction and its last CTA per sample finishes mean|g| from them
+    #: (``ta_normalize_bwd_colsum``): the tail is the streaming kernel alone and the gradient is not read a second time for the mean.
     #: Same bits (self-checked per device and shape against torch's ops); False keeps the separate mean kernel.
     colsum_adjoint = os.environ.get("TA_B200_COLSUM_ADJOINT", "1") == "1"
     #: OPT-IN, NOT THE PARITY PATH. The surrogate's forward/backward runs on a private copy of
@@ -332,8 +332,7 @@ class Attack(object):
         if fold is not None:
             norm = dict(mean=fold[2], std=fold[3], emit_normalized=True, grad_wrt_xn=fold[4])
         with torch.no_grad():
-            if col_sums is not None:       # mean|g| from the column sums the adjoint kernel left (torch's bits), then the streaming form
-                be.abs_mean_from_colsums(col_sums, scale_out, grad.shape[0], grad[0].numel())
+            if col_sums is not None:       # mean|g| was finished by the adjoint kernel (torch's bits) into scale_out: the streaming form
                 if not be.fused_tail(grad, momentum, m_out, delta, delta_out, data, xadv, scale_out, scale_out, self.decay, self.alpha,
                                      self.epsilon, img_min, img_max, gbar_out=gbar_out, **norm):
                     raise RuntimeError("ta_fused_tail refused the streaming form: %s" % _lib.last_error())
@@ -361,9 +360,9 @@ class Attack(object):
         if fold is not None:
             pre, net, mean, std, defer, colsum = fold
             xadv = self._first_normalized(pre, data, delta)          # holds the NORMALISED model input from here on
-            if colsum:
-                col_sums = torch.empty(data.shape[0] * be.colsum_size(data.shape[0], data[0].numel(), data.device), device=data.device,
-                                       dtype=torch.float32)
+            if colsum:                  # (column sums, where the adjoint kernel leaves mean|g|, its ticket counters)
+                col_sums = (torch.empty(data.shape[0] * be.colsum_size(data.shape[0], data[0].numel(), data.device), device=data.device,
+                                        dtype=torch.float32), scale_out, torch.zeros(data.shape[0], device=data.device, dtype=torch.int32))
         else:
             xadv = torch.empty_like(data)
         momentum, pre_x = None, None
@@ -436,8 +435,8 @@ class Attack(object):
               "fold": fold, "kmode": kmode}
         if fold is not None and fold[5]:
             be = ops.backend()
-            st["col_sums"] = torch.empty(data.shape[0] * be.colsum_size(data.shape[0], data[0].numel(), data.device), device=data.device,
-                                         dtype=torch.float32)
+            st["col_sums"] = (torch.empty(data.shape[0] * be.colsum_size(data.shape[0], data[0].numel(), data.device), device=data.device,
+                                          dtype=torch.float32), st["scale_out"], torch.zeros(data.shape[0], device=data.device, dtype=torch.int32))
         self._graph_reset(st, data, label, delta0)
         cur = torch.cuda.current_stream(data.device)
         side = torch.cuda.Stream(device=data.device)

@@ -127,39 +127,63 @@ __global__ void __launch_bounds__(kAtenThreads, 2) aten_abs_mean_kernel(const fl
 // Normalize's adjoint gin = gout / std[c] (the bits of ta_normalize_bwd) with the thread <-> data mapping of ATen's mean
 // reduction over gin: CTA (x, b) owns virtual threads [512 x, 512 x + 512) of sample b, thread t the 128-bit vectors t, t + S, ...
 // — so that besides storing gin it can leave that virtual thread's column value of |gin| in col_sums[b * S + t].
+// FINISH: the last CTA of a sample to arrive (ticket counter per sample, reset by that CTA: ATen's own global_reduce scheme)
+// copies the sample's S column values into shared memory and runs the trees → mean_out[b]; no separate launch for the mean.
+template <bool FINISH>
 __global__ void __launch_bounds__(kAtenThreads, 3) normalize_bwd_colsum_kernel(const float* __restrict__ gout, const float* __restrict__ std,
                                                                             float* __restrict__ gin, float* __restrict__ col_sums,
-                                                                            int64_t n, int S, int plane_vec, int C) {
+                                                                            float* __restrict__ mean_out, int* __restrict__ counters,
+                                                                            int64_t n, AtenMeanCfg cfg, int plane_vec, int C) {
+  extern __shared__ __align__(16) float s_cols[];
+  __shared__ float s_row[FINISH ? kAtenThreads : 1];
+  __shared__ float s_blk[FINISH ? kAtenThreads : 1];
+  __shared__ int s_last;
+  const int S = cfg.S;
   const int b = blockIdx.y;
   const float4* gp = reinterpret_cast<const float4*>(gout + (int64_t)b * n);
   float4* ip = reinterpret_cast<float4*>(gin + (int64_t)b * n);
   const int nvec = (int)(n >> 2);
   const int col = blockIdx.x * kAtenThreads + threadIdx.x;
-  if (col >= S) return;
-  float sd[4];
+  if (col < S) {
+    float sd[4];
 #pragma unroll
-  for (int c = 0; c < 4; ++c) sd[c] = c < C ? __ldg(std + c) : 1.0f;
-  const int rows = col < nvec ? (nvec - col + S - 1) / S : 0;
-  ColAcc A;
-  constexpr int NB = 4;
-  for (int j0 = 0; j0 < rows; j0 += NB) {
-    float4 x[NB];
+    for (int c = 0; c < 4; ++c) sd[c] = c < C ? __ldg(std + c) : 1.0f;
+    const int rows = col < nvec ? (nvec - col + S - 1) / S : 0;
+    ColAcc A;
+    constexpr int NB = 4;
+    for (int j0 = 0; j0 < rows; j0 += NB) {
+      float4 x[NB];
 #pragma unroll
-    for (int u = 0; u < NB; ++u)
-      if (j0 + u < rows) x[u] = __ldg(gp + col + (int64_t)(j0 + u) * S);
+      for (int u = 0; u < NB; ++u)
+        if (j0 + u < rows) x[u] = __ldg(gp + col + (int64_t)(j0 + u) * S);
 #pragma unroll
-    for (int u = 0; u < NB; ++u)
-      if (j0 + u < rows) {
-        const int v = col + (j0 + u) * S;
-        const float4 t = div4(x[u], pick4(sd, (v >= plane_vec ? 1 : 0) + (v >= 2 * plane_vec ? 1 : 0) + (v >= 3 * plane_vec ? 1 : 0)));
-        ip[v] = t;
-        aten_column_add(A, t);
-      }
+      for (int u = 0; u < NB; ++u)
+        if (j0 + u < rows) {
+          const int v = col + (j0 + u) * S;
+          const float4 t = div4(x[u], pick4(sd, (v >= plane_vec ? 1 : 0) + (v >= 2 * plane_vec ? 1 : 0) + (v >= 3 * plane_vec ? 1 : 0)));
+          ip[v] = t;
+          aten_column_add(A, t);
+        }
+    }
+    col_sums[(int64_t)b * S + col] = aten_column_value(A);
   }
-  col_sums[(int64_t)b * S + col] = aten_column_value(A);
+  if (FINISH) {
+    __threadfence();                                   // this CTA's column values are visible device-wide before its ticket
+    __syncthreads();
+    if (threadIdx.x == 0) s_last = (atomicAdd(counters + b, 1) == (int)gridDim.x - 1) ? 1 : 0;
+    __syncthreads();
+    if (s_last) {
+      __threadfence();
+      const float4* s4 = reinterpret_cast<const float4*>(col_sums + (int64_t)b * S);
+      float4* d4 = reinterpret_cast<float4*>(s_cols);
+      for (int i = threadIdx.x; i < (S >> 2); i += kAtenThreads) d4[i] = __ldcg(s4 + i);     // L2: written by other CTAs of this launch
+      __syncthreads();
+      const float mu = aten_tree_mean_src(cfg, ColSrcShared{s_cols}, s_row, s_blk);
+      if (threadIdx.x == 0) { mean_out[b] = mu; counters[b] = 0; }                          // leave the counter ready for the next launch
+    }
+  }
 }
 
-// block_x / block_y / final trees over the S column values of one sample (one CTA per sample)
 // STAGE: the S values are first copied into shared memory with one batch of independent 128-bit loads per thread (one global
 // latency instead of one per pair of block rows), then the trees read them from there
 template <bool STAGE>
@@ -184,9 +208,10 @@ __global__ void __launch_bounds__(kAtenThreads) aten_colsum_tree_kernel(const fl
 
 }  // namespace
 
-int aten_colsum_normalize_bwd(const float* gout, const float* std, float* gin, float* col_sums, int B, int C, int64_t plane, cudaStream_t s) {
+int aten_colsum_normalize_bwd(const float* gout, const float* std, float* gin, float* col_sums, float* mean_out, int* counters, int B, int C,
+                              int64_t plane, cudaStream_t s) {
   const int64_t n = (int64_t)C * plane;
-  if (C < 1 || C > 4 || plane % 4 != 0 || !aligned16(gout) || !aligned16(gin) || n >= ((int64_t)1 << 31) || B > 65535) {
+  if (C < 1 || C > 4 || plane % 4 != 0 || !aligned16(gout) || !aligned16(gin) || !aligned16(col_sums) || n >= ((int64_t)1 << 31) || B > 65535) {
     set_error("ta_normalize_bwd_colsum: needs C <= 4, H*W %% 4 == 0, 16-byte aligned tensors, B <= 65535");
     return TA_EUNSUPPORTED;
   }
@@ -194,7 +219,17 @@ int aten_colsum_normalize_bwd(const float* gout, const float* std, float* gin, f
   const int rc = aten_mean_plan("ta_normalize_bwd_colsum", B, n, 0, &c);
   if (rc != TA_OK) return rc;
   dim3 grid((unsigned)((c.S + kAtenThreads - 1) / kAtenThreads), (unsigned)B);
-  normalize_bwd_colsum_kernel<<<grid, kAtenThreads, 0, s>>>(gout, std, gin, col_sums, n, c.S, (int)(plane / 4), C);
+  const size_t smem = sizeof(float) * (size_t)c.S;
+  if (mean_out && counters && smem <= 64 * 1024 && c.cpo * c.bh <= kAtenThreads) {
+    static SmemOptIn optin = {};
+    const int ro = ensure_dyn_smem("ta_normalize_bwd_colsum", normalize_bwd_colsum_kernel<true>, smem, optin);
+    if (ro != TA_OK) return ro;
+    normalize_bwd_colsum_kernel<true><<<grid, kAtenThreads, smem, s>>>(gout, std, gin, col_sums, mean_out, counters, n, c, (int)(plane / 4), C);
+  } else if (mean_out) {
+    set_error("ta_normalize_bwd_colsum: the in-kernel finish serves S <= 16384 column values per sample (here %d)", c.S);
+    return TA_EUNSUPPORTED;
+  } else
+    normalize_bwd_colsum_kernel<false><<<grid, kAtenThreads, 0, s>>>(gout, std, gin, col_sums, nullptr, nullptr, n, c, (int)(plane / 4), C);
   count_launch();
   return check_launch("ta_normalize_bwd_colsum");
 }
@@ -251,11 +286,13 @@ extern "C" int ta_aten_mean_policy(int B, int64_t n, int sm_count, int max_threa
 // Normalize's adjoint gin = gout / std[c] (utils.py:72-79; same bits as ta_normalize_bwd) that ALSO leaves, per sample, the S
 // column values of |gin| of torch's `gin.abs().mean(dim=(1,2,3))` reduction (attack.py:128) in col_sums [B, S], S = block_w *
 // block_h * ctas_per_output of ta_aten_mean_policy: ta_abs_mean_from_colsums then finishes that mean (bit-identical to torch's)
-// from 4*S bytes per sample instead of a pass over the gradient. TA_EUNSUPPORTED outside the replayed launch family.
-extern "C" int ta_normalize_bwd_colsum(const float* gout, const float* std, float* gin, float* col_sums, int B, int C, int64_t plane,
-                                       ta_stream_t stream) {
+// from 4*S bytes per sample instead of a pass over the gradient — or, with mean_out [B] and counters [B] (int, zero before the
+// first call, left zero), the last CTA of every sample finishes it inside this launch. TA_EUNSUPPORTED outside the replayed family.
+extern "C" int ta_normalize_bwd_colsum(const float* gout, const float* std, float* gin, float* col_sums, float* mean_out, int* counters,
+                                       int B, int C, int64_t plane, ta_stream_t stream) {
   TA_REQUIRE(gout && std && gin && col_sums && B > 0 && C > 0 && plane > 0, "ta_normalize_bwd_colsum: bad arguments");
-  return ta::aten_colsum_normalize_bwd(gout, std, gin, col_sums, B, C, plane, (cudaStream_t)stream);
+  TA_REQUIRE((mean_out == nullptr) == (counters == nullptr), "ta_normalize_bwd_colsum: mean_out and counters go together");
+  return ta::aten_colsum_normalize_bwd(gout, std, gin, col_sums, mean_out, counters, B, C, plane, (cudaStream_t)stream);
 }
 extern "C" int ta_abs_mean_from_colsums(const float* col_sums, float* mean_out, int B, int64_t n, ta_stream_t stream) {
   TA_REQUIRE(col_sums && mean_out && B > 0 && n > 0, "ta_abs_mean_from_colsums: bad arguments");

@@ -194,7 +194,8 @@ __device__ __forceinline__ float aten_tree_mean(const AtenMeanCfg& c, const floa
 // Normalize's adjoint that also leaves ATen's per-virtual-thread column sums of |gin| (ta_normalize_bwd_colsum), and the trees
 // over such column sums (ta_abs_mean_from_colsums): the mean kernel's two halves, the first riding on a pass over the gradient
 // that exists anyway
-int aten_colsum_normalize_bwd(const float* gout, const float* std, float* gin, float* col_sums, int B, int C, int64_t plane, cudaStream_t s);
+int aten_colsum_normalize_bwd(const float* gout, const float* std, float* gin, float* col_sums, float* mean_out, int* counters, int B, int C,
+                              int64_t plane, cudaStream_t s);
 int aten_colsum_tree(const float* col_sums, float* mean_out, int B, int64_t n, cudaStream_t s);
 
 }  // namespace ta

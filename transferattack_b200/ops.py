@@ -245,13 +245,15 @@ class CudaBackend:
         rc = self.lib.ta_aten_mean_policy(int(B), int(n), prop[0], prop[1], ctypes.byref(bw), ctypes.byref(bh), ctypes.byref(cpo))
         return bw.value * bh.value * cpo.value if rc == _lib.TA_OK else None
 
-    def normalize_bwd_colsum(self, gout, std, col_sums):
+    def normalize_bwd_colsum(self, gout, std, col_sums, mean_out=None, counters=None):
         """Normalize's adjoint gout / std[c] (the bits of ``normalize(..., forward=False)``) that also fills `col_sums` [B, S] with
-        the column values of torch's ``gin.abs().mean(dim=(1,2,3))`` reduction; None when the library does not cover the shape."""
+        the column values of torch's ``gin.abs().mean(dim=(1,2,3))`` reduction — and, given `mean_out` [B] fp32 and `counters` [B]
+        int32 (zero; left zero), finishes that mean inside the same launch. None when the library does not cover the shape."""
         gout = _f32c(gout, "gout"); B, C = gout.shape[0], gout.shape[1]; plane = gout.numel() // (B * C)
         out = torch.empty_like(gout)
         with _DeviceOf(gout):
-            rc = self.lib.ta_normalize_bwd_colsum(_ptr(gout), _ptr(std), _ptr(out), _ptr(col_sums), B, C, plane, _stream())
+            rc = self.lib.ta_normalize_bwd_colsum(_ptr(gout), _ptr(std), _ptr(out), _ptr(col_sums), _ptr(mean_out), _ptr(counters), B, C, plane,
+                                                  _stream())
         if rc == _lib.TA_EUNSUPPORTED:
             return None
         _lib.check(rc, "ta_normalize_bwd_colsum")
@@ -533,7 +535,12 @@ def colsum_adjoint_ok(t, std):
                     break
                 ref = be.normalize(g, None, std, False)
                 mu = be.abs_mean_from_colsums(cs, out, B, n)
-                if not torch.equal(gin, ref) or not torch.equal(mu, ref.abs().mean(dim=(1, 2, 3))):
+                cnt = torch.zeros(B, device=t.device, dtype=torch.int32)
+                mu2 = torch.empty(B, device=t.device, dtype=torch.float32)
+                gin2 = be.normalize_bwd_colsum(g, std, cs, mu2, cnt)             # the form the attack loop uses: mean finished in-launch
+                want = ref.abs().mean(dim=(1, 2, 3))
+                if (gin2 is None or not torch.equal(gin, ref) or not torch.equal(gin2, ref) or not torch.equal(mu, want)
+                        or not torch.equal(mu2, want) or int(cnt.abs().sum()) != 0):
                     ok = False
                     import warnings
                     warnings.warn("transferattack_b200: the column-sum form of Normalize's adjoint does not reproduce this torch "
@@ -617,7 +624,7 @@ class StageNormalized(torch.autograd.Function):
             return gout, None, None, None, None
         (std,) = ctx.saved_tensors
         if ctx.col_sums is not None:          # the adjoint also leaves the column sums of |g| for the tail's mean (same gradient bits)
-            gin = backend().normalize_bwd_colsum(gout, std, ctx.col_sums)
+            gin = backend().normalize_bwd_colsum(gout, std, *ctx.col_sums)
             if gin is None:
                 raise RuntimeError("ta_normalize_bwd_colsum refused a shape colsum_adjoint_ok accepted: %s" % _lib.last_error())
             return gin, None, None, None, None
