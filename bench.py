@@ -70,6 +70,8 @@ class ClockSampler:
         self.p = None
 
     def __enter__(self):
+        if self.gpu is None:
+            return self
         try:
             self.f = tempfile.NamedTemporaryFile("w+", suffix=".csv", delete=False)
             self.p = subprocess.Popen(["nvidia-smi", "-i", str(self.gpu), "--query-gpu=" + self.Q, "--format=csv,noheader,nounits",
@@ -370,10 +372,15 @@ def run_ours(args, rank, local_rank, world, dist):
 
     def step_resident():
         keep["d"] = atk(x_dev, y_dev)
-    launches0 = _lib.launch_count()
-    with ClockSampler(local_rank) as clk:
+    # nvidia-smi is started on rank 0 only and BEFORE the timed region (its start-up enumerates every GPU of the box through NVML:
+    # measured at N = 2 as +10 ms per step on the rank it overlapped with); one more untimed step runs while it comes up, then the
+    # timed region is sampled every 100 ms
+    with ClockSampler(local_rank if rank == 0 else None) as clk:
+        step_resident()
+        torch.cuda.synchronize(device)
+        launches0 = _lib.launch_count()
         ms = timed_steps(step_resident, args.steps, dist, device)
-    launches = _lib.launch_count() - launches0
+        launches = _lib.launch_count() - launches0
     clocks = clk.summary()
     value = world * B * args.steps / (ms / 1e3)
     gstat = graph_status(atk, args.graph)
