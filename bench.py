@@ -860,6 +860,9 @@ def run_kernels(args):
     hc, hr = kc3.cpu().numpy(), kr3.cpu().numpy()
     _lib.tune_set("tim.band", 4)
     add("dwconv2d_sep k=15 [unrolled band walk, paired weights, tap-exact column pass (default)]", 8, lambda: be.dwconv2d_sep(g, kc3, kr3, host=(hc, hr)))
+    _lib.tune_set("tim.band", 5)
+    add("dwconv2d_sep k=15 [the same walk fed from a warp-private cp.async ring]", 8, lambda: be.dwconv2d_sep(g, kc3, kr3, host=(hc, hr)))
+    _lib.tune_set("tim.band", 4)
     _lib.tune_set("tim.split", 1)
     add("dwconv2d_sep k=15 [unrolled band walk, interior / edge windows in separate CTAs]", 8, lambda: be.dwconv2d_sep(g, kc3, kr3, host=(hc, hr)))
     _lib.tune_set("tim.split", 0)
