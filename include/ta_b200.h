@@ -193,8 +193,9 @@ int ta_normalize_bwd(const float* gout, const float* std, float* gin,
  * `gin.abs().mean(dim=(1,2,3))` reduction (attack.py:128) in col_sums [B, S], S = block_w * block_h * ctas_per_output of
  * ta_aten_mean_policy for (B, C*plane) on the current device; ta_abs_mean_from_colsums finishes that mean (bit-identical to
  * torch's op, like TA_MEAN_TORCH) from those 4*S bytes per sample — the gradient is not read a second time. With mean_out [B]
- * and counters [B] (int32, zero before the first call; the kernel leaves them zero) the last CTA of every sample to finish does
- * that inside the same launch (both NULL: column sums only).
+ * and counters [B] (int32, zero before the first call; the kernel leaves them zero) the mean is finished inside the same launch:
+ * every CTA reduces its block, the last CTA of a sample to arrive adds the per-block partials (col_sums is then only scratch for
+ * those partials and does NOT hold the column values). Both NULL: column sums only.
  * C <= 4, plane % 4 == 0, 16-byte aligned tensors; TA_EUNSUPPORTED otherwise or outside the replayed launch family. */
 int ta_normalize_bwd_colsum(const float* gout, const float* std, float* gin, float* col_sums,
                             float* mean_out, int* counters, int B, int C, int64_t plane, ta_stream_t stream);

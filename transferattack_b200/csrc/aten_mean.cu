@@ -127,8 +127,9 @@ __global__ void __launch_bounds__(kAtenThreads, 2) aten_abs_mean_kernel(const fl
 // Normalize's adjoint gin = gout / std[c] (the bits of ta_normalize_bwd) with the thread <-> data mapping of ATen's mean
 // reduction over gin: CTA (x, b) owns virtual threads [512 x, 512 x + 512) of sample b, thread t the 128-bit vectors t, t + S, ...
 // — so that besides storing gin it can leave that virtual thread's column value of |gin| in col_sums[b * S + t].
-// FINISH: the last CTA of a sample to arrive (ticket counter per sample, reset by that CTA: ATen's own global_reduce scheme)
-// copies the sample's S column values into shared memory and runs the trees → mean_out[b]; no separate launch for the mean.
+// FINISH: ATen's own structure — every CTA reduces its virtual block (block_x_reduce, block_y_reduce) from shared memory and
+// stores one partial; the last CTA of a sample to arrive (ticket counter per sample, reset by that CTA) runs global_reduce's
+// final tree over the cpo partials → mean_out[b]; no separate launch for the mean, no column values through global memory.
 template <bool FINISH>
 __global__ void __launch_bounds__(kAtenThreads, 3) normalize_bwd_colsum_kernel(const float* __restrict__ gout, const float* __restrict__ std,
                                                                             float* __restrict__ gin, float* __restrict__ col_sums,
@@ -165,21 +166,70 @@ __global__ void __launch_bounds__(kAtenThreads, 3) normalize_bwd_colsum_kernel(c
           aten_column_add(A, t);
         }
     }
-    col_sums[(int64_t)b * S + col] = aten_column_value(A);
+    if (FINISH) s_cols[threadIdx.x] = aten_column_value(A);
+    else col_sums[(int64_t)b * S + col] = aten_column_value(A);
+  } else if (FINISH) {
+    s_cols[threadIdx.x] = 0.0f;
   }
   if (FINISH) {
-    __threadfence();                                   // this CTA's column values are visible device-wide before its ticket
+    // CTA x IS ATen's virtual block x of this sample (S = 512 * cpo, thread id = virtual thread id inside the block): its
+    // block_x_reduce and block_y_reduce run here, on the values still in this CTA; only the per-block partial goes through global
+    // memory (ATen's staging buffer: col_sums[b * S + x], x < cpo) and the last CTA of the sample to arrive runs global_reduce's
+    // final tree over the cpo partials.
     __syncthreads();
-    if (threadIdx.x == 0) s_last = (atomicAdd(counters + b, 1) == (int)gridDim.x - 1) ? 1 : 0;
+    {
+      AtenMeanCfg one = cfg; one.cpo = 1;                                         // the trees of ONE block over s_cols[0 .. 512)
+      const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+      const int K = cfg.bw >> 5;
+      switch (K) {
+        case 1: aten_rows_x_tree<1>(one, ColSrcShared{s_cols}, s_row, warp, lane); break;
+        case 2: aten_rows_x_tree<2>(one, ColSrcShared{s_cols}, s_row, warp, lane); break;
+        case 4: aten_rows_x_tree<4>(one, ColSrcShared{s_cols}, s_row, warp, lane); break;
+        case 8: aten_rows_x_tree<8>(one, ColSrcShared{s_cols}, s_row, warp, lane); break;
+        default: aten_rows_x_tree<16>(one, ColSrcShared{s_cols}, s_row, warp, lane); break;
+      }
+    }
+    __syncthreads();
+    float* partials = col_sums + (int64_t)b * S;                                  // the first cpo floats of the sample's slice (no column values are stored in this form)
+    if (threadIdx.x == 0) {
+      float a[16];
+#pragma unroll
+      for (int y = 0; y < 16; ++y) a[y] = (y < cfg.bh) ? s_row[y] : 0.0f;
+      // block_y_reduce, offsets bh/2 .. 1 (bh is a power of two <= 16; levels above bh do not exist)
+#pragma unroll
+      for (int h = 8; h >= 1; h >>= 1)
+        if (h < cfg.bh) {
+#pragma unroll
+          for (int y = 0; y < h; ++y) a[y] = add_rn(a[y], a[y + h]);
+        }
+      s_blk[0] = a[0];
+    }
+    if (threadIdx.x == 0) {
+      __stcg(partials + blockIdx.x, s_blk[0]);
+      __threadfence();
+      s_last = (atomicAdd(counters + b, 1) == (int)gridDim.x - 1) ? 1 : 0;
+    }
     __syncthreads();
     if (s_last) {
       __threadfence();
-      const float4* s4 = reinterpret_cast<const float4*>(col_sums + (int64_t)b * S);
-      float4* d4 = reinterpret_cast<float4*>(s_cols);
-      for (int i = threadIdx.x; i < (S >> 2); i += kAtenThreads) d4[i] = __ldcg(s4 + i);     // L2: written by other CTAs of this launch
-      __syncthreads();
-      const float mu = aten_tree_mean_src(cfg, ColSrcShared{s_cols}, s_row, s_blk);
-      if (threadIdx.x == 0) { mean_out[b] = mu; counters[b] = 0; }                          // leave the counter ready for the next launch
+      const float* pp = partials;
+      const int lane = threadIdx.x & 31;
+      if (threadIdx.x < 32) {
+        float v;
+        if (cfg.cpo == 1) {
+          v = __ldcg(pp);
+        } else if (cfg.cpo <= 32) {
+          float a1[1] = {lane < cfg.cpo ? __ldcg(pp + lane) : 0.0f};
+          v = aten_x_tree<1>(a1);
+        } else {
+          float a16[16];
+          const int K = cfg.bw >> 5;
+#pragma unroll
+          for (int k = 0; k < 16; ++k) { const int i = lane + 32 * k; a16[k] = (k < K && i < cfg.cpo) ? __ldcg(pp + i) : 0.0f; }
+          v = aten_x_tree<16>(a16);
+        }
+        if (lane == 0) { mean_out[b] = mul_rn(v, cfg.factor); counters[b] = 0; }
+      }
     }
   }
 }
@@ -219,14 +269,11 @@ int aten_colsum_normalize_bwd(const float* gout, const float* std, float* gin, f
   const int rc = aten_mean_plan("ta_normalize_bwd_colsum", B, n, 0, &c);
   if (rc != TA_OK) return rc;
   dim3 grid((unsigned)((c.S + kAtenThreads - 1) / kAtenThreads), (unsigned)B);
-  const size_t smem = sizeof(float) * (size_t)c.S;
-  if (mean_out && counters && smem <= 64 * 1024 && c.cpo * c.bh <= kAtenThreads) {
-    static SmemOptIn optin = {};
-    const int ro = ensure_dyn_smem("ta_normalize_bwd_colsum", normalize_bwd_colsum_kernel<true>, smem, optin);
-    if (ro != TA_OK) return ro;
-    normalize_bwd_colsum_kernel<true><<<grid, kAtenThreads, smem, s>>>(gout, std, gin, col_sums, mean_out, counters, n, c, (int)(plane / 4), C);
+  if (mean_out && counters && c.nt == kAtenThreads && c.S == kAtenThreads * c.cpo) {
+    normalize_bwd_colsum_kernel<true><<<grid, kAtenThreads, sizeof(float) * kAtenThreads, s>>>(gout, std, gin, col_sums, mean_out, counters, n, c,
+                                                                                            (int)(plane / 4), C);
   } else if (mean_out) {
-    set_error("ta_normalize_bwd_colsum: the in-kernel finish serves S <= 16384 column values per sample (here %d)", c.S);
+    set_error("ta_normalize_bwd_colsum: the in-kernel finish needs ATen blocks of %d threads (here %d)", kAtenThreads, c.nt);
     return TA_EUNSUPPORTED;
   } else
     normalize_bwd_colsum_kernel<false><<<grid, kAtenThreads, 0, s>>>(gout, std, gin, col_sums, nullptr, nullptr, n, c, (int)(plane / 4), C);
