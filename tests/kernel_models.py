@@ -5,6 +5,8 @@ band, a destination row written twice or never, a band boundary off by one) is e
 oracle. fp32 fused multiply-adds are emulated through float64 (the 24x24-bit product is exact; one rounding).
 
   rs_conv_model          transferattack_b200/csrc/dwconv.cu   dwconv_sep_rs_kernel / dwconv_sep_rg_kernel
+  rg2_conv_model         … dwconv_sep_rg2_kernel / dwconv_sep_rg3_kernel (paired row weights, tap-exact column pass, zero-row reads)
+  colsum_adjoint_model   transferattack_b200/csrc/aten_mean.cu   normalize_bwd_colsum_kernel<FINISH> (per-block trees + ticket)
   dim_tables             transferattack_b200/csrc/dim_direct.cu   host_taps / host_inverse / band table
   dim_fwd_model          … dim_fwd_direct_kernel
   dim_bwd_scatter_model  … dim_bwd_direct_kernel (gather_scatter)
@@ -59,6 +61,107 @@ def rs_conv_model(g, kcol, krow, bhr=32):
                 yl += 1
     assert (written == 1).all(), "an output row was stored twice or never"
     return out
+
+
+def rg2_conv_model(g, kcol, krow, bhr=32):
+    """dwconv_sep_rg2_kernel (round 2): the band's bhr + ks - 1 rows fully unrolled; per input row
+      * row pass with the DATA broadcast and the WEIGHTS paired: pair (out[x], out[x+1]) += (w[m], w[m-1]) * v[OFF + x + m], m = 1 .. ks-1,
+        the two end taps (m = 0 on the low lane, m = ks on the high lane) as scalar fmas;
+      * column pass only for the taps that exist: input row r is tap i of output row y = r - i, 0 <= y < bhr; tap 0 starts from +0;
+      * rows above / below the image are skipped (only possible in the first / last band: H % bhr == 0); a slot whose first tap
+        was skipped is set to +0 instead; window quarters outside the row read zeros (the device reads its static zero rows);
+      * output row y leaves after input row y + ks - 1.  Shared (channel-independent) factors, W % 4 == 0, H % bhr == 0."""
+    B, C, H, W = g.shape
+    ks = kcol.shape[1]; R = ks // 2; padx = (R + 3) & ~3; off = padx - R; nv = (off + ks + 3 + 3) // 4
+    assert H % bhr == 0 and W % 4 == 0
+    rows = bhr + ks - 1
+    nbands = H // bhr
+    out = np.full_like(g, np.nan)
+    written = np.zeros(g.shape, np.int32)
+    T = W // 4
+    kr, kc = krow[0], kcol[0]
+    wp = [(kr[m] if m < ks else f32(0), kr[m - 1] if m >= 1 else f32(0)) for m in range(ks + 1)]
+    for plane in range(B * C):
+        gp = g.reshape(B * C, H, W)[plane]; op = out.reshape(B * C, H, W)[plane]; wr = written.reshape(B * C, H, W)[plane]
+        for band in range(nbands):
+            y0 = band * bhr
+            top_ok, bot_ok = band > 0, band < nbands - 1
+            acc = np.full((ks, T, 4), np.nan, f32)                     # no slot may be read before its first tap (or its +0) was written
+            for r in range(rows):
+                rv = top_ok if r < R else (bot_ok if r >= rows - R else True)
+                if rv:
+                    yy = y0 - R + r
+                    assert 0 <= yy < H
+                    win = np.zeros((T, 4 * nv), f32)
+                    for t in range(T):
+                        for k in range(nv):
+                            col = 4 * t - padx + 4 * k
+                            if 0 <= col < W:
+                                win[t, 4 * k:4 * k + 4] = gp[yy, col:col + 4]
+                    t4 = np.zeros((T, 4), f32)
+                    for pair in (0, 2):                                # pair 0 = outputs (0, 1), pair 1 = outputs (2, 3)
+                        lo = fma(kr[0], win[:, off + pair], f32(0)); hi = np.zeros(T, f32)
+                        for m in range(1, ks):
+                            v = win[:, off + pair + m]
+                            lo = fma(wp[m][0], v, lo); hi = fma(wp[m][1], v, hi)
+                        hi = fma(kr[ks - 1], win[:, off + pair + ks], hi)
+                        t4[:, pair] = lo; t4[:, pair + 1] = hi
+                    for i in range(ks):
+                        y = r - i
+                        if 0 <= y < bhr:
+                            s = y % ks
+                            acc[s] = fma(kc[i], t4, np.zeros_like(t4) if i == 0 else acc[s])
+                elif r < bhr:
+                    acc[r % ks] = 0
+                if r >= ks - 1:
+                    y = r - (ks - 1)
+                    assert not np.isnan(acc[y % ks]).any()
+                    op[y0 + y] = acc[y % ks].reshape(-1); wr[y0 + y] += 1
+    assert (written == 1).all(), "an output row was stored twice or never"
+    return out
+
+
+def colsum_adjoint_model(gout, std, cfg):
+    """normalize_bwd_colsum_kernel<FINISH = true>: CTA (x, b) = ATen's virtual block x of sample b; thread t owns the 128-bit vectors
+    col, col + S, ... (col = 512 x + t), divides by std[channel], accumulates |.| component-wise; the CTA runs block_x_reduce /
+    block_y_reduce on its 512 values; the per-block partials are added by global_reduce's final tree. Returns (gin, mean)."""
+    B = gout.shape[0]; C = gout.shape[1]
+    n = gout[0].size
+    bw, bh, cpo = cfg["bw"], cfg["bh"], cfg["cpo"]; S = bw * bh * cpo
+    assert bw * bh == 512
+    nvec = n // 4; plane_vec = nvec // C
+    K = bw // 32
+    gin = np.empty_like(gout).reshape(B, nvec, 4)
+    src = gout.reshape(B, nvec, 4)
+    mean = np.zeros(B, f32)
+    for b in range(B):
+        partial = np.zeros(cpo, f32)
+        for x in range(cpo):
+            vals = np.zeros(512, f32)
+            for t in range(512):
+                col = 512 * x + t
+                a = np.zeros(4, f32)
+                v = col
+                while v < nvec:
+                    ch = int(v >= plane_vec) + int(v >= 2 * plane_vec) + int(v >= 3 * plane_vec)
+                    q = (src[b, v] / std[ch]).astype(f32)
+                    gin[b, v] = q
+                    a = (a + np.abs(q)).astype(f32)
+                    v += S
+                vals[t] = f32(f32(f32(a[0] + a[1]) + a[2]) + a[3])
+            rows = np.zeros(bh, f32)
+            for ty in range(bh):                                        # block_x_reduce of row ty: lane l holds tx = l + 32 k
+                a = [vals[ty * bw + np.arange(32) + 32 * k].copy() for k in range(K)]
+                rows[ty] = _x_tree(a, K)
+            h = bh // 2
+            while h >= 1:                                               # block_y_reduce
+                rows[:h] = (rows[:h] + rows[h:2 * h]).astype(f32); h //= 2
+            partial[x] = rows[0]
+        lanes = np.zeros(32 * max(K, 1), f32); lanes[:cpo] = partial     # global_reduce: partial i at tx = i, ty = 0
+        a = [lanes[np.arange(32) + 32 * k].copy() for k in range(K)]
+        tot = _x_tree(a, K)
+        mean[b] = f32(tot * f32(f32(B) / f32(B * n)))
+    return gin.reshape(gout.shape), mean
 
 
 # ---- DIM: host tables ------------------------------------------------------------------------------------------------------------

@@ -19,6 +19,38 @@ def test_register_sliding_convolution_model(ks, H, W, bhr):
     assert bits_equal(KM.rs_conv_model(g, kc, kr, bhr), oracle.dwconv2d_sep(g, kc, kr))
 
 
+@pytest.mark.parametrize("ks,H,W,bhr", [(15, 64, 32, 32), (15, 96, 64, 32), (7, 64, 32, 32), (3, 64, 36, 32), (5, 32, 40, 32)])
+def test_unrolled_band_walk_model(ks, H, W, bhr):
+    """dwconv_sep_rg2_kernel / dwconv_sep_rg3_kernel (the TIM kernel that ships in round 2): paired row weights with scalar end taps,
+    the tap-exact column pass (a halo row feeds only the output rows that exist; tap 0 starts from +0; no slot is read before it
+    was started), skipped out-of-image rows in the first / last band, zero reads outside the row — every output row stored
+    exactly once and bit-identical to orc_dwconv2d_sep (a single band, H == bhr, has both halos outside the image)"""
+    rng = np.random.default_rng(ks * 77 + H)
+    g = rng.standard_normal((1, 2, H, W)).astype(np.float32)
+    k1c = rng.random(ks).astype(np.float32); k1r = rng.random(ks).astype(np.float32)
+    kc = np.stack([k1c] * 2); kr = np.stack([k1r] * 2)
+    assert bits_equal(KM.rg2_conv_model(g, kc, kr, bhr), oracle.dwconv2d_sep(g, kc, kr))
+
+
+@pytest.mark.parametrize("B,shape", [(64, (3, 32, 32 * 4)), (5, (3, 64, 64)), (2, (3, 64, 64)), (16, (4, 32, 64))])
+def test_adjoint_with_block_trees_model_equals_the_aten_restatement(B, shape):
+    """normalize_bwd_colsum_kernel<FINISH> step by step in numpy: the adjoint g / std[channel] per 128-bit vector in ATen's
+    thread <-> data mapping, block_x_reduce / block_y_reduce per CTA, the final tree over the per-block partials — must equal
+    oracle/aten_reduce.py's restatement of torch's `(g / std).abs().mean(dim=(1,2,3))` bit for bit (that restatement is pinned against
+    torch on the GPU box) and the plain quotient for the gradient."""
+    from oracle import aten_reduce
+    n = int(np.prod(shape))
+    cfg = aten_reduce.config(B, n)
+    assert cfg is not None and cfg["bw"] * cfg["bh"] == 512
+    rng = np.random.default_rng(B * 31 + n)
+    g = (rng.standard_normal((B,) + shape) * 10.0 ** rng.integers(-3, 2)).astype(np.float32)
+    std = np.asarray([0.229, 0.224, 0.225, 0.31][:shape[0]], np.float32)
+    gin, mean = KM.colsum_adjoint_model(g, std, cfg)
+    want = (g / std.reshape(1, -1, 1, 1)).astype(np.float32)
+    assert bits_equal(gin, want)
+    assert bits_equal(mean, aten_reduce.emulate_numpy(np.abs(want).reshape(B, n)))
+
+
 DIM_GEOMETRIES = [(32, 33, 35, 1, 2), (32, 32, 35, 0, 3), (32, 34, 35, 1, 0), (20, 21, 22, 0, 0), (40, 43, 44, 1, 1),
                   (24, 24, 48, 10, 20), (33, 36, 36, 0, 0), (48, 52, 52, 0, 0), (16, 30, 40, 5, 5)]
 
