@@ -866,9 +866,9 @@ def run_kernels(args):
     _lib.tune_set("tim.split", 1)
     add("dwconv2d_sep k=15 [unrolled band walk, interior / edge windows in separate CTAs]", 8, lambda: be.dwconv2d_sep(g, kc3, kr3, host=(hc, hr)))
     _lib.tune_set("tim.split", 0)
-    _lib.tune_set("tim.deep", 0)
-    add("dwconv2d_sep k=15 [unrolled band walk, loads one row ahead]", 8, lambda: be.dwconv2d_sep(g, kc3, kr3, host=(hc, hr)))
     _lib.tune_set("tim.deep", 1)
+    add("dwconv2d_sep k=15 [unrolled band walk, loads two rows ahead]", 8, lambda: be.dwconv2d_sep(g, kc3, kr3, host=(hc, hr)))
+    _lib.tune_set("tim.deep", 0)
     for pf in (2, 1, 0):
         _lib.tune_set("tim.prefetch2", pf)
         add("dwconv2d_sep k=15 [unrolled band walk, prefetch mode %d]" % pf, 8, lambda: be.dwconv2d_sep(g, kc3, kr3, host=(hc, hr)))

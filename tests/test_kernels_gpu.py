@@ -288,11 +288,11 @@ def test_tim_sep_all_launch_paths_bit_identical(be, ks):
                     _lib.tune_set("tim.band", band); _lib.tune_set("tim.bh", bh); _lib.tune_set("tim.f2", f2)
                     got = npy(be.dwconv2d_sep(cu(x), cu(kc), cu(kr)))
                     assert bits_equal(got, want), (shp, "device factors", band, bh, f2)
-                    for split in ((0, 1) if band == 4 else (0,)):
-                        _lib.tune_set("tim.split", split)
+                    for split, deep in (((0, 0), (1, 0), (0, 1)) if band == 4 else ((0, 0),)):
+                        _lib.tune_set("tim.split", split); _lib.tune_set("tim.deep", deep)
                         got = npy(be.dwconv2d_sep(cu(x), cu(kc), cu(kr), host=(kc, kr)))
-                        assert bits_equal(got, want), (shp, "host factors", band, bh, f2, split)
-                    _lib.tune_set("tim.split", 0)
+                        assert bits_equal(got, want), (shp, "host factors", band, bh, f2, split, deep)
+                    _lib.tune_set("tim.split", 0); _lib.tune_set("tim.deep", 0)
     finally:
         _lib.tune_set("tim.band", 4); _lib.tune_set("tim.bh", 32); _lib.tune_set("tim.f2", 1)
 

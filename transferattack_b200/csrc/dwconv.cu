@@ -824,7 +824,7 @@ int launch_rg2(const float* g, const float* kcol_host, const float* krow_host, f
     const int64_t blocks = (items + 127) / 128;
     TA_REQUIRE(blocks <= 0x7fffffff, "ta_dwconv2d_sep: too many work items");
     if (W == 224 && tune_get("tim.wconst", 1) != 0) {
-      if (tune_get("tim.deep", 1) != 0)
+      if (tune_get("tim.deep", 0) != 0)       // loads two rows ahead: same time, but 128 registers then spill (ptxas: 28 B)
         dwconv_sep_rg2_kernel<KS, BHR, false, 224, true><<<(unsigned)blocks, 128, 0, s>>>(g, w, out, H, W, nbands, 0, items, 0, pf);
       else
         dwconv_sep_rg2_kernel<KS, BHR, false, 224, false><<<(unsigned)blocks, 128, 0, s>>>(g, w, out, H, W, nbands, 0, items, 0, pf);
