@@ -131,7 +131,7 @@ __global__ void __launch_bounds__(kAtenThreads, 2) aten_abs_mean_kernel(const fl
 // stores one partial; the last CTA of a sample to arrive (ticket counter per sample, reset by that CTA) runs global_reduce's
 // final tree over the cpo partials → mean_out[b]; no separate launch for the mean, no column values through global memory.
 template <bool FINISH>
-__global__ void __launch_bounds__(kAtenThreads, 3) normalize_bwd_colsum_kernel(const float* __restrict__ gout, const float* __restrict__ std,
+__global__ void __launch_bounds__(kAtenThreads, 2) normalize_bwd_colsum_kernel(const float* __restrict__ gout, const float* __restrict__ std,
                                                                             float* __restrict__ gin, float* __restrict__ col_sums,
                                                                             float* __restrict__ mean_out, int* __restrict__ counters,
                                                                             int64_t n, AtenMeanCfg cfg, int plane_vec, int C) {
