@@ -128,15 +128,16 @@ class Attack(object):
     #: SURVEY §8 f1: when the surrogate is ``Sequential(PreprocessingModel, net)`` (what ``wrap_model`` builds), its Resize is a
     #: no-op at the input size and neither ``transform`` nor ``get_logits`` is overridden, the fused tail writes the NORMALISED
     #: next input ((data + delta') - mean) / std itself (``ta_fused_update_linf_nf``) and ``net`` is entered directly: the
-    #: Normalize forward kernel disappears from every iteration. Its adjoint g / std stays a ``ta_normalize_bwd`` launch in
-    #: strict mean mode (torch's own mean op needs the gradient w.r.t. delta in memory) and moves into the fused kernel too
-    #: in 'exact' mode with the base ``get_grad``. Same arithmetic in the same order → same bits. Env TA_B200_FOLD=0 disables.
+    #: Normalize forward kernel disappears from every iteration. Its adjoint g / std stays ONE launch at the end of the backward
+    #: pass (``ta_normalize_bwd``; by default the variant that also finishes mean|g|, see ``colsum_adjoint``) or moves into the
+    #: fused kernel too (``fold_adjoint``; default in 'exact' mode with the base ``get_grad``). Same arithmetic in the same
+    #: order → same bits. Env TA_B200_FOLD=0 disables.
     fold_normalize = os.environ.get("TA_B200_FOLD", "1") == "1"
     #: with an in-kernel mean and the base get_grad, Normalize's ADJOINT (g / std) can be applied inside the tail kernels too
     #: instead of as a `ta_normalize_bwd` launch at the end of the backward pass. Same bits either way. Measured on B200 at B = 64
-    #:: folded = 2 launches, 64 us of tail; not folded = 3 launches, 13 us (inside autograd.grad) + 55 us of tail —
-    #: the IEEE division has to be done in the mean kernel AND in the streaming kernel when folded, so the saving is 4 us per
-    #: iteration. Default: not folded for mean_mode 'torch' (the division-free mean kernel), folded for 'exact' (one cluster launch).
+    #:: folded = 2 launches, 64 us of tail; not folded = adjoint kernel (inside autograd.grad) + 45-55 us of tail —
+    #: the IEEE division has to be done in the mean kernel AND in the streaming kernel when folded. Default: not folded for
+    #: mean_mode 'torch' (the adjoint kernel finishes the mean, see below), folded for 'exact' (one cluster launch).
     fold_adjoint = {"1": True, "0": False}.get(os.environ.get("TA_B200_FOLD_ADJOINT", ""), None)
     #: with mean_mode 'torch', the folded Normalize and the base get_grad: the Normalize-adjoint kernel at the end of the backward
     #: pass also forms the per-column sums of |g| of torch's mean reduction and its last CTA per sample finishes mean|g| from them
