@@ -11,6 +11,7 @@ oracle. fp32 fused multiply-adds are emulated through float64 (the 24x24-bit pro
   dim_fwd_model          … dim_fwd_direct_kernel
   dim_bwd_scatter_model  … dim_bwd_direct_kernel (gather_scatter)
   dim_bwd_gather_model   … dim_bwd_gather_kernel
+  dim_bwd_sep_model      … dim_bwd_sep_kernel (the four passes transposed; default adjoint)
 """
 import numpy as np
 
@@ -347,6 +348,60 @@ def dim_bwd_gather_model(g, rnd, R, top, left):
                 for col in range(S):
                     lx, cx = inv1[col]
                     gin[pl, sy, col] = gather(bufG, lo - q0, roww, lx, [tap_w(t1[lx + b], col) for b in range(cx)]) if nq else f32(0)
+    return gin
+
+
+def dim_bwd_sep_model(g, rnd, R, top, left):
+    """dim_bwd_sep_kernel (the default adjoint in round 2): per band of RB source rows the four passes transposed, every one a
+    gather over an inverse range with the nan-poisoned buffers the device uses (a read outside what a pass wrote shows up as NaN):
+      vT2  V[q][ox]  = sum_a w(oy = lo + a, p = q0 + q + top) * U[lo + a - oyA][ox]       (rows: the band's y1 rows as y2 rows)
+      hT2  G[q][qx]  = sum_b w(ox = lo + b, px = qx + left)   * V[q][lo + b]               (crop = the pad's adjoint)
+      vT1  W[r][qx]  = sum_a w(q = lo + a, sy = sy0 + r)      * G[lo + a - q0][qx]
+      hT1  gin[sy][sx] = sum_b w(qx = lo + b, sx)             * W[r][lo + b]"""
+    P, S, _ = g.shape
+    t2, t1, inv2, inv1 = dim_tables(S, rnd, R)
+    gin = np.full_like(g, np.nan)
+    wrote = np.zeros(g.shape, np.int32)
+    for pl in range(P):
+        for sy0 in range(0, S, RB):
+            sy1, q0, nq, oyA, nu = _band(sy0, S, top, inv1, inv2)
+            nb = sy1 - sy0 + 1
+            if nq == 0:
+                gin[pl, sy0:sy1 + 1] = 0; wrote[pl, sy0:sy1 + 1] += 1
+                continue
+            U = g[pl, oyA:oyA + nu]
+            V = np.full((nq, S), np.nan, f32)
+            for q in range(nq):
+                p = q0 + q + top; lo, c = inv2[p]
+                acc = np.zeros(S, f32)
+                for a in range(c):
+                    assert 0 <= lo + a - oyA < nu
+                    acc = fma(tap_w(t2[lo + a], p), U[lo + a - oyA], acc)
+                V[q] = acc
+            G = np.full((nq, rnd), np.nan, f32)
+            for qx in range(rnd):
+                px = qx + left; lo, c = inv2[px]
+                for q in range(nq):
+                    h = f32(0)
+                    for b in range(c):
+                        h = fma(tap_w(t2[lo + b], px), V[q, lo + b], h)
+                    G[q, qx] = h
+            Wb = np.full((nb, rnd), np.nan, f32)
+            for r in range(nb):
+                sy = sy0 + r; lo, c = inv1[sy]
+                acc = np.zeros(rnd, f32)
+                for a in range(c):
+                    assert 0 <= lo + a - q0 < nq
+                    acc = fma(tap_w(t1[lo + a], sy), G[lo + a - q0], acc)
+                Wb[r] = acc
+            for sx in range(S):
+                lo, c = inv1[sx]
+                for r in range(nb):
+                    h = f32(0)
+                    for b in range(c):
+                        h = fma(tap_w(t1[lo + b], sx), Wb[r, lo + b], h)
+                    gin[pl, sy0 + r, sx] = h; wrote[pl, sy0 + r, sx] += 1
+    assert (wrote == 1).all(), "a source element was written twice or never"
     return gin
 
 

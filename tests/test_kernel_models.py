@@ -58,12 +58,13 @@ DIM_GEOMETRIES = [(32, 33, 35, 1, 2), (32, 32, 35, 0, 3), (32, 34, 35, 1, 0), (2
 @pytest.mark.parametrize("S,rnd,R,top,left", DIM_GEOMETRIES)
 def test_dim_direct_models(S, rnd, R, top, left):
     """host tap / inverse tables and band table; forward: zero row + zero column as the padding → bit-identical to orc_dim_fwd
-    (blend 1); both adjoint forms: every destination written exactly once, equal to the fp64 scatter oracle to rounding"""
+    (blend 1); the three adjoint forms (separable passes = the default, scatter, gather): every destination written exactly once, no
+    read outside what a previous pass wrote, equal to the fp64 scatter oracle to rounding"""
     rng = np.random.default_rng(S * 100 + rnd)
     x = rng.random((1, S, S)).astype(np.float32); g = rng.standard_normal((1, S, S)).astype(np.float32)
     assert bits_equal(KM.dim_fwd_model(x, rnd, R, top, left), oracle.dim_fwd(x[None], rnd, R, top, left, blend=1)[0])
     want = oracle.dim_bwd(g[None], rnd, R, top, left)[0]
-    for model in (KM.dim_bwd_scatter_model, KM.dim_bwd_gather_model):
+    for model in (KM.dim_bwd_sep_model, KM.dim_bwd_scatter_model, KM.dim_bwd_gather_model):
         got = model(g, rnd, R, top, left)
         assert not np.isnan(got).any()
         np.testing.assert_allclose(got, want, rtol=0, atol=2e-6)
